@@ -1,0 +1,385 @@
+"""Shape / dtype boundary of the nphusl API and chunked application.
+
+Host-side mirror of the reference's ``nphusl/transform.py`` (public names,
+argument meaning and error behaviour are kept so callers and tests written for
+the reference keep working):
+
+* dtype coercion -- ``ensure_{int,float,rgb_int,rgb_float}`` and the
+  ``*_input`` / ``*_output`` decorators (reference ``transform.py:16-103``);
+* shape normalisation -- ``reshape_image_input`` (triplets, flat lists,
+  grayscale floats, RGBA), ``reshape_husl_input``, ``reshape_rgba_input``,
+  ``squeeze_output`` (reference ``transform.py:137-246``);
+* chunked application -- ``in_chunks``, ``chunk_img``, ``chunk``,
+  ``chunk_apply``, ``chunk_apply_1d``, ``chunk_many`` (reference
+  ``transform.py:251-308``).
+
+Differences from the reference, all deliberate:
+
+* objects exposing ``__cuda_array_interface__`` (device-resident frames) pass
+  through every decorator untouched -- nothing here may call
+  ``np.ascontiguousarray`` on them, that would drag the frame to the host;
+* ``np.floating`` / ``np.integer`` replace the removed ``np.float`` alias, so
+  float32 inputs are recognised as floats (App. D-7);
+* ``in_chunks`` implements the documented ``chunksize`` / ``out`` behaviour
+  (reference ``README.md:55-57``); in 1.5.0 the two arguments are swapped at the
+  call sites (App. D-1).  Both argument orders are accepted.
+"""
+
+import warnings
+from collections import namedtuple
+from enum import Enum
+from functools import partial, wraps
+
+import numpy as np
+from numpy import ndarray
+
+
+def is_device_array(obj) -> bool:
+    """True for anything that lives in GPU memory (torch CUDA tensors, our own
+    ``DeviceArray``, ...) -- recognised by ``__cuda_array_interface__``."""
+    return hasattr(obj, "__cuda_array_interface__")
+
+
+def _dtype_of(arr):
+    if is_device_array(arr):
+        return np.dtype(arr.__cuda_array_interface__["typestr"])
+    return arr.dtype
+
+
+# --------------------------------------------------------------------------
+# dtype coercion
+# --------------------------------------------------------------------------
+
+type_tuple = namedtuple("type_tuple", "base exact convert exact_required")
+
+
+def scale_up_rgb(rgb: ndarray):
+    """[0, 1] floats -> [0, 255], rounded half-to-even like ``np.round``."""
+    return np.round(rgb * 255.0)
+
+
+def scale_down_rgb(rgb: ndarray):
+    """[0, 255] integers -> [0, 1] floats."""
+    return rgb / 255.0
+
+
+def to_dtype(dtype, arr: ndarray):
+    return arr.astype(dtype.exact)
+
+
+def to_rgb_int(dtype, arr: ndarray):
+    """float RGB in [0, 1] -> uint8; integer input is only cast.  No clamp:
+    negative values are mirrored by ``abs`` and values past 255 wrap, exactly
+    like the reference (``transform.py:16-20``, App. D-6)."""
+    if not np.issubdtype(arr.dtype, dtype.base):
+        arr = scale_up_rgb(arr)
+    return to_dtype(dtype, np.abs(arr))
+
+
+def to_rgb_float(dtype, arr: ndarray):
+    """integer RGB in [0, 255] -> float64 in [0, 1]; float input is only cast."""
+    if not np.issubdtype(arr.dtype, dtype.base):
+        arr = scale_down_rgb(arr)
+    return to_dtype(dtype, arr)
+
+
+class Dtype(type_tuple, Enum):
+    int = type_tuple(np.integer, np.int64, to_dtype, False)
+    float = type_tuple(np.floating, np.float64, to_dtype, False)
+    rgb_int = type_tuple(np.integer, np.uint8, to_rgb_int, True)
+    rgb_float = type_tuple(np.floating, np.float64, to_rgb_float, True)
+
+
+def ensure_dtype(dtype: Dtype, arr):
+    """Return ``arr`` unchanged when it already has an acceptable dtype, else a
+    converted copy.  Device arrays are never touched: the CUDA backend accepts
+    uint8 / float32 / float64 and converts inside its kernels."""
+    if is_device_array(arr):
+        return arr
+    wanted = dtype.exact if dtype.exact_required else dtype.base
+    if np.issubdtype(arr.dtype, wanted):
+        return arr
+    return dtype.convert(dtype, arr)
+
+
+ensure_int = partial(ensure_dtype, Dtype.int)
+ensure_float = partial(ensure_dtype, Dtype.float)
+ensure_rgb_int = partial(ensure_dtype, Dtype.rgb_int)
+ensure_rgb_float = partial(ensure_dtype, Dtype.rgb_float)
+
+
+def ensure_input_dtype(dtype: Dtype):
+    """Decorator factory: first positional argument is coerced to ``dtype``."""
+    def decorate(fn):
+        @wraps(fn)
+        def wrapped(arr, *args, **kwargs):
+            return fn(ensure_dtype(dtype, arr), *args, **kwargs)
+        return wrapped
+    return decorate
+
+
+def ensure_output_dtype(dtype: Dtype):
+    """Decorator factory: the return value is coerced to ``dtype``."""
+    def decorate(fn):
+        @wraps(fn)
+        def wrapped(*args, **kwargs):
+            return ensure_dtype(dtype, fn(*args, **kwargs))
+        return wrapped
+    return decorate
+
+
+int_input = ensure_input_dtype(Dtype.int)
+float_input = ensure_input_dtype(Dtype.float)
+rgb_int_input = ensure_input_dtype(Dtype.rgb_int)
+rgb_float_input = ensure_input_dtype(Dtype.rgb_float)
+int_output = ensure_output_dtype(Dtype.int)
+float_output = ensure_output_dtype(Dtype.float)
+rgb_int_output = ensure_output_dtype(Dtype.rgb_int)
+rgb_float_output = ensure_output_dtype(Dtype.rgb_float)
+
+
+# --------------------------------------------------------------------------
+# reshape alerts
+# --------------------------------------------------------------------------
+
+Alert = Enum("Alert", "error warn quiet")
+
+
+class ReshapeAlert(str, Enum):
+    grayscale = "Conversion from grayscale input"
+    flat = "Conversion from a 1-dimensional input"
+    rgba = "Conversion from RGBA"
+
+
+# user-tunable: error / warn / quiet per kind of guess
+alert_levels = {
+    ReshapeAlert.grayscale: Alert.warn,
+    ReshapeAlert.flat: Alert.warn,
+    ReshapeAlert.rgba: Alert.warn,
+}
+
+
+def _alert(kind: ReshapeAlert, msg: str):
+    level = alert_levels[kind]
+    text = "{}: {}".format(kind, msg)
+    if level == Alert.error:
+        raise ValueError(text)
+    if level == Alert.warn:
+        warnings.warn(text)
+
+
+_alert_flat = partial(_alert, ReshapeAlert.flat)
+_alert_gray = partial(_alert, ReshapeAlert.grayscale)
+_alert_rgba = partial(_alert, ReshapeAlert.rgba)
+
+
+# --------------------------------------------------------------------------
+# shape normalisation
+# --------------------------------------------------------------------------
+
+def _as_array(arr):
+    if is_device_array(arr) or isinstance(arr, (np.ndarray, np.generic)):
+        return arr
+    return np.ascontiguousarray(arr)
+
+
+def _is_float(arr) -> bool:
+    return np.issubdtype(_dtype_of(arr), np.floating)
+
+
+def from_grayscale(img):
+    """(...,) single-channel floats -> (..., 3) with the value in R, G and B.
+    Device arrays are returned as they are: the CUDA backend has grayscale
+    kernels that broadcast in registers instead of in memory."""
+    if is_device_array(img):
+        return img
+    rgb = np.empty(img.shape + (3,), dtype=img.dtype)
+    rgb[...] = img[..., None]
+    return rgb
+
+
+def reshape_image_input(fn):
+    """RGB-side entry guard: lists become arrays, ``[r, g, b]`` becomes
+    ``[[r, g, b]]``, flat multiples of 3 (or 4) become rows of triplets
+    (quadruplets), 1-D / 2-D float arrays that cannot be pixels are taken as
+    grayscale; anything else raises ``ValueError``."""
+    @wraps(fn)
+    def wrapped(arr, *args, **kwargs):
+        arr = _as_array(arr)
+        shape = tuple(arr.shape)
+        ndim = len(shape)
+        size = int(np.prod(shape)) if shape else 1
+        channels = shape[-1] if shape else 0
+        bad = ValueError("Unrecognized image shape: {}".format(shape))
+        if ndim == 1:
+            if size in (3, 4):
+                arr = arr.reshape((1, size))
+            elif size % 3 == 0:
+                _alert_flat("Assuming 1D RGB")
+                arr = arr.reshape((size // 3, 3))
+            elif size % 4 == 0:
+                _alert_flat("Assuming 1D RGBA")
+                arr = arr.reshape((size // 4, 4))
+            elif _is_float(arr):
+                _alert_flat("Assuming 1D grayscale")
+                _alert_gray("Assuming 1D grayscale")
+                arr = from_grayscale(arr)
+            else:
+                raise bad
+        elif ndim == 2 and channels not in (3, 4):
+            if not _is_float(arr):
+                raise bad
+            _alert_gray("Assuming 2D grayscale")
+            arr = from_grayscale(arr)
+        elif channels not in (3, 4):
+            raise bad
+        return fn(arr, *args, **kwargs)
+    return wrapped
+
+
+def reshape_husl_input(fn):
+    """HUSL-side entry guard: last axis must hold (H, S, L)."""
+    @wraps(fn)
+    def wrapped(arr, *args, **kwargs):
+        arr = _as_array(arr)
+        shape = tuple(arr.shape)
+        size = int(np.prod(shape)) if shape else 1
+        bad = ValueError("Unrecognized HSL shape: {}".format(shape))
+        if len(shape) == 1:
+            if size == 3:
+                arr = arr.reshape((1, 3))
+            elif size % 3 == 0:
+                _alert_flat("Assuming 1D HSL")
+                arr = arr.reshape((size // 3, 3))
+            else:
+                raise bad
+        elif not shape or shape[-1] != 3:
+            raise bad
+        return fn(arr, *args, **kwargs)
+    return wrapped
+
+
+def reshape_rgba_input(fn):
+    """4-channel input is premultiplied by its alpha (i.e. composited over
+    black, reference ``transform.py:221-230``) and handed on as float RGB.
+    Integer RGBA keeps the reference's quirk of yielding *float64 values in
+    0..255* (App. D-5); only float RGBA is meaningful end to end."""
+    @wraps(fn)
+    def wrapped(arr, *args, **kwargs):
+        if len(arr.shape) in (2, 3) and arr.shape[-1] == 4:
+            _alert_rgba("Assumed RGBA with white background")
+            if is_device_array(arr):
+                raise ValueError("RGBA device arrays are not supported: "
+                                 "premultiply on the device first")
+            is_int = np.issubdtype(arr.dtype, np.integer)
+            alpha = arr[..., 3] / 255.0 if is_int else arr[..., 3]
+            arr = arr[..., :3] * alpha[..., None]
+            if is_int:
+                arr = np.round(arr).astype(arr.dtype)
+        return fn(arr, *args, **kwargs)
+    return wrapped
+
+
+def squeeze_output(fn):
+    """``[[h, s, l]]`` -> ``[h, s, l]`` for single-triplet calls."""
+    @wraps(fn)
+    def wrapped(*args, **kwargs):
+        out = fn(*args, **kwargs)
+        if isinstance(out, np.ndarray) and out.size == 3 and out.ndim == 2:
+            out = np.squeeze(out)
+        return out
+    return wrapped
+
+
+# --------------------------------------------------------------------------
+# chunked application
+# --------------------------------------------------------------------------
+
+def chunk(end: int, chunksize: int):
+    """(start, stop) pairs that tile ``range(end)`` in steps of ``chunksize``;
+    the last pair is short when ``chunksize`` does not divide ``end``."""
+    start = 0
+    if chunksize and end > chunksize:
+        for stop in range(chunksize, end, chunksize):
+            yield start, stop
+            start = stop
+    yield start, end
+
+
+def chunk_img(img, chunksize: int = None):
+    """Yield ``(tile, ((r0, r1), (c0, c1)))`` over ``chunksize`` x ``chunksize``
+    square tiles of the first two axes (views, not copies).  Without a
+    ``chunksize`` the whole image is the single tile."""
+    rows, cols = img.shape[:2]
+    if not chunksize:
+        yield img, ((0, rows), (0, cols))
+        return
+    for r0, r1 in chunk(rows, chunksize):
+        for c0, c1 in chunk(cols, chunksize):
+            yield img[r0:r1, c0:c1], ((r0, r1), (c0, c1))
+
+
+def _chunk_no_idx(img, chunksize: int = None):
+    for tile, _ in chunk_img(img, chunksize):
+        yield tile
+
+
+def chunk_many(*arrays, chunksize: int = None):
+    """Walk several same-shaped images tile by tile, in lock step."""
+    return zip(*(_chunk_no_idx(a, chunksize) for a in arrays))
+
+
+def chunk_apply(transform, chunks, out) -> None:
+    """``out[tile] = transform(tile)`` for every (tile, bounds) of ``chunks``."""
+    for tile, ((r0, r1), (c0, c1)) in chunks:
+        out[r0:r1, c0:c1] = transform(tile)
+
+
+def chunk_apply_1d(transform, chunks, out) -> None:
+    """Row-only variant for 1-D outputs."""
+    for tile, ((r0, r1), _) in chunks:
+        out[r0:r1] = transform(tile)
+
+
+def in_chunks(img, transform: callable, chunksize=None, out=None):
+    """Apply ``transform`` to ``img``, optionally tile by tile.
+
+    * no ``chunksize``: ``transform(img)``, copied into ``out`` when given;
+    * ``chunksize``: the image is walked in square tiles (``chunk_img``) so the
+      transform's temporaries -- for the CUDA backend: the device staging
+      buffers -- stay bounded by one tile; results land in ``out``, which is
+      allocated here from the first tile's result when the caller gave none.
+
+    The reference declares ``(img, transform, out, chunksize)`` but is called
+    with ``(img, transform, chunksize, out)``; an array in the ``chunksize``
+    slot / an int in the ``out`` slot is therefore understood as the other order.
+    """
+    if hasattr(chunksize, "shape") and (out is None or np.isscalar(out)):
+        chunksize, out = out, chunksize
+    if not chunksize:
+        result = transform(img)
+        if out is None:
+            return result
+        if is_device_array(out):
+            raise ValueError("device `out` arrays are filled by the CUDA "
+                             "backend itself; pass them through the public API")
+        out[...] = result
+        return out
+    if is_device_array(img):
+        raise ValueError("`chunksize` applies to host arrays only: a device-"
+                         "resident frame is already where the kernels read it")
+    chunks = chunk_img(img, chunksize)
+    if out is None:
+        # learn dtype and trailing shape from the first tile
+        first, ((r0, r1), (c0, c1)) = next(chunks)
+        res = np.asarray(transform(first))
+        lead = img.shape[:1] if res.ndim == 1 else img.shape[:2]
+        out = np.empty(tuple(lead) + res.shape[2:] if res.ndim > 1 else lead,
+                       dtype=res.dtype)
+        if res.ndim == 1:
+            out[r0:r1] = res
+        else:
+            out[r0:r1, c0:c1] = res
+    apply = chunk_apply_1d if len(out.shape) == 1 else chunk_apply
+    apply(transform, chunks, out)
+    return out

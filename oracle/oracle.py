@@ -1,0 +1,237 @@
+"""ctypes front-end of the CPU oracle (``husl_oracle.c``) and of the reference
+builds under ``oracle/_ref/``.
+
+TEST INFRASTRUCTURE, NOT PRODUCT: imported only by ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs.  The product
+package never imports this module and has no CPU fallback.
+
+* ``rgb_to_husl / rgb_to_hue / husl_to_rgb[_float]`` -- the float64
+  restatement of the reference NumPy path (nphusl/nphusl.py:110-392);
+* ``simd_rgb_to_husl(variant=...)`` -- restatement of nphusl/_simd.c;
+* ``light_table / chroma_table / linear_table6`` -- restatement of
+  LUT/light.py, LUT/chroma.py and nphusl/_linear_lookup.c:45-75;
+* ``ref_simd(...)``, ``ref_tables()``, ``ref_cython()`` -- the reference's own
+  compiled code (``oracle/_ref``, built by ``oracle/build_ref.sh`` from the
+  sources under /root/reference; present on the GPU box as prebuilt files).
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+_LIB = None
+
+_c_u8p = ctypes.POINTER(ctypes.c_uint8)
+_c_u16p = ctypes.POINTER(ctypes.c_uint16)
+_c_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force=False):
+    """Compile husl_oracle.c (gcc, seconds)."""
+    so = os.path.join(HERE, "libhusl_oracle.so")
+    src = os.path.join(HERE, "husl_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "-s"], check=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.oracle_max_chroma.restype = ctypes.c_double
+        _LIB.oracle_max_chroma.argtypes = [ctypes.c_double, ctypes.c_double]
+        _LIB.oracle_omp_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def _p(arr, typ):
+    return arr.ctypes.data_as(typ)
+
+
+def _rgb_in(rgb):
+    rgb = np.asarray(rgb)
+    if rgb.dtype == np.uint8:
+        return np.ascontiguousarray(rgb), True
+    return np.ascontiguousarray(rgb, dtype=np.float64), False
+
+
+def rgb_to_husl(rgb):
+    """uint8 RGB (scaled by /255, transform.py:35-37) or float RGB in [0,1]
+    -> float64 HUSL, same shape."""
+    a, is_u8 = _rgb_in(rgb)
+    out = np.empty(a.shape, dtype=np.float64)
+    n = a.size // 3
+    if is_u8:
+        lib().oracle_rgb_u8_to_husl(_p(a, _c_u8p), _p(out, _c_f64p), ctypes.c_size_t(n))
+    else:
+        lib().oracle_rgb_to_husl_f64(_p(a, _c_f64p), _p(out, _c_f64p), ctypes.c_size_t(n))
+    return out
+
+
+def rgb_to_hue(rgb):
+    a, is_u8 = _rgb_in(rgb)
+    out = np.empty(a.shape[:-1], dtype=np.float64)
+    n = a.size // 3
+    if is_u8:
+        lib().oracle_rgb_u8_to_hue(_p(a, _c_u8p), _p(out, _c_f64p), ctypes.c_size_t(n))
+    else:
+        lib().oracle_rgb_to_hue_f64(_p(a, _c_f64p), _p(out, _c_f64p), ctypes.c_size_t(n))
+    return out
+
+
+def husl_to_rgb_float(hsl):
+    """HUSL -> float64 RGB in [0,1] (what the reference's _husl_to_rgb returns)."""
+    a = np.ascontiguousarray(hsl, dtype=np.float64)
+    out = np.empty(a.shape, dtype=np.float64)
+    lib().oracle_husl_to_rgb_f64(_p(a, _c_f64p), _p(out, _c_f64p), ctypes.c_size_t(a.size // 3))
+    return out
+
+
+def husl_to_rgb(hsl):
+    """HUSL -> uint8 RGB (to_rgb's output: round-half-even, abs, uint8 cast)."""
+    a = np.ascontiguousarray(hsl, dtype=np.float64)
+    out = np.empty(a.shape, dtype=np.uint8)
+    lib().oracle_husl_to_rgb_u8(_p(a, _c_f64p), _p(out, _c_u8p), ctypes.c_size_t(a.size // 3))
+    return out
+
+
+def max_chroma(l, h):
+    return lib().oracle_max_chroma(float(l), float(h))
+
+
+# ---- tables -------------------------------------------------------------
+
+def linear_table6():
+    t = np.empty(256, dtype=np.float64)
+    lib().oracle_linear_table6(_p(t, _c_f64p))
+    return t
+
+
+def light_table(seg=1024):
+    """-> (uint16[3*seg], Y_IDX_STEP[3], Y_THRESH[2])"""
+    t = np.empty(3 * seg, dtype=np.uint16)
+    steps = np.empty(3, dtype=np.float64)
+    thresh = np.empty(2, dtype=np.float64)
+    lib().oracle_light_table(_p(t, _c_u16p), ctypes.c_int(seg), _p(steps, _c_f64p), _p(thresh, _c_f64p))
+    return t, steps, thresh
+
+
+def chroma_table(nh=1024, nl=1024):
+    """-> (uint16[nh, nl], H_IDX_STEP, L_IDX_STEP)"""
+    t = np.empty((nh, nl), dtype=np.uint16)
+    hs = ctypes.c_double()
+    ls = ctypes.c_double()
+    lib().oracle_chroma_table(_p(t, _c_u16p), ctypes.c_int(nh), ctypes.c_int(nl),
+                              ctypes.byref(hs), ctypes.byref(ls))
+    return t, hs.value, ls.value
+
+
+_TABLE_CACHE = {}
+
+
+def simd_rgb_to_husl(rgb, variant="lut", tables=None):
+    """Restatement of nphusl/_simd.c::rgb_to_husl_nd.  variant: "exact" (no -D
+    flags), "lut" (setup.py default), "lut_interp" (+INTERPOLATE_CHROMA).
+    ``tables`` = (light_u16, ystep3, ythresh2, chroma_u16, hstep, lstep); made
+    by the oracle's own generators when omitted."""
+    v = {"exact": 0, "lut": 1, "lut_interp": 2}[variant]
+    a = np.ascontiguousarray(rgb, dtype=np.uint8)
+    out = np.empty(a.shape, dtype=np.float64)
+    lin = _TABLE_CACHE.setdefault("lin", linear_table6())
+    if tables is None:
+        if "tab" not in _TABLE_CACHE:
+            lt, st, th = light_table()
+            ct, hs, ls = chroma_table()
+            _TABLE_CACHE["tab"] = (lt, st, th, ct, hs, ls)
+        tables = _TABLE_CACHE["tab"]
+    lt, st, th, ct, hs, ls = tables
+    lt = np.ascontiguousarray(lt, dtype=np.uint16)
+    ct = np.ascontiguousarray(ct, dtype=np.uint16)
+    st = np.ascontiguousarray(st, dtype=np.float64)
+    th = np.ascontiguousarray(th, dtype=np.float64)
+    lib().oracle_simd_rgb_to_husl(
+        _p(a, _c_u8p), _p(out, _c_f64p), ctypes.c_size_t(a.size // 3), ctypes.c_int(v),
+        _p(lin, _c_f64p), _p(lt, _c_u16p), ctypes.c_int(lt.size // 3),
+        _p(st, _c_f64p), _p(th, _c_f64p), _p(ct, _c_u16p),
+        ctypes.c_int(ct.shape[0]), ctypes.c_int(ct.shape[1]),
+        ctypes.c_double(hs), ctypes.c_double(ls))
+    return out
+
+
+# ---- the reference's own compiled code (oracle/_ref) ---------------------
+
+_REF_LIBS = {}
+_LIBC = None
+
+
+def have_ref():
+    return os.path.exists(os.path.join(REF_DIR, "libsimd_lut.so"))
+
+
+def _ref_lib(name):
+    if name not in _REF_LIBS:
+        path = os.path.join(REF_DIR, "libsimd_%s.so" % name)
+        l = ctypes.CDLL(path)
+        l.rgb_to_husl_nd.restype = ctypes.c_void_p       # _simd.h:4-5
+        l.rgb_to_husl_nd.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+        _REF_LIBS[name] = l
+    return _REF_LIBS[name]
+
+
+def ref_simd(rgb, build="lut", copy=True):
+    """Call the reference's rgb_to_husl_nd (nphusl/_simd.c:87) the way its
+    Cython wrapper does (_simd_opt.pyx:20-39): uint8 C-contiguous in, malloc'd
+    doubles out, copied and freed.  build: lut | lut_strict | lut_interp |
+    lut_interp_strict | exact."""
+    global _LIBC
+    if _LIBC is None:
+        _LIBC = ctypes.CDLL(None)
+        _LIBC.free.argtypes = [ctypes.c_void_p]
+    a = np.ascontiguousarray(rgb, dtype=np.uint8)
+    ptr = _ref_lib(build).rgb_to_husl_nd(a.ctypes.data, a.size)
+    try:
+        buf = (ctypes.c_double * a.size).from_address(ptr)
+        out = np.frombuffer(buf, dtype=np.float64).reshape(a.shape)
+        return out.copy() if copy else None
+    finally:
+        _LIBC.free(ptr)
+
+
+def ref_tables():
+    """Tables baked into the reference build (generated by its own
+    LUT/light.py and LUT/chroma.py) -> same tuple as simd_rgb_to_husl(tables=)."""
+    l = _ref_lib("lut_strict")
+    seg = ctypes.c_ushort.in_dll(l, "L_SEGMENT_SIZE").value
+    nh = ctypes.c_ushort.in_dll(l, "CH_TABLE_SIZE").value
+    nl = ctypes.c_ushort.in_dll(l, "CL_TABLE_SIZE").value
+    lt = np.frombuffer((ctypes.c_uint16 * (3 * seg)).in_dll(l, "light_table_big"), dtype=np.uint16).copy()
+    ct = np.frombuffer((ctypes.c_uint16 * (nh * nl)).in_dll(l, "chroma_table"), dtype=np.uint16).reshape(nh, nl).copy()
+    st = np.array([ctypes.c_double.in_dll(l, "Y_IDX_STEP_%d" % i).value for i in range(3)])
+    th = np.array([ctypes.c_double.in_dll(l, "Y_THRESH_%d" % i).value for i in range(2)])
+    hs = ctypes.c_double.in_dll(l, "H_IDX_STEP").value
+    ls = ctypes.c_double.in_dll(l, "L_IDX_STEP").value
+    return lt, st, th, ct, hs, ls
+
+
+def ref_linear_table():
+    l = _ref_lib("lut_strict")
+    return np.frombuffer((ctypes.c_double * 256).in_dll(l, "linear_table"), dtype=np.float64).copy()
+
+
+def ref_cython():
+    """The reference's Cython+OpenMP module (nphusl/_cython_opt.pyx), compiled
+    by build_ref.sh as ``refhost._cython_opt``: the only compiled HUSL->RGB /
+    hue-only code the reference has.  Needs this repo's host package on
+    sys.path (it supplies the `constants` / `transform` modules the .pyx
+    imports from its parent package)."""
+    pkg = os.path.join(HERE, "..", "husl-numpy_b200")
+    for p in (os.path.abspath(pkg), REF_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import refhost._cython_opt as m
+    return m
