@@ -1,0 +1,195 @@
+// husl_lut.cuh -- optional LUT mode: the reference's DEFAULT _simd.c build
+// (-DUSE_LIGHT_LUT -DUSE_CHROMA_LUT -DUSE_HUE_ATAN2_APPROX, setup.py:99-128,
+// optionally -DINTERPOLATE_CHROMA) reproduced on the device, plus device-side
+// generation of the tables make_lookup_tables / _linear_lookup.c produce.
+//
+// The goal here is BIT-EXACT agreement with nphusl/_simd.c compiled without
+// -ffast-math, so this file is IEEE double arithmetic in the reference's
+// operation order, written with __dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn so
+// nvcc can neither contract a*b+c into an FMA nor reassociate.  It is a
+// gather-bound float64 kernel (2 MB chroma table lives in L2); the fast path of
+// the library is the float32 EXACT mode in husl_kernels.cuh.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace husl {
+
+struct LutParams {
+    const double *linear;     // 256, 6-decimal values (_linear_lookup.c:9-42)
+    const uint16_t *light;    // 3*seg, L*100 (light_table_big)
+    const uint16_t *chroma;   // nh*nl, max chroma * 100 (chroma_table)
+    int seg, nh, nl;
+    double ystep[3], ythresh[2], hstep, lstep;
+};
+
+__device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double ds(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dd(double a, double b) { return __ddiv_rn(a, b); }
+
+// _simd.c:485-496
+__device__ __forceinline__ double lut_light(const LutParams &t, double y) {
+    double idx;
+    if (y < t.ythresh[0]) idx = dd(y, t.ystep[0]);
+    else if (y < t.ythresh[1]) idx = da(dd(ds(y, t.ythresh[0]), t.ystep[1]), (double)t.seg);
+    else idx = da(dd(ds(y, t.ythresh[1]), t.ystep[2]), (double)(t.seg * 2));
+    const double r = fmax(0.0, fmin((double)(3 * t.seg - 1), (double)roundf(__double2float_rn(idx))));
+    return dd((double)t.light[(unsigned short)r], 100.0);
+}
+
+// _simd.c:279-281
+__device__ __forceinline__ double lut_atan(double z) {
+    const double az = fabs(z);
+    return ds(dm(0.78539816339744830962, z), dm(dm(z, ds(az, 1.0)), da(0.2447, dm(0.0663, az))));
+}
+
+// _simd.c:288-315
+__device__ __forceinline__ double lut_atan2(double y, double x) {
+    const double PI_ = 3.141592653589793, PIBY2 = 1.5707963267948966;
+    if (x == 0.0) {
+        if (y > 0.0) return PIBY2;
+        if (y == 0.0) return 0.0;
+        return -PIBY2;
+    }
+    const double z = dd(y, x);
+    double at;
+    if (fabs(z) < 1.0) {
+        at = dd(z, da(1.0, dm(dm(0.28, z), z)));
+        if (x < 0.0) return (y < 0.0) ? ds(at, PI_) : da(at, PI_);
+    } else {
+        at = ds(PIBY2, dd(z, da(dm(z, z), 0.28)));
+        if (y < 0.0) return ds(at, PI_);
+    }
+    return at;
+}
+
+// _simd.c:246-266
+__device__ __forceinline__ double lut_hue(double u, double v) {
+    const double DEG_PER_RAD = 180.0 / 3.14159265358979323846;
+    const double z = dd(v, u);
+    double hue;
+    if (fabs(z) < 1.0) {
+        hue = dm(lut_atan(z), DEG_PER_RAD);
+        if (u < 0) hue = da(hue, 180.0);
+        else if (v < 0) hue = da(hue, 360.0);
+    } else {
+        hue = dm(lut_atan2(v, u), DEG_PER_RAD);
+        if (hue < 0.0) hue = da(hue, 360.0);
+    }
+    return hue;
+}
+
+// _simd.c:399-406 / :360-387
+template <bool INTERP>
+__device__ __forceinline__ double lut_chroma(const LutParams &t, double l, double h) {
+    const double hs = dd(h, t.hstep), ls = dd(l, t.lstep);
+    if (!INTERP) {
+        const unsigned short hi = (unsigned short)fmax(0.0, fmin((double)(t.nh - 1), (double)roundf(__double2float_rn(hs))));
+        const unsigned short li = (unsigned short)fmax(0.0, fmin((double)(t.nl - 1), (double)roundf(__double2float_rn(ls))));
+        return fmax(1e-10, (double)t.chroma[(size_t)hi * t.nl + li]);
+    }
+    const unsigned short hf = (unsigned short)fmax(0.0, fmin((double)(t.nh - 2), (double)floorf(__double2float_rn(hs))));
+    const unsigned short lf = (unsigned short)fmax(0.0, fmin((double)(t.nl - 2), (double)floorf(__double2float_rn(ls))));
+    const double c00 = t.chroma[(size_t)hf * t.nl + lf];
+    const double c10 = t.chroma[(size_t)(hf + 1) * t.nl + lf];
+    const double c01 = t.chroma[(size_t)hf * t.nl + lf + 1];
+    const double c11 = t.chroma[(size_t)(hf + 1) * t.nl + lf + 1];
+    const double hn = ds(hs, (double)hf), ln = ds(ls, (double)lf);
+    const double hv = ds(1.0, hn), lv = ds(1.0, ln);
+    const double c = da(da(da(dm(dm(c00, hv), lv), dm(dm(c10, hn), lv)), dm(dm(c01, hv), ln)), dm(dm(c11, hn), ln));
+    return fmax((double)1e-10f, c);
+}
+
+// rgb_to_husl_nd, default build: _simd.c:87-225
+template <bool INTERP>
+__global__ void __launch_bounds__(256)
+k_fwd_lut(const uint8_t *__restrict__ rgb, double *__restrict__ hsl, long long n, LutParams t) {
+    const double REF_U = 0.19783000664283, REF_V = 0.46831999493879;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+        double *o = hsl + 3 * i;
+        if (r == 255 && g == 255 && b == 255) { o[0] = 19.916405993809086; o[1] = 0.0; o[2] = 100.0; continue; }
+        if (!r && !g && !b) { o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; continue; }
+        const double rl = t.linear[r], gl = t.linear[g], bl = t.linear[b];
+        const double x = da(da(dm(0.412391, rl), dm(0.357584, gl)), dm(0.180481, bl));
+        const double y = da(da(dm(0.212639, rl), dm(0.715169, gl)), dm(0.072192, bl));
+        const double z = da(da(dm(0.019331, rl), dm(0.119195, gl)), dm(0.950532, bl));
+        const double vs = da(da(x, dm(15.0, y)), dm(3.0, z));
+        const double var_u = dd(dm(4.0, x), vs), var_v = dd(dm(9.0, y), vs);
+        const double l = lut_light(t, y);
+        const double l13 = dm(l, 13.0);
+        const double u = dm(l13, ds(var_u, REF_U)), v = dm(l13, ds(var_v, REF_V));
+        const double h = lut_hue(u, v);
+        const double mc = lut_chroma<INTERP>(t, l, h);
+        const double sat = dd(dm(10000.0, __dsqrt_rn(da(dm(u, u), dm(v, v)))), mc);
+        o[0] = h;
+        o[1] = fmin(sat, 100.0);
+        o[2] = l;
+    }
+}
+
+// ---- device-side table generation (make_lookup_tables:8-9) -------------------------------
+// float64 restatement of nphusl.py:268-275 / :165-220 evaluated per table entry.
+__device__ __forceinline__ double gen_to_light(double y) {
+    if (y > 0.0088564516) return pow(y, 1.0 / 3.0) * 116 - 16;
+    return y * 903.2962962;
+}
+
+__device__ double gen_max_chroma(double L, double H) {
+    const double M[3][3] = {{3.240969941904521, -1.537383177570093, -0.498610760293},
+                            {-0.96924363628087, 1.87596750150772, 0.041555057407175},
+                            {0.055630079696993, -0.20397695888897, 1.056971514242878}};
+    const double hrad = (H / 360.0) * (3.14159265358979323846 * 2);
+    const double sub1 = pow(L + 16.0, 3.0) / 1560896.0;
+    const double sub2 = (sub1 < 0.0088564516) ? (L / 903.2962962) : sub1;
+    const double sn = sin(hrad), cs = cos(hrad);
+    double best = INFINITY;
+    for (int i = 0; i < 3; i++) {
+        const double t1 = 284517.0 * M[i][0] - 94839.0 * M[i][2];
+        const double t2 = 838422.0 * M[i][2] + 769860.0 * M[i][1] + 731718.0 * M[i][0];
+        const double bt = 632260.0 * M[i][2] - 126452.0 * M[i][1];
+        for (int t = 0; t < 2; t++) {
+            const double top1 = sub2 * t1;
+            double top2 = L * sub2 * t2;
+            double bottom = sub2 * bt;
+            if (t) { top2 -= L * 769860.0; bottom += 126452.0; }
+            double len = (top2 / bottom) / (sn - (top1 / bottom) * cs);
+            if (isnan(len) || len < 0) len = INFINITY;
+            if (len < best) best = len;
+        }
+    }
+    return best;
+}
+
+// compute_linear((float)j / 255.0), _linear_lookup.c:45-61 (before "%f" rounding)
+__global__ void k_gen_linear(double *out) {
+    const int j = threadIdx.x;
+    // (float)j / 255.0 in C promotes to double; j is exact in float, so == j/255.0
+    const double x = (double)j / 255.0;
+    out[j] = x > 0.04045 ? pow((x + 0.055) / (1.0 + 0.055), 2.4) : x / 12.92;
+}
+
+// LUT/light.py:62-80, 100-107: entry k of segment i = round(to_light(start_i + k*step_i) * 100)
+__global__ void k_gen_light(uint16_t *table, int seg, double s0, double s1, double s2,
+                            double st0, double st1, double st2) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3 * seg) return;
+    const int i = idx / seg, k = idx % seg;
+    const double start = i == 0 ? s0 : (i == 1 ? s1 : s2);
+    const double step = i == 0 ? st0 : (i == 1 ? st1 : st2);
+    table[idx] = (uint16_t)(long long)rint(gen_to_light(start + k * step) * 100);
+}
+
+// LUT/chroma.py:73-84: entry [h][l] = round(max_chroma(l*lstep, h*hstep) * 100), column l = 0 left 0
+__global__ void k_gen_chroma(uint16_t *table, int nh, int nl, double hstep, double lstep) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nh * nl) return;
+    const int i = (int)(idx / nl), j = (int)(idx % nl);
+    uint16_t v = 0;
+    if (j > 0) v = (uint16_t)(long long)rint(gen_max_chroma(0.0 + j * lstep, 0.0 + i * hstep) * 100);
+    table[idx] = v;
+}
+
+}  // namespace husl

@@ -1,0 +1,197 @@
+// husl_math.cuh -- per-pixel HUSL <-> RGB arithmetic for sm_100a.
+//
+// What is computed is the reference's float64 chain (nphusl/nphusl.py:110-392,
+// nphusl/_cython_opt.pyx:53-309); HOW is different:
+//
+//  * forward works on linear-light DIFFERENCES dr = r-g, db = b-g and on
+//    1-g, formed from hi+lo float pairs, so the near-grey hue and near-white
+//    saturation cancellations of U = 13L(u'-REF_U) never happen in float32;
+//  * hue is atan2 of two linear forms (no division by D, no L);
+//  * saturation is the six-line ray intersection in closed form:
+//        S/100 = max( (D - sD*min(r,g,b)) / D,
+//                     1 - sD*Y*(1-max(r,g,b)) / (D*(1-Y)) )
+//    -- no trigonometry, one reciprocal;
+//  * inverse intersects the hue ray with the same six lines in (u',v') and
+//    evaluates lin_i = Y*A_i(u',v')/(4v') with ONE reciprocal, then the sRGB
+//    companding with MUFU lg2/ex2 and a magic-number round-half-even to uint8.
+//
+// All constants come from husl_coeffs.h (float64-derived, gen_coeffs.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "husl_coeffs.h"
+
+namespace husl {
+
+// ---- MUFU wrappers -----------------------------------------------------------
+__device__ __forceinline__ float mufu_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_sin(float x) {
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_cos(float x) {
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ---- hue: atan2 in degrees, [0, 360] -------------------------------------------
+// reference: H = degrees(arctan2(V, U)), +360 if negative (nphusl.py:231-239,
+// _cython_opt.pyx:75-79).  U, V share the positive factor 13L/D, so the hue is
+// atan2(Nv, Nu).  atan2(0,0) = 0 like libm.
+__device__ __forceinline__ float hue_deg(float nv, float nu) {
+    const float ax = fabsf(nu), ay = fabsf(nv);
+    const float a = fminf(ax, ay);
+    const float b = fmaxf(fmaxf(ax, ay), 1e-37f);
+    const float q = a * mufu_rcp(b);
+    const float s = q * q;
+    static_assert(ATAN_TERMS == 8, "Horner chain below is written for 8 terms");
+    float p = fmaf(ATAN_C7, s, ATAN_C6);
+    p = fmaf(p, s, ATAN_C5);
+    p = fmaf(p, s, ATAN_C4);
+    p = fmaf(p, s, ATAN_C3);
+    p = fmaf(p, s, ATAN_C2);
+    p = fmaf(p, s, ATAN_C1);
+    p = fmaf(p, s, ATAN_C0);
+    float r = p * q;                       // [0, 45]
+    r = (ay > ax) ? 90.0f - r : r;         // [0, 90]
+    r = (nu < 0.0f) ? 180.0f - r : r;      // [0, 180]
+    r = (nv < 0.0f) ? 360.0f - r : r;      // [0, 360]
+    return r;
+}
+
+// ---- forward core --------------------------------------------------------------
+// Linear-light channel values arrive as hi+lo float pairs (exact to ~2^-48):
+// from the 256-entry table for uint8 input, from a float64 pow for float input.
+struct LinPx {
+    float hr, lr, hg, lg, hb, lb;
+};
+
+struct Diff {       // dr = r-g, db = b-g, cg = 1-g, g
+    float dr, db, cg, g;
+};
+
+__device__ __forceinline__ Diff make_diff(const LinPx &p) {
+    Diff d;
+    d.dr = (p.hr - p.hg) + (p.lr - p.lg);
+    d.db = (p.hb - p.hg) + (p.lb - p.lg);
+    d.cg = (1.0f - p.hg) - p.lg;
+    d.g = p.hg;
+    return d;
+}
+
+// IS_U8: lightness clamps can only fire for pure black / pure white (nearest
+// neighbours (0,0,1) -> L = 0.0198, (255,255,254) -> L = 99.975), where the
+// float64 path yields H = 0 / H = WHITE_HUE (reference _simd.c:79-81, 205-212).
+template <bool IS_U8>
+__device__ __forceinline__ void husl_from_diff(const Diff &d, float &H, float &S, float &L) {
+    const float t = fmaf(Y_DR, d.dr, Y_DB * d.db);
+    const float Y = fmaf(Y_S, d.g, t);                     // luminance
+    const float omY = fmaf(Y_S, d.cg, ONE_M_SY - t);       // 1 - Y, cancellation-free
+    const float Dp = fmaf(D_DR, d.dr, D_DB * d.db);
+    const float D = fmaf(D_S, d.g, Dp);                    // X + 15Y + 3Z
+    const float nu = fmaf(U_DR, d.dr, U_DB * d.db);        // 4X - REF_U*D
+    const float nv = fmaf(V_DR, d.dr, V_DB * d.db);        // 9Y - REF_V*D
+    float h = hue_deg(nv, nu);
+
+    // saturation: channel-hits-0 and channel-hits-1 gamut faces
+    const float mnd = fminf(fminf(d.dr, d.db), 0.0f);      // min(r,g,b) - g
+    const float mxd = fmaxf(fmaxf(d.dr, d.db), 0.0f);      // max(r,g,b) - g
+    const float T0 = fmaf(-D_S, mnd, Dp);                  // D - sD*min(r,g,b) >= 0
+    const float omx = d.cg - mxd;                          // 1 - max(r,g,b)  >= 0
+    const float R100 = 100.0f * mufu_rcp(D * omY);
+    const float s0 = (T0 * omY) * R100;
+    const float s1 = fmaf((-D_S * Y) * omx, R100, 100.0f);
+    float s = fmaxf(s0, s1);
+
+    // lightness: 116*cbrt(Y)-16 above EPSILON, KAPPA*Y below (nphusl.py:268-275)
+    const float cb = mufu_ex2(mufu_lg2(Y) * (1.0f / 3.0f));
+    float l = (Y > EPSILON) ? fmaf(116.0f, cb, -16.0f) : KAPPA * Y;
+
+    // L > 99.99 -> (S,L) = (0,100); L < 0.01 -> (0,0)  (nphusl.py:146-152),
+    // expressed on Y so the clamp does not depend on the cbrt approximation
+    const bool white = Y > Y_HI;
+    const bool black = Y < Y_LO;
+    s = (white || black) ? 0.0f : s;
+    l = white ? 100.0f : l;
+    l = black ? 0.0f : l;
+    if (IS_U8) {
+        h = white ? WHITE_HUE : h;
+    } else {
+        h = (white && nu == 0.0f && nv == 0.0f) ? WHITE_HUE : h;
+    }
+    H = h; S = s; L = l;
+}
+
+__device__ __forceinline__ float hue_from_diff(const Diff &d) {
+    const float nu = fmaf(U_DR, d.dr, U_DB * d.db);
+    const float nv = fmaf(V_DR, d.dr, V_DB * d.db);
+    return hue_deg(nv, nu);
+}
+
+// ---- inverse core --------------------------------------------------------------
+// sRGB companding of one linear channel, scaled to 0..255 (nphusl.py:330-335)
+__device__ __forceinline__ float from_linear_255(float v) {
+    const float pw = mufu_ex2(mufu_lg2(v) * (1.0f / 2.4f));
+    return (v <= 0.0031308f) ? (12.92f * 255.0f) * v : fmaf(1.055f * 255.0f, pw, -0.055f * 255.0f);
+}
+
+// (H,S,L) -> companded RGB scaled to 0..255 (not rounded)
+__device__ __forceinline__ void rgb255_from_husl(float H, float S, float L,
+                                                 float &R, float &G, float &B) {
+    const float th = H * 0.017453292519943295f;
+    const float sn = mufu_sin(th), cs = mufu_cos(th);
+    // Y and 1-Y from L (nphusl.py:385-392); 1-Y = (1-w)(1+w+w^2), w = (L+16)/116
+    const float w = fmaf(L, 1.0f / 116.0f, 16.0f / 116.0f);
+    const float omw = fmaf(L, -1.0f / 116.0f, 100.0f / 116.0f);
+    const bool big = L > 8.0f;
+    float Y = big ? w * w * w : L * INV_KAPPA;
+    const float omY = big ? omw * fmaf(w, w, 1.0f + w) : 1.0f - Y;
+    // directional derivatives of the three channel forms along the hue ray
+    const float g0 = fmaf(AU0, cs, AV0 * sn);
+    const float g1 = fmaf(AU1, cs, AV1 * sn);
+    const float g2 = fmaf(AU2, cs, AV2 * sn);
+    const float gmin = fminf(fminf(g0, g1), g2);
+    const float gmax = fmaxf(fmaxf(g0, g1), g2);
+    // 1/tau_max = max(-gmin/AN, (Y*gmax - 4 sin)/(4 REF_V (1-Y)))  (six lines)
+    const float c = REF_V4 * omY;
+    float den = fmaxf((gmin * (-1.0f / AN)) * c, fmaf(Y, gmax, -4.0f * sn));
+    float N = (S * 0.01f) * c;                              // tau = N / den
+    // L > 99.99 -> white, L < 0.01 -> black (nphusl.py:351-357)
+    const bool white = L > 99.99f;
+    const bool black = L < 0.01f;
+    const bool ext = white || black;
+    N = ext ? 0.0f : N;
+    den = ext ? 1.0f : den;
+    Y = white ? 1.0f : Y;
+    Y = black ? 0.0f : Y;
+    // lin_i = Y*(AN*den + N*g_i) / (4*(REF_V*den + N*sin))
+    const float yr = Y * mufu_rcp(fmaf(4.0f * N, sn, REF_V4 * den));
+    const float base = AN * den;
+    R = from_linear_255(fmaf(N, g0, base) * yr);
+    G = from_linear_255(fmaf(N, g1, base) * yr);
+    B = from_linear_255(fmaf(N, g2, base) * yr);
+}
+
+// transform.to_rgb_int (transform.py:16-20): round-half-even, abs, uint8 wrap.
+// |v| + 1.5*2^23 leaves round-half-even(|v|) in the low mantissa bits.
+__device__ __forceinline__ uint32_t round_u8_bits(float v255) {
+    return __float_as_uint(fabsf(v255) + 12582912.0f);
+}
+
+}  // namespace husl

@@ -1,0 +1,661 @@
+// nphusl_cuda_api.cu -- the C ABI of include/nphusl_cuda.h: argument checking,
+// per-device state, kernel dispatch and the host-buffer streaming pipeline.
+//
+// No CPU implementation of any conversion lives here (or anywhere in this
+// library): a call either runs the CUDA kernels or returns a non-zero status.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/nphusl_cuda.h"
+#include "husl_kernels.cuh"
+#include "husl_lut.cuh"
+
+namespace {
+
+using namespace husl;
+
+thread_local std::string t_err;
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<size_t> g_chunk_px{0};
+
+constexpr int MAX_DEV = 16;
+constexpr int NSLOT = 3;                       // host streaming pipeline depth
+constexpr size_t DEFAULT_CHUNK_PX = 1u << 21;  // 2 Mpx per slot (<= 48 MB per buffer)
+constexpr size_t PAR_COPY_MIN = 4u << 20;      // host memcpy goes multi-threaded above this
+
+int fail(int code, const std::string &msg) {
+    t_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(NPHUSL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+size_t dsize(int dt) { return dt == NPHUSL_U8 ? 1 : dt == NPHUSL_F32 ? 4 : dt == NPHUSL_F64 ? 8 : 0; }
+
+struct Lut {
+    bool ready = false;
+    int seg = 0, nh = 0, nl = 0;
+    uint16_t *light = nullptr, *chroma = nullptr;
+    double *linear = nullptr;
+    LutParams p{};
+};
+
+struct DevCtx {
+    std::mutex mu;
+    bool init = false;
+    int dev = -1, sms = 0;
+    cudaStream_t st[NSLOT] = {};
+    cudaEvent_t done[NSLOT] = {};
+    cudaEvent_t gate = nullptr;
+    void *din[NSLOT] = {}, *dout[NSLOT] = {};
+    void *pin[NSLOT] = {}, *pout[NSLOT] = {};
+    size_t din_cap = 0, dout_cap = 0, pin_cap = 0, pout_cap = 0;
+    bool attr_set = false;
+    Lut lut;
+};
+
+DevCtx g_ctx[MAX_DEV];
+
+// ---- per-device initialisation -------------------------------------------------
+int ctx_get(int device, DevCtx **out) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(NPHUSL_ERR_NO_DEVICE, "no CUDA device available");
+    }
+    if (device < 0 || device >= n || device >= MAX_DEV)
+        return fail(NPHUSL_ERR_ARG, "device index out of range");
+    DevCtx &c = g_ctx[device];
+    std::lock_guard<std::mutex> lk(c.mu);
+    CU(cudaSetDevice(device));
+    if (!c.init) {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(NPHUSL_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) +
+                                                  std::to_string(prop.minor) + "; this library is built for sm_100a only");
+        c.dev = device;
+        c.sms = prop.multiProcessorCount;
+        // linearisation table in float64 (nphusl.py:278-286 at c/255), split hi+lo
+        float2 tab[256];
+        for (int i = 0; i < 256; ++i) {
+            const double x = i / 255.0;
+            const double v = x > 0.04045 ? std::pow((x + 0.055) / 1.055, 2.4) : x / 12.92;
+            tab[i].x = (float)v;
+            tab[i].y = (float)(v - (double)tab[i].x);
+        }
+        CU(cudaMemcpyToSymbol(g_lin_tab, tab, sizeof tab));
+        for (int s = 0; s < NSLOT; ++s) {
+            CU(cudaStreamCreateWithFlags(&c.st[s], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&c.done[s], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&c.gate, cudaEventDisableTiming));
+        c.init = true;
+    }
+    *out = &c;
+    return NPHUSL_OK;
+}
+
+// ---- kernel dispatch --------------------------------------------------------------
+constexpr int FWD_BLOCK = 512;
+constexpr int INV_BLOCK = 256;
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return NPHUSL_OK;
+}
+
+int set_attrs(DevCtx &c) {
+    if (c.attr_set) return NPHUSL_OK;
+    int rc;
+    constexpr int W = FWD_BLOCK / 32;
+    if ((rc = set_smem(k_fwd_u8<float, false, FWD_BLOCK, 2>, TAB_BYTES + W * Pack<float>::STAGE))) return rc;
+    if ((rc = set_smem(k_fwd_u8<double, false, FWD_BLOCK, 1>, TAB_BYTES + W * Pack<double>::STAGE))) return rc;
+    if ((rc = set_smem(k_fwd_u8<float, true, FWD_BLOCK, 2>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_fwd_u8<double, true, FWD_BLOCK, 2>, TAB_BYTES))) return rc;
+    c.attr_set = true;
+    return NPHUSL_OK;
+}
+
+int grid_for(long long work_items, int per_block, int max_blocks) {
+    long long g = (work_items + per_block - 1) / per_block;
+    if (g > max_blocks) g = max_blocks;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(NPHUSL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return NPHUSL_OK;
+}
+
+template <typename TIn, typename TOut, bool HUE>
+int launch_fwd_any(DevCtx &c, const void *in, void *out, long long n, int channels, cudaStream_t s) {
+    if (n <= 0) return NPHUSL_OK;
+    const int grid = grid_for(n, 256, c.sms * 8);
+    k_fwd_any<TIn, TOut, HUE><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n, channels);
+    g_launches++;
+    return check_launch("k_fwd_any");
+}
+
+template <typename TIn, typename TOut>
+int launch_inv_any(DevCtx &c, const void *in, void *out, long long n, cudaStream_t s) {
+    if (n <= 0) return NPHUSL_OK;
+    const int grid = grid_for(n, 256, c.sms * 8);
+    k_inv_any<TIn, TOut><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n);
+    g_launches++;
+    return check_launch("k_inv_any");
+}
+
+bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// forward on device pointers: streaming kernel on the 128-pixel tiles when the
+// layout allows it, generic kernel on the tail / on everything else
+template <bool HUE>
+int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, int out_dt,
+                long long n, cudaStream_t s) {
+    int rc;
+    const size_t out_px = (HUE ? 1 : 3) * dsize(out_dt);
+    long long done = 0;
+    if (in_dt == NPHUSL_U8 && channels == 3 && aligned(in, 4) && aligned(out, 16) && n >= TILE_PX) {
+        if ((rc = set_attrs(c))) return rc;
+        const long long tiles = n / TILE_PX;
+        constexpr int W = FWD_BLOCK / 32;
+        if (out_dt == NPHUSL_F32) {
+            const size_t sm = TAB_BYTES + (HUE ? 0 : W * Pack<float>::STAGE);
+            const int grid = grid_for(tiles, W, c.sms * 2);
+            k_fwd_u8<float, HUE, FWD_BLOCK, 2><<<grid, FWD_BLOCK, sm, s>>>((const uint32_t *)in, (float *)out, tiles);
+        } else {
+            const size_t sm = TAB_BYTES + (HUE ? 0 : W * Pack<double>::STAGE);
+            const int grid = grid_for(tiles, W, c.sms * (HUE ? 2 : 1));
+            k_fwd_u8<double, HUE, FWD_BLOCK, (HUE ? 2 : 1)><<<grid, FWD_BLOCK, sm, s>>>((const uint32_t *)in, (double *)out, tiles);
+        }
+        g_launches++;
+        if ((rc = check_launch("k_fwd_u8"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    const long long rest = n - done;
+    if (rest <= 0) return NPHUSL_OK;
+    const char *ip = (const char *)in + done * channels * dsize(in_dt);
+    char *op = (char *)out + done * out_px;
+#define FWD_ANY(TI, TO) return launch_fwd_any<TI, TO, HUE>(c, ip, op, rest, channels, s)
+    if (in_dt == NPHUSL_U8) { if (out_dt == NPHUSL_F32) FWD_ANY(uint8_t, float); else FWD_ANY(uint8_t, double); }
+    if (in_dt == NPHUSL_F32) { if (out_dt == NPHUSL_F32) FWD_ANY(float, float); else FWD_ANY(float, double); }
+    if (out_dt == NPHUSL_F32) FWD_ANY(double, float); else FWD_ANY(double, double);
+#undef FWD_ANY
+}
+
+int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, long long n, cudaStream_t s) {
+    int rc;
+    long long done = 0;
+    if (out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 4) && n >= TILE_PX) {
+        const long long tiles = n / TILE_PX;
+        constexpr int W = INV_BLOCK / 32;
+        if (in_dt == NPHUSL_F32) {
+            const int grid = grid_for(tiles, W, c.sms * 4);
+            k_inv_u8<float, INV_BLOCK, 4><<<grid, INV_BLOCK, W * Pack<float>::STAGE, s>>>((const float *)in, (uint32_t *)out, tiles);
+        } else {
+            const int grid = grid_for(tiles, W, c.sms * 4);
+            k_inv_u8<double, INV_BLOCK, 4><<<grid, INV_BLOCK, W * Pack<double>::STAGE, s>>>((const double *)in, (uint32_t *)out, tiles);
+        }
+        g_launches++;
+        if ((rc = check_launch("k_inv_u8"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    const long long rest = n - done;
+    if (rest <= 0) return NPHUSL_OK;
+    const char *ip = (const char *)in + done * 3 * dsize(in_dt);
+    char *op = (char *)out + done * 3 * dsize(out_dt);
+#define INV_ANY(TI, TO) return launch_inv_any<TI, TO>(c, ip, op, rest, s)
+    if (in_dt == NPHUSL_F32) {
+        if (out_dt == NPHUSL_U8) INV_ANY(float, uint8_t);
+        if (out_dt == NPHUSL_F32) INV_ANY(float, float);
+        INV_ANY(float, double);
+    }
+    if (out_dt == NPHUSL_U8) INV_ANY(double, uint8_t);
+    if (out_dt == NPHUSL_F32) INV_ANY(double, float);
+    INV_ANY(double, double);
+#undef INV_ANY
+}
+
+int run_lut_dev(DevCtx &c, const void *in, void *out, long long n, int mode, cudaStream_t s) {
+    if (!c.lut.ready) return fail(NPHUSL_ERR_NO_LUT, "LUT mode: call nphusl_cuda_lut_generate or nphusl_cuda_lut_upload first");
+    if (n <= 0) return NPHUSL_OK;
+    const int grid = grid_for(n, 256, c.sms * 8);
+    if (mode == NPHUSL_LUT)
+        k_fwd_lut<false><<<grid, 256, 0, s>>>((const uint8_t *)in, (double *)out, n, c.lut.p);
+    else
+        k_fwd_lut<true><<<grid, 256, 0, s>>>((const uint8_t *)in, (double *)out, n, c.lut.p);
+    g_launches++;
+    return check_launch("k_fwd_lut");
+}
+
+// ---- host-buffer streaming ----------------------------------------------------------
+void par_memcpy(void *dst, const void *src, size_t bytes) {
+    if (bytes < PAR_COPY_MIN) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 2 ? 1 : (nt > 8 ? 8 : nt);
+    const size_t per = ((bytes / nt) + 4095) & ~size_t(4095);
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) {
+        const size_t off = per * t;
+        if (off >= bytes) break;
+        const size_t len = (off + per > bytes) ? bytes - off : per;
+        th.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    std::memcpy(dst, src, per < bytes ? per : bytes);
+    for (auto &t : th) t.join();
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure(void **buf, size_t *cap, size_t need, bool pinned, int nbuf) {
+    if (*cap >= need) return NPHUSL_OK;
+    for (int s = 0; s < nbuf; ++s) {
+        if (buf[s]) {
+            if (pinned) cudaFreeHost(buf[s]); else cudaFree(buf[s]);
+            buf[s] = nullptr;
+        }
+    }
+    *cap = 0;
+    for (int s = 0; s < nbuf; ++s) {
+        if (pinned) CU(cudaHostAlloc(&buf[s], need, cudaHostAllocDefault));
+        else CU(cudaMalloc(&buf[s], need));
+    }
+    *cap = need;
+    return NPHUSL_OK;
+}
+
+// Generic driver for "n pixels, in_px bytes in, out_px bytes out per pixel".
+// kernel(in_dev, out_dev, npx, stream) runs the conversion on device pointers.
+template <typename F>
+int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *dst, int dst_loc,
+                 size_t out_px, long long n, cudaStream_t user, F kernel) {
+    if (n <= 0) return NPHUSL_OK;
+    if (src_loc == NPHUSL_DEVICE && dst_loc == NPHUSL_DEVICE) return kernel(src, dst, n, user);
+
+    std::lock_guard<std::mutex> lk(c.mu);   // staging buffers are per device
+    size_t chunk = g_chunk_px.load();
+    if (!chunk) chunk = DEFAULT_CHUNK_PX;
+    chunk = (chunk + TILE_PX - 1) / TILE_PX * TILE_PX;
+    if ((long long)chunk > n) chunk = (size_t)((n + TILE_PX - 1) / TILE_PX * TILE_PX);
+    const bool src_host = src_loc == NPHUSL_HOST, dst_host = dst_loc == NPHUSL_HOST;
+    const bool src_pin = src_host && is_pinned(src), dst_pin = dst_host && is_pinned(dst);
+    int rc;
+    if (src_host && (rc = ensure(c.din, &c.din_cap, chunk * in_px, false, NSLOT))) return rc;
+    if (dst_host && (rc = ensure(c.dout, &c.dout_cap, chunk * out_px, false, NSLOT))) return rc;
+    if (src_host && !src_pin && (rc = ensure(c.pin, &c.pin_cap, chunk * in_px, true, NSLOT))) return rc;
+    if (dst_host && !dst_pin && (rc = ensure(c.pout, &c.pout_cap, chunk * out_px, true, NSLOT))) return rc;
+
+    // work submitted earlier on the caller's stream must be visible to ours
+    CU(cudaEventRecord(c.gate, user));
+    for (int s = 0; s < NSLOT; ++s) CU(cudaStreamWaitEvent(c.st[s], c.gate, 0));
+
+    struct Pending { char *dst; size_t bytes; bool live; } pend[NSLOT] = {};
+    long long off = 0;
+    for (long long ci = 0; off < n; ++ci, off += chunk) {
+        const int s = (int)(ci % NSLOT);
+        const long long npx = (n - off < (long long)chunk) ? n - off : (long long)chunk;
+        if (ci >= NSLOT) {                    // slot reuse: its previous chunk must be finished
+            CU(cudaEventSynchronize(c.done[s]));
+            if (pend[s].live) { par_memcpy(pend[s].dst, c.pout[s], pend[s].bytes); pend[s].live = false; }
+        }
+        const void *in_dev;
+        if (src_host) {
+            const char *hp = (const char *)src + off * in_px;
+            if (!src_pin) { par_memcpy(c.pin[s], hp, npx * in_px); hp = (const char *)c.pin[s]; }
+            CU(cudaMemcpyAsync(c.din[s], hp, npx * in_px, cudaMemcpyHostToDevice, c.st[s]));
+            in_dev = c.din[s];
+        } else {
+            in_dev = (const char *)src + off * in_px;
+        }
+        void *out_dev = dst_host ? c.dout[s] : (void *)((char *)dst + off * out_px);
+        if ((rc = kernel(in_dev, out_dev, npx, c.st[s]))) return rc;
+        if (dst_host) {
+            char *hp = (char *)dst + off * out_px;
+            if (dst_pin) {
+                CU(cudaMemcpyAsync(hp, c.dout[s], npx * out_px, cudaMemcpyDeviceToHost, c.st[s]));
+            } else {
+                CU(cudaMemcpyAsync(c.pout[s], c.dout[s], npx * out_px, cudaMemcpyDeviceToHost, c.st[s]));
+                pend[s] = {hp, (size_t)npx * out_px, true};
+            }
+        }
+        CU(cudaEventRecord(c.done[s], c.st[s]));
+    }
+    for (int s = 0; s < NSLOT; ++s) {
+        CU(cudaStreamSynchronize(c.st[s]));
+        if (pend[s].live) { par_memcpy(pend[s].dst, c.pout[s], pend[s].bytes); pend[s].live = false; }
+    }
+    return NPHUSL_OK;
+}
+
+bool ok_loc(int l) { return l == NPHUSL_HOST || l == NPHUSL_DEVICE; }
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int nphusl_cuda_abi_version(void) { return NPHUSL_CUDA_ABI_VERSION; }
+
+int nphusl_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *nphusl_cuda_last_error(void) { return t_err.c_str(); }
+
+unsigned long long nphusl_cuda_launch_count(void) { return g_launches.load(); }
+
+int nphusl_cuda_set_chunk_pixels(size_t pixels) {
+    g_chunk_px.store(pixels);
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_rgb_to_husl(const void *rgb, int rgb_dtype, int rgb_loc, int channels,
+                            void *hsl, int hsl_dtype, int hsl_loc,
+                            size_t n_pixels, int mode, int device, void *stream) {
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!rgb || !hsl) return fail(NPHUSL_ERR_ARG, "rgb_to_husl: null buffer");
+    if (!dsize(rgb_dtype) || (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64))
+        return fail(NPHUSL_ERR_ARG, "rgb_to_husl: rgb must be u8/f32/f64 and hsl f32/f64");
+    if (channels != 3 && channels != 1) return fail(NPHUSL_ERR_ARG, "rgb_to_husl: channels must be 3 (RGB) or 1 (grayscale)");
+    if (!ok_loc(rgb_loc) || !ok_loc(hsl_loc)) return fail(NPHUSL_ERR_ARG, "rgb_to_husl: bad buffer location");
+    if (mode != NPHUSL_EXACT && mode != NPHUSL_LUT && mode != NPHUSL_LUT_INTERP)
+        return fail(NPHUSL_ERR_ARG, "rgb_to_husl: unknown mode");
+    if (mode != NPHUSL_EXACT && (rgb_dtype != NPHUSL_U8 || hsl_dtype != NPHUSL_F64 || channels != 3))
+        return fail(NPHUSL_ERR_ARG, "rgb_to_husl: LUT modes take uint8 RGB and produce float64, like the reference's _simd.c");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    const size_t in_px = channels * dsize(rgb_dtype), out_px = 3 * dsize(hsl_dtype);
+    auto kern = [=](const void *i, void *o, long long n, cudaStream_t s) -> int {
+        if (mode != NPHUSL_EXACT) return run_lut_dev(*c, i, o, n, mode, s);
+        return run_fwd_dev<false>(*c, i, rgb_dtype, channels, o, hsl_dtype, n, s);
+    };
+    return run_streamed(*c, rgb, rgb_loc, in_px, hsl, hsl_loc, out_px, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+int nphusl_cuda_rgb_to_hue(const void *rgb, int rgb_dtype, int rgb_loc, int channels,
+                           void *hue, int hue_dtype, int hue_loc,
+                           size_t n_pixels, int device, void *stream) {
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!rgb || !hue) return fail(NPHUSL_ERR_ARG, "rgb_to_hue: null buffer");
+    if (!dsize(rgb_dtype) || (hue_dtype != NPHUSL_F32 && hue_dtype != NPHUSL_F64))
+        return fail(NPHUSL_ERR_ARG, "rgb_to_hue: rgb must be u8/f32/f64 and hue f32/f64");
+    if (channels != 3 && channels != 1) return fail(NPHUSL_ERR_ARG, "rgb_to_hue: channels must be 3 or 1");
+    if (!ok_loc(rgb_loc) || !ok_loc(hue_loc)) return fail(NPHUSL_ERR_ARG, "rgb_to_hue: bad buffer location");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    const size_t in_px = channels * dsize(rgb_dtype), out_px = dsize(hue_dtype);
+    auto kern = [=](const void *i, void *o, long long n, cudaStream_t s) -> int {
+        return run_fwd_dev<true>(*c, i, rgb_dtype, channels, o, hue_dtype, n, s);
+    };
+    return run_streamed(*c, rgb, rgb_loc, in_px, hue, hue_loc, out_px, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+int nphusl_cuda_husl_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc,
+                            void *rgb, int rgb_dtype, int rgb_loc,
+                            size_t n_pixels, int device, void *stream) {
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!hsl || !rgb) return fail(NPHUSL_ERR_ARG, "husl_to_rgb: null buffer");
+    if ((hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) || !dsize(rgb_dtype))
+        return fail(NPHUSL_ERR_ARG, "husl_to_rgb: hsl must be f32/f64 and rgb u8/f32/f64");
+    if (!ok_loc(hsl_loc) || !ok_loc(rgb_loc)) return fail(NPHUSL_ERR_ARG, "husl_to_rgb: bad buffer location");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    const size_t in_px = 3 * dsize(hsl_dtype), out_px = 3 * dsize(rgb_dtype);
+    auto kern = [=](const void *i, void *o, long long n, cudaStream_t s) -> int {
+        return run_inv_dev(*c, i, hsl_dtype, o, rgb_dtype, n, s);
+    };
+    return run_streamed(*c, hsl, hsl_loc, in_px, rgb, rgb_loc, out_px, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+// ---- lookup tables ---------------------------------------------------------------------
+static int lut_alloc(DevCtx &c, int seg, int nh, int nl) {
+    Lut &l = c.lut;
+    if (l.light) cudaFree(l.light);
+    if (l.chroma) cudaFree(l.chroma);
+    if (!l.linear) CU(cudaMalloc(&l.linear, 256 * sizeof(double)));
+    l.light = l.chroma = nullptr;
+    l.ready = false;
+    CU(cudaMalloc(&l.light, sizeof(uint16_t) * 3 * seg));
+    CU(cudaMalloc(&l.chroma, sizeof(uint16_t) * (size_t)nh * nl));
+    l.seg = seg; l.nh = nh; l.nl = nl;
+    l.p.linear = l.linear; l.p.light = l.light; l.p.chroma = l.chroma;
+    l.p.seg = seg; l.p.nh = nh; l.p.nl = nl;
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_lut_generate(int device, int light_seg, int nh, int nl) {
+    if (light_seg < 2 || nh < 2 || nl < 2 || light_seg > 21845 || nh > 65535 || nl > 65535)
+        return fail(NPHUSL_ERR_ARG, "lut_generate: table sizes must fit 16 bits (LUT/light.py:27, LUT/chroma.py:27-28)");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if ((rc = lut_alloc(*c, light_seg, nh, nl))) return rc;
+    Lut &l = c->lut;
+    // index steps exactly as LUT/light.py:62-80 and LUT/chroma.py:63-65 compute them
+    const double ysteps[3] = {0.070, 0.350, 1.0};
+    double start = 0.0, seg_start[3];
+    for (int i = 0; i < 3; ++i) {
+        double stop = ysteps[i], step;
+        if (i == 2) {
+            step = (stop - start) / (light_seg - 1);
+            stop += step;
+            step = (stop - start) / light_seg;
+        } else {
+            step = (stop - start) / light_seg;
+        }
+        l.p.ystep[i] = step;
+        seg_start[i] = start;
+        if (i < 2) {   // "{:0.04f}".format(step), light.py:77
+            char buf[64];
+            std::snprintf(buf, sizeof buf, "%0.4f", stop);
+            l.p.ythresh[i] = std::strtod(buf, nullptr);
+        }
+        start = stop;
+    }
+    l.p.hstep = 360.0 / (nh - 1);
+    l.p.lstep = 100.0 / (nl - 1);
+    // linear table: compute_linear((float)j/255.0) printed with "%f" (_linear_lookup.c:45-75);
+    // the decimal rounding is a formatting step, done on the host from device values
+    k_gen_linear<<<1, 256>>>(l.linear);
+    g_launches++;
+    if ((rc = check_launch("k_gen_linear"))) return rc;
+    double lin[256];
+    CU(cudaMemcpy(lin, l.linear, sizeof lin, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < 256; ++j) {
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "%f", lin[j]);
+        lin[j] = std::strtod(buf, nullptr);
+    }
+    CU(cudaMemcpy(l.linear, lin, sizeof lin, cudaMemcpyHostToDevice));
+    k_gen_light<<<(3 * light_seg + 255) / 256, 256>>>(l.light, light_seg, seg_start[0], seg_start[1], seg_start[2],
+                                                        l.p.ystep[0], l.p.ystep[1], l.p.ystep[2]);
+    g_launches++;
+    if ((rc = check_launch("k_gen_light"))) return rc;
+    const long long total = (long long)nh * nl;
+    k_gen_chroma<<<(int)((total + 255) / 256), 256>>>(l.chroma, nh, nl, l.p.hstep, l.p.lstep);
+    g_launches++;
+    if ((rc = check_launch("k_gen_chroma"))) return rc;
+    CU(cudaDeviceSynchronize());
+    l.ready = true;
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
+                           const double *y_idx_step3, const double *y_thresh2,
+                           const uint16_t *chroma, int nh, int nl,
+                           double h_idx_step, double l_idx_step, const double *linear256) {
+    if (!light || !chroma || !y_idx_step3 || !y_thresh2 || !linear256 || light_seg < 2 || nh < 2 || nl < 2)
+        return fail(NPHUSL_ERR_ARG, "lut_upload: null table or bad size");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if ((rc = lut_alloc(*c, light_seg, nh, nl))) return rc;
+    Lut &l = c->lut;
+    CU(cudaMemcpy(l.light, light, sizeof(uint16_t) * 3 * light_seg, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(l.chroma, chroma, sizeof(uint16_t) * (size_t)nh * nl, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(l.linear, linear256, 256 * sizeof(double), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 3; ++i) l.p.ystep[i] = y_idx_step3[i];
+    for (int i = 0; i < 2; ++i) l.p.ythresh[i] = y_thresh2[i];
+    l.p.hstep = h_idx_step;
+    l.p.lstep = l_idx_step;
+    l.ready = true;
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_lut_download(int device, uint16_t *light, uint16_t *chroma, double *linear256,
+                             int *dims4, double *steps7) {
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    Lut &l = c->lut;
+    if (!l.ready) return fail(NPHUSL_ERR_NO_LUT, "lut_download: no tables installed");
+    if (light) CU(cudaMemcpy(light, l.light, sizeof(uint16_t) * 3 * l.seg, cudaMemcpyDeviceToHost));
+    if (chroma) CU(cudaMemcpy(chroma, l.chroma, sizeof(uint16_t) * (size_t)l.nh * l.nl, cudaMemcpyDeviceToHost));
+    if (linear256) CU(cudaMemcpy(linear256, l.linear, 256 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dims4) { dims4[0] = l.seg; dims4[1] = l.nh; dims4[2] = l.nl; dims4[3] = 0; }
+    if (steps7) {
+        for (int i = 0; i < 3; ++i) steps7[i] = l.p.ystep[i];
+        steps7[3] = l.p.ythresh[0]; steps7[4] = l.p.ythresh[1];
+        steps7[5] = l.p.hstep; steps7[6] = l.p.lstep;
+    }
+    return NPHUSL_OK;
+}
+
+// ---- memory / stream helpers --------------------------------------------------------------
+int nphusl_cuda_malloc(void **ptr, size_t bytes, int device) {
+    if (!ptr) return fail(NPHUSL_ERR_ARG, "malloc: null out pointer");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    CU(cudaMalloc(ptr, bytes ? bytes : 1));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_free(void *ptr, int device) {
+    if (!ptr) return NPHUSL_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(ptr));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(NPHUSL_ERR_ARG, "host_alloc: null out pointer");
+    if (nphusl_cuda_device_count() <= 0) return fail(NPHUSL_ERR_NO_DEVICE, "no CUDA device available");
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_host_free(void *ptr) {
+    if (!ptr) return NPHUSL_OK;
+    CU(cudaFreeHost(ptr));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_memcpy(void *dst, const void *src, size_t bytes, int kind, int device, void *stream) {
+    static const cudaMemcpyKind k[4] = {cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice};
+    if (kind < 0 || kind > 3) return fail(NPHUSL_ERR_ARG, "memcpy: bad kind");
+    if (!bytes) return NPHUSL_OK;
+    CU(cudaSetDevice(device));
+    if (stream) CU(cudaMemcpyAsync(dst, src, bytes, k[kind], (cudaStream_t)stream));
+    else CU(cudaMemcpy(dst, src, bytes, k[kind]));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_stream_create(void **stream, int device) {
+    if (!stream) return fail(NPHUSL_ERR_ARG, "stream_create: null out pointer");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    cudaStream_t s;
+    CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_stream_destroy(void *stream, int device) {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamDestroy((cudaStream_t)stream));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_stream_synchronize(void *stream, int device) {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_device_synchronize(int device) {
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_pointer_info(const void *ptr, int *loc_out, int *device_out, int *pinned_out) {
+    cudaPointerAttributes a;
+    int loc = NPHUSL_HOST, dev = -1, pinned = 0;
+    if (cudaPointerGetAttributes(&a, ptr) == cudaSuccess) {
+        if (a.type == cudaMemoryTypeDevice) { loc = NPHUSL_DEVICE; dev = a.device; }
+        else if (a.type == cudaMemoryTypeManaged) { loc = NPHUSL_DEVICE; dev = a.device; pinned = 1; }
+        else if (a.type == cudaMemoryTypeHost) { pinned = 1; }
+    } else {
+        cudaGetLastError();
+    }
+    if (loc_out) *loc_out = loc;
+    if (device_out) *device_out = dev;
+    if (pinned_out) *pinned_out = pinned;
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_device_info(int device, char *name, size_t name_len, int *sm_count, size_t *total_mem) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len) {
+        std::strncpy(name, prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (total_mem) *total_mem = prop.totalGlobalMem;
+    return NPHUSL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+/*
+ * nphusl_cuda.h -- C ABI of the B200-native HUSL conversion backend
+ * (libnphusl_cuda.so, built from husl-numpy_b200/csrc with nvcc for sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of TadLeonard/husl-numpy.  The
+ * reference's only native entry point is
+ *
+ *     double *rgb_to_husl_nd(uint8_t *rgb, size_t size);      nphusl/_simd.h:4-5
+ *
+ * (callee mallocs, caller frees, errors call exit(): nphusl/_simd.c:87-124),
+ * wrapped by nphusl/_simd_opt.pyx:20-39; HUSL->RGB and hue-only exist only as
+ * Cython kernels (nphusl/_cython_opt.pyx:96-246).  The functions below replace
+ * those three backend callables (_rgb_to_husl, _husl_to_rgb, _rgb_to_hue) with:
+ *
+ *   - caller-owned buffers (plain pointers + sizes, no torch / numpy types);
+ *   - an int status (0 = ok) and a thread-local message instead of exit();
+ *   - host OR device pointers on either side: device-resident frames
+ *     (__cuda_array_interface__ / torch tensors) never touch the host, host
+ *     arrays are streamed through pinned staging buffers in chunks;
+ *   - an explicit device index and CUDA stream (device-pointer calls are
+ *     asynchronous on that stream; host-pointer calls return when the result is
+ *     in the caller's buffer).
+ *
+ * There is no CPU fallback anywhere behind this header: every conversion runs
+ * in the CUDA kernels or fails with a non-zero status.
+ *
+ * Reference-side binding: see INTEGRATION.md (ctypes stub for nphusl/_cuda.py).
+ */
+#ifndef NPHUSL_CUDA_H
+#define NPHUSL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPHUSL_CUDA_ABI_VERSION 1
+
+/* status codes */
+enum {
+    NPHUSL_OK = 0,
+    NPHUSL_ERR_ARG = 1,        /* bad dtype / mode / null pointer */
+    NPHUSL_ERR_CUDA = 2,       /* a CUDA runtime call failed (see last_error) */
+    NPHUSL_ERR_NO_DEVICE = 3,  /* no usable GPU */
+    NPHUSL_ERR_NO_LUT = 4      /* LUT mode requested before lut_generate/lut_upload */
+};
+
+/* element types of the image buffers */
+enum { NPHUSL_U8 = 0, NPHUSL_F32 = 1, NPHUSL_F64 = 2 };
+/* where a buffer lives */
+enum { NPHUSL_HOST = 0, NPHUSL_DEVICE = 1 };
+/* RGB -> HUSL arithmetic:
+ *   EXACT      closed-form max chroma, atan2 hue, cube-root lightness
+ *              (== reference NumPy/Cython float64 path within 1e-3 abs)
+ *   LUT        reference default _simd.c build: light LUT + rounded chroma LUT +
+ *              atan approximations, IEEE double in the reference's operation
+ *              order (bit-exact vs _simd.c compiled without -ffast-math)
+ *   LUT_INTERP same with -DINTERPOLATE_CHROMA (bilinear chroma LUT) */
+enum { NPHUSL_EXACT = 0, NPHUSL_LUT = 1, NPHUSL_LUT_INTERP = 2 };
+
+/* ---- library / device ---------------------------------------------------- */
+int nphusl_cuda_abi_version(void);
+/* number of CUDA devices (0 when there is no driver / GPU) */
+int nphusl_cuda_device_count(void);
+/* message of the last failing call on this thread ("" if none) */
+const char *nphusl_cuda_last_error(void);
+/* kernels launched by this library since load (all threads); the bench reports
+ * the difference across its timed region as "gpu_launches" */
+unsigned long long nphusl_cuda_launch_count(void);
+/* streaming chunk (pixels) used for host-pointer calls; 0 restores the default */
+int nphusl_cuda_set_chunk_pixels(size_t pixels);
+
+/* ---- the hot path ---------------------------------------------------------- */
+
+/* RGB -> HUSL.  Replaces rgb_to_husl_nd (_simd.h:4-5, _simd.c:87-112) and
+ * _cython_opt._rgb_to_husl (_cython_opt.pyx:22-93).
+ *   rgb       n_pixels * channels elements, C-contiguous.  channels = 3:
+ *             interleaved R,G,B; channels = 1: grayscale (the value is used for
+ *             R, G and B: transform.from_grayscale, transform.py:210-215).
+ *             NPHUSL_U8 holds 0..255, NPHUSL_F32/F64 hold [0,1].
+ *   hsl       n_pixels * 3 elements (H,S,L interleaved), NPHUSL_F32 or F64.
+ *   mode      NPHUSL_EXACT | NPHUSL_LUT | NPHUSL_LUT_INTERP (LUT modes: uint8
+ *             RGB in, F64 out only, like the reference).
+ *   stream    cudaStream_t (NULL = default stream) on `device`. */
+int nphusl_cuda_rgb_to_husl(const void *rgb, int rgb_dtype, int rgb_loc, int channels,
+                            void *hsl, int hsl_dtype, int hsl_loc,
+                            size_t n_pixels, int mode, int device, void *stream);
+
+/* RGB -> hue only (degrees, [0,360]).  Replaces _cython_opt._rgb_to_hue
+ * (_cython_opt.pyx:96-156).  hue: n_pixels elements, F32 or F64. */
+int nphusl_cuda_rgb_to_hue(const void *rgb, int rgb_dtype, int rgb_loc, int channels,
+                           void *hue, int hue_dtype, int hue_loc,
+                           size_t n_pixels, int device, void *stream);
+
+/* HUSL -> RGB.  Replaces _cython_opt._husl_to_rgb (_cython_opt.pyx:177-246) and,
+ * for rgb_dtype == NPHUSL_U8, the to_rgb_int tail fused in (transform.py:16-20:
+ * round-half-even of c*255, abs, uint8 wrap; no clamp).
+ *   hsl       n_pixels * 3, F32 or F64
+ *   rgb       n_pixels * 3, U8 (0..255) or F32/F64 (float RGB in [0,1]) */
+int nphusl_cuda_husl_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc,
+                            void *rgb, int rgb_dtype, int rgb_loc,
+                            size_t n_pixels, int device, void *stream);
+
+/* ---- lookup tables (optional LUT mode) -------------------------------------- */
+
+/* Generate, ON THE DEVICE, the tables make_lookup_tables:8-9 produces with
+ * LUT/light.py (3 x light_seg uint16, L*100, Y segments split at 0.07 / 0.35)
+ * and LUT/chroma.py (nh x nl uint16, max chroma * 100), plus the 6-decimal
+ * linear table of nphusl/_linear_lookup.c:9-42, and keep them on `device`. */
+int nphusl_cuda_lut_generate(int device, int light_seg, int nh, int nl);
+/* Install caller-provided tables instead (e.g. the reference's own). */
+int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
+                           const double *y_idx_step3, const double *y_thresh2,
+                           const uint16_t *chroma, int nh, int nl,
+                           double h_idx_step, double l_idx_step,
+                           const double *linear256);
+/* Copy the installed tables back to the host (any pointer may be NULL).
+ * dims4 = {light_seg, nh, nl, 0}; steps7 = {Y_IDX_STEP_0..2, Y_THRESH_0..1,
+ * H_IDX_STEP, L_IDX_STEP}. */
+int nphusl_cuda_lut_download(int device, uint16_t *light, uint16_t *chroma,
+                             double *linear256, int *dims4, double *steps7);
+
+/* ---- memory / stream helpers (so a host needs no other CUDA binding) -------- */
+int nphusl_cuda_malloc(void **ptr, size_t bytes, int device);
+int nphusl_cuda_free(void *ptr, int device);
+int nphusl_cuda_host_alloc(void **ptr, size_t bytes);       /* pinned */
+int nphusl_cuda_host_free(void *ptr);
+/* kind: 0 h2h, 1 h2d, 2 d2h, 3 d2d; asynchronous when stream != NULL and the
+ * host side is pinned */
+int nphusl_cuda_memcpy(void *dst, const void *src, size_t bytes, int kind, int device, void *stream);
+int nphusl_cuda_stream_create(void **stream, int device);
+int nphusl_cuda_stream_destroy(void *stream, int device);
+int nphusl_cuda_stream_synchronize(void *stream, int device);
+int nphusl_cuda_device_synchronize(int device);
+/* loc_out: NPHUSL_HOST (pageable or pinned; *pinned_out says which) or NPHUSL_DEVICE */
+int nphusl_cuda_pointer_info(const void *ptr, int *loc_out, int *device_out, int *pinned_out);
+/* "NVIDIA B200", SM count, bytes of global memory */
+int nphusl_cuda_device_info(int device, char *name, size_t name_len, int *sm_count, size_t *total_mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPHUSL_CUDA_H */
