@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""Headline benchmark of the HUSL hot path (BASELINE.json: "Mpix/s to_husl &
+to_rgb, 4K frame batches, 1/2/4/8 B200; % of roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference]
+
+One STEP = one pass of the hot path over one batch of synthetic 3840x2160x3
+uint8 frames: ``to_husl`` (uint8 RGB -> float64 HUSL, the reference's dtype)
+followed by ``to_rgb`` (float64 HUSL -> uint8 RGB).  The metric counts every
+pixel once per step (a pixel that went through both conversions).
+
+* ``value``  : frames already resident in HBM, both kernels back to back on one
+  stream, CUDA-event timing, max over ranks (weak scaling: every GPU owns its
+  own batch, no data-path collective -- the path is embarrassingly parallel).
+* ``e2e``    : the same step through the public API (``nphusl.to_husl`` /
+  ``nphusl.to_rgb`` -> ctypes -> C ABI) with HOST buffers: uint8 frames start
+  in pinned host memory and uint8 results end in pinned host memory, H2D and
+  D2H inside the timed region (the HUSL intermediate stays on the GPU, as in
+  README.md:77-98 style pipelines to_husl -> edit -> to_rgb).
+* ``roofline``: dominant kernel's algorithmic bytes / its mean CUDA-event
+  duration against the measured HBM copy peak (MEASURED_PEAKS.json).
+* ``cpu_baseline`` / ``--impl reference``: the reference's own CPU code for the
+  same step (``rgb_to_husl_nd`` of nphusl/_simd.c in its default LUT build +
+  ``_cython_opt._husl_to_rgb`` + the uint8 tail of transform.py:16-20), built
+  from /root/reference into oracle/_ref, all host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "husl-numpy_b200"), os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+FRAME = (2160, 3840, 3)
+FRAME_PX = FRAME[0] * FRAME[1]
+METRIC = "Mpix/s to_husl+to_rgb, 4K frame batches"
+UNIT = "Mpix/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--frames", type=int, default=8, help="4K frames per GPU per step")
+    ap.add_argument("--husl-dtype", default="float64", choices=["float64", "float32"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
+    return ap.parse_args()
+
+
+def make_frames(n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (n,) + FRAME, dtype=np.uint8)
+
+
+def config(args, n_gpus, frames):
+    return {"workload": "configs[3]: batch of %d synthetic 3840x2160x3 uint8 frames per GPU, to_husl -> to_rgb "
+                        "(lightness edit is a caller-side op, not timed)" % frames,
+            "frames_per_gpu": frames, "pixels_per_step": frames * FRAME_PX * n_gpus,
+            "husl_dtype": args.husl_dtype,
+            "l2": "inputs larger than L2: %.0f MB read+written per kernel launch vs 126 MB L2"
+                  % (frames * FRAME_PX * (3 + 3 * np.dtype(args.husl_dtype).itemsize) / 1e6),
+            "parallelism": "frames sharded over %d GPU(s), one process per GPU, no collective" % n_gpus}
+
+
+# ---------------------------------------------------------------------------
+# reference CPU implementation (oracle/_ref, built from /root/reference)
+# ---------------------------------------------------------------------------
+
+class ReferenceCPU:
+    """The reference's own compiled code for the step; see module docstring."""
+
+    def __init__(self):
+        import oracle as orc
+        self.orc = orc
+        self.kind = "reference" if orc.have_ref() else "port"
+        self.cy = None
+        if self.kind == "reference":
+            try:
+                self.cy = orc.ref_cython()
+            except Exception:
+                self.cy = None
+        self.cores = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(self.cores))
+
+    def to_husl(self, rgb):
+        if self.kind == "reference":
+            return self.orc.ref_simd(rgb, "lut")            # _simd_opt.pyx:20-33 incl. its copy
+        return self.orc.simd_rgb_to_husl(rgb, "lut")
+
+    def to_rgb(self, hsl):
+        if self.cy is not None:
+            f = np.asarray(self.cy._husl_to_rgb(hsl))        # _cython_opt.pyx:177-192
+            return np.abs(np.round(f * 255.0)).astype(np.uint8)   # transform.py:16-20
+        return self.orc.husl_to_rgb(hsl)
+
+    def step(self, rgb):
+        return self.to_rgb(self.to_husl(rgb))
+
+    def describe(self):
+        if self.kind == "reference":
+            return ("reference rgb_to_husl_nd (nphusl/_simd.c, default LUT build, -O3 -ffast-math -fopenmp) + "
+                    + ("_cython_opt._husl_to_rgb (OpenMP) + numpy uint8 tail" if self.cy is not None
+                       else "oracle husl_to_rgb (Cython module unavailable)"))
+        return "oracle/husl_oracle.c restatement (reference build absent)"
+
+
+def time_cpu(ref, budget_s, max_frames=1):
+    """best-of-N of the step on one 4K frame (timeit.repeat(number=1) style,
+    reference tests/performance_test.py:82-83) within ~budget_s seconds."""
+    rgb = make_frames(max_frames, 12345)[0]
+    ref.step(rgb[:64])                                       # load libraries, spin up OpenMP
+    best, t_husl, t_rgb, spent, reps = float("inf"), None, None, 0.0, 0
+    while reps < 2 or (spent < budget_s and reps < 50):
+        t0 = time.perf_counter()
+        hsl = ref.to_husl(rgb)
+        t1 = time.perf_counter()
+        ref.to_rgb(hsl)
+        t2 = time.perf_counter()
+        if t2 - t0 < best:
+            best, t_husl, t_rgb = t2 - t0, t1 - t0, t2 - t1
+        spent += t2 - t0
+        reps += 1
+    px = rgb.size // 3
+    return {"value": px / best / 1e6, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+            "sample": "one 3840x2160 frame, best of %d repeats; %s" % (reps, ref.describe()),
+            "to_husl_mpix_s": px / t_husl / 1e6, "to_rgb_mpix_s": px / t_rgb / 1e6}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref = ReferenceCPU()
+    rgb = make_frames(1, 12345)[0]
+    px = rgb.size // 3
+    for _ in range(max(1, min(args.warmup, 2))):
+        ref.step(rgb)
+    steps = max(1, min(args.steps, 8))                       # bounded: ~0.7 s per step per frame
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.step(rgb)
+    dt = time.perf_counter() - t0
+    val = px * steps / dt / 1e6
+    cfg = config(args, 1, args.frames)
+    cfg["reference_sample"] = "one 3840x2160 frame per step (bounded sample of the batch), steps capped at 8"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                             "sample": "one 3840x2160 frame per step, %d steps; %s" % (steps, ref.describe())},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap,
+                 "hw_power_brake": nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ---------------------------------------------------------------------------
+# the CUDA arm
+# ---------------------------------------------------------------------------
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_for(kernel):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    import nphusl
+    from nphusl import _cuda
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not _cuda.available():
+        raise SystemExit("bench.py: libnphusl_cuda.so / GPU not available -- there is no CPU fallback")
+    torch.cuda.set_device(local)
+    _cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nphusl.enable_cuda()
+
+    B, K, W = args.frames, args.steps, max(args.warmup, 3)
+    hdt = np.dtype(args.husl_dtype)
+    tdt = torch.float64 if hdt == np.float64 else torch.float32
+    px = B * FRAME_PX
+    bpp = 3 + 3 * hdt.itemsize                       # algorithmic bytes per pixel per kernel
+
+    # inputs: pinned host frames (e2e) and a device-resident copy (value)
+    host_in = _cuda.pinned_empty((B,) + FRAME, np.uint8)
+    host_in[...] = make_frames(B, 1000 + rank)
+    host_out = _cuda.pinned_empty((B,) + FRAME, np.uint8)
+    dev_in = torch.from_numpy(np.asarray(host_in)).cuda()
+    dev_hsl = torch.empty((B,) + FRAME, dtype=tdt, device="cuda")
+    dev_out = torch.empty_like(dev_in)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        nphusl.to_husl(dev_in, out=dev_hsl, stream=stream)
+        nphusl.to_rgb(dev_hsl, out=dev_out, stream=stream)
+
+    # ---- value: device-resident ------------------------------------------------
+    for _ in range(W):
+        step_dev()
+    barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    n0 = _cuda.launch_count()
+    barrier()
+    for k in range(K):
+        ev[k][0].record(stream)
+        nphusl.to_husl(dev_in, out=dev_hsl, stream=stream)
+        ev[k][1].record(stream)
+        nphusl.to_rgb(dev_hsl, out=dev_out, stream=stream)
+        ev[k][2].record(stream)
+    torch.cuda.synchronize()
+    launches = _cuda.launch_count() - n0
+    clocks = sampler.stop()
+    total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
+    t_fwd = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    t_inv = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    if not torch.equal(dev_out, dev_in):
+        raise SystemExit("bench.py: round trip is not exact -- refusing to report a number")
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = px * world * K / (total_ms * 1e-3) / 1e6
+
+    # ---- e2e: public API, host buffers ------------------------------------------
+    def step_e2e():
+        nphusl.to_husl(host_in, out=dev_hsl, stream=stream)     # H2D + kernel, chunk-pipelined
+        nphusl.to_rgb(dev_hsl, out=host_out, stream=stream)     # kernel + D2H
+    Ke = max(3, min(K, 20))
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(Ke):
+        step_e2e()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)        # host-blocking calls: wall clock is the honest one
+    if not np.array_equal(np.asarray(host_out), np.asarray(host_in)):
+        raise SystemExit("bench.py: e2e round trip is not exact")
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = px * world * Ke / (float(t.item()) * 1e-3) / 1e6
+
+    # ---- per-kernel variants (rank 0, informational) -------------------------------
+    variants = {}
+    if rank == 0 and not args.no_variants:
+        def timed(fn, reps=20):
+            for _ in range(3):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        hbm, _ = peaks()
+        h32 = torch.empty((B,) + FRAME, dtype=torch.float32, device="cuda")
+        hue64 = torch.empty((B,) + FRAME[:2], dtype=torch.float64, device="cuda")
+        hue32 = torch.empty((B,) + FRAME[:2], dtype=torch.float32, device="cuda")
+        _cuda._rgb_to_husl(dev_in, out=h32, stream=stream)
+        for name, fn, nbytes in (
+                ("to_husl_u8_f64", lambda: _cuda._rgb_to_husl(dev_in, out=dev_hsl, stream=stream), 27),
+                ("to_rgb_f64_u8", lambda: _cuda._husl_to_rgb(dev_hsl, out=dev_out, stream=stream), 27),
+                ("to_husl_u8_f32", lambda: _cuda._rgb_to_husl(dev_in, out=h32, stream=stream), 15),
+                ("to_rgb_f32_u8", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream), 15),
+                ("to_hue_u8_f64", lambda: _cuda._rgb_to_hue(dev_in, out=hue64, stream=stream), 11),
+                ("to_hue_u8_f32", lambda: _cuda._rgb_to_hue(dev_in, out=hue32, stream=stream), 7)):
+            if hdt != np.float64 and "f64" in name and "hue" not in name:
+                continue
+            ms = timed(fn)
+            variants[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 2),
+                              "gb_s": round(px * nbytes / ms / 1e6, 1), "hbm_frac": round(px * nbytes / ms / 1e6 / hbm, 3)}
+        del h32, hue64, hue32
+
+    # ---- cpu baseline (rank 0, N=1 only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = time_cpu(ReferenceCPU(), args.cpu_seconds)
+        except Exception as e:          # the checker is optional for the number, never for the tests
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+
+    if rank == 0:
+        hbm, which = peaks()
+        dom = ("to_husl", "k_fwd_u8", t_fwd) if t_fwd >= t_inv else ("to_rgb", "k_inv_u8", t_inv)
+        achieved = px * bpp / (dom[2] * 1e-3) / 1e9
+        kname = "%s<%s>" % (dom[1], "double" if hdt == np.float64 else "float")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(args, world, B),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px * 3,
+                    "steps": Ke, "path": "nphusl.to_husl(pinned host u8 -> device HUSL) + nphusl.to_rgb(device HUSL -> pinned host u8)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": traffic_for(kname), "peak_source": which,
+                         "bytes_per_pixel": bpp, "pixels_per_launch": px,
+                         "ms_per_launch": {"to_husl": t_fwd, "to_rgb": t_inv}},
+            "kernels": variants,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,532 @@
+"""CUDA backend of nphusl: a thin ctypes binding of ``libnphusl_cuda.so``
+(C ABI in ``include/nphusl_cuda.h``, kernels in ``csrc/``).
+
+A backend, in the reference, is a module that exposes callables named
+``_rgb_to_husl``, ``_husl_to_rgb`` and ``_rgb_to_hue`` (harvested by
+``nphusl/nphusl.py:84-101``); this module is the fifth one, next to NumPy,
+NumExpr, Cython (``nphusl/_cython_opt.pyx:22,96,177``) and C/SIMD
+(``nphusl/_simd_opt.pyx:20-33``).  Contract kept from those:
+
+* ``_rgb_to_husl(rgb)``  ``(..., 3)`` uint8 / float RGB -> float64 HUSL, same shape
+* ``_rgb_to_hue(rgb)``   ``(..., 3)`` RGB -> float64 hue, shape ``rgb.shape[:-1]``
+* ``_husl_to_rgb(hsl)``  ``(..., 3)`` float HUSL -> **uint8** RGB (the
+  ``to_rgb_int`` tail of ``transform.py:16-20`` is fused into the kernel; a
+  uint8 return passes ``rgb_int_output`` untouched, ``transform.py:57-61``)
+
+Added by this backend:
+
+* any object exposing ``__cuda_array_interface__`` (torch CUDA tensors, the
+  ``DeviceArray`` below) is converted where it lives and a ``DeviceArray`` is
+  returned: device-resident frames never touch the host;
+* ``out=`` (host or device), ``dtype=`` (float32 halves the HUSL bytes),
+  ``mode=`` ("exact" | "lut" | "lut_interp"), ``stream=``, ``device=``.
+
+There is NO CPU implementation here: when the shared library or a GPU is
+missing, importing works but ``available()`` is False and every conversion
+raises ``CudaUnavailable``.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+__all__ = ["_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue", "DeviceArray", "available",
+           "CudaUnavailable", "CudaError"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("NPHUSL_CUDA_LIB", os.path.join(_HERE, "libnphusl_cuda.so"))
+
+U8, F32, F64 = 0, 1, 2
+HOST, DEVICE = 0, 1
+MODES = {"exact": 0, "lut": 1, "lut_interp": 2}
+_DT = {np.dtype(np.uint8): U8, np.dtype(np.float32): F32, np.dtype(np.float64): F64}
+
+
+class CudaUnavailable(RuntimeError):
+    """libnphusl_cuda.so could not be loaded or there is no usable GPU."""
+
+
+class CudaError(RuntimeError):
+    """A call into libnphusl_cuda.so returned a non-zero status."""
+
+
+# every exported symbol of include/nphusl_cuda.h: (restype, argtypes)
+_vp, _sz, _i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+_ip, _dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+_u16p = ctypes.POINTER(ctypes.c_uint16)
+SIGNATURES = {
+    "nphusl_cuda_abi_version": (_i, []),
+    "nphusl_cuda_device_count": (_i, []),
+    "nphusl_cuda_last_error": (ctypes.c_char_p, []),
+    "nphusl_cuda_launch_count": (ctypes.c_ulonglong, []),
+    "nphusl_cuda_set_chunk_pixels": (_i, [_sz]),
+    "nphusl_cuda_rgb_to_husl": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _sz, _i, _i, _vp]),
+    "nphusl_cuda_rgb_to_hue": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _sz, _i, _vp]),
+    "nphusl_cuda_husl_to_rgb": (_i, [_vp, _i, _i, _vp, _i, _i, _sz, _i, _vp]),
+    "nphusl_cuda_lut_generate": (_i, [_i, _i, _i, _i]),
+    "nphusl_cuda_lut_upload": (_i, [_i, _u16p, _i, _dp, _dp, _u16p, _i, _i,
+                                    ctypes.c_double, ctypes.c_double, _dp]),
+    "nphusl_cuda_lut_download": (_i, [_i, _u16p, _u16p, _dp, _ip, _dp]),
+    "nphusl_cuda_malloc": (_i, [ctypes.POINTER(_vp), _sz, _i]),
+    "nphusl_cuda_free": (_i, [_vp, _i]),
+    "nphusl_cuda_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "nphusl_cuda_host_free": (_i, [_vp]),
+    "nphusl_cuda_memcpy": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
+    "nphusl_cuda_stream_create": (_i, [ctypes.POINTER(_vp), _i]),
+    "nphusl_cuda_stream_destroy": (_i, [_vp, _i]),
+    "nphusl_cuda_stream_synchronize": (_i, [_vp, _i]),
+    "nphusl_cuda_device_synchronize": (_i, [_i]),
+    "nphusl_cuda_pointer_info": (_i, [_vp, _ip, _ip, _ip]),
+    "nphusl_cuda_device_info": (_i, [_i, ctypes.c_char_p, _sz, _ip, ctypes.POINTER(_sz)]),
+}
+
+_lib = None
+_lib_error = None
+_lock = threading.Lock()
+_default_device = 0
+
+
+def load():
+    """dlopen the shared library once and type every entry point.  Raises
+    ``CudaUnavailable`` (loudly, no fallback) when it cannot be loaded."""
+    global _lib, _lib_error
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+        except (OSError, AttributeError) as e:
+            _lib_error = e
+            raise CudaUnavailable("cannot load {}: {} -- build it with `make -C husl-numpy_b200/csrc` "
+                                  "(there is no CPU fallback in the CUDA backend)".format(LIB_PATH, e))
+        _lib = lib
+    return _lib
+
+
+def device_count() -> int:
+    try:
+        return load().nphusl_cuda_device_count()
+    except CudaUnavailable:
+        return 0
+
+
+def available() -> bool:
+    """True when the library loads AND at least one GPU is visible."""
+    return device_count() > 0
+
+
+def _check(rc, what):
+    if rc:
+        msg = load().nphusl_cuda_last_error().decode("utf-8", "replace")
+        if rc == 3:
+            raise CudaUnavailable("{}: {}".format(what, msg))
+        raise CudaError("{} failed (status {}): {}".format(what, rc, msg))
+
+
+def set_device(device: int):
+    """Default GPU for host-array calls and new allocations of this process."""
+    global _default_device
+    _default_device = int(device)
+
+
+def get_device() -> int:
+    return _default_device
+
+
+def launch_count() -> int:
+    return int(load().nphusl_cuda_launch_count())
+
+
+def set_chunk_pixels(pixels: int):
+    """Pixels per staging slot of the host-array streaming pipeline (0 = default)."""
+    _check(load().nphusl_cuda_set_chunk_pixels(int(pixels)), "set_chunk_pixels")
+
+
+def synchronize(device=None, stream=None):
+    dev = _default_device if device is None else device
+    if stream:
+        _check(load().nphusl_cuda_stream_synchronize(_stream_ptr(stream), dev), "stream_synchronize")
+    else:
+        _check(load().nphusl_cuda_device_synchronize(dev), "device_synchronize")
+
+
+def device_info(device=None):
+    dev = _default_device if device is None else device
+    name = ctypes.create_string_buffer(256)
+    sms, mem = ctypes.c_int(), ctypes.c_size_t()
+    _check(load().nphusl_cuda_device_info(dev, name, 256, ctypes.byref(sms), ctypes.byref(mem)), "device_info")
+    return {"name": name.value.decode(), "sm_count": sms.value, "total_mem": mem.value}
+
+
+def _stream_ptr(stream):
+    """None | int | object with .cuda_stream (torch.cuda.Stream) | Stream below."""
+    if stream is None:
+        return None
+    if hasattr(stream, "cuda_stream"):
+        return ctypes.c_void_p(stream.cuda_stream)
+    if hasattr(stream, "ptr"):
+        return ctypes.c_void_p(stream.ptr)
+    return ctypes.c_void_p(int(stream))
+
+
+class Stream:
+    """A non-blocking CUDA stream owned through the C ABI."""
+
+    def __init__(self, device=None):
+        self.device = _default_device if device is None else device
+        p = ctypes.c_void_p()
+        _check(load().nphusl_cuda_stream_create(ctypes.byref(p), self.device), "stream_create")
+        self.ptr = p.value or 0
+
+    def synchronize(self):
+        _check(load().nphusl_cuda_stream_synchronize(ctypes.c_void_p(self.ptr), self.device), "stream_synchronize")
+
+    def close(self):
+        if self.ptr:
+            load().nphusl_cuda_stream_destroy(ctypes.c_void_p(self.ptr), self.device)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceArray:
+    """C-contiguous array in GPU memory, owned through the C ABI.  Speaks
+    ``__cuda_array_interface__`` v3, so ``torch.as_tensor(a, device="cuda")``
+    wraps it without a copy."""
+
+    def __init__(self, shape, dtype, device=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.device = _default_device if device is None else device
+        self.size = int(np.prod(self.shape)) if self.shape else 1
+        self.nbytes = self.size * self.dtype.itemsize
+        p = ctypes.c_void_p()
+        _check(load().nphusl_cuda_malloc(ctypes.byref(p), self.nbytes, self.device), "malloc")
+        self.ptr = p.value or 0
+        self._owner = True
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False),
+                "version": 3, "strides": None, "stream": None}
+
+    @classmethod
+    def from_host(cls, arr, device=None, stream=None):
+        arr = np.ascontiguousarray(arr)
+        d = cls(arr.shape, arr.dtype, device)
+        _check(load().nphusl_cuda_memcpy(d.ptr, arr.ctypes.data, d.nbytes, 1, d.device, _stream_ptr(stream)), "memcpy h2d")
+        return d
+
+    def copy_to_host(self, out=None, stream=None):
+        if out is None:
+            out = np.empty(self.shape, self.dtype)
+        assert out.nbytes == self.nbytes and out.flags.c_contiguous
+        _check(load().nphusl_cuda_memcpy(out.ctypes.data, self.ptr, self.nbytes, 2, self.device, _stream_ptr(stream)), "memcpy d2h")
+        return out
+
+    def reshape(self, *shape):
+        if len(shape) == 1 and not np.isscalar(shape[0]):
+            shape = tuple(shape[0])
+        v = object.__new__(DeviceArray)
+        v.__dict__.update(self.__dict__)
+        v.shape = tuple(int(s) for s in np.empty(self.shape, np.bool_).reshape(shape).shape) if self.size else tuple(shape)
+        v._owner = False
+        v._base = self
+        return v
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.copy_to_host()
+        return a if dtype is None else a.astype(dtype)
+
+    def free(self):
+        if getattr(self, "_owner", False) and self.ptr:
+            load().nphusl_cuda_free(ctypes.c_void_p(self.ptr), self.device)
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedArray(np.ndarray):
+    """numpy view over page-locked host memory (``pinned_empty``)."""
+    _pin_ptr = None
+
+    def __del__(self):
+        p = getattr(self, "_pin_ptr", None)
+        if p and _lib is not None:
+            _lib.nphusl_cuda_host_free(ctypes.c_void_p(p))
+
+
+def pinned_empty(shape, dtype):
+    """Page-locked host array: host-pointer calls then DMA straight from/into
+    it instead of staging through the library's own pinned slots."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = ctypes.c_void_p()
+    _check(load().nphusl_cuda_host_alloc(ctypes.byref(p), n), "host_alloc")
+    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape).view(PinnedArray)
+    arr._pin_ptr = p.value
+    return arr
+
+
+# ---------------------------------------------------------------------------
+# buffer description
+# ---------------------------------------------------------------------------
+
+class _Buf:
+    __slots__ = ("ptr", "shape", "dtype", "loc", "device", "keep", "channels")
+
+
+def _is_device(obj):
+    return hasattr(obj, "__cuda_array_interface__")
+
+
+def _device_of_ptr(ptr):
+    loc, dev, pin = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    load().nphusl_cuda_pointer_info(ctypes.c_void_p(ptr), ctypes.byref(loc), ctypes.byref(dev), ctypes.byref(pin))
+    return dev.value if loc.value == DEVICE and dev.value >= 0 else None
+
+
+def _describe_device(obj, what, allow_gray=False):
+    cai = obj.__cuda_array_interface__
+    shape = tuple(cai["shape"])
+    dtype = np.dtype(cai["typestr"])
+    strides = cai.get("strides")
+    channels = 3
+    if allow_gray and strides is not None and shape and shape[-1] == 3 and strides[-1] == 0:
+        # transform.GrayDevice: one stored value per pixel, broadcast over R, G, B
+        channels = 1
+        strides = tuple(strides[:-1]) + (dtype.itemsize,)
+        full_shape, shape = shape, shape[:-1] + (1,)
+    if strides is not None:
+        expect, acc = [], dtype.itemsize
+        for s in reversed(shape):
+            expect.append(acc)
+            acc *= s
+        if any(s != e for s, e, n in zip(strides, reversed(expect), shape) if n > 1):
+            raise ValueError("{}: device arrays must be C-contiguous (got strides {})".format(what, strides))
+    b = _Buf()
+    b.ptr = int(cai["data"][0]) if cai["data"][0] else 0
+    b.shape, b.dtype, b.loc, b.keep, b.channels = shape, dtype, DEVICE, obj, channels
+    if channels == 1:
+        b.shape = full_shape
+    dev = getattr(obj, "device", None)
+    if isinstance(dev, int):
+        b.device = dev
+    elif dev is not None and hasattr(dev, "index") and dev.index is not None:
+        b.device = int(dev.index)
+    else:
+        b.device = _device_of_ptr(b.ptr) if b.ptr else None
+    return b
+
+
+def _describe_rgb_in(rgb):
+    """RGB-side input: uint8 stays uint8, float32/float64 stay, every other
+    integer type is cast to uint8 (what rgb_int_input does, transform.py:16-20);
+    a zero-stride last axis (transform.from_grayscale's broadcast view) is sent
+    as ONE channel and broadcast in registers."""
+    if _is_device(rgb):
+        b = _describe_device(rgb, "rgb", allow_gray=True)
+        if b.dtype not in _DT:
+            raise ValueError("rgb device array dtype {} unsupported (uint8/float32/float64)".format(b.dtype))
+        return b
+    a = np.asarray(rgb)
+    b = _Buf()
+    b.loc, b.device, b.channels = HOST, None, 3
+    b.shape = a.shape
+    if a.ndim >= 1 and a.shape[-1] == 3 and a.strides[-1] == 0 and a.size:
+        a = a[..., 0]
+        b.channels = 1
+    if a.dtype not in _DT:
+        if np.issubdtype(a.dtype, np.integer) or a.dtype == np.bool_:
+            a = a.astype(np.uint8)
+        else:
+            a = a.astype(np.float64)
+    a = np.ascontiguousarray(a)
+    b.ptr, b.dtype, b.keep = a.ctypes.data, a.dtype, a
+    return b
+
+
+def _describe_out(out, shape, dtype, allowed, what):
+    """Validate a caller-provided ``out`` (host ndarray or device array)."""
+    if _is_device(out):
+        b = _describe_device(out, what)
+    else:
+        if not isinstance(out, np.ndarray):
+            raise TypeError("{} must be a numpy array or a device array".format(what))
+        if not out.flags.c_contiguous or not out.flags.writeable:
+            raise ValueError("{} must be C-contiguous and writeable".format(what))
+        b = _Buf()
+        b.ptr, b.shape, b.dtype, b.loc, b.device, b.keep, b.channels = out.ctypes.data, out.shape, out.dtype, HOST, None, out, 3
+    if int(np.prod(b.shape)) != int(np.prod(shape)):
+        raise ValueError("{} has {} elements, expected shape {}".format(what, int(np.prod(b.shape)), tuple(shape)))
+    if b.dtype not in allowed:
+        raise ValueError("{} dtype {} unsupported here (allowed: {})".format(what, b.dtype, ", ".join(str(np.dtype(d)) for d in allowed)))
+    return b
+
+
+def _pick_device(device, *bufs):
+    if device is not None:
+        return int(device)
+    for b in bufs:
+        if b is not None and b.loc == DEVICE and b.device is not None:
+            return b.device
+    return _default_device
+
+
+def _make_out(src, out, shape, dtype, allowed, device, what):
+    """-> (_Buf, object to return)"""
+    if out is not None:
+        b = _describe_out(out, shape, dtype, allowed, what)
+        return b, out
+    if src.loc == DEVICE:
+        d = DeviceArray(shape, dtype, device)
+        b = _Buf()
+        b.ptr, b.shape, b.dtype, b.loc, b.device, b.keep, b.channels = d.ptr, d.shape, d.dtype, DEVICE, d.device, d, 3
+        return b, d
+    a = np.empty(shape, dtype)
+    b = _Buf()
+    b.ptr, b.shape, b.dtype, b.loc, b.device, b.keep, b.channels = a.ctypes.data, a.shape, a.dtype, HOST, None, a, 3
+    return b, a
+
+
+_FLOATS = (np.dtype(np.float32), np.dtype(np.float64))
+_ANY = (np.dtype(np.uint8),) + _FLOATS
+
+
+# ---------------------------------------------------------------------------
+# the three backend callables
+# ---------------------------------------------------------------------------
+
+def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, device=None):
+    """RGB -> HUSL on the GPU (kernel (a) husl_from_rgb).  Replaces
+    ``_simd_opt._rgb_to_husl`` (_simd_opt.pyx:20-33) / ``_cython_opt._rgb_to_husl``
+    (_cython_opt.pyx:22-50)."""
+    lib = load()
+    src = _describe_rgb_in(rgb)
+    if not src.shape or src.shape[-1] != 3:
+        raise ValueError("expected (..., 3) RGB, got shape {}".format(src.shape))
+    dev = _pick_device(device, src)
+    if out is not None:
+        dtype = _describe_out(out, src.shape, dtype, _FLOATS, "out").dtype
+    dst, ret = _make_out(src, out, src.shape, np.dtype(dtype), _FLOATS, dev, "out")
+    n = int(np.prod(src.shape[:-1]))
+    _check(lib.nphusl_cuda_rgb_to_husl(src.ptr, _DT[src.dtype], src.loc, src.channels,
+                                       dst.ptr, _DT[dst.dtype], dst.loc, n, MODES[mode], dev,
+                                       _stream_ptr(stream)), "rgb_to_husl")
+    return ret
+
+
+def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None):
+    """RGB -> hue on the GPU (kernel (c) hue_from_rgb).  Replaces
+    ``_cython_opt._rgb_to_hue`` (_cython_opt.pyx:96-111)."""
+    lib = load()
+    src = _describe_rgb_in(rgb)
+    if not src.shape or src.shape[-1] != 3:
+        raise ValueError("expected (..., 3) RGB, got shape {}".format(src.shape))
+    dev = _pick_device(device, src)
+    shape = src.shape[:-1]
+    if out is not None:
+        dtype = _describe_out(out, shape, dtype, _FLOATS, "out").dtype
+    dst, ret = _make_out(src, out, shape, np.dtype(dtype), _FLOATS, dev, "out")
+    n = int(np.prod(shape))
+    _check(lib.nphusl_cuda_rgb_to_hue(src.ptr, _DT[src.dtype], src.loc, src.channels,
+                                      dst.ptr, _DT[dst.dtype], dst.loc, n, dev,
+                                      _stream_ptr(stream)), "rgb_to_hue")
+    return ret
+
+
+def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None):
+    """HUSL -> RGB on the GPU (kernel (b) rgb_from_husl).  Replaces
+    ``_cython_opt._husl_to_rgb`` (_cython_opt.pyx:177-192); with the default
+    ``dtype=uint8`` the round/abs/cast tail of ``to_rgb`` is fused in, float
+    dtypes return RGB in [0, 1] like the reference callable."""
+    lib = load()
+    if _is_device(hsl):
+        src = _describe_device(hsl, "hsl")
+        if src.dtype not in _FLOATS:
+            raise ValueError("hsl device array must be float32/float64, got {}".format(src.dtype))
+    else:
+        a = np.asarray(hsl)
+        if a.dtype not in _FLOATS:
+            a = a.astype(np.float64)           # float_input, transform.py:57-61
+        a = np.ascontiguousarray(a)
+        src = _Buf()
+        src.ptr, src.shape, src.dtype, src.loc, src.device, src.keep, src.channels = a.ctypes.data, a.shape, a.dtype, HOST, None, a, 3
+    if not src.shape or src.shape[-1] != 3:
+        raise ValueError("expected (..., 3) HUSL, got shape {}".format(src.shape))
+    dev = _pick_device(device, src)
+    if out is not None:
+        dtype = _describe_out(out, src.shape, dtype, _ANY, "out").dtype
+    dst, ret = _make_out(src, out, src.shape, np.dtype(dtype), _ANY, dev, "out")
+    n = int(np.prod(src.shape[:-1]))
+    _check(lib.nphusl_cuda_husl_to_rgb(src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
+                                       n, dev, _stream_ptr(stream)), "husl_to_rgb")
+    return ret
+
+
+# backends that can write straight into a caller's `out` advertise it
+# (transform.in_chunks then skips its copy)
+for _f in (_rgb_to_husl, _rgb_to_hue, _husl_to_rgb):
+    _f.accepts_out = True
+
+
+# ---------------------------------------------------------------------------
+# lookup tables (optional LUT mode)
+# ---------------------------------------------------------------------------
+
+def lut_generate(light_seg=1024, nh=1024, nl=1024, device=None):
+    """Build the reference's light / chroma / linear tables ON THE DEVICE
+    (make_lookup_tables:8-9, LUT/light.py, LUT/chroma.py, _linear_lookup.c)."""
+    dev = _default_device if device is None else device
+    _check(load().nphusl_cuda_lut_generate(dev, light_seg, nh, nl), "lut_generate")
+
+
+def lut_upload(light, y_idx_step, y_thresh, chroma, h_idx_step, l_idx_step, linear, device=None):
+    dev = _default_device if device is None else device
+    light = np.ascontiguousarray(light, np.uint16)
+    chroma = np.ascontiguousarray(chroma, np.uint16)
+    st = np.ascontiguousarray(y_idx_step, np.float64)
+    th = np.ascontiguousarray(y_thresh, np.float64)
+    lin = np.ascontiguousarray(linear, np.float64)
+    assert chroma.ndim == 2 and light.size % 3 == 0 and lin.size == 256
+    _check(load().nphusl_cuda_lut_upload(
+        dev, light.ctypes.data_as(_u16p), light.size // 3, st.ctypes.data_as(_dp), th.ctypes.data_as(_dp),
+        chroma.ctypes.data_as(_u16p), chroma.shape[0], chroma.shape[1], float(h_idx_step), float(l_idx_step),
+        lin.ctypes.data_as(_dp)), "lut_upload")
+
+
+def lut_download(device=None):
+    """-> dict(light, chroma, linear, y_idx_step, y_thresh, h_idx_step, l_idx_step)"""
+    dev = _default_device if device is None else device
+    dims = (ctypes.c_int * 4)()
+    steps = (ctypes.c_double * 7)()
+    _check(load().nphusl_cuda_lut_download(dev, None, None, None, dims, steps), "lut_download")
+    seg, nh, nl = dims[0], dims[1], dims[2]
+    light = np.empty(3 * seg, np.uint16)
+    chroma = np.empty((nh, nl), np.uint16)
+    lin = np.empty(256, np.float64)
+    _check(load().nphusl_cuda_lut_download(dev, light.ctypes.data_as(_u16p), chroma.ctypes.data_as(_u16p),
+                                           lin.ctypes.data_as(_dp), dims, steps), "lut_download")
+    s = list(steps)
+    return {"light": light, "chroma": chroma, "linear": lin, "y_idx_step": np.array(s[0:3]),
+            "y_thresh": np.array(s[3:5]), "h_idx_step": s[5], "l_idx_step": s[6]}

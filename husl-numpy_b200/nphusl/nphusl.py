@@ -1,0 +1,87 @@
+"""Public conversion API and the backend registry.
+
+Host-side mirror of the reference's ``nphusl/nphusl.py:30-101`` for the hot
+path: the three public functions keep their names, positional signature
+``(arr, chunksize=None, out=None)``, decorator stack and return types, and the
+backend is looked up in this module's globals at call time, under the private
+names ``_rgb_to_husl`` / ``_husl_to_rgb`` / ``_rgb_to_hue`` -- so
+``enable_*`` / ``*_enabled`` switch implementations exactly like the reference
+(``nphusl/__init__.py:45-88``).
+
+What differs: the registry has a fifth dictionary,
+``CUDA``, filled from ``nphusl/_cuda.py`` and preferred over everything else;
+this repository ships NO CPU implementation of the path (the reference's
+NumPy / NumExpr / Cython / SIMD modules are not part of it), so the other four
+dictionaries are only filled when such a module is registered from outside
+(``register_backend``).  With no backend bound the public functions raise
+``RuntimeError`` -- they never compute on the CPU behind the caller's back.
+"""
+from . import transform
+
+__all__ = ["to_husl", "to_rgb", "to_hue", "CUDA", "SIMD", "CYTHON", "NUMEXPR", "NUMPY",
+           "register_backend", "BACKEND_NAMES"]
+
+# the three swappable callables of the hot path (reference nphusl.py:110,122,305)
+BACKEND_NAMES = ("_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue")
+
+CUDA = {}      # nphusl/_cuda.py -> libnphusl_cuda.so (sm_100a kernels)
+SIMD = {}      # reference: nphusl/_simd_opt.pyx (not shipped here)
+CYTHON = {}    # reference: nphusl/_cython_opt.pyx (not shipped here)
+NUMEXPR = {}   # reference: nphusl/_numexpr_opt.py (not shipped here)
+NUMPY = {}     # reference: nphusl/nphusl.py:104-392 (not shipped here)
+
+
+def _unbound(name):
+    def missing(*args, **kwargs):
+        raise RuntimeError(
+            "nphusl: no backend is bound for {}: libnphusl_cuda.so is not built or no GPU is "
+            "visible, and this package has no CPU implementation (see nphusl._cuda.load())".format(name))
+    missing.__name__ = name
+    missing.unbound = True
+    return missing
+
+
+_rgb_to_husl = _unbound("_rgb_to_husl")
+_husl_to_rgb = _unbound("_husl_to_rgb")
+_rgb_to_hue = _unbound("_rgb_to_hue")
+
+
+def register_backend(registry: dict, module) -> dict:
+    """Harvest the backend callables a module defines into ``registry`` (what
+    ``optimized()`` does name by name in the reference, nphusl.py:84-101)."""
+    for name in BACKEND_NAMES:
+        fn = getattr(module, name, None)
+        if fn is not None:
+            registry[name] = fn
+    return registry
+
+
+### The API
+### From RGB: to_husl, to_hue
+### From HUSL: to_rgb
+
+@transform.squeeze_output
+@transform.reshape_image_input
+@transform.reshape_rgba_input
+def to_hue(rgb_img, chunksize: int = None, out=None, **backend_args):
+    """RGB image (uint8, float in [0, 1], or grayscale float) -> array of HUSL
+    hues in degrees, shape ``rgb_img.shape[:-1]``.  Reference: nphusl.py:30-36."""
+    return transform.in_chunks(rgb_img, _rgb_to_hue, chunksize, out, **backend_args)
+
+
+@transform.squeeze_output
+@transform.reshape_husl_input
+@transform.rgb_int_output
+def to_rgb(husl_img, chunksize: int = None, out=None, **backend_args):
+    """HUSL float array ``(..., 3)`` -> uint8 RGB array of the same shape.
+    Reference: nphusl.py:39-45."""
+    return transform.in_chunks(husl_img, _husl_to_rgb, chunksize, out, **backend_args)
+
+
+@transform.squeeze_output
+@transform.reshape_image_input
+@transform.reshape_rgba_input
+def to_husl(rgb_img, chunksize: int = None, out=None, **backend_args):
+    """RGB image (uint8, float in [0, 1], or grayscale float) -> float64 HUSL
+    array ``(..., 3)`` holding (H, S, L).  Reference: nphusl.py:48-54."""
+    return transform.in_chunks(rgb_img, _rgb_to_husl, chunksize, out, **backend_args)

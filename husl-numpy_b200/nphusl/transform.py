@@ -187,15 +187,41 @@ def _is_float(arr) -> bool:
     return np.issubdtype(_dtype_of(arr), np.floating)
 
 
+class GrayDevice:
+    """(...,) device array presented as (..., 3): same pointer, channel stride
+    0 in its ``__cuda_array_interface__`` (the CUDA backend reads one value per
+    pixel and uses it for R, G and B)."""
+
+    def __init__(self, base):
+        cai = dict(base.__cuda_array_interface__)
+        shape = tuple(cai["shape"])
+        item = np.dtype(cai["typestr"]).itemsize
+        strides = cai.get("strides")
+        if strides is None:
+            strides, acc = [], item
+            for n in reversed(shape):
+                strides.append(acc)
+                acc *= n
+            strides = tuple(reversed(strides))
+        cai["shape"] = shape + (3,)
+        cai["strides"] = tuple(strides) + (0,)
+        self.__cuda_array_interface__ = cai
+        self.base = base
+        self.shape = cai["shape"]
+        self.dtype = np.dtype(cai["typestr"])
+        self.device = getattr(base, "device", None)
+
+
 def from_grayscale(img):
     """(...,) single-channel floats -> (..., 3) with the value in R, G and B.
-    Device arrays are returned as they are: the CUDA backend has grayscale
-    kernels that broadcast in registers instead of in memory."""
+    Nothing is materialised: the CUDA backend has grayscale kernels that
+    broadcast in registers instead of in memory."""
     if is_device_array(img):
-        return img
-    rgb = np.empty(img.shape + (3,), dtype=img.dtype)
-    rgb[...] = img[..., None]
-    return rgb
+        return GrayDevice(img)
+    # zero-copy (..., 3) view with a 0 stride on the channel axis: any backend
+    # reads it as RGB, the CUDA backend recognises the stride and ships ONE
+    # channel to the GPU instead of three
+    return np.broadcast_to(img[..., None], img.shape + (3,))
 
 
 def reshape_image_input(fn):
@@ -341,7 +367,7 @@ def chunk_apply_1d(transform, chunks, out) -> None:
         out[r0:r1] = transform(tile)
 
 
-def in_chunks(img, transform: callable, chunksize=None, out=None):
+def in_chunks(img, transform: callable, chunksize=None, out=None, **kwargs):
     """Apply ``transform`` to ``img``, optionally tile by tile.
 
     * no ``chunksize``: ``transform(img)``, copied into ``out`` when given;
@@ -353,17 +379,21 @@ def in_chunks(img, transform: callable, chunksize=None, out=None):
     The reference declares ``(img, transform, out, chunksize)`` but is called
     with ``(img, transform, chunksize, out)``; an array in the ``chunksize``
     slot / an int in the ``out`` slot is therefore understood as the other order.
+    Extra keyword arguments (``dtype=``, ``stream=``, ``mode=`` ... of the CUDA
+    backend) are handed to ``transform`` unchanged.
     """
     if hasattr(chunksize, "shape") and (out is None or np.isscalar(out)):
         chunksize, out = out, chunksize
     if not chunksize:
-        result = transform(img)
         if out is None:
-            return result
+            return transform(img, **kwargs)
+        if getattr(transform, "accepts_out", False):
+            # the backend writes into `out` itself (host or device memory)
+            return transform(img, out=out, **kwargs)
         if is_device_array(out):
-            raise ValueError("device `out` arrays are filled by the CUDA "
-                             "backend itself; pass them through the public API")
-        out[...] = result
+            raise ValueError("device `out` arrays can only be filled by a backend "
+                             "that accepts `out` (the CUDA backend)")
+        out[...] = transform(img, **kwargs)
         return out
     if is_device_array(img):
         raise ValueError("`chunksize` applies to host arrays only: a device-"
@@ -372,7 +402,7 @@ def in_chunks(img, transform: callable, chunksize=None, out=None):
     if out is None:
         # learn dtype and trailing shape from the first tile
         first, ((r0, r1), (c0, c1)) = next(chunks)
-        res = np.asarray(transform(first))
+        res = np.asarray(transform(first, **kwargs))
         lead = img.shape[:1] if res.ndim == 1 else img.shape[:2]
         out = np.empty(tuple(lead) + res.shape[2:] if res.ndim > 1 else lead,
                        dtype=res.dtype)
@@ -380,6 +410,8 @@ def in_chunks(img, transform: callable, chunksize=None, out=None):
             out[r0:r1] = res
         else:
             out[r0:r1, c0:c1] = res
+    if kwargs:
+        transform = partial(transform, **kwargs)
     apply = chunk_apply_1d if len(out.shape) == 1 else chunk_apply
     apply(transform, chunks, out)
     return out

@@ -1,0 +1,342 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libnphusl_cuda.so,
+bound by nphusl/_cuda.py) against the CPU oracle on the same inputs, against
+the committed reference-made fixtures, and -- at BASELINE.json's full sizes --
+through size-independent properties (exact uint8 round trip, chunk invariance).
+
+Tolerances (BASELINE.json north_star): float HUSL within 1e-3 absolute of the
+reference NumPy float64 path (hue compared circularly, masked where S < 0.1 as
+reference tests/accuracy_test.py:80 does: only the 256 greys of the cube);
+to_rgb round trip within +-1 LSB (we require 0); LUT mode bit-exact."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from conftest import hue_diff
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def cu():
+    from nphusl import _cuda
+    _cuda.load()                      # loud failure if the .so is missing
+    assert _cuda.available(), "no CUDA device visible"
+    return _cuda
+
+
+def _grey(rgb):
+    return (rgb[..., 0] == rgb[..., 1]) & (rgb[..., 1] == rgb[..., 2])
+
+
+def check_husl(got, ref, hue_mask, tol=TOL):
+    got = np.asarray(got, np.float64)
+    dh = hue_diff(got[..., 0], ref[..., 0])[hue_mask]
+    ds = np.abs(got[..., 1] - ref[..., 1])
+    dl = np.abs(got[..., 2] - ref[..., 2])
+    assert dh.size == 0 or dh.max() < tol, "hue off by %g" % dh.max()
+    assert ds.max() < tol, "saturation off by %g" % ds.max()
+    assert dl.max() < tol, "lightness off by %g" % dl.max()
+    assert np.all(got[..., 0] >= 0) and np.all(got[..., 0] <= 360.0)
+
+
+# ---- fixtures made by the reference -------------------------------------------
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_to_husl_golden(cu, golden, dtype):
+    rgb, ref = golden["rgb"], golden["hsl"]
+    got = cu._rgb_to_husl(rgb, dtype=dtype)
+    assert got.dtype == dtype and got.shape == ref.shape
+    check_husl(got, ref, ~_grey(rgb))
+    # greys: S ~ 0 and the same lightness
+    g = _grey(rgb)
+    assert np.abs(got[g, 1]).max() < TOL
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_to_hue_golden(cu, golden, dtype):
+    rgb = golden["rgb"]
+    got = cu._rgb_to_hue(rgb, dtype=dtype)
+    ng = ~_grey(rgb)
+    assert got.shape == rgb.shape[:-1] and got.dtype == dtype
+    assert hue_diff(got[ng], golden["hue"][ng]).max() < TOL
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_to_rgb_golden(cu, golden, dtype):
+    hsl = golden["hsl_in"].astype(dtype)
+    got = cu._husl_to_rgb(hsl)
+    assert got.dtype == np.uint8
+    ref = golden["rgb_u8"]
+    d = np.abs(got.astype(int) - ref.astype(int))
+    # a float32 kernel may land on the other side of a .5 rounding boundary
+    # for an arbitrary HUSL triplet: +-1 LSB allowed, rarely used
+    assert d.max() <= 1
+    assert (d != 0).mean() < 2e-3
+    f = cu._husl_to_rgb(hsl, dtype=np.float64)
+    assert np.abs(f - golden["rgb_float"]).max() < 2e-4
+    # exact round trip of reference-made HUSL (tests/test.py:373-377)
+    assert np.array_equal(cu._husl_to_rgb(golden["hsl"].astype(dtype)), golden["rgb"])
+
+
+def test_float_rgb_and_grayscale_inputs(cu, golden):
+    frgb, ref = golden["frgb"], golden["frgb_hsl"]
+    for dt in (np.float64, np.float32):
+        got = cu._rgb_to_husl(frgb.astype(dt))
+        tol = TOL if dt == np.float64 else 5e-3       # float32 INPUT quantises the colour itself
+        check_husl(got, ref, ref[:, 1] > 0.1, tol)
+    grey = golden["grey"]
+    g3 = np.broadcast_to(grey[..., None], grey.shape + (3,))   # 0-stride view -> 1-channel kernel
+    got = cu._rgb_to_husl(g3)
+    assert got.shape == grey.shape + (3,)
+    assert np.abs(got[..., 2] - golden["grey_hsl"][..., 2]).max() < TOL
+    assert np.abs(got[..., 1] - golden["grey_hsl"][..., 1]).max() < TOL
+    got_m = cu._rgb_to_husl(np.repeat(grey[..., None], 3, -1))  # materialised 3-channel
+    assert np.array_equal(got_m[..., 1:], got[..., 1:])
+
+
+def test_known_answers_through_public_api(cu, golden_meta):
+    import warnings
+    import nphusl
+    lit = golden_meta["literals"]
+    with nphusl.cuda_enabled():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            hsl = nphusl.to_husl([0.5, 0.2, 0.0, 0.5])                  # tests/test.py:671-673
+            assert hsl.shape == (3,)
+            assert np.allclose(hsl, lit["to_husl_rgba_0.5_0.2_0_0.5"], atol=TOL)
+            a = nphusl.to_husl(np.array([0.1, 0.1]))                    # tests/test.py:677-684
+            b = nphusl.to_husl(np.array([[.1, .1, .1]] * 2))
+            assert np.allclose(a[..., 1:], b[..., 1:], atol=1e-6)
+        assert nphusl.to_rgb([360.0, 100.0, 100.0]).tolist() == [255, 255, 255]  # tests/test.py:665-667
+        assert nphusl.to_husl(np.array([255, 0, 0], np.uint8))[0] < 13            # tests/test.py:656-661
+        assert nphusl.to_husl(np.array([30, 30, 30], np.uint8))[1] < 0.01
+        h8 = nphusl.to_husl(np.array([0x80] * 3, np.uint8))
+        hf = nphusl.to_husl(np.array([0.5] * 3))
+        assert abs(h8[2] - hf[2]) < 0.3
+        w = nphusl.to_husl(np.array([255, 255, 255], np.uint8))
+        assert abs(w[0] - lit["white_hue"]) < TOL and w[1] == 0 and w[2] == 100
+        assert nphusl.to_husl(np.array([0, 0, 0], np.uint8)).tolist() == [0, 0, 0]
+
+
+# ---- the full 2^24 cube vs the oracle (BASELINE config 2) -----------------------
+
+@pytest.fixture(scope="module")
+def cube_oracle(cube):
+    return orc.rgb_to_husl(cube)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cube_to_husl(cu, cube, cube_oracle, cube_slices, dtype):
+    got = cu._rgb_to_husl(cube, dtype=dtype)
+    ng = ~_grey(cube)
+    check_husl(got, cube_oracle, ng)
+    # and directly against the reference-made samples of the cube
+    idx = cube_slices["sample_idx"]
+    s = got.reshape(-1, 3)[idx]
+    check_husl(s, cube_slices["sample_hsl"], ~_grey(cube.reshape(-1, 3)[idx]))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cube_round_trip_exact(cu, cube, dtype):
+    hsl = cu._rgb_to_husl(cube, dtype=dtype)
+    back = cu._husl_to_rgb(hsl)
+    bad = np.count_nonzero(back != cube)
+    assert bad == 0, "%d channel values differ after the round trip" % bad
+
+
+def test_cube_to_rgb_from_oracle_husl(cu, cube, cube_oracle):
+    assert np.array_equal(cu._husl_to_rgb(cube_oracle), cube)
+
+
+def test_cube_to_hue(cu, cube, cube_oracle):
+    got = cu._rgb_to_hue(cube)
+    ng = ~_grey(cube)
+    assert hue_diff(got[ng], cube_oracle[..., 0][ng]).max() < TOL
+    husl = cu._rgb_to_husl(cube)
+    assert np.array_equal(got[ng], husl[..., 0][ng])    # README.md:44
+
+
+# ---- LUT mode: bit-exact vs the reference's C path ------------------------------
+
+def test_lut_tables_generated_on_device(cu, simd_golden, golden_meta):
+    cu.lut_generate(1024, 1024, 1024)
+    t = cu.lut_download()
+    assert hashlib.sha256(t["light"].tobytes()).hexdigest() == golden_meta["light_table_sha256"]
+    assert np.array_equal(t["linear"], simd_golden["linear_table"])
+    assert np.array_equal(t["y_idx_step"], simd_golden["y_idx_step"])
+    assert np.array_equal(t["y_thresh"], simd_golden["y_thresh"])
+    assert t["h_idx_step"] == float(simd_golden["h_idx_step"])
+    assert t["l_idx_step"] == float(simd_golden["l_idx_step"])
+    ref_chroma, _, _ = orc.chroma_table()
+    diff = np.count_nonzero(t["chroma"] != ref_chroma)
+    # device pow/sin/cos are not bit-identical to glibc: entries sitting on a
+    # .5 rounding boundary may differ by one count
+    assert diff <= 64, "%d chroma entries differ" % diff
+    assert np.abs(t["chroma"].astype(int) - ref_chroma.astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("mode,key,variant", [("lut", "lut_strict_cube_sha256", "lut"),
+                                              ("lut_interp", "lut_interp_strict_cube_sha256", "lut_interp")])
+def test_lut_mode_bit_exact_on_cube(cu, cube, golden_meta, mode, key, variant):
+    lt, st, th = orc.light_table()
+    ct, hs, ls = orc.chroma_table()
+    cu.lut_upload(lt, st, th, ct, hs, ls, orc.linear_table6())
+    got = cu._rgb_to_husl(cube, mode=mode)
+    ref = orc.simd_rgb_to_husl(cube, variant)
+    nbad = np.count_nonzero(got.view(np.uint64) != ref.view(np.uint64))
+    assert nbad == 0, "%d values not bit-identical" % nbad
+    assert hashlib.sha256(got.tobytes()).hexdigest() == golden_meta[key]
+
+
+def test_lut_mode_golden_samples(cu, simd_golden):
+    g = simd_golden
+    lt, st, th = orc.light_table()
+    ct, hs, ls = orc.chroma_table()
+    cu.lut_upload(lt, st, th, ct, hs, ls, g["linear_table"])
+    assert np.array_equal(cu._rgb_to_husl(g["rgb"], mode="lut"), g["hsl_lut_strict"])
+    assert np.array_equal(cu._rgb_to_husl(g["rgb"], mode="lut_interp"), g["hsl_lut_interp_strict"])
+
+
+# ---- edge cases: empty, ragged, unaligned, chunked ---------------------------------
+
+def test_empty_and_ragged_sizes(cu):
+    rng = np.random.default_rng(3)
+    assert cu._rgb_to_husl(np.empty((0, 3), np.uint8)).shape == (0, 3)
+    assert cu._husl_to_rgb(np.empty((0, 3))).shape == (0, 3)
+    assert cu._rgb_to_hue(np.empty((0, 3), np.uint8)).shape == (0,)
+    for n in (1, 2, 3, 31, 127, 128, 129, 255, 257, 1000, 4099, 128 * 37 + 5):
+        rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+        ref = orc.rgb_to_husl(rgb)
+        for dt in (np.float32, np.float64):
+            got = cu._rgb_to_husl(rgb, dtype=dt)
+            check_husl(got, ref, ref[:, 1] > 0.1)
+            assert np.array_equal(cu._husl_to_rgb(got), rgb)
+            hue = cu._rgb_to_hue(rgb, dtype=dt)
+            assert np.array_equal(hue, got[:, 0])
+
+
+def test_unaligned_device_pointers(cu):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(4)
+    n = 5000
+    rgb = rng.integers(0, 256, (n + 8, 3), dtype=np.uint8)
+    t = torch.from_numpy(rgb.reshape(-1)).cuda()
+    for off in (0, 1, 2, 3, 5):
+        view = t[off * 3 + off: off * 3 + off + n * 3].view(n, 3)   # odd byte offsets
+        host = view.cpu().numpy()
+        got = cu._rgb_to_husl(view, dtype=np.float32)
+        got_h = np.asarray(got)
+        ref = cu._rgb_to_husl(host, dtype=np.float32)
+        assert np.array_equal(got_h, ref)
+
+
+def test_streaming_chunks_do_not_change_results(cu):
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)   # BASELINE config 1 shape
+    whole = cu._rgb_to_husl(rgb)
+    try:
+        cu.set_chunk_pixels(100_000)
+        parts = cu._rgb_to_husl(rgb)
+        back = cu._husl_to_rgb(parts)
+    finally:
+        cu.set_chunk_pixels(0)
+    assert np.array_equal(whole, parts)
+    assert np.array_equal(back, rgb)
+
+
+def test_public_api_chunksize_and_out(cu):
+    import nphusl
+    rng = np.random.default_rng(6)
+    rgb = rng.integers(0, 256, (300, 200, 3), dtype=np.uint8)
+    with nphusl.cuda_enabled():
+        whole = nphusl.to_husl(rgb)
+        out = np.empty(rgb.shape, np.float64)
+        r = nphusl.to_husl(rgb, out=out)
+        assert r is out and np.array_equal(out, whole)
+        tiled = nphusl.to_husl(rgb, chunksize=64)
+        assert np.array_equal(tiled, whole)
+        out2 = np.zeros(rgb.shape, np.float64)
+        nphusl.to_husl(rgb, chunksize=97, out=out2)
+        assert np.array_equal(out2, whole)
+        hue = nphusl.to_hue(rgb, chunksize=50)
+        assert hue.shape == rgb.shape[:2] and np.array_equal(hue, whole[..., 0])
+        back = nphusl.to_rgb(whole, chunksize=128)
+        assert back.dtype == np.uint8 and np.array_equal(back, rgb)
+
+
+# ---- device-resident frames (__cuda_array_interface__) ---------------------------------
+
+def test_device_arrays_never_touch_the_host(cu):
+    torch = pytest.importorskip("torch")
+    import nphusl
+    rng = np.random.default_rng(7)
+    rgb = rng.integers(0, 256, (2, 270, 480, 3), dtype=np.uint8)
+    ref = cu._rgb_to_husl(rgb, dtype=np.float32)
+    t = torch.from_numpy(rgb).cuda()
+    with nphusl.cuda_enabled():
+        d = nphusl.to_husl(t, dtype=np.float32)
+        assert isinstance(d, cu.DeviceArray) and d.shape == rgb.shape
+        assert np.array_equal(d.copy_to_host(), ref)
+        # zero-copy view in torch, edit lightness on the device (README.md:77-81), convert back
+        th = torch.as_tensor(d, device="cuda")
+        assert th.data_ptr() == d.ptr
+        out = torch.empty_like(t)
+        nphusl.to_rgb(th, out=out)
+        torch.cuda.synchronize()
+        assert torch.equal(out, t)
+        hue = torch.empty(rgb.shape[:-1], dtype=torch.float64, device="cuda")
+        nphusl.to_hue(t, out=hue)
+        torch.cuda.synchronize()
+        assert np.array_equal(hue.cpu().numpy(), cu._rgb_to_hue(rgb))
+    # stream argument: asynchronous on a torch stream
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        o = torch.empty(rgb.shape, dtype=torch.float32, device="cuda")
+        cu._rgb_to_husl(t, out=o, stream=s)
+    s.synchronize()
+    assert np.array_equal(o.cpu().numpy(), ref)
+
+
+def test_device_non_contiguous_rejected(cu):
+    torch = pytest.importorskip("torch")
+    t = torch.zeros((8, 8, 3), dtype=torch.uint8, device="cuda")[:, ::2]
+    with pytest.raises(ValueError):
+        cu._rgb_to_husl(t)
+
+
+# ---- BASELINE full-size workloads: size-independent properties -----------------------
+
+def test_4k_batch_round_trip_and_edit(cu):
+    """BASELINE config 4: batch of 3840x2160 frames, to_husl -> lightness edit
+    -> to_rgb, device-resident."""
+    torch = pytest.importorskip("torch")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    frames = torch.randint(0, 256, (4, 2160, 3840, 3), dtype=torch.uint8, device="cuda", generator=g)
+    hsl = torch.empty(frames.shape, dtype=torch.float32, device="cuda")
+    back = torch.empty_like(frames)
+    cu._rgb_to_husl(frames, out=hsl)
+    cu._husl_to_rgb(hsl, out=back)
+    torch.cuda.synchronize()
+    assert torch.equal(back, frames)                       # exact at full size
+    assert float(hsl[..., 1].max()) <= 100.0 + TOL and float(hsl[..., 2].max()) <= 100.0
+    # spot-check a strided sample against the oracle
+    smp = frames.view(-1, 3)[::9973].cpu().numpy()
+    check_husl(hsl.view(-1, 3)[::9973].cpu().numpy(), orc.rgb_to_husl(smp), orc.rgb_to_husl(smp)[:, 1] > 0.1)
+    # lightness edit: darker frame must convert to an RGB that maps back to the edited L
+    hsl[..., 2] *= 0.5
+    cu._husl_to_rgb(hsl, out=back)
+    again = torch.empty_like(hsl)
+    cu._rgb_to_husl(back, out=again)
+    torch.cuda.synchronize()
+    dl = (again[..., 2] - hsl[..., 2]).abs().max().item()
+    assert dl < 0.5          # uint8 quantisation of RGB, measured in L units
+
+
+def test_launch_counter_moves(cu):
+    n0 = cu.launch_count()
+    cu._rgb_to_husl(np.zeros((1000, 3), np.uint8))
+    assert cu.launch_count() > n0
