@@ -24,6 +24,16 @@
 namespace husl {
 
 // ---- MUFU wrappers -----------------------------------------------------------
+#ifdef HUSL_HOST_EMUL
+// host build of this header for tests/emul (development tool, never shipped):
+// float32 libm stands in for the MUFU unit, emul_noise() perturbs by a few ulp
+__device__ __forceinline__ float mufu_rcp(float x) { return emul_noise(1.0f / x); }
+__device__ __forceinline__ float mufu_lg2(float x) { return emul_noise(log2f(x)); }
+__device__ __forceinline__ float mufu_ex2(float x) { return emul_noise(exp2f(x)); }
+__device__ __forceinline__ float mufu_sin(float x) { return emul_noise(sinf(x)); }
+__device__ __forceinline__ float mufu_cos(float x) { return emul_noise(cosf(x)); }
+__device__ __forceinline__ uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+#else
 __device__ __forceinline__ float mufu_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -49,6 +59,7 @@ __device__ __forceinline__ float mufu_cos(float x) {
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+#endif
 
 // ---- hue: atan2 in degrees, [0, 360] -------------------------------------------
 // reference: H = degrees(arctan2(V, U)), +360 if negative (nphusl.py:231-239,

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Launch every streaming kernel of the hot path on the bench workload (8
+device-resident 4K frames) a few times -- the command ncu wraps:
+
+  python profiles/prof_kernels.py > gpurun_out/plain.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:'k_(fwd|inv)_u8' \
+      -o gpurun_out/prof python profiles/prof_kernels.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "husl-numpy_b200"))
+import torch  # noqa: E402
+from nphusl import _cuda  # noqa: E402
+
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+g = torch.Generator(device="cuda").manual_seed(0)
+rgb = torch.randint(0, 256, (frames, 2160, 3840, 3), dtype=torch.uint8, device="cuda", generator=g)
+h64 = torch.empty(rgb.shape, dtype=torch.float64, device="cuda")
+h32 = torch.empty(rgb.shape, dtype=torch.float32, device="cuda")
+hue64 = torch.empty(rgb.shape[:-1], dtype=torch.float64, device="cuda")
+hue32 = torch.empty(rgb.shape[:-1], dtype=torch.float32, device="cuda")
+back = torch.empty_like(rgb)
+for _ in range(reps):
+    _cuda._rgb_to_husl(rgb, out=h64)
+    _cuda._husl_to_rgb(h64, out=back)
+    _cuda._rgb_to_husl(rgb, out=h32)
+    _cuda._husl_to_rgb(h32, out=back)
+    _cuda._rgb_to_hue(rgb, out=hue64)
+    _cuda._rgb_to_hue(rgb, out=hue32)
+torch.cuda.synchronize()
+assert torch.equal(back, rgb)
+print("ok", _cuda.launch_count(), "launches")

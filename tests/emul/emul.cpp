@@ -1,0 +1,70 @@
+// emul.cpp -- DEVELOPMENT/TEST TOOL, NOT PRODUCT.
+// Compiles the per-pixel device math of csrc/husl_math.cuh for the HOST (g++),
+// with the MUFU approximations replaced by float32 libm calls plus an optional
+// pseudo-random perturbation of a few ulp, so the float32 FORMULATION can be
+// swept over all 2^24 colours against the float64 oracle on a CPU-only box
+// before GPU time is spent (tests/test_emul_math.py).  The real kernels are
+// only ever checked on the GPU (tests/test_cuda_parity.py); nothing in the
+// product imports or links this file.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#define HUSL_HOST_EMUL 1
+static int g_noise_ulps = 0;
+static inline float emul_noise(float v) {
+    if (!g_noise_ulps || v == 0.0f || !isfinite(v)) return v;
+    static thread_local uint32_t s = 0x9E3779B9u;
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    int k = (int)(s % (2 * g_noise_ulps + 1)) - g_noise_ulps;
+    uint32_t b; memcpy(&b, &v, 4); b += k; memcpy(&v, &b, 4);
+    return v;
+}
+#include "../../husl-numpy_b200/csrc/husl_math.cuh"
+
+using namespace husl;
+
+static void split(double v, float &hi, float &lo) { hi = (float)v; lo = (float)(v - (double)hi); }
+static double lin_d(double c) { return c > 0.04045 ? pow((c + 0.055) / 1.055, 2.4) : c / 12.92; }
+
+extern "C" {
+void emul_set_noise(int ulps) { g_noise_ulps = ulps; }
+
+void emul_fwd_u8(const uint8_t *rgb, float *out, long long n) {
+    float hi[256], lo[256];
+    for (int i = 0; i < 256; ++i) split(lin_d(i / 255.0), hi[i], lo[i]);
+#pragma omp parallel for
+    for (long long i = 0; i < n; ++i) {
+        LinPx p;
+        p.hr = hi[rgb[3 * i]]; p.lr = lo[rgb[3 * i]];
+        p.hg = hi[rgb[3 * i + 1]]; p.lg = lo[rgb[3 * i + 1]];
+        p.hb = hi[rgb[3 * i + 2]]; p.lb = lo[rgb[3 * i + 2]];
+        husl_from_diff<true>(make_diff(p), out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+    }
+}
+
+void emul_fwd_f64(const double *rgb, float *out, long long n) {
+#pragma omp parallel for
+    for (long long i = 0; i < n; ++i) {
+        LinPx p;
+        split(lin_d(rgb[3 * i]), p.hr, p.lr);
+        split(lin_d(rgb[3 * i + 1]), p.hg, p.lg);
+        split(lin_d(rgb[3 * i + 2]), p.hb, p.lb);
+        husl_from_diff<false>(make_diff(p), out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+    }
+}
+
+// HUSL float32 -> companded RGB scaled to 0..255 (unrounded) and the uint8 bytes
+void emul_inv(const float *hsl, float *rgb255, uint8_t *u8, long long n) {
+#pragma omp parallel for
+    for (long long i = 0; i < n; ++i) {
+        float R, G, B;
+        rgb255_from_husl(hsl[3 * i], hsl[3 * i + 1], hsl[3 * i + 2], R, G, B);
+        if (rgb255) { rgb255[3 * i] = R; rgb255[3 * i + 1] = G; rgb255[3 * i + 2] = B; }
+        if (u8) {
+            u8[3 * i] = (uint8_t)(round_u8_bits(R) & 0xFF);
+            u8[3 * i + 1] = (uint8_t)(round_u8_bits(G) & 0xFF);
+            u8[3 * i + 2] = (uint8_t)(round_u8_bits(B) & 0xFF);
+        }
+    }
+}
+}
