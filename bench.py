@@ -90,8 +90,19 @@ class ReferenceCPU:
                 self.cy = orc.ref_cython()
             except Exception:
                 self.cy = None
-        self.cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(self.cores))
+        # all host threads the box has: torchrun exports OMP_NUM_THREADS=1, undo that
+        # for this CPU leg (libgomp may already be loaded, so set the ICV as well)
+        want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        os.environ["OMP_NUM_THREADS"] = str(want)
+        try:
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(want)
+        except OSError:
+            pass
+        try:
+            self.cores = int(orc.lib().oracle_omp_threads())
+        except Exception:
+            self.cores = want
 
     def to_husl(self, rgb):
         if self.kind == "reference":
@@ -302,7 +313,6 @@ def run_cuda(args):
         ev[k][2].record(stream)
     torch.cuda.synchronize()
     launches = _cuda.launch_count() - n0
-    clocks = sampler.stop()
     total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
     t_fwd = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     t_inv = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
@@ -331,6 +341,7 @@ def run_cuda(args):
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max(e0.elapsed_time(e1), wall_ms)        # host-blocking calls: wall clock is the honest one
+    clocks = sampler.stop()                           # sampled across the value and e2e timed regions
     if not np.array_equal(np.asarray(host_out), np.asarray(host_in)):
         raise SystemExit("bench.py: e2e round trip is not exact")
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
