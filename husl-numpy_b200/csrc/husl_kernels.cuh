@@ -38,6 +38,11 @@ constexpr int TAB_BYTES = 256 * 32 * 8; // replicated table: [value][lane] float
 
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t *p) { return __ldg(p); }
 
+// 256-bit global store (PTX 8.8+, sm_100+); p must be 32-byte aligned
+__device__ __forceinline__ void stg_f64x4(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // table lookup for byte K of word w: ONE PRMT builds (byte << 8) | lane*8, the
 // byte offset of tab[byte][lane]
 template <int K>
@@ -126,9 +131,9 @@ k_fwd_u8(const uint32_t *__restrict__ in, TOut *__restrict__ out, long long n_ti
                 float4 *o = reinterpret_cast<float4 *>(out) + tile * 32 + lane;
                 *o = make_float4(h[0], h[1], h[2], h[3]);
             } else {
-                double2 *o = reinterpret_cast<double2 *>(out) + tile * 64 + lane * 2;
-                o[0] = make_double2((double)h[0], (double)h[1]);
-                o[1] = make_double2((double)h[2], (double)h[3]);
+                // one 256-bit store per lane (sm_100: STG.E.256): 32 lanes x 32 B contiguous
+                stg_f64x4(reinterpret_cast<double *>(out) + tile * 128 + lane * 4,
+                          (double)h[0], (double)h[1], (double)h[2], (double)h[3]);
             }
         } else {
             float r[12];

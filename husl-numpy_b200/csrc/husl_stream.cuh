@@ -1,0 +1,255 @@
+// husl_stream.cuh -- TMA-staged streaming kernels of the HUSL hot path (sm_100a).
+//
+//   k_fwd_tma<TOut>   (a) husl_from_rgb : uint8 RGB -> float32 / float64 HUSL
+//   k_inv_tma<TIn>    (b) rgb_from_husl : float32 / float64 HUSL -> uint8 RGB
+//
+// Same per-pixel math as husl_kernels.cuh (husl_math.cuh); what changes is how
+// the wide side of each kernel (the 12 / 24 B-per-pixel HUSL stream) moves:
+//
+//   * a warp owns a tile of 128 consecutive pixels; its HUSL tile is ONE
+//     contiguous 1536 B (float) / 3072 B (double) block of global memory;
+//   * the inverse kernel fetches tiles with the bulk async-copy engine
+//     (`cp.async.bulk.shared::cluster.global`, SASS UBLKCP) into a per-warp
+//     ring of STAGES shared-memory buffers, completion signalled on an
+//     mbarrier per stage: loads run STAGES tiles ahead of the math without
+//     holding registers, and no LDG/STS instruction is issued for them;
+//   * the forward kernel writes its results straight into a shared-memory image
+//     of the output tile (lane l owns bytes [l*48, l*48+48) resp. [l*96, ..+96),
+//     i.e. its 4 pixels) and one elected lane hands the tile to the bulk engine
+//     (`cp.async.bulk.global.shared::cta`): no LDS/STG instruction is issued for
+//     the transposition to coalesced stores;
+//   * the uint8 side (3 B/px) of the inverse goes out the same way (384 B per
+//     tile); the uint8 side of the forward stays a register-prefetched LDG of 3
+//     words per lane (12 B = 4 whole pixels).
+//
+// Requirements (checked by the host before launching; otherwise the generic
+// kernels run): HUSL pointer 16-byte aligned, uint8 pointer 16-byte aligned
+// (inverse) / 4-byte aligned (forward).
+#pragma once
+#include "husl_kernels.cuh"
+
+namespace husl {
+
+// ---- PTX wrappers: mbarrier + bulk async copy ------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N groups have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async (bulk copy) proxy
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T> struct Tile {
+    static constexpr int BYTES = TILE_PX * 3 * (int)sizeof(T);   // 1536 / 3072
+    static constexpr int LANE = BYTES / 32;                       // 48 / 96
+};
+constexpr int U8_TILE = TILE_PX * 3;                               // 384
+
+// ---------------------------------------------------------------------------------
+// (a) husl_from_rgb, uint8 interleaved RGB -> interleaved HUSL through TMA stores
+// ---------------------------------------------------------------------------------
+// shared memory: [ 64 KB table | warps x OST x Tile<TOut>::BYTES ]
+template <typename TOut, int BLOCK, int MINB, int OST>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_fwd_tma(const uint32_t *__restrict__ in, TOut *__restrict__ out, long long n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    fill_table(smem);
+    const unsigned char *tab = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane8 = lane * 8;
+    constexpr int TB = Tile<TOut>::BYTES;
+    unsigned char *obuf = smem + TAB_BYTES + warp * (OST * TB);
+    const uint32_t obuf_s = smem_addr(obuf);
+    const long long nw = (long long)gridDim.x * (BLOCK / 32);
+    long long tile = (long long)blockIdx.x * (BLOCK / 32) + warp;
+
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    if (tile < n_tiles) {
+        const uint32_t *p = in + tile * 96 + lane * 3;
+        w0 = ldg_u32(p); w1 = ldg_u32(p + 1); w2 = ldg_u32(p + 2);
+    }
+    int st = 0;
+    for (; tile < n_tiles; tile += nw) {
+        uint32_t n0 = 0, n1 = 0, n2 = 0;
+        if (tile + nw < n_tiles) {
+            const uint32_t *p = in + (tile + nw) * 96 + lane * 3;
+            n0 = ldg_u32(p); n1 = ldg_u32(p + 1); n2 = ldg_u32(p + 2);
+        }
+        LinPx px[4];
+        {
+            float2 v;
+            v = lut_lin<0>(tab, w0, lane8); px[0].hr = v.x; px[0].lr = v.y;
+            v = lut_lin<1>(tab, w0, lane8); px[0].hg = v.x; px[0].lg = v.y;
+            v = lut_lin<2>(tab, w0, lane8); px[0].hb = v.x; px[0].lb = v.y;
+            v = lut_lin<3>(tab, w0, lane8); px[1].hr = v.x; px[1].lr = v.y;
+            v = lut_lin<0>(tab, w1, lane8); px[1].hg = v.x; px[1].lg = v.y;
+            v = lut_lin<1>(tab, w1, lane8); px[1].hb = v.x; px[1].lb = v.y;
+            v = lut_lin<2>(tab, w1, lane8); px[2].hr = v.x; px[2].lr = v.y;
+            v = lut_lin<3>(tab, w1, lane8); px[2].hg = v.x; px[2].lg = v.y;
+            v = lut_lin<0>(tab, w2, lane8); px[2].hb = v.x; px[2].lb = v.y;
+            v = lut_lin<1>(tab, w2, lane8); px[3].hr = v.x; px[3].lr = v.y;
+            v = lut_lin<2>(tab, w2, lane8); px[3].hg = v.x; px[3].lg = v.y;
+            v = lut_lin<3>(tab, w2, lane8); px[3].hb = v.x; px[3].lb = v.y;
+        }
+        float r[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            husl_from_diff<true>(make_diff(px[j]), r[3 * j], r[3 * j + 1], r[3 * j + 2]);
+
+        // the bulk store that last used this buffer must have finished reading it
+        if (lane == 0) bulk_wait_read<OST - 1>();
+        __syncwarp();
+        unsigned char *wr = obuf + st * TB + lane * Tile<TOut>::LANE;
+        if (sizeof(TOut) == 4) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                *reinterpret_cast<float4 *>(wr + 16 * k) =
+                    make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                *reinterpret_cast<double2 *>(wr + 16 * k) = make_double2((double)r[2 * k], (double)r[2 * k + 1]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(reinterpret_cast<unsigned char *>(out) + tile * TB, obuf_s + st * TB, TB);
+            bulk_commit();
+        }
+        st = (st + 1 == OST) ? 0 : st + 1;
+        w0 = n0; w1 = n1; w2 = n2;
+    }
+    if (lane == 0) bulk_wait_all<0>();     // shared memory must outlive the copies
+}
+
+// ---------------------------------------------------------------------------------
+// (b) rgb_from_husl: interleaved HUSL through TMA loads -> uint8 RGB through TMA stores
+// ---------------------------------------------------------------------------------
+// shared memory per warp: [ IST x Tile<TIn>::BYTES | 2 x 384 B uint8 tiles | IST mbarriers ]
+template <typename TIn, int IST>
+struct InvSmem {
+    static constexpr int PER_WARP = IST * Tile<TIn>::BYTES + 2 * U8_TILE + 64;
+};
+
+template <typename TIn, int BLOCK, int MINB, int IST>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TB = Tile<TIn>::BYTES;
+    unsigned char *base = smem + warp * InvSmem<TIn, IST>::PER_WARP;
+    unsigned char *ibuf = base;
+    unsigned char *obuf = base + IST * TB;
+    const uint32_t ibuf_s = smem_addr(ibuf), obuf_s = smem_addr(obuf);
+    const uint32_t bar_s = smem_addr(base + IST * TB + 2 * U8_TILE);
+    const long long nw = (long long)gridDim.x * (BLOCK / 32);
+    const long long first = (long long)blockIdx.x * (BLOCK / 32) + warp;
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(in);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < IST; ++s) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+#pragma unroll
+        for (int s = 0; s < IST; ++s) {
+            const long long t = first + s * nw;
+            if (t < n_tiles) {
+                mbar_expect_tx(bar_s + 8 * s, TB);
+                bulk_load(ibuf_s + s * TB, src + t * TB, TB, bar_s + 8 * s);
+            }
+        }
+    }
+    __syncwarp();
+
+    int st = 0, ost = 0;
+    uint32_t phase = 0;
+    for (long long tile = first; tile < n_tiles; tile += nw) {
+        mbar_wait(bar_s + 8 * st, phase);
+        float hsl[12];
+        const unsigned char *rd = ibuf + st * TB + lane * Tile<TIn>::LANE;
+        if (sizeof(TIn) == 4) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 f = *reinterpret_cast<const float4 *>(rd + 16 * k);
+                hsl[4 * k] = f.x; hsl[4 * k + 1] = f.y; hsl[4 * k + 2] = f.z; hsl[4 * k + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double2 d = *reinterpret_cast<const double2 *>(rd + 16 * k);
+                hsl[2 * k] = (float)d.x; hsl[2 * k + 1] = (float)d.y;
+            }
+        }
+        __syncwarp();                       // every lane has its 4 pixels in registers
+        if (lane == 0) {                    // refill this stage IST tiles ahead
+            const long long t = tile + (long long)IST * nw;
+            if (t < n_tiles) {
+                mbar_expect_tx(bar_s + 8 * st, TB);
+                bulk_load(ibuf_s + st * TB, src + t * TB, TB, bar_s + 8 * st);
+            }
+        }
+        uint32_t q[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float R, G, B;
+            rgb255_from_husl(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
+            q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
+        }
+        const uint32_t o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+        const uint32_t o1 = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+        const uint32_t o2 = __byte_perm(__byte_perm(q[8], q[9], 0x0040), __byte_perm(q[10], q[11], 0x0040), 0x5410);
+        if (lane == 0) bulk_wait_read<1>();          // the store issued two tiles ago has released its buffer
+        __syncwarp();
+        uint32_t *sw = reinterpret_cast<uint32_t *>(obuf + ost * U8_TILE);
+        sw[lane * 3] = o0; sw[lane * 3 + 1] = o1; sw[lane * 3 + 2] = o2;
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(reinterpret_cast<unsigned char *>(out) + tile * U8_TILE, obuf_s + ost * U8_TILE, U8_TILE);
+            bulk_commit();
+        }
+        ost ^= 1;
+        if (++st == IST) { st = 0; phase ^= 1; }
+    }
+    if (lane == 0) bulk_wait_all<0>();
+}
+
+}  // namespace husl

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -16,6 +17,7 @@
 
 #include "../../include/nphusl_cuda.h"
 #include "husl_kernels.cuh"
+#include "husl_stream.cuh"
 #include "husl_lut.cuh"
 
 namespace {
@@ -23,6 +25,7 @@ namespace {
 using namespace husl;
 
 thread_local std::string t_err;
+thread_local bool t_host_async = false;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<size_t> g_chunk_px{0};
 
@@ -53,16 +56,26 @@ struct Lut {
     LutParams p{};
 };
 
+// One staging set = NSLOT streams, each with a device-side chunk buffer per
+// direction and (for pageable callers) a pinned bounce buffer.  A device owns
+// three sets so that an upload-type call (host -> device result), a
+// download-type call (device -> host result) and a host -> host call never
+// queue behind one another: H2D of one call overlaps D2H of another.
+struct Staging {
+    cudaStream_t st[NSLOT] = {};
+    cudaEvent_t done[NSLOT] = {};
+    void *din[NSLOT] = {}, *dout[NSLOT] = {};
+    void *pin[NSLOT] = {}, *pout[NSLOT] = {};
+    size_t din_cap = 0, dout_cap = 0, pin_cap = 0, pout_cap = 0;
+};
+enum { SET_UP = 0, SET_DOWN = 1, SET_BOTH = 2, NSETS = 3 };
+
 struct DevCtx {
     std::mutex mu;
     bool init = false;
     int dev = -1, sms = 0;
-    cudaStream_t st[NSLOT] = {};
-    cudaEvent_t done[NSLOT] = {};
+    Staging set[NSETS];
     cudaEvent_t gate = nullptr;
-    void *din[NSLOT] = {}, *dout[NSLOT] = {};
-    void *pin[NSLOT] = {}, *pout[NSLOT] = {};
-    size_t din_cap = 0, dout_cap = 0, pin_cap = 0, pout_cap = 0;
     bool attr_set = false;
     Lut lut;
 };
@@ -98,10 +111,11 @@ int ctx_get(int device, DevCtx **out) {
             tab[i].y = (float)(v - (double)tab[i].x);
         }
         CU(cudaMemcpyToSymbol(g_lin_tab, tab, sizeof tab));
-        for (int s = 0; s < NSLOT; ++s) {
-            CU(cudaStreamCreateWithFlags(&c.st[s], cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&c.done[s], cudaEventDisableTiming));
-        }
+        for (int k = 0; k < NSETS; ++k)
+            for (int s = 0; s < NSLOT; ++s) {
+                CU(cudaStreamCreateWithFlags(&c.set[k].st[s], cudaStreamNonBlocking));
+                CU(cudaEventCreateWithFlags(&c.set[k].done[s], cudaEventDisableTiming));
+            }
         CU(cudaEventCreateWithFlags(&c.gate, cudaEventDisableTiming));
         c.init = true;
     }
@@ -127,6 +141,14 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_u8<double, false, FWD_BLOCK, 1>, TAB_BYTES + W * Pack<double>::STAGE))) return rc;
     if ((rc = set_smem(k_fwd_u8<float, true, FWD_BLOCK, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_u8<double, true, FWD_BLOCK, 2>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_fwd_tma<float, 512, 2, 2>, TAB_BYTES + 16 * 2 * Tile<float>::BYTES))) return rc;
+    if ((rc = set_smem(k_fwd_tma<double, 512, 1, 2>, TAB_BYTES + 16 * 2 * Tile<double>::BYTES))) return rc;
+    if ((rc = set_smem(k_fwd_tma<double, 1024, 1, 1>, TAB_BYTES + 32 * 1 * Tile<double>::BYTES))) return rc;
+#define INV_ATTR(T, MINB, IST) \
+    if ((rc = set_smem(k_inv_tma<T, INV_BLOCK, MINB, IST>, (INV_BLOCK / 32) * InvSmem<T, IST>::PER_WARP))) return rc
+    INV_ATTR(float, 4, 2); INV_ATTR(float, 4, 3); INV_ATTR(float, 4, 4);
+    INV_ATTR(double, 4, 2); INV_ATTR(double, 3, 2); INV_ATTR(double, 2, 3); INV_ATTR(double, 2, 4);
+#undef INV_ATTR
     c.attr_set = true;
     return NPHUSL_OK;
 }
@@ -164,6 +186,26 @@ int launch_inv_any(DevCtx &c, const void *in, void *out, long long n, cudaStream
 
 bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
+// NPHUSL_STREAM selects the streaming-kernel family for A/B measurements:
+//   "ldg"  register/LDG+STG transposition kernels (husl_kernels.cuh)
+//   "tma"  bulk-async-copy staged kernels (husl_stream.cuh)            [default]
+// NPHUSL_VARIANT picks a tuning variant inside the family (0 = default).
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+bool use_tma() {
+    static const bool v = [] {
+        const char *e = std::getenv("NPHUSL_STREAM");
+        return !(e && std::strcmp(e, "ldg") == 0);
+    }();
+    return v;
+}
+int variant() {
+    static const int v = env_int("NPHUSL_VARIANT", 0);
+    return v;
+}
+
 // forward on device pointers: streaming kernel on the 128-pixel tiles when the
 // layout allows it, generic kernel on the tail / on everything else
 template <bool HUE>
@@ -172,11 +214,22 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
     int rc;
     const size_t out_px = (HUE ? 1 : 3) * dsize(out_dt);
     long long done = 0;
-    if (in_dt == NPHUSL_U8 && channels == 3 && aligned(in, 4) && aligned(out, 16) && n >= TILE_PX) {
+    if (in_dt == NPHUSL_U8 && channels == 3 && aligned(in, 4) && aligned(out, HUE ? 32 : 16) && n >= TILE_PX) {
         if ((rc = set_attrs(c))) return rc;
         const long long tiles = n / TILE_PX;
         constexpr int W = FWD_BLOCK / 32;
-        if (out_dt == NPHUSL_F32) {
+        if (!HUE && use_tma()) {
+            if (out_dt == NPHUSL_F32) {
+                const int grid = grid_for(tiles, 16, c.sms * 2);
+                k_fwd_tma<float, 512, 2, 2><<<grid, 512, TAB_BYTES + 16 * 2 * Tile<float>::BYTES, s>>>((const uint32_t *)in, (float *)out, tiles);
+            } else if (variant() == 1) {
+                const int grid = grid_for(tiles, 32, c.sms);
+                k_fwd_tma<double, 1024, 1, 1><<<grid, 1024, TAB_BYTES + 32 * Tile<double>::BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
+            } else {
+                const int grid = grid_for(tiles, 16, c.sms);
+                k_fwd_tma<double, 512, 1, 2><<<grid, 512, TAB_BYTES + 16 * 2 * Tile<double>::BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
+            }
+        } else if (out_dt == NPHUSL_F32) {
             const size_t sm = TAB_BYTES + (HUE ? 0 : W * Pack<float>::STAGE);
             const int grid = grid_for(tiles, W, c.sms * 2);
             k_fwd_u8<float, HUE, FWD_BLOCK, 2><<<grid, FWD_BLOCK, sm, s>>>((const uint32_t *)in, (float *)out, tiles);
@@ -206,7 +259,24 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
     if (out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 4) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
         constexpr int W = INV_BLOCK / 32;
-        if (in_dt == NPHUSL_F32) {
+        if (use_tma() && aligned(out, 16)) {
+            if ((rc = set_attrs(c))) return rc;
+            const int v = variant();
+#define INV_GO(T, MINB, IST) \
+    k_inv_tma<T, INV_BLOCK, MINB, IST><<<grid_for(tiles, W, c.sms * MINB), INV_BLOCK, W * InvSmem<T, IST>::PER_WARP, s>>>( \
+        (const T *)in, (uint32_t *)out, tiles)
+            if (in_dt == NPHUSL_F32) {
+                if (v == 1) INV_GO(float, 4, 4);
+                else if (v == 3) INV_GO(float, 4, 2);
+                else INV_GO(float, 4, 3);
+            } else {
+                if (v == 1) INV_GO(double, 3, 2);
+                else if (v == 2) INV_GO(double, 2, 4);
+                else if (v == 3) INV_GO(double, 4, 2);
+                else INV_GO(double, 2, 3);
+            }
+#undef INV_GO
+        } else if (in_dt == NPHUSL_F32) {
             const int grid = grid_for(tiles, W, c.sms * 4);
             k_inv_u8<float, INV_BLOCK, 4><<<grid, INV_BLOCK, W * Pack<float>::STAGE, s>>>((const float *)in, (uint32_t *)out, tiles);
         } else {
@@ -293,6 +363,14 @@ int ensure(void **buf, size_t *cap, size_t need, bool pinned, int nbuf) {
 
 // Generic driver for "n pixels, in_px bytes in, out_px bytes out per pixel".
 // kernel(in_dev, out_dev, npx, stream) runs the conversion on device pointers.
+//
+// Host buffers are streamed in chunks through an NSLOT-deep pipeline (H2D,
+// kernel, D2H of different chunks overlap).  Pageable host memory is bounced
+// through pinned slots with a multi-threaded memcpy and the call returns when
+// the result is in the caller's buffer.  When every host buffer is pinned the
+// copies are DMA'd directly and the whole call is expressed in stream order;
+// with nphusl_cuda_set_host_async(1) it then returns WITHOUT waiting: `user`
+// (the caller's stream) is made to wait on the work instead.
 template <typename F>
 int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *dst, int dst_loc,
                  size_t out_px, long long n, cudaStream_t user, F kernel) {
@@ -306,50 +384,60 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
     if ((long long)chunk > n) chunk = (size_t)((n + TILE_PX - 1) / TILE_PX * TILE_PX);
     const bool src_host = src_loc == NPHUSL_HOST, dst_host = dst_loc == NPHUSL_HOST;
     const bool src_pin = src_host && is_pinned(src), dst_pin = dst_host && is_pinned(dst);
+    const bool all_pinned = (!src_host || src_pin) && (!dst_host || dst_pin);
+    Staging &g = c.set[src_host && dst_host ? SET_BOTH : (src_host ? SET_UP : SET_DOWN)];
     int rc;
-    if (src_host && (rc = ensure(c.din, &c.din_cap, chunk * in_px, false, NSLOT))) return rc;
-    if (dst_host && (rc = ensure(c.dout, &c.dout_cap, chunk * out_px, false, NSLOT))) return rc;
-    if (src_host && !src_pin && (rc = ensure(c.pin, &c.pin_cap, chunk * in_px, true, NSLOT))) return rc;
-    if (dst_host && !dst_pin && (rc = ensure(c.pout, &c.pout_cap, chunk * out_px, true, NSLOT))) return rc;
+    if (src_host && (rc = ensure(g.din, &g.din_cap, chunk * in_px, false, NSLOT))) return rc;
+    if (dst_host && (rc = ensure(g.dout, &g.dout_cap, chunk * out_px, false, NSLOT))) return rc;
+    if (src_host && !src_pin && (rc = ensure(g.pin, &g.pin_cap, chunk * in_px, true, NSLOT))) return rc;
+    if (dst_host && !dst_pin && (rc = ensure(g.pout, &g.pout_cap, chunk * out_px, true, NSLOT))) return rc;
 
     // work submitted earlier on the caller's stream must be visible to ours
     CU(cudaEventRecord(c.gate, user));
-    for (int s = 0; s < NSLOT; ++s) CU(cudaStreamWaitEvent(c.st[s], c.gate, 0));
+    for (int s = 0; s < NSLOT; ++s) CU(cudaStreamWaitEvent(g.st[s], c.gate, 0));
 
     struct Pending { char *dst; size_t bytes; bool live; } pend[NSLOT] = {};
-    long long off = 0;
-    for (long long ci = 0; off < n; ++ci, off += chunk) {
+    long long off = 0, nchunks = 0;
+    for (long long ci = 0; off < n; ++ci, off += chunk, ++nchunks) {
         const int s = (int)(ci % NSLOT);
         const long long npx = (n - off < (long long)chunk) ? n - off : (long long)chunk;
-        if (ci >= NSLOT) {                    // slot reuse: its previous chunk must be finished
-            CU(cudaEventSynchronize(c.done[s]));
-            if (pend[s].live) { par_memcpy(pend[s].dst, c.pout[s], pend[s].bytes); pend[s].live = false; }
+        // slot reuse: device-side buffers are protected by the slot stream's own
+        // order; the pinned bounce buffers are touched by the HOST, so a pageable
+        // call must wait for the slot's previous chunk before refilling it
+        if (!all_pinned && ci >= NSLOT) {
+            CU(cudaEventSynchronize(g.done[s]));
+            if (pend[s].live) { par_memcpy(pend[s].dst, g.pout[s], pend[s].bytes); pend[s].live = false; }
         }
         const void *in_dev;
         if (src_host) {
             const char *hp = (const char *)src + off * in_px;
-            if (!src_pin) { par_memcpy(c.pin[s], hp, npx * in_px); hp = (const char *)c.pin[s]; }
-            CU(cudaMemcpyAsync(c.din[s], hp, npx * in_px, cudaMemcpyHostToDevice, c.st[s]));
-            in_dev = c.din[s];
+            if (!src_pin) { par_memcpy(g.pin[s], hp, npx * in_px); hp = (const char *)g.pin[s]; }
+            CU(cudaMemcpyAsync(g.din[s], hp, npx * in_px, cudaMemcpyHostToDevice, g.st[s]));
+            in_dev = g.din[s];
         } else {
             in_dev = (const char *)src + off * in_px;
         }
-        void *out_dev = dst_host ? c.dout[s] : (void *)((char *)dst + off * out_px);
-        if ((rc = kernel(in_dev, out_dev, npx, c.st[s]))) return rc;
+        void *out_dev = dst_host ? g.dout[s] : (void *)((char *)dst + off * out_px);
+        if ((rc = kernel(in_dev, out_dev, npx, g.st[s]))) return rc;
         if (dst_host) {
             char *hp = (char *)dst + off * out_px;
             if (dst_pin) {
-                CU(cudaMemcpyAsync(hp, c.dout[s], npx * out_px, cudaMemcpyDeviceToHost, c.st[s]));
+                CU(cudaMemcpyAsync(hp, g.dout[s], npx * out_px, cudaMemcpyDeviceToHost, g.st[s]));
             } else {
-                CU(cudaMemcpyAsync(c.pout[s], c.dout[s], npx * out_px, cudaMemcpyDeviceToHost, c.st[s]));
+                CU(cudaMemcpyAsync(g.pout[s], g.dout[s], npx * out_px, cudaMemcpyDeviceToHost, g.st[s]));
                 pend[s] = {hp, (size_t)npx * out_px, true};
             }
         }
-        CU(cudaEventRecord(c.done[s], c.st[s]));
+        CU(cudaEventRecord(g.done[s], g.st[s]));
     }
-    for (int s = 0; s < NSLOT; ++s) {
-        CU(cudaStreamSynchronize(c.st[s]));
-        if (pend[s].live) { par_memcpy(pend[s].dst, c.pout[s], pend[s].bytes); pend[s].live = false; }
+    const int used = nchunks < NSLOT ? (int)nchunks : NSLOT;
+    if (all_pinned && t_host_async) {
+        for (int s = 0; s < used; ++s) CU(cudaStreamWaitEvent(user, g.done[s], 0));
+        return NPHUSL_OK;
+    }
+    for (int s = 0; s < used; ++s) {
+        CU(cudaStreamSynchronize(g.st[s]));
+        if (pend[s].live) { par_memcpy(pend[s].dst, g.pout[s], pend[s].bytes); pend[s].live = false; }
     }
     return NPHUSL_OK;
 }
@@ -380,6 +468,11 @@ unsigned long long nphusl_cuda_launch_count(void) { return g_launches.load(); }
 
 int nphusl_cuda_set_chunk_pixels(size_t pixels) {
     g_chunk_px.store(pixels);
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_set_host_async(int enabled) {
+    t_host_async = enabled != 0;
     return NPHUSL_OK;
 }
 

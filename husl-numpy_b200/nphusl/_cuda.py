@@ -19,7 +19,8 @@ Added by this backend:
   ``DeviceArray`` below) is converted where it lives and a ``DeviceArray`` is
   returned: device-resident frames never touch the host;
 * ``out=`` (host or device), ``dtype=`` (float32 halves the HUSL bytes),
-  ``mode=`` ("exact" | "lut" | "lut_interp"), ``stream=``, ``device=``.
+  ``mode=`` ("exact" | "lut" | "lut_interp"), ``stream=``, ``device=``,
+  ``blocking=False`` (pinned host buffers: enqueue only, caller syncs ``stream``).
 
 There is NO CPU implementation here: when the shared library or a GPU is
 missing, importing works but ``available()`` is False and every conversion
@@ -61,6 +62,7 @@ SIGNATURES = {
     "nphusl_cuda_last_error": (ctypes.c_char_p, []),
     "nphusl_cuda_launch_count": (ctypes.c_ulonglong, []),
     "nphusl_cuda_set_chunk_pixels": (_i, [_sz]),
+    "nphusl_cuda_set_host_async": (_i, [_i]),
     "nphusl_cuda_rgb_to_husl": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _sz, _i, _i, _vp]),
     "nphusl_cuda_rgb_to_hue": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _sz, _i, _vp]),
     "nphusl_cuda_husl_to_rgb": (_i, [_vp, _i, _i, _vp, _i, _i, _sz, _i, _vp]),
@@ -417,7 +419,24 @@ _ANY = (np.dtype(np.uint8),) + _FLOATS
 # the three backend callables
 # ---------------------------------------------------------------------------
 
-def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, device=None):
+class _host_async:
+    """``blocking=False``: for this one call, on this thread, pinned-host
+    buffers are only enqueued (nphusl_cuda_set_host_async); pageable memory
+    still completes before the call returns."""
+
+    def __init__(self, lib, blocking):
+        self.lib, self.on = lib, not blocking
+
+    def __enter__(self):
+        if self.on:
+            self.lib.nphusl_cuda_set_host_async(1)
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.lib.nphusl_cuda_set_host_async(0)
+
+
+def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, device=None, blocking=True):
     """RGB -> HUSL on the GPU (kernel (a) husl_from_rgb).  Replaces
     ``_simd_opt._rgb_to_husl`` (_simd_opt.pyx:20-33) / ``_cython_opt._rgb_to_husl``
     (_cython_opt.pyx:22-50)."""
@@ -430,13 +449,15 @@ def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, dev
         dtype = _describe_out(out, src.shape, dtype, _FLOATS, "out").dtype
     dst, ret = _make_out(src, out, src.shape, np.dtype(dtype), _FLOATS, dev, "out")
     n = int(np.prod(src.shape[:-1]))
-    _check(lib.nphusl_cuda_rgb_to_husl(src.ptr, _DT[src.dtype], src.loc, src.channels,
-                                       dst.ptr, _DT[dst.dtype], dst.loc, n, MODES[mode], dev,
-                                       _stream_ptr(stream)), "rgb_to_husl")
+    with _host_async(lib, blocking):
+        rc = lib.nphusl_cuda_rgb_to_husl(src.ptr, _DT[src.dtype], src.loc, src.channels,
+                                         dst.ptr, _DT[dst.dtype], dst.loc, n, MODES[mode], dev,
+                                         _stream_ptr(stream))
+    _check(rc, "rgb_to_husl")
     return ret
 
 
-def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None):
+def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None, blocking=True):
     """RGB -> hue on the GPU (kernel (c) hue_from_rgb).  Replaces
     ``_cython_opt._rgb_to_hue`` (_cython_opt.pyx:96-111)."""
     lib = load()
@@ -449,13 +470,14 @@ def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None):
         dtype = _describe_out(out, shape, dtype, _FLOATS, "out").dtype
     dst, ret = _make_out(src, out, shape, np.dtype(dtype), _FLOATS, dev, "out")
     n = int(np.prod(shape))
-    _check(lib.nphusl_cuda_rgb_to_hue(src.ptr, _DT[src.dtype], src.loc, src.channels,
-                                      dst.ptr, _DT[dst.dtype], dst.loc, n, dev,
-                                      _stream_ptr(stream)), "rgb_to_hue")
+    with _host_async(lib, blocking):
+        rc = lib.nphusl_cuda_rgb_to_hue(src.ptr, _DT[src.dtype], src.loc, src.channels,
+                                        dst.ptr, _DT[dst.dtype], dst.loc, n, dev, _stream_ptr(stream))
+    _check(rc, "rgb_to_hue")
     return ret
 
 
-def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None):
+def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocking=True):
     """HUSL -> RGB on the GPU (kernel (b) rgb_from_husl).  Replaces
     ``_cython_opt._husl_to_rgb`` (_cython_opt.pyx:177-192); with the default
     ``dtype=uint8`` the round/abs/cast tail of ``to_rgb`` is fused in, float
@@ -479,8 +501,10 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None):
         dtype = _describe_out(out, src.shape, dtype, _ANY, "out").dtype
     dst, ret = _make_out(src, out, src.shape, np.dtype(dtype), _ANY, dev, "out")
     n = int(np.prod(src.shape[:-1]))
-    _check(lib.nphusl_cuda_husl_to_rgb(src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
-                                       n, dev, _stream_ptr(stream)), "husl_to_rgb")
+    with _host_async(lib, blocking):
+        rc = lib.nphusl_cuda_husl_to_rgb(src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
+                                         n, dev, _stream_ptr(stream))
+    _check(rc, "husl_to_rgb")
     return ret
 
 

@@ -71,6 +71,13 @@ const char *nphusl_cuda_last_error(void);
 unsigned long long nphusl_cuda_launch_count(void);
 /* streaming chunk (pixels) used for host-pointer calls; 0 restores the default */
 int nphusl_cuda_set_chunk_pixels(size_t pixels);
+/* Per calling thread.  0 (default): a call with a host buffer returns when the
+ * result is in the caller's memory, like the reference's synchronous functions.
+ * 1: when EVERY host buffer of a call is pinned (nphusl_cuda_host_alloc /
+ * cudaHostAlloc), the call only enqueues its copies and kernels and makes
+ * `stream` wait for them; the caller synchronises `stream` before touching the
+ * buffers.  Lets H2D of one batch overlap D2H of the previous one. */
+int nphusl_cuda_set_host_async(int enabled);
 
 /* ---- the hot path ---------------------------------------------------------- */
 

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""A/B timing of the streaming kernels under the current NPHUSL_STREAM /
+NPHUSL_VARIANT environment: median-of-N CUDA-event time per launch on the bench
+workload (8 device-resident 4K frames), with a parity check of each output."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(ROOT, "husl-numpy_b200"))
+import torch  # noqa: E402
+from nphusl import _cuda  # noqa: E402
+
+frames = int(os.environ.get("AB_FRAMES", "8"))
+g = torch.Generator(device="cuda").manual_seed(0)
+rgb = torch.randint(0, 256, (frames, 2160, 3840, 3), dtype=torch.uint8, device="cuda", generator=g)
+px = rgb.numel() // 3
+h64 = torch.empty(rgb.shape, dtype=torch.float64, device="cuda")
+h32 = torch.empty(rgb.shape, dtype=torch.float32, device="cuda")
+hue64 = torch.empty(rgb.shape[:-1], dtype=torch.float64, device="cuda")
+hue32 = torch.empty(rgb.shape[:-1], dtype=torch.float32, device="cuda")
+back = torch.empty_like(rgb)
+
+
+def timed(fn, reps=7, inner=20):
+    """median over `reps` of (CUDA-event time of `inner` back-to-back launches) / inner:
+    back-to-back so the host launch gap is hidden behind the previous kernel"""
+    for _ in range(5):
+        fn()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(inner):
+            fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) / inner)
+    return float(np.median(ts))
+
+
+res = {"stream": os.environ.get("NPHUSL_STREAM", "tma"), "variant": os.environ.get("NPHUSL_VARIANT", "0")}
+cases = [("to_husl_f64", lambda: _cuda._rgb_to_husl(rgb, out=h64), 27),
+         ("to_rgb_f64", lambda: _cuda._husl_to_rgb(h64, out=back), 27),
+         ("to_husl_f32", lambda: _cuda._rgb_to_husl(rgb, out=h32), 15),
+         ("to_rgb_f32", lambda: _cuda._husl_to_rgb(h32, out=back), 15),
+         ("to_hue_f64", lambda: _cuda._rgb_to_hue(rgb, out=hue64), 11),
+         ("to_hue_f32", lambda: _cuda._rgb_to_hue(rgb, out=hue32), 7)]
+for name, fn, b in cases:
+    ms = timed(fn)
+    res[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 1), "hbm_frac": round(px * b / ms / 1e6 / 6547.2, 3)}
+    if name.startswith("to_rgb"):
+        torch.cuda.synchronize()
+        res[name]["exact"] = bool(torch.equal(back, rgb))
+        back.zero_()
+print(json.dumps(res))

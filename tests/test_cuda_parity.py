@@ -340,3 +340,33 @@ def test_launch_counter_moves(cu):
     n0 = cu.launch_count()
     cu._rgb_to_husl(np.zeros((1000, 3), np.uint8))
     assert cu.launch_count() > n0
+
+
+def test_non_blocking_pinned_calls(cu):
+    """blocking=False: pinned host buffers are only enqueued; results are valid
+    after the stream is synchronised; two streams may be in flight at once."""
+    rng = np.random.default_rng(8)
+    n = 5
+    src = [cu.pinned_empty((1080, 1920, 3), np.uint8) for _ in range(n)]
+    dst = [cu.pinned_empty((1080, 1920, 3), np.uint8) for _ in range(n)]
+    for a, b in zip(src, dst):
+        a[...] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+        b[...] = 0
+    streams = [cu.Stream(), cu.Stream()]
+    hsl = [cu.DeviceArray((1080, 1920, 3), np.float32), cu.DeviceArray((1080, 1920, 3), np.float32)]
+    try:
+        cu.set_chunk_pixels(300_000)          # several chunks per call
+        for k in range(n):
+            s = streams[k & 1]
+            cu._rgb_to_husl(src[k], out=hsl[k & 1], stream=s, blocking=False)
+            cu._husl_to_rgb(hsl[k & 1], out=dst[k], stream=s, blocking=False)
+        for s in streams:
+            s.synchronize()
+    finally:
+        cu.set_chunk_pixels(0)
+    for a, b in zip(src, dst):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    # pageable memory ignores blocking=False and completes before returning
+    rgb = rng.integers(0, 256, (1000, 3), dtype=np.uint8)
+    out = cu._rgb_to_husl(rgb, blocking=False)
+    assert np.array_equal(cu._husl_to_rgb(out, blocking=False), rgb)
