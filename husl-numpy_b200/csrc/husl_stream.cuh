@@ -181,7 +181,11 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
     const uint32_t bar_s = smem_addr(base + IST * TB + 2 * U8_TILE);
     const long long nw = (long long)gridDim.x * (BLOCK / 32);
     const long long first = (long long)blockIdx.x * (BLOCK / 32) + warp;
-    const unsigned char *src = reinterpret_cast<const unsigned char *>(in);
+    // Tiles are walked from the END of the image: in a to_husl -> (edit) -> to_rgb
+    // pipeline the producer wrote the HUSL array front to back, so its last
+    // ~100 MB are still in the 126 MB L2 when this kernel starts.
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(in) + (n_tiles - 1) * (long long)Tile<TIn>::BYTES;
+    unsigned char *dstb = reinterpret_cast<unsigned char *>(out) + (n_tiles - 1) * (long long)U8_TILE;
 
     if (lane == 0) {
 #pragma unroll
@@ -193,7 +197,7 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
             const long long t = first + s * nw;
             if (t < n_tiles) {
                 mbar_expect_tx(bar_s + 8 * s, TB);
-                bulk_load(ibuf_s + s * TB, src + t * TB, TB, bar_s + 8 * s);
+                bulk_load(ibuf_s + s * TB, src - t * TB, TB, bar_s + 8 * s);
             }
         }
     }
@@ -223,7 +227,7 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
             const long long t = tile + (long long)IST * nw;
             if (t < n_tiles) {
                 mbar_expect_tx(bar_s + 8 * st, TB);
-                bulk_load(ibuf_s + st * TB, src + t * TB, TB, bar_s + 8 * st);
+                bulk_load(ibuf_s + st * TB, src - t * TB, TB, bar_s + 8 * st);
             }
         }
         uint32_t q[12];
@@ -243,13 +247,102 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            bulk_store(reinterpret_cast<unsigned char *>(out) + tile * U8_TILE, obuf_s + ost * U8_TILE, U8_TILE);
+            bulk_store(dstb - tile * U8_TILE, obuf_s + ost * U8_TILE, U8_TILE);
             bulk_commit();
         }
         ost ^= 1;
         if (++st == IST) { st = 0; phase ^= 1; }
     }
     if (lane == 0) bulk_wait_all<0>();
+}
+
+// ---------------------------------------------------------------------------------
+// (b') rgb_from_husl, float32 HUSL: per-lane 16-byte async copies (LDGSTS) ring
+// ---------------------------------------------------------------------------------
+// The float32 inverse is bound by instruction issue (about 80 instructions per
+// pixel against 15 bytes), so the ~60 warp-instructions of mbarrier / elect /
+// proxy-fence bookkeeping the bulk engine needs per 128-pixel tile cost more
+// than they save.  This variant keeps the asynchronous, register-free prefetch
+// ring but fills it with three coalesced `cp.async.cg` 16-byte copies per lane
+// (the shared-memory image equals the global one, so lanes read their 48-byte
+// records conflict-free exactly as in k_inv_tma) and commits / waits with plain
+// async-groups.  uint8 results go out through a 384-byte staging transposition.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int IST>
+struct InvCpSmem {
+    static constexpr int PER_WARP = IST * Tile<float>::BYTES + U8_TILE;
+};
+
+template <int BLOCK, int MINB, int IST>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TB = Tile<float>::BYTES;
+    unsigned char *ibuf = smem + warp * InvCpSmem<IST>::PER_WARP;
+    uint32_t *sw = reinterpret_cast<uint32_t *>(ibuf + IST * TB);
+    const uint32_t ld_s = smem_addr(ibuf) + lane * 16;       // chunk `lane` of a stage
+    const long long nw = (long long)gridDim.x * (BLOCK / 32);
+    const long long first = (long long)blockIdx.x * (BLOCK / 32) + warp;
+    // walked from the end of the image (see k_inv_tma)
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(in) + (n_tiles - 1) * (long long)TB + lane * 16;
+    uint32_t *dst = out + (n_tiles - 1) * 96LL + lane;
+
+#pragma unroll
+    for (int s = 0; s < IST; ++s) {
+        const long long t = first + s * nw;
+        if (t < n_tiles) {
+            const unsigned char *g = src - t * TB;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) cp_async16(ld_s + s * TB + 512 * k, g + 512 * k);
+        }
+        cp_async_commit();
+    }
+    int st = 0;
+    for (long long tile = first; tile < n_tiles; tile += nw) {
+        cp_async_wait<IST - 1>();
+        __syncwarp();
+        float hsl[12];
+        const unsigned char *rd = ibuf + st * TB + lane * 48;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 f = *reinterpret_cast<const float4 *>(rd + 16 * k);
+            hsl[4 * k] = f.x; hsl[4 * k + 1] = f.y; hsl[4 * k + 2] = f.z; hsl[4 * k + 3] = f.w;
+        }
+        __syncwarp();
+        {
+            const long long t = tile + (long long)IST * nw;
+            if (t < n_tiles) {
+                const unsigned char *g = src - t * TB;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) cp_async16(ld_s + st * TB + 512 * k, g + 512 * k);
+            }
+            cp_async_commit();
+        }
+        uint32_t q[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float R, G, B;
+            rgb255_from_husl(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
+            q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
+        }
+        const uint32_t o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+        const uint32_t o1 = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+        const uint32_t o2 = __byte_perm(__byte_perm(q[8], q[9], 0x0040), __byte_perm(q[10], q[11], 0x0040), 0x5410);
+        sw[lane * 3] = o0; sw[lane * 3 + 1] = o1; sw[lane * 3 + 2] = o2;
+        __syncwarp();
+        uint32_t *d = dst - tile * 96;
+        d[0] = sw[lane]; d[32] = sw[lane + 32]; d[64] = sw[lane + 64];
+        __syncwarp();
+        st = (st + 1 == IST) ? 0 : st + 1;
+    }
+    cp_async_wait<0>();
 }
 
 }  // namespace husl

@@ -141,14 +141,9 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_u8<double, false, FWD_BLOCK, 1>, TAB_BYTES + W * Pack<double>::STAGE))) return rc;
     if ((rc = set_smem(k_fwd_u8<float, true, FWD_BLOCK, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_u8<double, true, FWD_BLOCK, 2>, TAB_BYTES))) return rc;
-    if ((rc = set_smem(k_fwd_tma<float, 512, 2, 2>, TAB_BYTES + 16 * 2 * Tile<float>::BYTES))) return rc;
     if ((rc = set_smem(k_fwd_tma<double, 512, 1, 2>, TAB_BYTES + 16 * 2 * Tile<double>::BYTES))) return rc;
-    if ((rc = set_smem(k_fwd_tma<double, 1024, 1, 1>, TAB_BYTES + 32 * 1 * Tile<double>::BYTES))) return rc;
-#define INV_ATTR(T, MINB, IST) \
-    if ((rc = set_smem(k_inv_tma<T, INV_BLOCK, MINB, IST>, (INV_BLOCK / 32) * InvSmem<T, IST>::PER_WARP))) return rc
-    INV_ATTR(float, 4, 2); INV_ATTR(float, 4, 3); INV_ATTR(float, 4, 4);
-    INV_ATTR(double, 4, 2); INV_ATTR(double, 3, 2); INV_ATTR(double, 2, 3); INV_ATTR(double, 2, 4);
-#undef INV_ATTR
+    if ((rc = set_smem(k_inv_tma<double, INV_BLOCK, 2, 3>, (INV_BLOCK / 32) * InvSmem<double, 3>::PER_WARP))) return rc;
+    if ((rc = set_smem(k_inv_cp<INV_BLOCK, 4, 3>, (INV_BLOCK / 32) * InvCpSmem<3>::PER_WARP))) return rc;
     c.attr_set = true;
     return NPHUSL_OK;
 }
@@ -189,20 +184,11 @@ bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) &
 // NPHUSL_STREAM selects the streaming-kernel family for A/B measurements:
 //   "ldg"  register/LDG+STG transposition kernels (husl_kernels.cuh)
 //   "tma"  bulk-async-copy staged kernels (husl_stream.cuh)            [default]
-// NPHUSL_VARIANT picks a tuning variant inside the family (0 = default).
-int env_int(const char *name, int dflt) {
-    const char *v = std::getenv(name);
-    return v && *v ? std::atoi(v) : dflt;
-}
 bool use_tma() {
     static const bool v = [] {
         const char *e = std::getenv("NPHUSL_STREAM");
         return !(e && std::strcmp(e, "ldg") == 0);
     }();
-    return v;
-}
-int variant() {
-    static const int v = env_int("NPHUSL_VARIANT", 0);
     return v;
 }
 
@@ -218,17 +204,11 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
         if ((rc = set_attrs(c))) return rc;
         const long long tiles = n / TILE_PX;
         constexpr int W = FWD_BLOCK / 32;
-        if (!HUE && use_tma()) {
-            if (out_dt == NPHUSL_F32) {
-                const int grid = grid_for(tiles, 16, c.sms * 2);
-                k_fwd_tma<float, 512, 2, 2><<<grid, 512, TAB_BYTES + 16 * 2 * Tile<float>::BYTES, s>>>((const uint32_t *)in, (float *)out, tiles);
-            } else if (variant() == 1) {
-                const int grid = grid_for(tiles, 32, c.sms);
-                k_fwd_tma<double, 1024, 1, 1><<<grid, 1024, TAB_BYTES + 32 * Tile<double>::BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
-            } else {
-                const int grid = grid_for(tiles, 16, c.sms);
-                k_fwd_tma<double, 512, 1, 2><<<grid, 512, TAB_BYTES + 16 * 2 * Tile<double>::BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
-            }
+        if (!HUE && use_tma() && out_dt == NPHUSL_F64) {
+            // float64 output is HBM-bound: results leave through TMA bulk stores;
+            // float32 output is issue-bound and keeps the leaner LDS/STG transposition
+            const int grid = grid_for(tiles, 16, c.sms);
+            k_fwd_tma<double, 512, 1, 2><<<grid, 512, TAB_BYTES + 16 * 2 * Tile<double>::BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
         } else if (out_dt == NPHUSL_F32) {
             const size_t sm = TAB_BYTES + (HUE ? 0 : W * Pack<float>::STAGE);
             const int grid = grid_for(tiles, W, c.sms * 2);
@@ -261,20 +241,16 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
         constexpr int W = INV_BLOCK / 32;
         if (use_tma() && aligned(out, 16)) {
             if ((rc = set_attrs(c))) return rc;
-            const int v = variant();
 #define INV_GO(T, MINB, IST) \
     k_inv_tma<T, INV_BLOCK, MINB, IST><<<grid_for(tiles, W, c.sms * MINB), INV_BLOCK, W * InvSmem<T, IST>::PER_WARP, s>>>( \
         (const T *)in, (uint32_t *)out, tiles)
-            if (in_dt == NPHUSL_F32) {
-                if (v == 1) INV_GO(float, 4, 4);
-                else if (v == 3) INV_GO(float, 4, 2);
-                else INV_GO(float, 4, 3);
-            } else {
-                if (v == 1) INV_GO(double, 3, 2);
-                else if (v == 2) INV_GO(double, 2, 4);
-                else if (v == 3) INV_GO(double, 4, 2);
-                else INV_GO(double, 2, 3);
-            }
+            // tuned on B200 (profiles/r01_ab_variants.txt).  float32 input is issue-bound:
+            // 3-stage LDGSTS ring, 4 CTAs/SM; float64 input is HBM-bound: 3-stage bulk-copy
+            // (TMA) ring with mbarriers, 2 CTAs/SM
+            if (in_dt == NPHUSL_F32)
+                k_inv_cp<INV_BLOCK, 4, 3><<<grid_for(tiles, W, c.sms * 4), INV_BLOCK, W * InvCpSmem<3>::PER_WARP, s>>>(
+                    (const float *)in, (uint32_t *)out, tiles);
+            else INV_GO(double, 2, 3);
 #undef INV_GO
         } else if (in_dt == NPHUSL_F32) {
             const int grid = grid_for(tiles, W, c.sms * 4);

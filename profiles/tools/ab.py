@@ -55,4 +55,17 @@ for name, fn, b in cases:
         torch.cuda.synchronize()
         res[name]["exact"] = bool(torch.equal(back, rgb))
         back.zero_()
+def pipe64():
+    _cuda._rgb_to_husl(rgb, out=h64)
+    _cuda._husl_to_rgb(h64, out=back)
+
+
+def pipe32():
+    _cuda._rgb_to_husl(rgb, out=h32)
+    _cuda._husl_to_rgb(h32, out=back)
+
+
+for name, fn, b in (("pipeline_f64", pipe64, 54), ("pipeline_f32", pipe32, 30)):
+    ms = timed(fn)
+    res[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 1), "hbm_frac": round(px * b / ms / 1e6 / 6547.2, 3)}
 print(json.dumps(res))
