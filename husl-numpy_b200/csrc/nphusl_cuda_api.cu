@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 #include "husl_kernels.cuh"
 #include "husl_stream.cuh"
 #include "husl_lut.cuh"
+#include "husl_fused.cuh"
 
 namespace {
 
@@ -31,8 +33,25 @@ std::atomic<size_t> g_chunk_px{0};
 
 constexpr int MAX_DEV = 16;
 constexpr int NSLOT = 3;                       // host streaming pipeline depth
-constexpr size_t DEFAULT_CHUNK_PX = 1u << 21;  // 2 Mpx per slot (<= 48 MB per buffer)
-constexpr size_t PAR_COPY_MIN = 4u << 20;      // host memcpy goes multi-threaded above this
+constexpr size_t DEFAULT_CHUNK_PX = 1u << 21;  // at most 2 Mpx per slot (<= 48 MB per buffer)
+constexpr size_t MIN_CHUNK_PX = 1u << 17;
+constexpr size_t PAR_COPY_MIN = 1u << 20;      // host memcpy goes multi-threaded above this
+
+// The entry points select `device` for the calling thread; the caller's own
+// current device (torch tracks it through the same runtime state) is put back
+// when the call returns.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 int fail(int code, const std::string &msg) {
     t_err = msg;
@@ -144,6 +163,9 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_tma<double, 512, 1, 2>, TAB_BYTES + 16 * 2 * Tile<double>::BYTES))) return rc;
     if ((rc = set_smem(k_inv_tma<double, INV_BLOCK, 2, 3>, (INV_BLOCK / 32) * InvSmem<double, 3>::PER_WARP))) return rc;
     if ((rc = set_smem(k_inv_cp<INV_BLOCK, 4, 3>, (INV_BLOCK / 32) * InvCpSmem<3>::PER_WARP))) return rc;
+    if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_edit<512, 2>, TAB_BYTES + 16 * 384))) return rc;
     c.attr_set = true;
     return NPHUSL_OK;
 }
@@ -292,24 +314,75 @@ int run_lut_dev(DevCtx &c, const void *in, void *out, long long n, int mode, cud
 }
 
 // ---- host-buffer streaming ----------------------------------------------------------
-void par_memcpy(void *dst, const void *src, size_t bytes) {
-    if (bytes < PAR_COPY_MIN) {
-        std::memcpy(dst, src, bytes);
-        return;
+// Pageable <-> pinned bounce copies are the bottleneck of plain-numpy calls
+// (a 1080p float64 result is 50 MB of first-touch page faults), so they run on
+// a small persistent pool of host threads instead of one memcpy.
+class CopyPool {
+  public:
+    static CopyPool &get() {
+        static CopyPool p;
+        return p;
     }
-    unsigned nt = std::thread::hardware_concurrency();
-    nt = nt < 2 ? 1 : (nt > 8 ? 8 : nt);
-    const size_t per = ((bytes / nt) + 4095) & ~size_t(4095);
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; ++t) {
-        const size_t off = per * t;
-        if (off >= bytes) break;
-        const size_t len = (off + per > bytes) ? bytes - off : per;
-        th.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
+    void copy(void *dst, const void *src, size_t bytes) {
+        if (bytes < PAR_COPY_MIN || workers_.empty()) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        std::unique_lock<std::mutex> call(call_mu_);          // one parallel copy at a time
+        const size_t parts = workers_.size() + 1;
+        const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = (char *)dst; src_ = (const char *)src; bytes_ = bytes; per_ = per;
+            pending_ = (int)workers_.size();
+            ++epoch_;
+        }
+        cv_.notify_all();
+        std::memcpy(dst, src, per < bytes ? per : bytes);     // part 0 on the calling thread
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
     }
-    std::memcpy(dst, src, per < bytes ? per : bytes);
-    for (auto &t : th) t.join();
-}
+
+  private:
+    CopyPool() {
+        unsigned n = std::thread::hardware_concurrency();
+        n = n < 2 ? 1 : (n > 16 ? 16 : n);
+        for (unsigned i = 1; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void run(unsigned idx) {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+            if (stop_) return;
+            seen = epoch_;
+            char *d = dst_; const char *s = src_; const size_t bytes = bytes_, per = per_;
+            lk.unlock();
+            const size_t off = per * idx;
+            if (off < bytes) std::memcpy(d + off, s + off, off + per > bytes ? bytes - off : per);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_;
+    char *dst_ = nullptr; const char *src_ = nullptr;
+    size_t bytes_ = 0, per_ = 0;
+    int pending_ = 0;
+    unsigned long long epoch_ = 0;
+    bool stop_ = false;
+};
+
+void par_memcpy(void *dst, const void *src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
 
 bool is_pinned(const void *p) {
     cudaPointerAttributes a;
@@ -355,7 +428,13 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
 
     std::lock_guard<std::mutex> lk(c.mu);   // staging buffers are per device
     size_t chunk = g_chunk_px.load();
-    if (!chunk) chunk = DEFAULT_CHUNK_PX;
+    if (!chunk) {
+        // default: about 8 chunks per call so copies and kernels of neighbouring
+        // chunks overlap, within [128 Kpx, 2 Mpx] per chunk
+        chunk = (size_t)((n + 7) / 8);
+        if (chunk < MIN_CHUNK_PX) chunk = MIN_CHUNK_PX;
+        if (chunk > DEFAULT_CHUNK_PX) chunk = DEFAULT_CHUNK_PX;
+    }
     chunk = (chunk + TILE_PX - 1) / TILE_PX * TILE_PX;
     if ((long long)chunk > n) chunk = (size_t)((n + TILE_PX - 1) / TILE_PX * TILE_PX);
     const bool src_host = src_loc == NPHUSL_HOST, dst_host = dst_loc == NPHUSL_HOST;
@@ -455,6 +534,7 @@ int nphusl_cuda_set_host_async(int enabled) {
 int nphusl_cuda_rgb_to_husl(const void *rgb, int rgb_dtype, int rgb_loc, int channels,
                             void *hsl, int hsl_dtype, int hsl_loc,
                             size_t n_pixels, int mode, int device, void *stream) {
+    DeviceGuard guard;
     if (n_pixels == 0) return NPHUSL_OK;
     if (!rgb || !hsl) return fail(NPHUSL_ERR_ARG, "rgb_to_husl: null buffer");
     if (!dsize(rgb_dtype) || (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64))
@@ -479,6 +559,7 @@ int nphusl_cuda_rgb_to_husl(const void *rgb, int rgb_dtype, int rgb_loc, int cha
 int nphusl_cuda_rgb_to_hue(const void *rgb, int rgb_dtype, int rgb_loc, int channels,
                            void *hue, int hue_dtype, int hue_loc,
                            size_t n_pixels, int device, void *stream) {
+    DeviceGuard guard;
     if (n_pixels == 0) return NPHUSL_OK;
     if (!rgb || !hue) return fail(NPHUSL_ERR_ARG, "rgb_to_hue: null buffer");
     if (!dsize(rgb_dtype) || (hue_dtype != NPHUSL_F32 && hue_dtype != NPHUSL_F64))
@@ -498,6 +579,7 @@ int nphusl_cuda_rgb_to_hue(const void *rgb, int rgb_dtype, int rgb_loc, int chan
 int nphusl_cuda_husl_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc,
                             void *rgb, int rgb_dtype, int rgb_loc,
                             size_t n_pixels, int device, void *stream) {
+    DeviceGuard guard;
     if (n_pixels == 0) return NPHUSL_OK;
     if (!hsl || !rgb) return fail(NPHUSL_ERR_ARG, "husl_to_rgb: null buffer");
     if ((hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) || !dsize(rgb_dtype))
@@ -511,6 +593,116 @@ int nphusl_cuda_husl_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc,
         return run_inv_dev(*c, i, hsl_dtype, o, rgb_dtype, n, s);
     };
     return run_streamed(*c, hsl, hsl_loc, in_px, rgb, rgb_loc, out_px, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+// ---- planar HUSL and the fused edit --------------------------------------------------------
+int nphusl_cuda_rgb_to_husl_planar(const void *rgb, void *h, void *s, void *l, int hsl_dtype,
+                                   size_t n_pixels, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!rgb || !h || !s || !l) return fail(NPHUSL_ERR_ARG, "rgb_to_husl_planar: null buffer");
+    if (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) return fail(NPHUSL_ERR_ARG, "rgb_to_husl_planar: planes must be f32/f64");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)n_pixels;
+    const size_t es = dsize(hsl_dtype), va = hsl_dtype == NPHUSL_F32 ? 16 : 32;
+    long long done = 0;
+    if (aligned(rgb, 4) && aligned(h, va) && aligned(s, va) && aligned(l, va) && n >= TILE_PX) {
+        if ((rc = set_attrs(*c))) return rc;
+        const long long tiles = n / TILE_PX;
+        const int grid = grid_for(tiles, 16, c->sms * 2);
+        if (hsl_dtype == NPHUSL_F32)
+            k_fwd_planar<float, 512, 2><<<grid, 512, TAB_BYTES, st>>>((const uint32_t *)rgb, (float *)h, (float *)s, (float *)l, tiles);
+        else
+            k_fwd_planar<double, 512, 2><<<grid, 512, TAB_BYTES, st>>>((const uint32_t *)rgb, (double *)h, (double *)s, (double *)l, tiles);
+        g_launches++;
+        if ((rc = check_launch("k_fwd_planar"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    if (n > done) {
+        const long long rest = n - done;
+        const int grid = grid_for(rest, 256, c->sms * 8);
+        const uint8_t *ip = (const uint8_t *)rgb + 3 * done;
+        if (hsl_dtype == NPHUSL_F32)
+            k_fwd_planar_any<float><<<grid, 256, 0, st>>>(ip, (float *)h + done, (float *)s + done, (float *)l + done, rest);
+        else
+            k_fwd_planar_any<double><<<grid, 256, 0, st>>>(ip, (double *)h + done, (double *)s + done, (double *)l + done, rest);
+        (void)es;
+        g_launches++;
+        if ((rc = check_launch("k_fwd_planar_any"))) return rc;
+    }
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_husl_planar_to_rgb(const void *h, const void *s, const void *l, int hsl_dtype,
+                                   void *rgb, size_t n_pixels, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!rgb || !h || !s || !l) return fail(NPHUSL_ERR_ARG, "husl_planar_to_rgb: null buffer");
+    if (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) return fail(NPHUSL_ERR_ARG, "husl_planar_to_rgb: planes must be f32/f64");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)n_pixels;
+    const size_t va = hsl_dtype == NPHUSL_F32 ? 16 : 32;
+    long long done = 0;
+    if (aligned(rgb, 4) && aligned(h, va) && aligned(s, va) && aligned(l, va) && n >= TILE_PX) {
+        const long long tiles = n / TILE_PX;
+        const int grid = grid_for(tiles, 8, c->sms * 4);
+        if (hsl_dtype == NPHUSL_F32)
+            k_inv_planar<float, 256, 4><<<grid, 256, 8 * 384, st>>>((const float *)h, (const float *)s, (const float *)l, (uint32_t *)rgb, tiles);
+        else
+            k_inv_planar<double, 256, 4><<<grid, 256, 8 * 384, st>>>((const double *)h, (const double *)s, (const double *)l, (uint32_t *)rgb, tiles);
+        g_launches++;
+        if ((rc = check_launch("k_inv_planar"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    if (n > done) {
+        const long long rest = n - done;
+        const int grid = grid_for(rest, 256, c->sms * 8);
+        uint8_t *op = (uint8_t *)rgb + 3 * done;
+        if (hsl_dtype == NPHUSL_F32)
+            k_inv_planar_any<float><<<grid, 256, 0, st>>>((const float *)h + done, (const float *)s + done, (const float *)l + done, op, rest);
+        else
+            k_inv_planar_any<double><<<grid, 256, 0, st>>>((const double *)h + done, (const double *)s + done, (const double *)l + done, op, rest);
+        g_launches++;
+        if ((rc = check_launch("k_inv_planar_any"))) return rc;
+    }
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_rgb_edit_rgb(const void *rgb_in, int in_loc, void *rgb_out, int out_loc,
+                             size_t n_pixels, const nphusl_edit *edit, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!rgb_in || !rgb_out || !edit) return fail(NPHUSL_ERR_ARG, "rgb_edit_rgb: null argument");
+    if (!ok_loc(in_loc) || !ok_loc(out_loc)) return fail(NPHUSL_ERR_ARG, "rgb_edit_rgb: bad buffer location");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    const nphusl_edit e = *edit;
+    auto kern = [=](const void *i, void *o, long long n, cudaStream_t st) -> int {
+        int r;
+        long long done = 0;
+        if (aligned(i, 4) && aligned(o, 4) && n >= TILE_PX) {
+            if ((r = set_attrs(*c))) return r;
+            const long long tiles = n / TILE_PX;
+            k_edit<512, 2><<<grid_for(tiles, 16, c->sms * 2), 512, TAB_BYTES + 16 * 384, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, e);
+            g_launches++;
+            if ((r = check_launch("k_edit"))) return r;
+            done = tiles * TILE_PX;
+        }
+        if (n > done) {
+            k_edit_any<<<grid_for(n - done, 256, c->sms * 8), 256, 0, st>>>((const uint8_t *)i + 3 * done, (uint8_t *)o + 3 * done, n - done, e);
+            g_launches++;
+            if ((r = check_launch("k_edit_any"))) return r;
+        }
+        return NPHUSL_OK;
+    };
+    return run_streamed(*c, rgb_in, in_loc, 3, rgb_out, out_loc, 3, (long long)n_pixels, (cudaStream_t)stream, kern);
 }
 
 // ---- lookup tables ---------------------------------------------------------------------
@@ -530,6 +722,7 @@ static int lut_alloc(DevCtx &c, int seg, int nh, int nl) {
 }
 
 int nphusl_cuda_lut_generate(int device, int light_seg, int nh, int nl) {
+    DeviceGuard guard;
     if (light_seg < 2 || nh < 2 || nl < 2 || light_seg > 21845 || nh > 65535 || nl > 65535)
         return fail(NPHUSL_ERR_ARG, "lut_generate: table sizes must fit 16 bits (LUT/light.py:27, LUT/chroma.py:27-28)");
     DevCtx *c;
@@ -591,6 +784,7 @@ int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
                            const double *y_idx_step3, const double *y_thresh2,
                            const uint16_t *chroma, int nh, int nl,
                            double h_idx_step, double l_idx_step, const double *linear256) {
+    DeviceGuard guard;
     if (!light || !chroma || !y_idx_step3 || !y_thresh2 || !linear256 || light_seg < 2 || nh < 2 || nl < 2)
         return fail(NPHUSL_ERR_ARG, "lut_upload: null table or bad size");
     DevCtx *c;
@@ -612,6 +806,7 @@ int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
 
 int nphusl_cuda_lut_download(int device, uint16_t *light, uint16_t *chroma, double *linear256,
                              int *dims4, double *steps7) {
+    DeviceGuard guard;
     DevCtx *c;
     int rc = ctx_get(device, &c);
     if (rc) return rc;
@@ -632,6 +827,7 @@ int nphusl_cuda_lut_download(int device, uint16_t *light, uint16_t *chroma, doub
 
 // ---- memory / stream helpers --------------------------------------------------------------
 int nphusl_cuda_malloc(void **ptr, size_t bytes, int device) {
+    DeviceGuard guard;
     if (!ptr) return fail(NPHUSL_ERR_ARG, "malloc: null out pointer");
     DevCtx *c;
     int rc = ctx_get(device, &c);
@@ -641,6 +837,7 @@ int nphusl_cuda_malloc(void **ptr, size_t bytes, int device) {
 }
 
 int nphusl_cuda_free(void *ptr, int device) {
+    DeviceGuard guard;
     if (!ptr) return NPHUSL_OK;
     CU(cudaSetDevice(device));
     CU(cudaFree(ptr));
@@ -661,6 +858,7 @@ int nphusl_cuda_host_free(void *ptr) {
 }
 
 int nphusl_cuda_memcpy(void *dst, const void *src, size_t bytes, int kind, int device, void *stream) {
+    DeviceGuard guard;
     static const cudaMemcpyKind k[4] = {cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice};
     if (kind < 0 || kind > 3) return fail(NPHUSL_ERR_ARG, "memcpy: bad kind");
     if (!bytes) return NPHUSL_OK;
@@ -671,6 +869,7 @@ int nphusl_cuda_memcpy(void *dst, const void *src, size_t bytes, int kind, int d
 }
 
 int nphusl_cuda_stream_create(void **stream, int device) {
+    DeviceGuard guard;
     if (!stream) return fail(NPHUSL_ERR_ARG, "stream_create: null out pointer");
     DevCtx *c;
     int rc = ctx_get(device, &c);
@@ -682,18 +881,21 @@ int nphusl_cuda_stream_create(void **stream, int device) {
 }
 
 int nphusl_cuda_stream_destroy(void *stream, int device) {
+    DeviceGuard guard;
     CU(cudaSetDevice(device));
     CU(cudaStreamDestroy((cudaStream_t)stream));
     return NPHUSL_OK;
 }
 
 int nphusl_cuda_stream_synchronize(void *stream, int device) {
+    DeviceGuard guard;
     CU(cudaSetDevice(device));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     return NPHUSL_OK;
 }
 
 int nphusl_cuda_device_synchronize(int device) {
+    DeviceGuard guard;
     CU(cudaSetDevice(device));
     CU(cudaDeviceSynchronize());
     return NPHUSL_OK;

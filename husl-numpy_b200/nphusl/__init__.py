@@ -22,18 +22,19 @@ somewhere else.
 """
 
 __version__ = "1.5.0+b200.1"
-__all__ = ["to_husl", "to_hue", "to_rgb", "chunk", "chunk_img"]
+__all__ = ["to_husl", "to_hue", "to_rgb", "edit", "chunk", "chunk_img"]
 
 from contextlib import contextmanager
 from functools import partial
 
-from .nphusl import to_husl, to_hue, to_rgb
+from .nphusl import to_husl, to_hue, to_rgb, edit
 from .nphusl import CUDA, SIMD, CYTHON, NUMEXPR, NUMPY, BACKEND_NAMES, register_backend
 from .transform import chunk, chunk_img
 from . import nphusl
 from . import constants
 from . import transform
 from . import _cuda
+from . import _shard
 
 if _cuda.available():
     register_backend(CUDA, _cuda)

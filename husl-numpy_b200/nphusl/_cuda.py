@@ -32,8 +32,8 @@ import threading
 
 import numpy as np
 
-__all__ = ["_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue", "DeviceArray", "available",
-           "CudaUnavailable", "CudaError"]
+__all__ = ["_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue", "rgb_to_husl_planar", "husl_planar_to_rgb",
+           "edit_rgb", "Edit", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NPHUSL_CUDA_LIB", os.path.join(_HERE, "libnphusl_cuda.so"))
@@ -66,6 +66,9 @@ SIGNATURES = {
     "nphusl_cuda_rgb_to_husl": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _sz, _i, _i, _vp]),
     "nphusl_cuda_rgb_to_hue": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _sz, _i, _vp]),
     "nphusl_cuda_husl_to_rgb": (_i, [_vp, _i, _i, _vp, _i, _i, _sz, _i, _vp]),
+    "nphusl_cuda_rgb_to_husl_planar": (_i, [_vp, _vp, _vp, _vp, _i, _sz, _i, _vp]),
+    "nphusl_cuda_husl_planar_to_rgb": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
+    "nphusl_cuda_rgb_edit_rgb": (_i, [_vp, _i, _vp, _i, _sz, _vp, _i, _vp]),
     "nphusl_cuda_lut_generate": (_i, [_i, _i, _i, _i]),
     "nphusl_cuda_lut_upload": (_i, [_i, _u16p, _i, _dp, _dp, _u16p, _i, _i,
                                     ctypes.c_double, ctypes.c_double, _dp]),
@@ -512,6 +515,121 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
 # (transform.in_chunks then skips its copy)
 for _f in (_rgb_to_husl, _rgb_to_hue, _husl_to_rgb):
     _f.accepts_out = True
+
+
+# ---------------------------------------------------------------------------
+# callers' side of the path on the GPU: planar HUSL, fused edit
+# ---------------------------------------------------------------------------
+
+def _to_device(arr, device, stream):
+    """host ndarray -> DeviceArray (device arrays pass through)"""
+    if _is_device(arr):
+        return arr
+    return DeviceArray.from_host(np.ascontiguousarray(arr), device, stream)
+
+
+def rgb_to_husl_planar(rgb, out=None, dtype=np.float32, stream=None, device=None):
+    """uint8 RGB ``(..., 3)`` -> planar HUSL ``(3, ...)``: ``out[0]`` is the hue
+    plane, ``out[1]`` saturation, ``out[2]`` lightness (what callers slice out
+    of the interleaved array anyway, README.md:77-98).  Device arrays stay on
+    the device; a host array is uploaded, converted and the planes downloaded."""
+    lib = load()
+    host_in = not _is_device(rgb)
+    dev = device
+    if host_in:
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        dev = _default_device if dev is None else dev
+    src = _describe_device(_to_device(rgb, dev, stream), "rgb")
+    if src.dtype != np.uint8 or not src.shape or src.shape[-1] != 3:
+        raise ValueError("planar conversion takes uint8 RGB (..., 3), got {} {}".format(src.dtype, src.shape))
+    dev = _pick_device(dev, src)
+    shape = (3,) + tuple(src.shape[:-1])
+    n = int(np.prod(src.shape[:-1]))
+    if out is not None and _is_device(out):
+        dst = _describe_out(out, shape, dtype, _FLOATS, "out")
+        ret = out
+    else:
+        d = DeviceArray(shape, np.dtype(dtype if out is None else out.dtype), dev)
+        dst = _describe_device(d, "out")
+        ret = d
+    plane = n * dst.dtype.itemsize
+    _check(lib.nphusl_cuda_rgb_to_husl_planar(src.ptr, dst.ptr, dst.ptr + plane, dst.ptr + 2 * plane, _DT[dst.dtype],
+                                              n, dev, _stream_ptr(stream)), "rgb_to_husl_planar")
+    if host_in or (out is not None and not _is_device(out)):
+        synchronize(dev, stream)
+        return ret.copy_to_host(out)
+    return ret
+
+
+def husl_planar_to_rgb(hsl, out=None, stream=None, device=None):
+    """planar HUSL ``(3, ...)`` float32/float64 -> uint8 RGB ``(..., 3)``."""
+    lib = load()
+    host_in = not _is_device(hsl)
+    dev = device
+    if host_in:
+        hsl = np.ascontiguousarray(hsl)
+        if hsl.dtype not in _FLOATS:
+            hsl = hsl.astype(np.float64)
+        dev = _default_device if dev is None else dev
+    src = _describe_device(_to_device(hsl, dev, stream), "hsl")
+    if src.dtype not in _FLOATS or not src.shape or src.shape[0] != 3:
+        raise ValueError("expected planar HUSL (3, ...), float32/float64; got {} {}".format(src.dtype, src.shape))
+    dev = _pick_device(dev, src)
+    shape = tuple(src.shape[1:]) + (3,)
+    n = int(np.prod(src.shape[1:]))
+    if out is not None and _is_device(out):
+        dst = _describe_out(out, shape, np.uint8, (np.dtype(np.uint8),), "out")
+        ret = out
+    else:
+        d = DeviceArray(shape, np.uint8, dev)
+        dst = _describe_device(d, "out")
+        ret = d
+    plane = n * src.dtype.itemsize
+    _check(lib.nphusl_cuda_husl_planar_to_rgb(src.ptr, src.ptr + plane, src.ptr + 2 * plane, _DT[src.dtype],
+                                              dst.ptr, n, dev, _stream_ptr(stream)), "husl_planar_to_rgb")
+    if host_in or (out is not None and not _is_device(out)):
+        synchronize(dev, stream)
+        return ret.copy_to_host(out)
+    return ret
+
+
+class Edit(ctypes.Structure):
+    """``nphusl_edit`` of include/nphusl_cuda.h: a selection box in HUSL space
+    and an affine edit applied to the selected pixels."""
+    _fields_ = [("h_lo", ctypes.c_float), ("h_hi", ctypes.c_float), ("s_lo", ctypes.c_float), ("s_hi", ctypes.c_float),
+                ("l_lo", ctypes.c_float), ("l_hi", ctypes.c_float), ("invert", ctypes.c_int),
+                ("h_mul", ctypes.c_float), ("h_add", ctypes.c_float), ("s_mul", ctypes.c_float), ("s_add", ctypes.c_float),
+                ("l_mul", ctypes.c_float), ("l_add", ctypes.c_float)]
+
+    def __init__(self, hue=(0.0, 360.0), saturation=(0.0, 100.0), lightness=(0.0, 100.0), invert=False,
+                 h=(1.0, 0.0), s=(1.0, 0.0), l=(1.0, 0.0)):     # noqa: E741
+        super().__init__(hue[0], hue[1], saturation[0], saturation[1], lightness[0], lightness[1], int(bool(invert)),
+                         h[0], h[1], s[0], s[1], l[0], l[1])
+
+
+def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, **edit_args):
+    """Fused ``to_rgb(edit(to_husl(rgb)))`` on uint8 pixels in one kernel pass.
+
+    ``edit`` is an ``Edit`` (or pass its fields as keywords):
+    ``edit_rgb(img, hue=(250, 290), invert=True, l=(0.5, 0))`` darkens every
+    non-bluish pixel (README.md:77-81); ``edit_rgb(img, lightness=(0, 62),
+    l=(0, 0))`` blacks out dim pixels (README.md:94-98).  Host or device arrays;
+    ``out`` may be the input itself."""
+    lib = load()
+    if edit is None:
+        edit = Edit(**edit_args)
+    elif edit_args:
+        raise TypeError("pass either an Edit or its fields as keywords, not both")
+    src = _describe_rgb_in(rgb)
+    if src.dtype != np.uint8 or src.channels != 3 or not src.shape or src.shape[-1] != 3:
+        raise ValueError("edit_rgb takes uint8 RGB (..., 3), got {} {}".format(src.dtype, src.shape))
+    dev = _pick_device(device, src)
+    dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out")
+    n = int(np.prod(src.shape[:-1]))
+    with _host_async(lib, blocking):
+        rc = lib.nphusl_cuda_rgb_edit_rgb(src.ptr, src.loc, dst.ptr, dst.loc, n, ctypes.byref(edit), dev, _stream_ptr(stream))
+    _check(rc, "rgb_edit_rgb")
+    return ret
 
 
 # ---------------------------------------------------------------------------

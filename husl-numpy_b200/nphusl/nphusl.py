@@ -18,7 +18,7 @@ dictionaries are only filled when such a module is registered from outside
 """
 from . import transform
 
-__all__ = ["to_husl", "to_rgb", "to_hue", "CUDA", "SIMD", "CYTHON", "NUMEXPR", "NUMPY",
+__all__ = ["to_husl", "to_rgb", "to_hue", "edit", "CUDA", "SIMD", "CYTHON", "NUMEXPR", "NUMPY",
            "register_backend", "BACKEND_NAMES"]
 
 # the three swappable callables of the hot path (reference nphusl.py:110,122,305)
@@ -85,3 +85,20 @@ def to_husl(rgb_img, chunksize: int = None, out=None, **backend_args):
     """RGB image (uint8, float in [0, 1], or grayscale float) -> float64 HUSL
     array ``(..., 3)`` holding (H, S, L).  Reference: nphusl.py:48-54."""
     return transform.in_chunks(rgb_img, _rgb_to_husl, chunksize, out, **backend_args)
+
+
+### Beyond the reference API (SURVEY.md section 8f): the callers' pipeline
+### to_husl -> select -> edit -> to_rgb as one GPU pass.  CUDA backend only.
+
+def edit(rgb_img, out=None, **edit_args):
+    """``to_rgb(edit(to_husl(rgb_img)))`` fused into one kernel over uint8 RGB.
+
+    Keywords (see ``nphusl._cuda.Edit``): ``hue=(lo, hi)``, ``saturation=(lo,
+    hi)``, ``lightness=(lo, hi)`` select pixels (``invert=True`` for the
+    complement); ``h=(mul, add)``, ``s=(mul, add)``, ``l=(mul, add)`` are applied
+    to the selected ones.  Example (reference README.md:77-81)::
+
+        out = nphusl.edit(img, hue=(250, 290), invert=True, l=(0.5, 0))
+    """
+    from . import _cuda
+    return _cuda.edit_rgb(rgb_img, out=out, **edit_args)

@@ -110,6 +110,33 @@ int nphusl_cuda_husl_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc,
                             void *rgb, int rgb_dtype, int rgb_loc,
                             size_t n_pixels, int device, void *stream);
 
+/* ---- callers' side of the path, on the GPU (no reference equivalent) --------- */
+
+/* Planar HUSL: three separate planes of n_pixels elements (H[], S[], L[]) instead
+ * of interleaved triplets -- what reference callers slice out with hsl[..., 0] and
+ * hsl[..., 2] (README.md:77-98).  uint8 interleaved RGB on the other side.  DEVICE
+ * pointers only; planes F32 or F64.  Asynchronous on `stream`. */
+int nphusl_cuda_rgb_to_husl_planar(const void *rgb, void *h, void *s, void *l, int hsl_dtype,
+                                   size_t n_pixels, int device, void *stream);
+int nphusl_cuda_husl_planar_to_rgb(const void *h, const void *s, const void *l, int hsl_dtype,
+                                   void *rgb, size_t n_pixels, int device, void *stream);
+
+/* Fused to_husl -> select -> edit -> to_rgb on uint8 pixels (the pipeline of
+ * README.md:77-98 in one pass, 6 bytes of memory traffic per pixel).
+ * A pixel is selected when H lies on the arc [h_lo, h_hi] (h_lo > h_hi: the arc
+ * through 0), S in [s_lo, s_hi] and L in [l_lo, l_hi]; invert != 0 selects the
+ * complement.  Selected pixels get H' = H*h_mul + h_add wrapped to [0, 360),
+ * S' = clamp(S*s_mul + s_add, 0, 100), L' = clamp(L*l_mul + l_add, 0, 100).
+ * Results equal husl_to_rgb(edit(rgb_to_husl(rgb -> F32))) bit for bit. */
+typedef struct nphusl_edit {
+    float h_lo, h_hi, s_lo, s_hi, l_lo, l_hi;
+    int invert;
+    float h_mul, h_add, s_mul, s_add, l_mul, l_add;
+} nphusl_edit;
+/* rgb_in / rgb_out: n_pixels * 3 uint8, host or device (may alias each other). */
+int nphusl_cuda_rgb_edit_rgb(const void *rgb_in, int in_loc, void *rgb_out, int out_loc,
+                             size_t n_pixels, const nphusl_edit *edit, int device, void *stream);
+
 /* ---- lookup tables (optional LUT mode) -------------------------------------- */
 
 /* Generate, ON THE DEVICE, the tables make_lookup_tables:8-9 produces with

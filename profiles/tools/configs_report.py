@@ -1,0 +1,212 @@
+#!/usr/bin/env python
+"""Run the five BASELINE.json configs on this box and print one JSON document
+(throughput in Mpix/s = pixels / best time, like reference
+tests/performance_test.py:96; accuracy for config 2).  GPU numbers go through
+the public nphusl API (CUDA backend); CPU numbers are the reference's own
+compiled code from oracle/_ref (or the oracle port if absent), all host cores.
+
+    python profiles/tools/configs_report.py [--devices 0,1,...] > gpurun_out/configs.json
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(ROOT, "husl-numpy_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import nphusl  # noqa: E402
+from nphusl import _cuda  # noqa: E402
+import oracle as orc  # noqa: E402
+from bench import ReferenceCPU  # noqa: E402
+
+
+def best(fn, reps=5):
+    fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts)
+
+
+def dev_time(fn, reps=10, inner=10):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(inner):
+            fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) / inner * 1e-3)
+    return float(np.median(ts))
+
+
+def mpix(px, sec):
+    return round(px / sec / 1e6, 1)
+
+
+def hue_diff(a, b):
+    d = np.abs(a - b) % 360.0
+    return np.minimum(d, 360.0 - d)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--devices", default="0")
+    ap.add_argument("--video-frames", type=int, default=1000)
+    args = ap.parse_args()
+    devices = [int(d) for d in args.devices.split(",")]
+    nphusl.enable_cuda()
+    ref = ReferenceCPU()
+    rng = np.random.default_rng(0)
+    out = {"device": _cuda.device_info(), "cpu": {"cores": ref.cores, "impl": ref.describe()}}
+
+    # ---- config 1: one 1080p frame, to_husl + to_rgb, host numpy arrays ----------------
+    img = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    px = img.size // 3
+    hsl = nphusl.to_husl(img)
+    c1 = {"gpu_to_husl_host_f64": mpix(px, best(lambda: nphusl.to_husl(img))),
+          "gpu_to_rgb_host_f64": mpix(px, best(lambda: nphusl.to_rgb(hsl))),
+          "round_trip_exact": bool(np.array_equal(nphusl.to_rgb(hsl), img)),
+          "cpu_ref_to_husl": mpix(px, best(lambda: ref.to_husl(img), 3)),
+          "cpu_ref_to_rgb": mpix(px, best(lambda: ref.to_rgb(hsl), 3))}
+    d_img = torch.from_numpy(img).cuda()
+    d_hsl = torch.empty(img.shape, dtype=torch.float64, device="cuda")
+    d_back = torch.empty_like(d_img)
+    c1["gpu_to_husl_device_f64"] = mpix(px, dev_time(lambda: nphusl.to_husl(d_img, out=d_hsl)))
+    c1["gpu_to_rgb_device_f64"] = mpix(px, dev_time(lambda: nphusl.to_rgb(d_hsl, out=d_back)))
+    out["config1_1080p"] = c1
+
+    # ---- config 2: the 2^24 cube, accuracy -----------------------------------------------
+    v = np.arange(256, dtype=np.uint8)
+    r, g, b = np.meshgrid(v, v, v, indexing="ij")
+    cube = np.ascontiguousarray(np.stack([r, g, b], -1).reshape(4096, 4096, 3))
+    t0 = time.perf_counter()
+    o = orc.rgb_to_husl(cube)
+    t_oracle = time.perf_counter() - t0
+    grey = (cube[..., 0] == cube[..., 1]) & (cube[..., 1] == cube[..., 2])
+    c2 = {"oracle_f64_seconds": round(t_oracle, 2)}
+    for dt in (np.float32, np.float64):
+        got = nphusl.to_husl(cube, dtype=dt)
+        back = nphusl.to_rgb(got)
+        c2[np.dtype(dt).name] = {
+            "max_dH_nongrey": float(hue_diff(got[..., 0].astype(np.float64), o[..., 0])[~grey].max()),
+            "max_dS": float(np.abs(got[..., 1] - o[..., 1]).max()),
+            "max_dL": float(np.abs(got[..., 2] - o[..., 2]).max()),
+            "round_trip_mismatching_values": int(np.count_nonzero(back != cube))}
+    lt, st, th = orc.light_table()
+    ct, hs, ls = orc.chroma_table()
+    _cuda.lut_upload(lt, st, th, ct, hs, ls, orc.linear_table6())
+    for mode, variant in (("lut", "lut"), ("lut_interp", "lut_interp")):
+        got = nphusl.to_husl(cube, mode=mode)
+        want = orc.simd_rgb_to_husl(cube, variant)
+        c2[mode + "_values_not_bit_identical"] = int(np.count_nonzero(got.view(np.uint64) != want.view(np.uint64)))
+    d_cube = torch.from_numpy(cube).cuda()
+    d_ch = torch.empty(cube.shape, dtype=torch.float64, device="cuda")
+    cpx = cube.size // 3
+    c2["gpu_to_husl_device_f64_mpix"] = mpix(cpx, dev_time(lambda: nphusl.to_husl(d_cube, out=d_ch)))
+    c2["gpu_lut_device_f64_mpix"] = mpix(cpx, dev_time(lambda: nphusl.to_husl(d_cube, out=d_ch, mode="lut"), 3, 3))
+    c2["cpu_ref_simd_lut_mpix"] = mpix(cpx, best(lambda: ref.to_husl(cube), 2))
+    out["config2_cube"] = c2
+    del d_cube, d_ch, got, back, want, o
+
+    # ---- config 3: to_hue on 4 Mpx uint8 and on float64 grayscale -----------------------
+    img4 = rng.integers(0, 256, (2000, 2000, 3), dtype=np.uint8)
+    grey4 = rng.random((2000, 2000))
+    import warnings
+    warnings.simplefilter("ignore")
+    px4 = 4_000_000
+    h_o = orc.rgb_to_hue(img4)
+    h_g = nphusl.to_hue(img4)
+    o_sat = orc.rgb_to_husl(img4)[..., 1] > 0.1
+    d4 = torch.from_numpy(img4).cuda()
+    dg = torch.from_numpy(grey4).cuda()
+    dh = torch.empty((2000, 2000), dtype=torch.float64, device="cuda")
+    c3 = {"gpu_to_hue_u8_host": mpix(px4, best(lambda: nphusl.to_hue(img4))),
+          "gpu_to_hue_gray_host": mpix(px4, best(lambda: nphusl.to_hue(grey4))),
+          "gpu_to_hue_u8_device": mpix(px4, dev_time(lambda: nphusl.to_hue(d4, out=dh))),
+          "gpu_to_hue_gray_device": mpix(px4, dev_time(lambda: nphusl.to_hue(dg, out=dh))),
+          "max_dH_vs_oracle": float(hue_diff(h_g, h_o)[o_sat].max()),
+          "gray_lightness_max_err": float(np.abs(nphusl.to_husl(grey4)[..., 2]
+                                                 - orc.rgb_to_husl(np.repeat(grey4[..., None], 3, -1))[..., 2]).max())}
+    if ref.cy is not None:
+        f4 = img4 / 255.0
+        c3["cpu_ref_cython_to_hue"] = mpix(px4, best(lambda: ref.cy._rgb_to_hue(f4), 3))
+    out["config3_hue_4Mpx"] = c3
+
+    # ---- config 4: device-resident 4K batches, to_husl -> lightness edit -> to_rgb --------
+    c4 = {}
+    for B in (1, 8):
+        gen = torch.Generator(device="cuda").manual_seed(B)
+        fr = torch.randint(0, 256, (B, 2160, 3840, 3), dtype=torch.uint8, device="cuda", generator=gen)
+        bpx = B * 2160 * 3840
+        for name, tdt in (("f64", torch.float64), ("f32", torch.float32)):
+            hs_ = torch.empty(fr.shape, dtype=tdt, device="cuda")
+            bk = torch.empty_like(fr)
+
+            def pipe(edit):
+                nphusl.to_husl(fr, out=hs_)
+                if edit:
+                    hs_[..., 2].mul_(0.5)               # README.md:77-81 lightness edit (caller-side torch op)
+                nphusl.to_rgb(hs_, out=bk)
+            c4["B%d_%s_to_husl_to_rgb" % (B, name)] = mpix(bpx, dev_time(lambda: pipe(False), 5, 10))
+            c4["B%d_%s_with_edit" % (B, name)] = mpix(bpx, dev_time(lambda: pipe(True), 5, 10))
+            del hs_, bk
+        del fr
+    out["config4_4k_device_batches"] = c4
+
+    # ---- config 5: synthetic 4K video, host -> GPU(s) -> host ------------------------------
+    n_frames, pool, B = args.video_frames, 32, 8
+
+    def run_device(dev, n_batches, res):
+        src = _cuda.pinned_empty((pool, 2160, 3840, 3), np.uint8)
+        src[...] = np.random.default_rng(100 + dev).integers(0, 256, src.shape, dtype=np.uint8)
+        dst = _cuda.pinned_empty((2, B, 2160, 3840, 3), np.uint8)
+        streams = [_cuda.Stream(dev), _cuda.Stream(dev)]
+        hs_ = [_cuda.DeviceArray((B, 2160, 3840, 3), np.float64, dev) for _ in range(2)]
+        res["barrier"].wait()                  # everybody has filled their pinned frame pool
+        p0 = 0
+        for k in range(n_batches):
+            p0 = (k * B) % (pool - B + 1)      # cycle through the pool of distinct frames
+            s = streams[k & 1]
+            _cuda._rgb_to_husl(src[p0:p0 + B], out=hs_[k & 1], stream=s, device=dev, blocking=False)
+            _cuda._husl_to_rgb(hs_[k & 1], out=dst[k & 1], stream=s, device=dev, blocking=False)
+        for s in streams:
+            s.synchronize()
+        res[dev] = bool(np.array_equal(np.asarray(dst[(n_batches - 1) & 1]), np.asarray(src[p0:p0 + B])))
+
+    c5 = {}
+    for ndev in sorted({1, len(devices)}):
+        devs = devices[:ndev]
+        bounds = nphusl._shard.shard_bounds(n_frames // B, ndev)      # batches per GPU
+        res = {"barrier": threading.Barrier(ndev + 1)}
+        ths = [threading.Thread(target=run_device, args=(d, b - a, res)) for d, (a, b) in zip(devs, bounds)]
+        for t in ths:
+            t.start()
+        res["barrier"].wait()
+        t0 = time.perf_counter()
+        for t in ths:
+            t.join()
+        dt = time.perf_counter() - t0
+        done = (n_frames // B) * B
+        c5["%d_gpu" % ndev] = {"frames": done, "seconds": round(dt, 3), "mpix_s": mpix(done * 2160 * 3840, dt),
+                               "fps_4k": round(done / dt, 1), "last_batch_exact": all(res[d] for d in devs)}
+    frame = np.asarray(rng.integers(0, 256, (2160, 3840, 3), dtype=np.uint8))
+    c5["cpu_ref_round_trip_mpix"] = mpix(2160 * 3840, best(lambda: ref.step(frame), 2))
+    out["config5_video_e2e"] = c5
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -370,3 +370,90 @@ def test_non_blocking_pinned_calls(cu):
     rgb = rng.integers(0, 256, (1000, 3), dtype=np.uint8)
     out = cu._rgb_to_husl(rgb, blocking=False)
     assert np.array_equal(cu._husl_to_rgb(out, blocking=False), rgb)
+
+
+# ---- callers' side on the GPU: planar HUSL, fused edit ---------------------------------------
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_planar_layout_equals_interleaved(cu, dtype):
+    rng = np.random.default_rng(9)
+    for shape in ((1000, 3), (37, 129, 3), (1080, 1920, 3)):
+        rgb = rng.integers(0, 256, shape, dtype=np.uint8)
+        inter = cu._rgb_to_husl(rgb, dtype=dtype)
+        planar = cu.rgb_to_husl_planar(rgb, dtype=dtype)
+        assert planar.shape == (3,) + shape[:-1] and planar.dtype == dtype
+        assert np.array_equal(planar, np.moveaxis(inter, -1, 0))
+        assert np.array_equal(cu.husl_planar_to_rgb(planar), rgb)
+
+
+def test_planar_device_arrays(cu):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(10)
+    rgb = rng.integers(0, 256, (2, 540, 960, 3), dtype=np.uint8)
+    t = torch.from_numpy(rgb).cuda()
+    planes = torch.empty((3, 2, 540, 960), dtype=torch.float32, device="cuda")
+    r = cu.rgb_to_husl_planar(t, out=planes)
+    assert r is planes
+    torch.cuda.synchronize()
+    assert np.array_equal(planes.cpu().numpy(), np.moveaxis(cu._rgb_to_husl(rgb, dtype=np.float32), -1, 0))
+    planes[2] *= 0.5                                   # contiguous plane edit
+    out = torch.empty_like(t)
+    cu.husl_planar_to_rgb(planes, out=out)
+    torch.cuda.synchronize()
+    hsl = cu._rgb_to_husl(rgb, dtype=np.float32)
+    hsl[..., 2] *= np.float32(0.5)
+    assert np.array_equal(out.cpu().numpy(), cu._husl_to_rgb(hsl))
+
+
+def test_fused_edit_equals_three_call_pipeline(cu):
+    """nphusl.edit == to_rgb(edit(to_husl(rgb, float32))) bit for bit; and within
+    +-1 LSB of the float64 oracle doing the same edit."""
+    import nphusl
+    rng = np.random.default_rng(11)
+    for shape in ((777, 3), (1080, 1920, 3)):
+        rgb = rng.integers(0, 256, shape, dtype=np.uint8)
+        # README.md:77-81: darken everything that is not bluish
+        hsl = cu._rgb_to_husl(rgb, dtype=np.float32)
+        bluish = (hsl[..., 0] >= 250) & (hsl[..., 0] <= 290)
+        hsl[..., 2][~bluish] *= np.float32(0.5)
+        want = cu._husl_to_rgb(hsl)
+        got = nphusl.edit(rgb, hue=(250, 290), invert=True, l=(0.5, 0))
+        assert got.dtype == np.uint8 and np.array_equal(got, want)
+        o = orc.rgb_to_husl(rgb)
+        ob = (o[..., 0] >= 250) & (o[..., 0] <= 290)
+        o[..., 2][~ob] *= 0.5
+        od = np.abs(orc.husl_to_rgb(o).astype(int) - got.astype(int))
+        edge = np.abs(np.minimum(np.abs(o[..., 0] - 250), np.abs(o[..., 0] - 290))) < 1e-3   # selection boundary
+        assert od[~edge].max() <= 1
+        # README.md:94-98: dim pixels to black
+        hsl = cu._rgb_to_husl(rgb, dtype=np.float32)
+        dark = hsl[..., 2] < 62
+        hsl[..., 2][dark] = 0
+        want = cu._husl_to_rgb(hsl)
+        hi = float(np.nextafter(np.float32(62), np.float32(0)))
+        got = nphusl.edit(rgb, lightness=(0, hi), l=(0, 0))
+        assert np.array_equal(got, want)
+        assert np.all(got[dark] == 0)
+        # hue rotation with wrap-around arc selection, saturation scaling
+        hsl = cu._rgb_to_husl(rgb, dtype=np.float32)
+        sel = (hsl[..., 0] >= 330) | (hsl[..., 0] <= 30)
+        h = hsl[..., 0][sel] + np.float32(90)
+        h = h - np.float32(360) * np.floor(h * np.float32(1.0 / 360.0))
+        hsl[..., 0][sel] = h
+        hsl[..., 1][sel] = np.minimum(hsl[..., 1][sel] * np.float32(0.5) + np.float32(10), np.float32(100))
+        want = cu._husl_to_rgb(hsl)
+        got = nphusl.edit(rgb, hue=(330, 30), h=(1, 90), s=(0.5, 10))
+        assert np.array_equal(got, want)
+        # identity edit = exact round trip
+        assert np.array_equal(nphusl.edit(rgb), rgb)
+
+
+def test_fused_edit_device_in_place(cu):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(12)
+    rgb = rng.integers(0, 256, (2160, 3840, 3), dtype=np.uint8)
+    want = cu.edit_rgb(rgb, lightness=(0, 50), l=(1, 20))
+    t = torch.from_numpy(rgb).cuda()
+    r = cu.edit_rgb(t, out=t, lightness=(0, 50), l=(1, 20))
+    torch.cuda.synchronize()
+    assert r is t and np.array_equal(t.cpu().numpy(), want)
