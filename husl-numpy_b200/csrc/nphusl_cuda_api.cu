@@ -34,7 +34,7 @@ std::atomic<size_t> g_chunk_px{0};
 constexpr int MAX_DEV = 16;
 constexpr int NSLOT = 3;                       // host streaming pipeline depth
 constexpr size_t DEFAULT_CHUNK_PX = 1u << 21;  // at most 2 Mpx per slot (<= 48 MB per buffer)
-constexpr size_t MIN_CHUNK_PX = 1u << 17;
+constexpr size_t MIN_CHUNK_PX = 1u << 18;
 constexpr size_t PAR_COPY_MIN = 1u << 20;      // host memcpy goes multi-threaded above this
 
 // The entry points select `device` for the calling thread; the caller's own
@@ -345,8 +345,14 @@ class CopyPool {
 
   private:
     CopyPool() {
-        unsigned n = std::thread::hardware_concurrency();
-        n = n < 2 ? 1 : (n > 16 ? 16 : n);
+        // 8 copy threads saturate the host memory system of the B200 boxes (16-24
+        // logical cores); more only adds wake-up latency (gpurun_out/hostpath.jsonl)
+        unsigned n = std::thread::hardware_concurrency() / 2;
+        n = n < 2 ? 1 : (n > 8 ? 8 : n);
+        if (const char *e = std::getenv("NPHUSL_COPY_THREADS")) {
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 64) n = (unsigned)v;
+        }
         for (unsigned i = 1; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
     }
     ~CopyPool() {
@@ -430,7 +436,7 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
     size_t chunk = g_chunk_px.load();
     if (!chunk) {
         // default: about 8 chunks per call so copies and kernels of neighbouring
-        // chunks overlap, within [128 Kpx, 2 Mpx] per chunk
+        // chunks overlap, within [256 Kpx, 2 Mpx] per chunk
         chunk = (size_t)((n + 7) / 8);
         if (chunk < MIN_CHUNK_PX) chunk = MIN_CHUNK_PX;
         if (chunk > DEFAULT_CHUNK_PX) chunk = DEFAULT_CHUNK_PX;

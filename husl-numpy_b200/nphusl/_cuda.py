@@ -601,7 +601,10 @@ class Edit(ctypes.Structure):
                 ("h_mul", ctypes.c_float), ("h_add", ctypes.c_float), ("s_mul", ctypes.c_float), ("s_add", ctypes.c_float),
                 ("l_mul", ctypes.c_float), ("l_add", ctypes.c_float)]
 
-    def __init__(self, hue=(0.0, 360.0), saturation=(0.0, 100.0), lightness=(0.0, 100.0), invert=False,
+    # unspecified ranges are unbounded (S can exceed 100 by an ulp on the gamut boundary)
+    ALL = (-float("inf"), float("inf"))
+
+    def __init__(self, hue=ALL, saturation=ALL, lightness=ALL, invert=False,
                  h=(1.0, 0.0), s=(1.0, 0.0), l=(1.0, 0.0)):     # noqa: E741
         super().__init__(hue[0], hue[1], saturation[0], saturation[1], lightness[0], lightness[1], int(bool(invert)),
                          h[0], h[1], s[0], s[1], l[0], l[1])

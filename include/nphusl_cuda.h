@@ -125,7 +125,8 @@ int nphusl_cuda_husl_planar_to_rgb(const void *h, const void *s, const void *l, 
  * README.md:77-98 in one pass, 6 bytes of memory traffic per pixel).
  * A pixel is selected when H lies on the arc [h_lo, h_hi] (h_lo > h_hi: the arc
  * through 0), S in [s_lo, s_hi] and L in [l_lo, l_hi]; invert != 0 selects the
- * complement.  Selected pixels get H' = H*h_mul + h_add wrapped to [0, 360),
+ * complement (use -INFINITY / +INFINITY for an unbounded range: S may exceed
+ * 100 by an ulp on the gamut boundary).  Selected pixels get H' = H*h_mul + h_add wrapped to [0, 360),
  * S' = clamp(S*s_mul + s_add, 0, 100), L' = clamp(L*l_mul + l_add, 0, 100).
  * Results equal husl_to_rgb(edit(rgb_to_husl(rgb -> F32))) bit for bit. */
 typedef struct nphusl_edit {

@@ -65,7 +65,16 @@ def pipe32():
     _cuda._husl_to_rgb(h32, out=back)
 
 
-for name, fn, b in (("pipeline_f64", pipe64, 54), ("pipeline_f32", pipe32, 30)):
+pl32 = torch.empty((3,) + tuple(rgb.shape[:-1]), dtype=torch.float32, device="cuda")
+pl64 = torch.empty((3,) + tuple(rgb.shape[:-1]), dtype=torch.float64, device="cuda")
+_cuda.rgb_to_husl_planar(rgb, out=pl32)
+_cuda.rgb_to_husl_planar(rgb, out=pl64)
+for name, fn, b in (("pipeline_f64", pipe64, 54), ("pipeline_f32", pipe32, 30),
+                    ("planar_fwd_f32", lambda: _cuda.rgb_to_husl_planar(rgb, out=pl32), 15),
+                    ("planar_inv_f32", lambda: _cuda.husl_planar_to_rgb(pl32, out=back), 15),
+                    ("planar_fwd_f64", lambda: _cuda.rgb_to_husl_planar(rgb, out=pl64), 27),
+                    ("planar_inv_f64", lambda: _cuda.husl_planar_to_rgb(pl64, out=back), 27),
+                    ("fused_edit_u8", lambda: _cuda.edit_rgb(rgb, out=back, hue=(250, 290), invert=True, l=(0.5, 0)), 6)):
     ms = timed(fn)
     res[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 1), "hbm_frac": round(px * b / ms / 1e6 / 6547.2, 3)}
 print(json.dumps(res))

@@ -163,7 +163,16 @@ def main():
             c4["B%d_%s_to_husl_to_rgb" % (B, name)] = mpix(bpx, dev_time(lambda: pipe(False), 5, 10))
             c4["B%d_%s_with_edit" % (B, name)] = mpix(bpx, dev_time(lambda: pipe(True), 5, 10))
             del hs_, bk
-        del fr
+        bk = torch.empty_like(fr)
+        pl = torch.empty((3,) + tuple(fr.shape[:-1]), dtype=torch.float32, device="cuda")
+
+        def planar_pipe():
+            _cuda.rgb_to_husl_planar(fr, out=pl)
+            pl[2].mul_(0.5)
+            _cuda.husl_planar_to_rgb(pl, out=bk)
+        c4["B%d_f32_planar_with_edit" % B] = mpix(bpx, dev_time(planar_pipe, 5, 10))
+        c4["B%d_fused_edit_kernel" % B] = mpix(bpx, dev_time(lambda: nphusl.edit(fr, out=bk, hue=(250, 290), invert=True, l=(0.5, 0)), 5, 10))
+        del fr, bk, pl
     out["config4_4k_device_batches"] = c4
 
     # ---- config 5: synthetic 4K video, host -> GPU(s) -> host ------------------------------
