@@ -228,15 +228,6 @@ k_inv_u8(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_til
 // ---------------------------------------------------------------------------------
 // generic kernels: one pixel per thread, any alignment, every dtype combination
 // ---------------------------------------------------------------------------------
-// sRGB linearisation of a float channel in float64 (nphusl.py:278-286) split
-// into the hi+lo pair the float32 core expects: differences of nearly equal
-// channels keep float64 accuracy.
-__device__ __forceinline__ void lin_f64(double c, float &hi, float &lo) {
-    const double v = (c > 0.04045) ? pow((c + 0.055) / 1.055, 2.4) : c / 12.92;
-    hi = (float)v;
-    lo = (float)(v - (double)hi);
-}
-
 template <typename TIn>
 __device__ __forceinline__ LinPx load_px(const TIn *in, long long i, int channels);
 

@@ -86,6 +86,29 @@ __device__ __forceinline__ float hue_deg(float nv, float nu) {
     return r;
 }
 
+// ---- sRGB linearisation of a FLOAT channel ------------------------------------------
+// reference: c/12.92 below 0.04045, ((c+0.055)/1.055)^2.4 above (nphusl.py:278-286).
+// Needed to ~1e-11 relative, not float32's 6e-8: hue and saturation are built
+// from DIFFERENCES of linear channels, so the result is returned as a hi+lo
+// float pair like the uint8 table entries.  x^2.4 = (x * r^2)^4 with r = x^(-1/5):
+// r is seeded by MUFU lg2/ex2 (1e-6 relative) and polished by ONE division-free
+// Newton step in float64, r <- r*(6 - x*r^5)/5 (error ~3e-12); 11 DP operations
+// instead of the ~120 instructions of a general pow().
+__device__ __forceinline__ void lin_f64(double c, float &hi, float &lo) {
+    const double x = fma(c, 1.0 / 1.055, 0.055 / 1.055);
+    const float xf = (float)x;
+    double r = (double)mufu_ex2(mufu_lg2(xf) * -0.2f);
+    const double r2 = r * r;
+    const double r5 = r2 * r2 * r;
+    r = r * fma(-x, r5, 6.0) * 0.2;
+    double t = x * (r * r);
+    t = t * t;
+    t = t * t;
+    const double v = (c > 0.04045) ? t : c * (1.0 / 12.92);
+    hi = (float)v;
+    lo = (float)(v - (double)hi);
+}
+
 // ---- forward core --------------------------------------------------------------
 // Linear-light channel values arrive as hi+lo float pairs (exact to ~2^-48):
 // from the 256-entry table for uint8 input, from a float64 pow for float input.

@@ -158,8 +158,8 @@ int set_attrs(DevCtx &c) {
     constexpr int W = FWD_BLOCK / 32;
     if ((rc = set_smem(k_fwd_u8<float, false, FWD_BLOCK, 2>, TAB_BYTES + W * Pack<float>::STAGE))) return rc;
     if ((rc = set_smem(k_fwd_u8<double, false, FWD_BLOCK, 1>, TAB_BYTES + W * Pack<double>::STAGE))) return rc;
-    if ((rc = set_smem(k_fwd_u8<float, true, FWD_BLOCK, 2>, TAB_BYTES))) return rc;
-    if ((rc = set_smem(k_fwd_u8<double, true, FWD_BLOCK, 2>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_fwd_u8<float, true, FWD_BLOCK, 3>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_fwd_u8<double, true, FWD_BLOCK, 3>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_tma<double, 512, 1, 2>, TAB_BYTES + 16 * 2 * Tile<double>::BYTES))) return rc;
     if ((rc = set_smem(k_inv_tma<double, INV_BLOCK, 2, 3>, (INV_BLOCK / 32) * InvSmem<double, 3>::PER_WARP))) return rc;
     if ((rc = set_smem(k_inv_cp<INV_BLOCK, 4, 3>, (INV_BLOCK / 32) * InvCpSmem<3>::PER_WARP))) return rc;
@@ -231,14 +231,21 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
             // float32 output is issue-bound and keeps the leaner LDS/STG transposition
             const int grid = grid_for(tiles, 16, c.sms);
             k_fwd_tma<double, 512, 1, 2><<<grid, 512, TAB_BYTES + 16 * 2 * Tile<double>::BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
+        } else if (HUE) {
+            // hue only: no staging buffer, 64 KB of table per CTA -> 3 CTAs (48 warps) per SM
+            const int grid = grid_for(tiles, W, c.sms * 3);
+            if (out_dt == NPHUSL_F32)
+                k_fwd_u8<float, true, FWD_BLOCK, 3><<<grid, FWD_BLOCK, TAB_BYTES, s>>>((const uint32_t *)in, (float *)out, tiles);
+            else
+                k_fwd_u8<double, true, FWD_BLOCK, 3><<<grid, FWD_BLOCK, TAB_BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
         } else if (out_dt == NPHUSL_F32) {
-            const size_t sm = TAB_BYTES + (HUE ? 0 : W * Pack<float>::STAGE);
+            const size_t sm = TAB_BYTES + W * Pack<float>::STAGE;
             const int grid = grid_for(tiles, W, c.sms * 2);
-            k_fwd_u8<float, HUE, FWD_BLOCK, 2><<<grid, FWD_BLOCK, sm, s>>>((const uint32_t *)in, (float *)out, tiles);
+            k_fwd_u8<float, false, FWD_BLOCK, 2><<<grid, FWD_BLOCK, sm, s>>>((const uint32_t *)in, (float *)out, tiles);
         } else {
-            const size_t sm = TAB_BYTES + (HUE ? 0 : W * Pack<double>::STAGE);
-            const int grid = grid_for(tiles, W, c.sms * (HUE ? 2 : 1));
-            k_fwd_u8<double, HUE, FWD_BLOCK, (HUE ? 2 : 1)><<<grid, FWD_BLOCK, sm, s>>>((const uint32_t *)in, (double *)out, tiles);
+            const size_t sm = TAB_BYTES + W * Pack<double>::STAGE;
+            const int grid = grid_for(tiles, W, c.sms);
+            k_fwd_u8<double, false, FWD_BLOCK, 1><<<grid, FWD_BLOCK, sm, s>>>((const uint32_t *)in, (double *)out, tiles);
         }
         g_launches++;
         if ((rc = check_launch("k_fwd_u8"))) return rc;

@@ -77,4 +77,18 @@ for name, fn, b in (("pipeline_f64", pipe64, 54), ("pipeline_f32", pipe32, 30),
                     ("fused_edit_u8", lambda: _cuda.edit_rgb(rgb, out=back, hue=(250, 290), invert=True, l=(0.5, 0)), 6)):
     ms = timed(fn)
     res[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 1), "hbm_frac": round(px * b / ms / 1e6 / 6547.2, 3)}
+# float RGB inputs / float RGB outputs (generic one-pixel-per-thread kernels), 2 frames
+f2 = rgb[:2]
+px2 = f2.numel() // 3
+rf32 = f2.to(torch.float32) / 255.0
+rf64 = f2.to(torch.float64) / 255.0
+o32 = torch.empty(f2.shape, dtype=torch.float32, device="cuda")
+o64 = torch.empty(f2.shape, dtype=torch.float64, device="cuda")
+g64 = rf64[..., 0].contiguous()
+for name, fn, b in (("frgb32_to_husl32", lambda: _cuda._rgb_to_husl(rf32, out=o32), 24),
+                    ("frgb64_to_husl64", lambda: _cuda._rgb_to_husl(rf64, out=o64), 48),
+                    ("husl64_to_frgb64", lambda: _cuda._husl_to_rgb(o64, out=rf64), 48),
+                    ("husl32_to_frgb32", lambda: _cuda._husl_to_rgb(o32, out=rf32), 24)):
+    ms = timed(fn)
+    res[name] = {"ms": round(ms, 4), "gpix_s": round(px2 / ms / 1e6, 1), "hbm_frac": round(px2 * b / ms / 1e6 / 6547.2, 3)}
 print(json.dumps(res))
