@@ -324,6 +324,32 @@ def run_cuda(args):
     total_ms = float(t.item())
     value = px * world * K / (total_ms * 1e-3) / 1e6
 
+    # ---- host link of THIS box (diagnostic beside e2e): plain pinned copies -----------
+    def link_gbs():
+        nbytes = host_in.nbytes
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        flat_in = torch.from_numpy(np.asarray(host_in).reshape(-1))
+        flat_out = torch.from_numpy(np.asarray(host_out).reshape(-1))
+
+        def run(h2d, d2h, reps=3):
+            best = 1e9
+            for _ in range(reps):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                if h2d:
+                    with torch.cuda.stream(s1):
+                        scratch.copy_(flat_in, non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(s2):
+                        flat_out.copy_(dev_in.reshape(-1), non_blocking=True)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            return nbytes / best / 1e9
+        return {"h2d": round(run(True, False), 1), "d2h": round(run(False, True), 1),
+                "duplex_each": round(run(True, True), 1)}
+    link = link_gbs()
+
     # ---- e2e: public API, host buffers ------------------------------------------
     # step k runs on user stream k%2 with its own HUSL buffer; calls are
     # non-blocking (pinned memory), so the H2D of step k+1 overlaps the D2H of step k
@@ -375,7 +401,9 @@ def run_cuda(args):
                 ("to_husl_u8_f32", lambda: _cuda._rgb_to_husl(dev_in, out=h32, stream=stream), 15),
                 ("to_rgb_f32_u8", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream), 15),
                 ("to_hue_u8_f64", lambda: _cuda._rgb_to_hue(dev_in, out=hue64, stream=stream), 11),
-                ("to_hue_u8_f32", lambda: _cuda._rgb_to_hue(dev_in, out=hue32, stream=stream), 7)):
+                ("to_hue_u8_f32", lambda: _cuda._rgb_to_hue(dev_in, out=hue32, stream=stream), 7),
+                ("fused_edit_u8_u8", lambda: _cuda.edit_rgb(dev_in, out=dev_out, stream=stream, hue=(250, 290),
+                                                            invert=True, l=(0.5, 0)), 6)):
             if hdt != np.float64 and "f64" in name and "hue" not in name:
                 continue
             ms = timed(fn)
@@ -393,15 +421,17 @@ def run_cuda(args):
 
     if rank == 0:
         hbm, which = peaks()
-        dom = ("to_husl", "k_fwd_u8", t_fwd) if t_fwd >= t_inv else ("to_rgb", "k_inv_u8", t_inv)
+        f64 = hdt == np.float64
+        dom = (("to_husl", "k_fwd_tma<double>" if f64 else "k_fwd_u8<float>", t_fwd) if t_fwd >= t_inv
+               else ("to_rgb", "k_inv_tma<double>" if f64 else "k_inv_cp<float>", t_inv))
         achieved = px * bpp / (dom[2] * 1e-3) / 1e9
-        kname = "%s<%s>" % (dom[1], "double" if hdt == np.float64 else "float")
+        kname = dom[1]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config(args, world, B),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px * 3,
-                    "steps": Ke, "path": "nphusl.to_husl(pinned host u8 -> device HUSL) + nphusl.to_rgb(device HUSL -> pinned host u8), "
+                    "steps": Ke, "link_gbs": link, "path": "nphusl.to_husl(pinned host u8 -> device HUSL) + nphusl.to_rgb(device HUSL -> pinned host u8), "
                             "blocking=False on two alternating streams; wall clock incl. final synchronize"},
             "gpu_launches": int(launches),
             "clocks": clocks,

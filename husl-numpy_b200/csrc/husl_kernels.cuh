@@ -94,16 +94,23 @@ k_fwd_u8(const uint32_t *__restrict__ in, TOut *__restrict__ out, long long n_ti
         rd_off[k] = (p / CH) * Pack<TOut>::LANE_STRIDE + (p % CH) * 16;
     }
 
-    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    // register prefetch of the next tile's words (PF2: two tiles ahead)
+    constexpr bool PF2 = false;   // measured: a second tile in flight does not pay (profiles/r01_ab_variants.txt)
+    uint32_t w0 = 0, w1 = 0, w2 = 0, x0 = 0, x1 = 0, x2 = 0;
     if (tile < n_tiles) {
         const uint32_t *p = in + tile * 96 + lane * 3;
         w0 = ldg_u32(p); w1 = ldg_u32(p + 1); w2 = ldg_u32(p + 2);
     }
+    if (PF2 && tile + nw < n_tiles) {
+        const uint32_t *p = in + (tile + nw) * 96 + lane * 3;
+        x0 = ldg_u32(p); x1 = ldg_u32(p + 1); x2 = ldg_u32(p + 2);
+    }
     for (; tile < n_tiles; tile += nw) {
-        // prefetch the next tile's words while this one is computed
+        // prefetch the words of the tile 1 (2) iterations ahead while this one is computed
         uint32_t n0 = 0, n1 = 0, n2 = 0;
-        if (tile + nw < n_tiles) {
-            const uint32_t *p = in + (tile + nw) * 96 + lane * 3;
+        const long long ahead = tile + (PF2 ? 2 : 1) * nw;
+        if (ahead < n_tiles) {
+            const uint32_t *p = in + ahead * 96 + lane * 3;
             n0 = ldg_u32(p); n1 = ldg_u32(p + 1); n2 = ldg_u32(p + 2);
         }
         // bytes: w0 = r0 g0 b0 r1 | w1 = g1 b1 r2 g2 | w2 = b2 r3 g3 b3
@@ -159,7 +166,8 @@ k_fwd_u8(const uint32_t *__restrict__ in, TOut *__restrict__ out, long long n_ti
                 o[32 * k] = *reinterpret_cast<const float4 *>(stage + rd_off[k]);
             __syncwarp();
         }
-        w0 = n0; w1 = n1; w2 = n2;
+        if (PF2) { w0 = x0; w1 = x1; w2 = x2; x0 = n0; x1 = n1; x2 = n2; }
+        else { w0 = n0; w1 = n1; w2 = n2; }
     }
 }
 

@@ -3,7 +3,7 @@
 device-resident 4K frames) a few times -- the command ncu wraps:
 
   python profiles/prof_kernels.py > gpurun_out/plain.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'k_(fwd|inv)_u8' \
+  ncu --set full --clock-control none --import-source on -k regex:'k_(fwd|inv|edit)' \
       -o gpurun_out/prof python profiles/prof_kernels.py
 """
 import os
@@ -25,6 +25,7 @@ h32 = torch.empty(rgb.shape, dtype=torch.float32, device="cuda")
 hue64 = torch.empty(rgb.shape[:-1], dtype=torch.float64, device="cuda")
 hue32 = torch.empty(rgb.shape[:-1], dtype=torch.float32, device="cuda")
 back = torch.empty_like(rgb)
+planes = torch.empty((3,) + tuple(rgb.shape[:-1]), dtype=torch.float32, device="cuda")
 for _ in range(reps):
     _cuda._rgb_to_husl(rgb, out=h64)
     _cuda._husl_to_rgb(h64, out=back)
@@ -32,6 +33,9 @@ for _ in range(reps):
     _cuda._husl_to_rgb(h32, out=back)
     _cuda._rgb_to_hue(rgb, out=hue64)
     _cuda._rgb_to_hue(rgb, out=hue32)
+    _cuda.rgb_to_husl_planar(rgb, out=planes)
+    _cuda.husl_planar_to_rgb(planes, out=back)
+    _cuda.edit_rgb(rgb, out=back)                 # identity edit: exact round trip
 torch.cuda.synchronize()
 assert torch.equal(back, rgb)
 print("ok", _cuda.launch_count(), "launches")

@@ -171,6 +171,20 @@ def main():
             pl[2].mul_(0.5)
             _cuda.husl_planar_to_rgb(pl, out=bk)
         c4["B%d_f32_planar_with_edit" % B] = mpix(bpx, dev_time(planar_pipe, 5, 10))
+        if B == 1:
+            # per-frame loop captured in a CUDA graph (launch-bound otherwise)
+            h1 = torch.empty(fr.shape, dtype=torch.float32, device="cuda")
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                _cuda._rgb_to_husl(fr, out=h1, stream=side)
+                _cuda._husl_to_rgb(h1, out=bk, stream=side)
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                _cuda._rgb_to_husl(fr, out=h1, stream=torch.cuda.current_stream())
+                _cuda._husl_to_rgb(h1, out=bk, stream=torch.cuda.current_stream())
+            c4["B1_f32_to_husl_to_rgb_cuda_graph"] = mpix(bpx, dev_time(graph.replay, 5, 20))
+            del h1
         c4["B%d_fused_edit_kernel" % B] = mpix(bpx, dev_time(lambda: nphusl.edit(fr, out=bk, hue=(250, 290), invert=True, l=(0.5, 0)), 5, 10))
         del fr, bk, pl
     out["config4_4k_device_batches"] = c4

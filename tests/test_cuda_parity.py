@@ -457,3 +457,31 @@ def test_fused_edit_device_in_place(cu):
     r = cu.edit_rgb(t, out=t, lightness=(0, 50), l=(1, 20))
     torch.cuda.synchronize()
     assert r is t and np.array_equal(t.cpu().numpy(), want)
+
+
+def test_cuda_graph_capture_of_per_frame_loop(cu):
+    """Per-frame pipelines are launch-bound (a 4K frame is ~40 us of kernel
+    time): device-pointer calls are plain launches on the caller's stream, so a
+    to_husl -> to_rgb frame loop can be captured in a CUDA graph and replayed."""
+    torch = pytest.importorskip("torch")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    frames = torch.randint(0, 256, (6, 720, 1280, 3), dtype=torch.uint8, device="cuda", generator=g)
+    cur = torch.empty_like(frames[0])
+    hsl = torch.empty(cur.shape, dtype=torch.float32, device="cuda")
+    out = torch.empty_like(cur)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        cu._rgb_to_husl(cur, out=hsl, stream=s)           # warm-up: one-time kernel attribute setup
+        cu._husl_to_rgb(hsl, out=out, stream=s)
+    s.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    n0 = cu.launch_count()
+    with torch.cuda.graph(graph, stream=s):
+        cu._rgb_to_husl(cur, out=hsl, stream=torch.cuda.current_stream())
+        cu._husl_to_rgb(hsl, out=out, stream=torch.cuda.current_stream())
+    assert cu.launch_count() - n0 == 2
+    for f in frames:
+        cur.copy_(f)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, f)
