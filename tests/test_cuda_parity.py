@@ -485,3 +485,43 @@ def test_cuda_graph_capture_of_per_frame_loop(cu):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, f)
+
+
+def test_guard_bands_stay_untouched(cu):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are
+    caught the old way: every output lives inside a larger canary-filled buffer
+    and the canaries on both sides must survive every kernel family (streaming
+    TMA / cp.async / LDG kernels, their tails, generic, planar, fused edit)."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(13)
+    GUARD = 4096
+
+    def guarded(nbytes, tdtype):
+        raw = torch.full((GUARD + nbytes + GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
+        view = raw[GUARD:GUARD + nbytes].view(tdtype)
+        return raw, view
+
+    def intact(raw, nbytes):
+        return bool((raw[:GUARD] == 0xA5).all()) and bool((raw[GUARD + nbytes:] == 0xA5).all())
+
+    for n in (1, 127, 128, 129, 128 * 37 + 5, 128 * 4000, 128 * 4000 + 91):
+        rgb = torch.from_numpy(rng.integers(0, 256, (n, 3), dtype=np.uint8)).cuda()
+        for tdt, isz in ((torch.float32, 4), (torch.float64, 8)):
+            raw, hsl = guarded(n * 3 * isz, tdt)
+            cu._rgb_to_husl(rgb, out=hsl.view(n, 3))
+            rawb, back = guarded(n * 3, torch.uint8)
+            cu._husl_to_rgb(hsl.view(n, 3), out=back.view(n, 3))
+            rawh, hue = guarded(n * isz, tdt)
+            cu._rgb_to_hue(rgb, out=hue)
+            rawp, planes = guarded(n * 3 * isz, tdt)
+            cu.rgb_to_husl_planar(rgb, out=planes.view(3, n))
+            rawq, back2 = guarded(n * 3, torch.uint8)
+            cu.husl_planar_to_rgb(planes.view(3, n), out=back2.view(n, 3))
+            torch.cuda.synchronize()
+            assert intact(raw, n * 3 * isz) and intact(rawb, n * 3) and intact(rawh, n * isz)
+            assert intact(rawp, n * 3 * isz) and intact(rawq, n * 3)
+            assert torch.equal(back.view(n, 3), rgb) and torch.equal(back2.view(n, 3), rgb)
+        rawe, ed = guarded(n * 3, torch.uint8)
+        cu.edit_rgb(rgb, out=ed.view(n, 3))
+        torch.cuda.synchronize()
+        assert intact(rawe, n * 3) and torch.equal(ed.view(n, 3), rgb)
