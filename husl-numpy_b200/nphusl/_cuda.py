@@ -244,15 +244,46 @@ class DeviceArray:
         _check(load().nphusl_cuda_memcpy(out.ctypes.data, self.ptr, self.nbytes, 2, self.device, _stream_ptr(stream)), "memcpy d2h")
         return out
 
+    def _view(self, shape, byte_offset=0):
+        v = object.__new__(DeviceArray)
+        v.shape = tuple(int(x) for x in shape)
+        v.dtype, v.device = self.dtype, self.device
+        v.size = int(np.prod(v.shape)) if v.shape else 1
+        v.nbytes = v.size * v.dtype.itemsize
+        v.ptr = self.ptr + byte_offset
+        v._owner = False
+        v._base = self                      # keeps the allocation alive
+        return v
+
     def reshape(self, *shape):
         if len(shape) == 1 and not np.isscalar(shape[0]):
             shape = tuple(shape[0])
-        v = object.__new__(DeviceArray)
-        v.__dict__.update(self.__dict__)
-        v.shape = tuple(int(s) for s in np.empty(self.shape, np.bool_).reshape(shape).shape) if self.size else tuple(shape)
-        v._owner = False
-        v._base = self
-        return v
+        shape = [int(x) for x in shape]
+        if shape.count(-1) > 1:
+            raise ValueError("can only specify one unknown dimension")
+        if -1 in shape:
+            known = int(np.prod([x for x in shape if x != -1])) or 1
+            shape[shape.index(-1)] = self.size // known
+        if int(np.prod(shape)) != self.size:
+            raise ValueError("cannot reshape array of size {} into shape {}".format(self.size, tuple(shape)))
+        return self._view(shape)
+
+    def __getitem__(self, key):
+        """Leading-axis indexing only (``a[i]``, ``a[i:j]``): such views stay C-contiguous."""
+        if not self.shape:
+            raise IndexError("too many indices")
+        row = (self.size // self.shape[0]) * self.dtype.itemsize if self.shape[0] else 0
+        if isinstance(key, (int, np.integer)):
+            k = int(key) + (self.shape[0] if key < 0 else 0)
+            if not 0 <= k < self.shape[0]:
+                raise IndexError("index out of range")
+            return self._view(self.shape[1:], k * row)
+        if isinstance(key, slice):
+            a, b, step = key.indices(self.shape[0])
+            if step != 1:
+                raise IndexError("DeviceArray slices must be contiguous")
+            return self._view((max(b - a, 0),) + self.shape[1:], a * row)
+        raise IndexError("DeviceArray supports integer and contiguous-slice indexing of the first axis")
 
     def __array__(self, dtype=None, copy=None):
         a = self.copy_to_host()

@@ -1,0 +1,103 @@
+"""Host-side logic of the ctypes binding that needs no GPU: buffer description,
+the Edit struct layout against the C header, DeviceArray view arithmetic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from nphusl import _cuda
+
+
+def test_edit_struct_matches_header():
+    text = open(os.path.join(ROOT, "include", "nphusl_cuda.h")).read()
+    body = re.search(r"typedef struct nphusl_edit \{(.*?)\} nphusl_edit;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, rest = decl.split(None, 1)
+        for n in rest.split(","):
+            names.append((n.strip(), ctype))
+    assert [(n, {"float": ctypes.c_float, "int": ctypes.c_int}[t]) for n, t in names] == list(_cuda.Edit._fields_)
+    assert ctypes.sizeof(_cuda.Edit) == 13 * 4
+    e = _cuda.Edit(hue=(250, 290), invert=True, l=(0.5, 0))
+    assert (e.h_lo, e.h_hi, e.invert, e.l_mul, e.l_add, e.s_mul) == (250.0, 290.0, 1, 0.5, 0.0, 1.0)
+    assert e.s_lo == -np.inf and e.l_hi == np.inf            # unspecified ranges are unbounded
+
+
+def test_rgb_input_description():
+    d = _cuda._describe_rgb_in(np.zeros((4, 5, 3), np.uint8))
+    assert (d.loc, d.channels, d.dtype, d.shape) == (_cuda.HOST, 3, np.uint8, (4, 5, 3))
+    assert _cuda._describe_rgb_in(np.zeros((4, 3), np.int32)).dtype == np.uint8        # other ints: cast like rgb_int_input
+    assert _cuda._describe_rgb_in(np.zeros((4, 3), np.float16)).dtype == np.float64
+    assert _cuda._describe_rgb_in(np.zeros((4, 3), np.float32)).dtype == np.float32
+    grey = np.random.default_rng(0).random((6, 7))
+    g3 = np.broadcast_to(grey[..., None], (6, 7, 3))
+    d = _cuda._describe_rgb_in(g3)
+    assert d.channels == 1 and d.shape == (6, 7, 3) and d.keep.shape == (6, 7)          # one channel travels
+    nc = np.zeros((8, 8, 3), np.uint8)[:, ::2]
+    d = _cuda._describe_rgb_in(nc)
+    assert d.keep.flags.c_contiguous and d.keep.shape == (8, 4, 3)                      # compacted copy
+
+
+class FakeDev:
+    def __init__(self, shape, typestr, strides=None, ptr=4096, device=None):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False),
+                                         "version": 3, "strides": strides}
+        if device is not None:
+            self.device = device
+
+
+def test_device_description_and_contiguity():
+    d = _cuda._describe_device(FakeDev((4, 5, 3), "|u1", device=2), "x")
+    assert (d.loc, d.device, d.ptr, d.shape) == (_cuda.DEVICE, 2, 4096, (4, 5, 3))
+    _cuda._describe_device(FakeDev((4, 5, 3), "<f4", strides=(60, 12, 4), device=0), "x")      # explicit C strides: fine
+    _cuda._describe_device(FakeDev((1, 5, 3), "<f4", strides=(999, 12, 4), device=0), "x")     # size-1 axis: stride ignored
+    with pytest.raises(ValueError):
+        _cuda._describe_device(FakeDev((4, 5, 3), "<f4", strides=(120, 12, 4), device=0), "x")
+    g = _cuda._describe_device(FakeDev((4, 5, 3), "<f8", strides=(40, 8, 0), device=0), "x", allow_gray=True)
+    assert g.channels == 1 and g.shape == (4, 5, 3)
+    with pytest.raises(ValueError):
+        _cuda._describe_device(FakeDev((4, 5, 3), "<f8", strides=(40, 8, 0), device=0), "x")
+
+
+def test_out_validation():
+    with pytest.raises(ValueError):
+        _cuda._describe_out(np.zeros((4, 3)), (5, 3), np.float64, _cuda._FLOATS, "out")           # wrong size
+    with pytest.raises(ValueError):
+        _cuda._describe_out(np.zeros((4, 3), np.int16), (4, 3), np.float64, _cuda._FLOATS, "out")  # wrong dtype
+    with pytest.raises(ValueError):
+        _cuda._describe_out(np.zeros((4, 6))[:, ::2], (4, 3), np.float64, _cuda._FLOATS, "out")    # not contiguous
+    with pytest.raises(TypeError):
+        _cuda._describe_out([1, 2, 3], (1, 3), np.float64, _cuda._FLOATS, "out")
+
+
+def test_device_array_views_without_gpu():
+    a = object.__new__(_cuda.DeviceArray)
+    a.shape, a.dtype, a.device, a.size, a.nbytes, a.ptr, a._owner = (3, 4, 5), np.dtype(np.float32), 0, 60, 240, 1 << 20, False
+    assert a.reshape(-1, 5).shape == (12, 5) and a.reshape((60,)).shape == (60,)
+    with pytest.raises(ValueError):
+        a.reshape(7, -1)
+    v = a[2]
+    assert v.shape == (4, 5) and v.ptr == a.ptr + 2 * 80 and v.nbytes == 80
+    assert a[-1].ptr == v.ptr
+    s = a[1:3]
+    assert s.shape == (2, 4, 5) and s.ptr == a.ptr + 80
+    assert s.__cuda_array_interface__["data"][0] == s.ptr and s.__cuda_array_interface__["strides"] is None
+    with pytest.raises(IndexError):
+        a[::2]
+    with pytest.raises(IndexError):
+        a[3]
+
+
+def test_stream_pointer_forms():
+    class TorchLike:
+        cuda_stream = 1234
+    assert _cuda._stream_ptr(None) is None
+    assert _cuda._stream_ptr(TorchLike()).value == 1234
+    assert _cuda._stream_ptr(77).value == 77

@@ -525,3 +525,26 @@ def test_guard_bands_stay_untouched(cu):
         cu.edit_rgb(rgb, out=ed.view(n, 3))
         torch.cuda.synchronize()
         assert intact(rawe, n * 3) and torch.equal(ed.view(n, 3), rgb)
+
+
+def test_shard_over_devices(cu):
+    """In-process fan-out of a host batch over every visible GPU (one host thread
+    per GPU, disjoint output slices, no collective) equals the single-GPU result."""
+    from nphusl import _shard
+    ndev = cu.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    rng = np.random.default_rng(14)
+    frames = rng.integers(0, 256, (2 * ndev + 1, 540, 960, 3), dtype=np.uint8)
+    devs = list(range(ndev))
+    hsl = _shard.to_husl(frames, devices=devs, dtype=np.float32)
+    assert np.array_equal(hsl, cu._rgb_to_husl(frames, dtype=np.float32, device=0))
+    assert np.array_equal(_shard.to_rgb(hsl, devices=devs), frames)
+    assert np.array_equal(_shard.to_hue(frames, devices=devs), cu._rgb_to_hue(frames, device=ndev - 1))
+    # a tensor living on GPU 1 is converted on GPU 1 and the caller's current device is left alone
+    torch = pytest.importorskip("torch")
+    t = torch.from_numpy(frames[0]).to("cuda:1")
+    assert torch.cuda.current_device() == 0
+    d = cu._rgb_to_husl(t, dtype=np.float32)
+    assert d.device == 1 and torch.cuda.current_device() == 0
+    assert np.array_equal(d.copy_to_host(), hsl[0])
