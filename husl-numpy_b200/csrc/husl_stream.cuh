@@ -1,7 +1,10 @@
-// husl_stream.cuh -- TMA-staged streaming kernels of the HUSL hot path (sm_100a).
+// husl_stream.cuh -- asynchronously staged streaming kernels of the HUSL hot path (sm_100a).
 //
-//   k_fwd_tma<TOut>   (a) husl_from_rgb : uint8 RGB -> float32 / float64 HUSL
-//   k_inv_tma<TIn>    (b) rgb_from_husl : float32 / float64 HUSL -> uint8 RGB
+//   k_fwd_tma<TOut>   (a) husl_from_rgb : uint8 RGB -> HUSL, results leave through TMA bulk stores
+//                         (dispatched for float64 output, the HBM-bound case)
+//   k_inv_tma<TIn>    (b) rgb_from_husl : HUSL arrives through a ring of TMA bulk loads + mbarriers
+//                         (dispatched for float64 input)
+//   k_inv_cp          (b) rgb_from_husl, float32 input: the same ring filled by per-lane cp.async
 //
 // Same per-pixel math as husl_kernels.cuh (husl_math.cuh); what changes is how
 // the wide side of each kernel (the 12 / 24 B-per-pixel HUSL stream) moves:
@@ -20,7 +23,11 @@
 //     the transposition to coalesced stores;
 //   * the uint8 side (3 B/px) of the inverse goes out the same way (384 B per
 //     tile); the uint8 side of the forward stays a register-prefetched LDG of 3
-//     words per lane (12 B = 4 whole pixels).
+//     words per lane (12 B = 4 whole pixels);
+//   * the bulk engine's bookkeeping (mbarrier arm/wait, elect, proxy fence) costs
+//     about 60 warp-instructions per tile: worth it where HBM is the limit
+//     (float64), not where the math pipes are (float32) -- measured in
+//     profiles/r01_ab_variants.txt.
 //
 // Requirements (checked by the host before launching; otherwise the generic
 // kernels run): HUSL pointer 16-byte aligned, uint8 pointer 16-byte aligned
