@@ -360,6 +360,19 @@ def run_cuda(args):
         s = streams[k & 1]
         nphusl.to_husl(host_in, out=hsl2[k & 1], stream=s, blocking=False)     # H2D + kernel, chunk-pipelined
         nphusl.to_rgb(hsl2[k & 1], out=host_out, stream=s, blocking=False)     # kernel + D2H
+    # the plain way first: blocking calls, one after the other (reported beside the headline)
+    def step_blocking():
+        nphusl.to_husl(host_in, out=dev_hsl)
+        nphusl.to_rgb(dev_hsl, out=host_out)
+    for _ in range(2):
+        step_blocking()
+    torch.cuda.synchronize()
+    tb = time.perf_counter()
+    for _ in range(5):
+        step_blocking()
+    torch.cuda.synchronize()
+    e2e_blocking = px * 5 / (time.perf_counter() - tb) / 1e6
+
     Ke = max(4, min(K, 20))
     for k in range(4):
         step_e2e(k)
@@ -431,7 +444,7 @@ def run_cuda(args):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config(args, world, B),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px * 3,
-                    "steps": Ke, "link_gbs": link, "path": "nphusl.to_husl(pinned host u8 -> device HUSL) + nphusl.to_rgb(device HUSL -> pinned host u8), "
+                    "steps": Ke, "link_gbs": link, "blocking_calls_mpix_s_this_rank": e2e_blocking, "path": "nphusl.to_husl(pinned host u8 -> device HUSL) + nphusl.to_rgb(device HUSL -> pinned host u8), "
                             "blocking=False on two alternating streams; wall clock incl. final synchronize"},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -548,3 +548,22 @@ def test_shard_over_devices(cu):
     d = cu._rgb_to_husl(t, dtype=np.float32)
     assert d.device == 1 and torch.cuda.current_device() == 0
     assert np.array_equal(d.copy_to_host(), hsl[0])
+
+
+def test_out_of_gamut_husl_wraps_like_the_reference(cu):
+    """to_rgb never clamps (reference transform.py:16-20): negative
+    channels are mirrored by abs(), values past 255 wrap modulo 256."""
+    rng = np.random.default_rng(15)
+    n = 20000
+    hsl = np.stack([rng.uniform(0, 360, n), rng.uniform(100, 180, n), rng.uniform(5, 95, n)], -1)
+    want = orc.husl_to_rgb(hsl).astype(int)
+    f = orc.husl_to_rgb_float(hsl)
+    assert (f.max() > 1.0) and (f.min() < 0.0)                       # really out of gamut
+    for dt in (np.float64, np.float32):
+        got = cu._husl_to_rgb(hsl.astype(dt)).astype(int)
+        d = np.abs(got - want)
+        d = np.minimum(d, 256 - d)                                   # wrap-around distance
+        assert d.max() <= 1 and (d != 0).mean() < 5e-3
+    # float RGB output is the unclamped value itself
+    gf = cu._husl_to_rgb(hsl, dtype=np.float64)
+    assert np.abs(gf - f).max() < 5e-4
