@@ -158,11 +158,11 @@ int set_attrs(DevCtx &c) {
     constexpr int W = FWD_BLOCK / 32;
     if ((rc = set_smem(k_fwd_u8<float, false, FWD_BLOCK, 2>, TAB_BYTES + W * Pack<float>::STAGE))) return rc;
     if ((rc = set_smem(k_fwd_u8<double, false, FWD_BLOCK, 1>, TAB_BYTES + W * Pack<double>::STAGE))) return rc;
-    if ((rc = set_smem(k_fwd_u8<float, true, FWD_BLOCK, 3>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_u8<double, true, FWD_BLOCK, 3>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_tma<double, 512, 1, 2>, TAB_BYTES + 16 * 2 * Tile<double>::BYTES))) return rc;
     if ((rc = set_smem(k_inv_tma<double, INV_BLOCK, 2, 3>, (INV_BLOCK / 32) * InvSmem<double, 3>::PER_WARP))) return rc;
-    if ((rc = set_smem(k_inv_cp<INV_BLOCK, 4, 3>, (INV_BLOCK / 32) * InvCpSmem<3>::PER_WARP))) return rc;
+    if ((rc = set_smem(k_fwd_u8<float, true, 1024, 2>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_inv_cp<384, 4, 3>, 12 * InvCpSmem<3>::PER_WARP))) return rc;
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_edit<512, 2>, TAB_BYTES + 16 * 384))) return rc;
@@ -234,8 +234,8 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
         } else if (HUE) {
             // hue only: no staging buffer, 64 KB of table per CTA -> 3 CTAs (48 warps) per SM
             const int grid = grid_for(tiles, W, c.sms * 3);
-            if (out_dt == NPHUSL_F32)
-                k_fwd_u8<float, true, FWD_BLOCK, 3><<<grid, FWD_BLOCK, TAB_BYTES, s>>>((const uint32_t *)in, (float *)out, tiles);
+            if (out_dt == NPHUSL_F32)   // float32 hue: 2 x 1024 threads (64 warps/SM, 32 registers) measured best
+                k_fwd_u8<float, true, 1024, 2><<<grid_for(tiles, 32, c.sms * 2), 1024, TAB_BYTES, s>>>((const uint32_t *)in, (float *)out, tiles);
             else
                 k_fwd_u8<double, true, FWD_BLOCK, 3><<<grid, FWD_BLOCK, TAB_BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
         } else if (out_dt == NPHUSL_F32) {
@@ -273,11 +273,11 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
 #define INV_GO(T, MINB, IST) \
     k_inv_tma<T, INV_BLOCK, MINB, IST><<<grid_for(tiles, W, c.sms * MINB), INV_BLOCK, W * InvSmem<T, IST>::PER_WARP, s>>>( \
         (const T *)in, (uint32_t *)out, tiles)
-            // tuned on B200 (profiles/r01_ab_variants.txt).  float32 input is issue-bound:
-            // 3-stage LDGSTS ring, 4 CTAs/SM; float64 input is HBM-bound: 3-stage bulk-copy
-            // (TMA) ring with mbarriers, 2 CTAs/SM
-            if (in_dt == NPHUSL_F32)
-                k_inv_cp<INV_BLOCK, 4, 3><<<grid_for(tiles, W, c.sms * 4), INV_BLOCK, W * InvCpSmem<3>::PER_WARP, s>>>(
+            // tuned on B200 (profiles/r01_ab_variants.txt).  float32 input is bound by the math
+            // pipes: 3-stage LDGSTS ring; float64 input is HBM-bound: 3-stage bulk-copy (TMA)
+            // ring with mbarriers, 2 CTAs/SM
+            if (in_dt == NPHUSL_F32)   // 4 CTAs x 384 threads = 48 warps/SM at 40 registers
+                k_inv_cp<384, 4, 3><<<grid_for(tiles, 12, c.sms * 4), 384, 12 * InvCpSmem<3>::PER_WARP, s>>>(
                     (const float *)in, (uint32_t *)out, tiles);
             else INV_GO(double, 2, 3);
 #undef INV_GO
