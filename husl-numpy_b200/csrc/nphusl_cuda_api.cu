@@ -166,6 +166,7 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_edit<512, 2>, TAB_BYTES + 16 * 384))) return rc;
+
     c.attr_set = true;
     return NPHUSL_OK;
 }
@@ -666,7 +667,7 @@ int nphusl_cuda_husl_planar_to_rgb(const void *h, const void *s, const void *l, 
         const long long tiles = n / TILE_PX;
         const int grid = grid_for(tiles, 8, c->sms * 4);
         if (hsl_dtype == NPHUSL_F32)
-            k_inv_planar<float, 256, 4><<<grid, 256, 8 * 384, st>>>((const float *)h, (const float *)s, (const float *)l, (uint32_t *)rgb, tiles);
+            k_inv_planar<float, 384, 4><<<grid_for(tiles, 12, c->sms * 4), 384, 12 * 384, st>>>((const float *)h, (const float *)s, (const float *)l, (uint32_t *)rgb, tiles);
         else
             k_inv_planar<double, 256, 4><<<grid, 256, 8 * 384, st>>>((const double *)h, (const double *)s, (const double *)l, (uint32_t *)rgb, tiles);
         g_launches++;
