@@ -245,6 +245,14 @@ __device__ __forceinline__ LinPx load_px<uint8_t>(const uint8_t *in, long long i
     float2 r, g, b;
     if (channels == 3) {
         r = g_lin_tab[in[3 * i]]; g = g_lin_tab[in[3 * i + 1]]; b = g_lin_tab[in[3 * i + 2]];
+    } else if (channels == 4) {
+        // RGBA: colour premultiplied by alpha (composited over black, the arithmetic of
+        // transform.reshape_rgba_input, transform.py:221-230), kept in float: c/255 * a/255
+        const double a = (double)in[4 * i + 3] * (1.0 / 65025.0);
+        lin_f64((double)in[4 * i] * a, p.hr, p.lr);
+        lin_f64((double)in[4 * i + 1] * a, p.hg, p.lg);
+        lin_f64((double)in[4 * i + 2] * a, p.hb, p.lb);
+        return p;
     } else {
         r = g = b = g_lin_tab[in[i]];
     }
@@ -259,6 +267,11 @@ __device__ __forceinline__ LinPx load_px(const TIn *in, long long i, int channel
         lin_f64((double)in[3 * i], p.hr, p.lr);
         lin_f64((double)in[3 * i + 1], p.hg, p.lg);
         lin_f64((double)in[3 * i + 2], p.hb, p.lb);
+    } else if (channels == 4) {      // float RGBA in [0,1]: rgb * alpha (transform.py:221-230)
+        const double a = (double)in[4 * i + 3];
+        lin_f64((double)in[4 * i] * a, p.hr, p.lr);
+        lin_f64((double)in[4 * i + 1] * a, p.hg, p.lg);
+        lin_f64((double)in[4 * i + 2] * a, p.hb, p.lb);
     } else {
         lin_f64((double)in[i], p.hg, p.lg);
         p.hr = p.hb = p.hg; p.lr = p.lb = p.lg;
@@ -276,7 +289,7 @@ k_fwd_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, int c
             out[i] = (TOut)hue_from_diff(d);
         } else {
             float H, S, L;
-            if (sizeof(TIn) == 1) husl_from_diff<true>(d, H, S, L);
+            if (sizeof(TIn) == 1 && channels != 4) husl_from_diff<true>(d, H, S, L);
             else husl_from_diff<false>(d, H, S, L);
             out[3 * i] = (TOut)H; out[3 * i + 1] = (TOut)S; out[3 * i + 2] = (TOut)L;
         }

@@ -553,7 +553,8 @@ int nphusl_cuda_rgb_to_husl(const void *rgb, int rgb_dtype, int rgb_loc, int cha
     if (!rgb || !hsl) return fail(NPHUSL_ERR_ARG, "rgb_to_husl: null buffer");
     if (!dsize(rgb_dtype) || (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64))
         return fail(NPHUSL_ERR_ARG, "rgb_to_husl: rgb must be u8/f32/f64 and hsl f32/f64");
-    if (channels != 3 && channels != 1) return fail(NPHUSL_ERR_ARG, "rgb_to_husl: channels must be 3 (RGB) or 1 (grayscale)");
+    if (channels != 3 && channels != 1 && channels != 4)
+        return fail(NPHUSL_ERR_ARG, "rgb_to_husl: channels must be 3 (RGB), 1 (grayscale) or 4 (RGBA)");
     if (!ok_loc(rgb_loc) || !ok_loc(hsl_loc)) return fail(NPHUSL_ERR_ARG, "rgb_to_husl: bad buffer location");
     if (mode != NPHUSL_EXACT && mode != NPHUSL_LUT && mode != NPHUSL_LUT_INTERP)
         return fail(NPHUSL_ERR_ARG, "rgb_to_husl: unknown mode");
@@ -578,7 +579,7 @@ int nphusl_cuda_rgb_to_hue(const void *rgb, int rgb_dtype, int rgb_loc, int chan
     if (!rgb || !hue) return fail(NPHUSL_ERR_ARG, "rgb_to_hue: null buffer");
     if (!dsize(rgb_dtype) || (hue_dtype != NPHUSL_F32 && hue_dtype != NPHUSL_F64))
         return fail(NPHUSL_ERR_ARG, "rgb_to_hue: rgb must be u8/f32/f64 and hue f32/f64");
-    if (channels != 3 && channels != 1) return fail(NPHUSL_ERR_ARG, "rgb_to_hue: channels must be 3 or 1");
+    if (channels != 3 && channels != 1 && channels != 4) return fail(NPHUSL_ERR_ARG, "rgb_to_hue: channels must be 3, 1 or 4");
     if (!ok_loc(rgb_loc) || !ok_loc(hue_loc)) return fail(NPHUSL_ERR_ARG, "rgb_to_hue: bad buffer location");
     DevCtx *c;
     int rc = ctx_get(device, &c);

@@ -384,6 +384,9 @@ def _describe_rgb_in(rgb):
         b = _describe_device(rgb, "rgb", allow_gray=True)
         if b.dtype not in _DT:
             raise ValueError("rgb device array dtype {} unsupported (uint8/float32/float64)".format(b.dtype))
+        if getattr(rgb, "rgba", False):          # transform.RgbaDevice: 4 stored channels, premultiplied on load
+            b.channels = 4
+            b.shape = tuple(b.shape[:-1]) + (3,)
         return b
     a = np.asarray(rgb)
     b = _Buf()

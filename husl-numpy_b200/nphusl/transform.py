@@ -212,6 +212,19 @@ class GrayDevice:
         self.device = getattr(base, "device", None)
 
 
+class RgbaDevice:
+    """(..., 4) RGBA device array presented as the (..., 3) RGB image it stands
+    for: the CUDA backend premultiplies by alpha while loading (no copy)."""
+    rgba = True
+
+    def __init__(self, base):
+        self.__cuda_array_interface__ = base.__cuda_array_interface__
+        self.base = base
+        self.shape = tuple(base.shape[:-1]) + (3,)
+        self.dtype = np.dtype(base.__cuda_array_interface__["typestr"])
+        self.device = getattr(base, "device", None)
+
+
 def from_grayscale(img):
     """(...,) single-channel floats -> (..., 3) with the value in R, G and B.
     Nothing is materialised: the CUDA backend has grayscale kernels that
@@ -295,8 +308,7 @@ def reshape_rgba_input(fn):
         if len(arr.shape) in (2, 3) and arr.shape[-1] == 4:
             _alert_rgba("Assumed RGBA with white background")
             if is_device_array(arr):
-                raise ValueError("RGBA device arrays are not supported: "
-                                 "premultiply on the device first")
+                return fn(RgbaDevice(arr), *args, **kwargs)
             is_int = np.issubdtype(arr.dtype, np.integer)
             alpha = arr[..., 3] / 255.0 if is_int else arr[..., 3]
             arr = arr[..., :3] * alpha[..., None]

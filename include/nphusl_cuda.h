@@ -85,7 +85,9 @@ int nphusl_cuda_set_host_async(int enabled);
  * _cython_opt._rgb_to_husl (_cython_opt.pyx:22-93).
  *   rgb       n_pixels * channels elements, C-contiguous.  channels = 3:
  *             interleaved R,G,B; channels = 1: grayscale (the value is used for
- *             R, G and B: transform.from_grayscale, transform.py:210-215).
+ *             R, G and B: transform.from_grayscale, transform.py:210-215);
+ *             channels = 4: interleaved R,G,B,A, colour premultiplied by alpha in
+ *             float (transform.reshape_rgba_input, transform.py:221-230).
  *             NPHUSL_U8 holds 0..255, NPHUSL_F32/F64 hold [0,1].
  *   hsl       n_pixels * 3 elements (H,S,L interleaved), NPHUSL_F32 or F64.
  *   mode      NPHUSL_EXACT | NPHUSL_LUT | NPHUSL_LUT_INTERP (LUT modes: uint8

@@ -567,3 +567,33 @@ def test_out_of_gamut_husl_wraps_like_the_reference(cu):
     # float RGB output is the unclamped value itself
     gf = cu._husl_to_rgb(hsl, dtype=np.float64)
     assert np.abs(gf - f).max() < 5e-4
+
+
+def test_rgba_device_arrays_are_premultiplied_on_load(cu):
+    """4-channel device input: rgb * alpha in the load stage of the kernel
+    (reference transform.py:221-230 does it as a host pass).  Float RGBA follows
+    the reference exactly (tests/test.py:547-556); uint8 RGBA is premultiplied in
+    float, c/255 * a/255 (the reference's integer branch is broken)."""
+    import warnings
+    torch = pytest.importorskip("torch")
+    import nphusl
+    rng = np.random.default_rng(16)
+    rgba = rng.random((33, 47, 4))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = nphusl.to_husl(rgba)                                   # host: NumPy premultiply, then the GPU
+        got = nphusl.to_husl(torch.from_numpy(rgba).cuda())
+        hue = nphusl.to_hue(torch.from_numpy(rgba).cuda())
+    assert isinstance(got, cu.DeviceArray) and got.shape == (33, 47, 3)
+    g = got.copy_to_host()
+    assert np.abs(g - want)[..., 1:].max() < 1e-4
+    assert hue_diff(g[..., 0], want[..., 0]).max() < 1e-4
+    assert np.array_equal(hue.copy_to_host(), g[..., 0])
+    u8 = rng.integers(0, 256, (1000, 4), dtype=np.uint8)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got8 = nphusl.to_husl(torch.from_numpy(u8).cuda()).copy_to_host()
+    ref8 = orc.rgb_to_husl((u8[:, :3] / 255.0) * (u8[:, 3:] / 255.0))
+    sat = ref8[:, 1] > 0.1
+    assert hue_diff(got8[sat, 0], ref8[sat, 0]).max() < TOL
+    assert np.abs(got8[:, 1:] - ref8[:, 1:]).max() < TOL
