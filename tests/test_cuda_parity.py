@@ -559,14 +559,18 @@ def test_out_of_gamut_husl_wraps_like_the_reference(cu):
     want = orc.husl_to_rgb(hsl).astype(int)
     f = orc.husl_to_rgb_float(hsl)
     assert (f.max() > 1.0) and (f.min() < 0.0)                       # really out of gamut
+    # near a gamut singularity (v' -> 0) a channel explodes to 1e6 and beyond, where the cast
+    # to uint8 is undefined behaviour in C and numpy alike: compare the sane 99 %
+    sane = (np.abs(f) < 16.0).all(-1)
+    assert sane.mean() > 0.9
     for dt in (np.float64, np.float32):
         got = cu._husl_to_rgb(hsl.astype(dt)).astype(int)
-        d = np.abs(got - want)
+        d = np.abs(got - want)[sane]
         d = np.minimum(d, 256 - d)                                   # wrap-around distance
         assert d.max() <= 1 and (d != 0).mean() < 5e-3
     # float RGB output is the unclamped value itself
     gf = cu._husl_to_rgb(hsl, dtype=np.float64)
-    assert np.abs(gf - f).max() < 5e-4
+    assert (np.abs(gf - f)[sane] / np.maximum(1.0, np.abs(f[sane]))).max() < 5e-4
 
 
 def test_rgba_device_arrays_are_premultiplied_on_load(cu):
