@@ -601,3 +601,28 @@ def test_rgba_device_arrays_are_premultiplied_on_load(cu):
     sat = ref8[:, 1] > 0.1
     assert hue_diff(got8[sat, 0], ref8[sat, 0]).max() < TOL
     assert np.abs(got8[:, 1:] - ref8[:, 1:]).max() < TOL
+
+
+def test_lut_mode_with_other_table_sizes(cu):
+    """make_lookup_tables takes the table sizes as arguments (reference
+    make_lookup_tables:4-6); the device generator and the LUT kernels follow."""
+    rng = np.random.default_rng(17)
+    rgb = rng.integers(0, 256, (50000, 3), dtype=np.uint8)
+    seg, nh, nl = 256, 300, 200
+    cu.lut_generate(seg, nh, nl)
+    t = cu.lut_download()
+    lt, st, th = orc.light_table(seg)
+    ct, hs, ls = orc.chroma_table(nh, nl)
+    assert t["light"].shape == (3 * seg,) and t["chroma"].shape == (nh, nl)
+    assert np.array_equal(t["light"], lt) and np.array_equal(t["y_idx_step"], st) and np.array_equal(t["y_thresh"], th)
+    assert t["h_idx_step"] == hs and t["l_idx_step"] == ls
+    assert np.abs(t["chroma"].astype(int) - ct.astype(int)).max() <= 1
+    assert np.count_nonzero(t["chroma"] != ct) <= 16
+    # with identical (oracle-made) tables the kernel is bit-exact for any size
+    cu.lut_upload(lt, st, th, ct, hs, ls, orc.linear_table6())
+    for mode, variant in (("lut", "lut"), ("lut_interp", "lut_interp")):
+        got = cu._rgb_to_husl(rgb, mode=mode)
+        want = orc.simd_rgb_to_husl(rgb, variant, tables=(lt, st, th, ct, hs, ls))
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    with pytest.raises(cu.CudaError):
+        cu._rgb_to_husl(rgb.astype(np.float32) / 255, mode="lut")      # LUT modes take uint8, like _simd.c
