@@ -235,4 +235,117 @@ k_edit_any(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, long long 
     }
 }
 
+// ---------------------------------------------------------------------------------
+// channels-first images (torch / vision layout): R[], G[], B[] uint8 planes <-> H[], S[], L[] planes
+// ---------------------------------------------------------------------------------
+// Every access is one natural vector per lane per plane (a 32-bit word = 4 pixels
+// of a uint8 plane, 16 / 32 bytes of a float / double plane): no staging at all.
+template <typename TOut, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_fwd_chw(const uint32_t *__restrict__ R, const uint32_t *__restrict__ G, const uint32_t *__restrict__ B,
+          TOut *__restrict__ H, TOut *__restrict__ S, TOut *__restrict__ L, long long n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    fill_table(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane8 = lane * 8;
+    const long long nw = (long long)gridDim.x * (BLOCK / 32);
+    long long tile = (long long)blockIdx.x * (BLOCK / 32) + warp;
+    uint32_t wr = 0, wg = 0, wb = 0;
+    if (tile < n_tiles) { const long long o = tile * 32 + lane; wr = ldg_u32(R + o); wg = ldg_u32(G + o); wb = ldg_u32(B + o); }
+    for (; tile < n_tiles; tile += nw) {
+        uint32_t nr = 0, ng = 0, nb = 0;
+        if (tile + nw < n_tiles) { const long long o = (tile + nw) * 32 + lane; nr = ldg_u32(R + o); ng = ldg_u32(G + o); nb = ldg_u32(B + o); }
+        LinPx px[4];
+        float2 v;
+#define CHW_PX(J)                                                                  \
+        v = lut_lin<J>(smem, wr, lane8); px[J].hr = v.x; px[J].lr = v.y;           \
+        v = lut_lin<J>(smem, wg, lane8); px[J].hg = v.x; px[J].lg = v.y;           \
+        v = lut_lin<J>(smem, wb, lane8); px[J].hb = v.x; px[J].lb = v.y;
+        CHW_PX(0) CHW_PX(1) CHW_PX(2) CHW_PX(3)
+#undef CHW_PX
+        float h[4], s[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) husl_from_diff<true>(make_diff(px[j]), h[j], s[j], l[j]);
+        const long long o = tile * TILE_PX + lane * 4;
+        if (sizeof(TOut) == 4) {
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(H) + o) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(S) + o) = make_float4(s[0], s[1], s[2], s[3]);
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(L) + o) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+            stg_f64x4(reinterpret_cast<double *>(H) + o, h[0], h[1], h[2], h[3]);
+            stg_f64x4(reinterpret_cast<double *>(S) + o, s[0], s[1], s[2], s[3]);
+            stg_f64x4(reinterpret_cast<double *>(L) + o, l[0], l[1], l[2], l[3]);
+        }
+        wr = nr; wg = ng; wb = nb;
+    }
+}
+
+template <typename TIn, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_inv_chw(const TIn *__restrict__ H, const TIn *__restrict__ S, const TIn *__restrict__ L,
+          uint32_t *__restrict__ R, uint32_t *__restrict__ G, uint32_t *__restrict__ B, long long n_tiles) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long nw = (long long)gridDim.x * (BLOCK / 32);
+    for (long long tile = (long long)blockIdx.x * (BLOCK / 32) + warp; tile < n_tiles; tile += nw) {
+        const long long o = tile * TILE_PX + lane * 4;
+        float h[4], s[4], l[4];
+        if (sizeof(TIn) == 4) {
+            const float4 a = __ldcs(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(H) + o));
+            const float4 b = __ldcs(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(S) + o));
+            const float4 c = __ldcs(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(L) + o));
+            h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w;
+            s[0] = b.x; s[1] = b.y; s[2] = b.z; s[3] = b.w;
+            l[0] = c.x; l[1] = c.y; l[2] = c.z; l[3] = c.w;
+        } else {
+            double d[12];
+            ldg_f64x4(reinterpret_cast<const double *>(H) + o, d[0], d[1], d[2], d[3]);
+            ldg_f64x4(reinterpret_cast<const double *>(S) + o, d[4], d[5], d[6], d[7]);
+            ldg_f64x4(reinterpret_cast<const double *>(L) + o, d[8], d[9], d[10], d[11]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { h[j] = (float)d[j]; s[j] = (float)d[4 + j]; l[j] = (float)d[8 + j]; }
+        }
+        uint32_t q[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float r, g, b;
+            rgb255_from_husl(h[j], s[j], l[j], r, g, b);
+            q[3 * j] = round_u8_bits(r); q[3 * j + 1] = round_u8_bits(g); q[3 * j + 2] = round_u8_bits(b);
+        }
+        // plane words: byte j of a word = pixel j of this lane
+        const long long w = tile * 32 + lane;
+        R[w] = __byte_perm(__byte_perm(q[0], q[3], 0x0040), __byte_perm(q[6], q[9], 0x0040), 0x5410);
+        G[w] = __byte_perm(__byte_perm(q[1], q[4], 0x0040), __byte_perm(q[7], q[10], 0x0040), 0x5410);
+        B[w] = __byte_perm(__byte_perm(q[2], q[5], 0x0040), __byte_perm(q[8], q[11], 0x0040), 0x5410);
+    }
+}
+
+// tails / unaligned planes, one pixel per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fwd_chw_any(const uint8_t *__restrict__ R, const uint8_t *__restrict__ G, const uint8_t *__restrict__ B,
+              T *__restrict__ H, T *__restrict__ S, T *__restrict__ L, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float2 r = g_lin_tab[R[i]], g = g_lin_tab[G[i]], b = g_lin_tab[B[i]];
+        LinPx p;
+        p.hr = r.x; p.lr = r.y; p.hg = g.x; p.lg = g.y; p.hb = b.x; p.lb = b.y;
+        float h, s, l;
+        husl_from_diff<true>(make_diff(p), h, s, l);
+        H[i] = (T)h; S[i] = (T)s; L[i] = (T)l;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_inv_chw_any(const T *__restrict__ H, const T *__restrict__ S, const T *__restrict__ L,
+              uint8_t *__restrict__ R, uint8_t *__restrict__ G, uint8_t *__restrict__ B, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float r, g, b;
+        rgb255_from_husl((float)H[i], (float)S[i], (float)L[i], r, g, b);
+        R[i] = (uint8_t)(round_u8_bits(r) & 0xFF);
+        G[i] = (uint8_t)(round_u8_bits(g) & 0xFF);
+        B[i] = (uint8_t)(round_u8_bits(b) & 0xFF);
+    }
+}
+
 }  // namespace husl

@@ -166,6 +166,8 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_edit<512, 2>, TAB_BYTES + 16 * 384))) return rc;
+    if ((rc = set_smem(k_fwd_chw<float, 512, 2>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_fwd_chw<double, 512, 2>, TAB_BYTES))) return rc;
 
     c.attr_set = true;
     return NPHUSL_OK;
@@ -685,6 +687,85 @@ int nphusl_cuda_husl_planar_to_rgb(const void *h, const void *s, const void *l, 
             k_inv_planar_any<double><<<grid, 256, 0, st>>>((const double *)h + done, (const double *)s + done, (const double *)l + done, op, rest);
         g_launches++;
         if ((rc = check_launch("k_inv_planar_any"))) return rc;
+    }
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_rgb_planes_to_husl_planes(const void *r, const void *g, const void *b,
+                                          void *h, void *s, void *l, int hsl_dtype,
+                                          size_t n_pixels, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!r || !g || !b || !h || !s || !l) return fail(NPHUSL_ERR_ARG, "rgb_planes_to_husl_planes: null buffer");
+    if (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) return fail(NPHUSL_ERR_ARG, "rgb_planes_to_husl_planes: planes must be f32/f64");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)n_pixels;
+    const size_t va = hsl_dtype == NPHUSL_F32 ? 16 : 32;
+    long long done = 0;
+    if (aligned(r, 4) && aligned(g, 4) && aligned(b, 4) && aligned(h, va) && aligned(s, va) && aligned(l, va) && n >= TILE_PX) {
+        if ((rc = set_attrs(*c))) return rc;
+        const long long tiles = n / TILE_PX;
+        const int grid = grid_for(tiles, 16, c->sms * 2);
+        if (hsl_dtype == NPHUSL_F32)
+            k_fwd_chw<float, 512, 2><<<grid, 512, TAB_BYTES, st>>>((const uint32_t *)r, (const uint32_t *)g, (const uint32_t *)b, (float *)h, (float *)s, (float *)l, tiles);
+        else
+            k_fwd_chw<double, 512, 2><<<grid, 512, TAB_BYTES, st>>>((const uint32_t *)r, (const uint32_t *)g, (const uint32_t *)b, (double *)h, (double *)s, (double *)l, tiles);
+        g_launches++;
+        if ((rc = check_launch("k_fwd_chw"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    if (n > done) {
+        const long long rest = n - done;
+        const int grid = grid_for(rest, 256, c->sms * 8);
+        const uint8_t *pr = (const uint8_t *)r + done, *pg = (const uint8_t *)g + done, *pb = (const uint8_t *)b + done;
+        if (hsl_dtype == NPHUSL_F32)
+            k_fwd_chw_any<float><<<grid, 256, 0, st>>>(pr, pg, pb, (float *)h + done, (float *)s + done, (float *)l + done, rest);
+        else
+            k_fwd_chw_any<double><<<grid, 256, 0, st>>>(pr, pg, pb, (double *)h + done, (double *)s + done, (double *)l + done, rest);
+        g_launches++;
+        if ((rc = check_launch("k_fwd_chw_any"))) return rc;
+    }
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_husl_planes_to_rgb_planes(const void *h, const void *s, const void *l, int hsl_dtype,
+                                          void *r, void *g, void *b,
+                                          size_t n_pixels, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!r || !g || !b || !h || !s || !l) return fail(NPHUSL_ERR_ARG, "husl_planes_to_rgb_planes: null buffer");
+    if (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) return fail(NPHUSL_ERR_ARG, "husl_planes_to_rgb_planes: planes must be f32/f64");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)n_pixels;
+    const size_t va = hsl_dtype == NPHUSL_F32 ? 16 : 32;
+    long long done = 0;
+    if (aligned(r, 4) && aligned(g, 4) && aligned(b, 4) && aligned(h, va) && aligned(s, va) && aligned(l, va) && n >= TILE_PX) {
+        const long long tiles = n / TILE_PX;
+        const int grid = grid_for(tiles, 12, c->sms * 4);
+        if (hsl_dtype == NPHUSL_F32)
+            k_inv_chw<float, 384, 4><<<grid, 384, 0, st>>>((const float *)h, (const float *)s, (const float *)l, (uint32_t *)r, (uint32_t *)g, (uint32_t *)b, tiles);
+        else
+            k_inv_chw<double, 384, 4><<<grid, 384, 0, st>>>((const double *)h, (const double *)s, (const double *)l, (uint32_t *)r, (uint32_t *)g, (uint32_t *)b, tiles);
+        g_launches++;
+        if ((rc = check_launch("k_inv_chw"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    if (n > done) {
+        const long long rest = n - done;
+        const int grid = grid_for(rest, 256, c->sms * 8);
+        uint8_t *pr = (uint8_t *)r + done, *pg = (uint8_t *)g + done, *pb = (uint8_t *)b + done;
+        if (hsl_dtype == NPHUSL_F32)
+            k_inv_chw_any<float><<<grid, 256, 0, st>>>((const float *)h + done, (const float *)s + done, (const float *)l + done, pr, pg, pb, rest);
+        else
+            k_inv_chw_any<double><<<grid, 256, 0, st>>>((const double *)h + done, (const double *)s + done, (const double *)l + done, pr, pg, pb, rest);
+        g_launches++;
+        if ((rc = check_launch("k_inv_chw_any"))) return rc;
     }
     return NPHUSL_OK;
 }

@@ -68,6 +68,8 @@ SIGNATURES = {
     "nphusl_cuda_husl_to_rgb": (_i, [_vp, _i, _i, _vp, _i, _i, _sz, _i, _vp]),
     "nphusl_cuda_rgb_to_husl_planar": (_i, [_vp, _vp, _vp, _vp, _i, _sz, _i, _vp]),
     "nphusl_cuda_husl_planar_to_rgb": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
+    "nphusl_cuda_rgb_planes_to_husl_planes": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _sz, _i, _vp]),
+    "nphusl_cuda_husl_planes_to_rgb_planes": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "nphusl_cuda_rgb_edit_rgb": (_i, [_vp, _i, _vp, _i, _sz, _vp, _i, _vp]),
     "nphusl_cuda_lut_generate": (_i, [_i, _i, _i, _i]),
     "nphusl_cuda_lut_upload": (_i, [_i, _u16p, _i, _dp, _dp, _u16p, _i, _i,
@@ -562,11 +564,13 @@ def _to_device(arr, device, stream):
     return DeviceArray.from_host(np.ascontiguousarray(arr), device, stream)
 
 
-def rgb_to_husl_planar(rgb, out=None, dtype=np.float32, stream=None, device=None):
-    """uint8 RGB ``(..., 3)`` -> planar HUSL ``(3, ...)``: ``out[0]`` is the hue
-    plane, ``out[1]`` saturation, ``out[2]`` lightness (what callers slice out
-    of the interleaved array anyway, README.md:77-98).  Device arrays stay on
-    the device; a host array is uploaded, converted and the planes downloaded."""
+def rgb_to_husl_planar(rgb, out=None, dtype=np.float32, stream=None, device=None, channels_first=False):
+    """uint8 RGB -> planar HUSL ``(3, ...)``: ``out[0]`` is the hue plane,
+    ``out[1]`` saturation, ``out[2]`` lightness (what callers slice out of the
+    interleaved array anyway, README.md:77-98).  ``rgb`` is ``(..., 3)``
+    interleaved, or ``(3, ...)`` planes with ``channels_first=True`` (the torch /
+    vision image layout).  Device arrays stay on the device; a host array is
+    uploaded, converted and the planes downloaded."""
     lib = load()
     host_in = not _is_device(rgb)
     dev = device
@@ -574,11 +578,14 @@ def rgb_to_husl_planar(rgb, out=None, dtype=np.float32, stream=None, device=None
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
         dev = _default_device if dev is None else dev
     src = _describe_device(_to_device(rgb, dev, stream), "rgb")
-    if src.dtype != np.uint8 or not src.shape or src.shape[-1] != 3:
-        raise ValueError("planar conversion takes uint8 RGB (..., 3), got {} {}".format(src.dtype, src.shape))
+    ok = src.shape and (src.shape[0] == 3 if channels_first else src.shape[-1] == 3)
+    if src.dtype != np.uint8 or not ok:
+        raise ValueError("planar conversion takes uint8 RGB {}, got {} {}".format(
+            "(3, ...)" if channels_first else "(..., 3)", src.dtype, src.shape))
     dev = _pick_device(dev, src)
-    shape = (3,) + tuple(src.shape[:-1])
-    n = int(np.prod(src.shape[:-1]))
+    lead = tuple(src.shape[1:]) if channels_first else tuple(src.shape[:-1])
+    shape = (3,) + lead
+    n = int(np.prod(lead))
     if out is not None and _is_device(out):
         dst = _describe_out(out, shape, dtype, _FLOATS, "out")
         ret = out
@@ -587,16 +594,22 @@ def rgb_to_husl_planar(rgb, out=None, dtype=np.float32, stream=None, device=None
         dst = _describe_device(d, "out")
         ret = d
     plane = n * dst.dtype.itemsize
-    _check(lib.nphusl_cuda_rgb_to_husl_planar(src.ptr, dst.ptr, dst.ptr + plane, dst.ptr + 2 * plane, _DT[dst.dtype],
-                                              n, dev, _stream_ptr(stream)), "rgb_to_husl_planar")
+    if channels_first:
+        _check(lib.nphusl_cuda_rgb_planes_to_husl_planes(src.ptr, src.ptr + n, src.ptr + 2 * n,
+                                                         dst.ptr, dst.ptr + plane, dst.ptr + 2 * plane, _DT[dst.dtype],
+                                                         n, dev, _stream_ptr(stream)), "rgb_planes_to_husl_planes")
+    else:
+        _check(lib.nphusl_cuda_rgb_to_husl_planar(src.ptr, dst.ptr, dst.ptr + plane, dst.ptr + 2 * plane, _DT[dst.dtype],
+                                                  n, dev, _stream_ptr(stream)), "rgb_to_husl_planar")
     if host_in or (out is not None and not _is_device(out)):
         synchronize(dev, stream)
         return ret.copy_to_host(out)
     return ret
 
 
-def husl_planar_to_rgb(hsl, out=None, stream=None, device=None):
-    """planar HUSL ``(3, ...)`` float32/float64 -> uint8 RGB ``(..., 3)``."""
+def husl_planar_to_rgb(hsl, out=None, stream=None, device=None, channels_first=False):
+    """planar HUSL ``(3, ...)`` float32/float64 -> uint8 RGB, ``(..., 3)``
+    interleaved or ``(3, ...)`` planes with ``channels_first=True``."""
     lib = load()
     host_in = not _is_device(hsl)
     dev = device
@@ -609,7 +622,7 @@ def husl_planar_to_rgb(hsl, out=None, stream=None, device=None):
     if src.dtype not in _FLOATS or not src.shape or src.shape[0] != 3:
         raise ValueError("expected planar HUSL (3, ...), float32/float64; got {} {}".format(src.dtype, src.shape))
     dev = _pick_device(dev, src)
-    shape = tuple(src.shape[1:]) + (3,)
+    shape = ((3,) + tuple(src.shape[1:])) if channels_first else (tuple(src.shape[1:]) + (3,))
     n = int(np.prod(src.shape[1:]))
     if out is not None and _is_device(out):
         dst = _describe_out(out, shape, np.uint8, (np.dtype(np.uint8),), "out")
@@ -619,8 +632,13 @@ def husl_planar_to_rgb(hsl, out=None, stream=None, device=None):
         dst = _describe_device(d, "out")
         ret = d
     plane = n * src.dtype.itemsize
-    _check(lib.nphusl_cuda_husl_planar_to_rgb(src.ptr, src.ptr + plane, src.ptr + 2 * plane, _DT[src.dtype],
-                                              dst.ptr, n, dev, _stream_ptr(stream)), "husl_planar_to_rgb")
+    if channels_first:
+        _check(lib.nphusl_cuda_husl_planes_to_rgb_planes(src.ptr, src.ptr + plane, src.ptr + 2 * plane, _DT[src.dtype],
+                                                         dst.ptr, dst.ptr + n, dst.ptr + 2 * n,
+                                                         n, dev, _stream_ptr(stream)), "husl_planes_to_rgb_planes")
+    else:
+        _check(lib.nphusl_cuda_husl_planar_to_rgb(src.ptr, src.ptr + plane, src.ptr + 2 * plane, _DT[src.dtype],
+                                                  dst.ptr, n, dev, _stream_ptr(stream)), "husl_planar_to_rgb")
     if host_in or (out is not None and not _is_device(out)):
         synchronize(dev, stream)
         return ret.copy_to_host(out)

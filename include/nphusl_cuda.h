@@ -123,6 +123,15 @@ int nphusl_cuda_rgb_to_husl_planar(const void *rgb, void *h, void *s, void *l, i
 int nphusl_cuda_husl_planar_to_rgb(const void *h, const void *s, const void *l, int hsl_dtype,
                                    void *rgb, size_t n_pixels, int device, void *stream);
 
+/* Channels-first images (torch / vision layout): separate uint8 planes R[], G[],
+ * B[] on the RGB side as well.  DEVICE pointers only. */
+int nphusl_cuda_rgb_planes_to_husl_planes(const void *r, const void *g, const void *b,
+                                          void *h, void *s, void *l, int hsl_dtype,
+                                          size_t n_pixels, int device, void *stream);
+int nphusl_cuda_husl_planes_to_rgb_planes(const void *h, const void *s, const void *l, int hsl_dtype,
+                                          void *r, void *g, void *b,
+                                          size_t n_pixels, int device, void *stream);
+
 /* Fused to_husl -> select -> edit -> to_rgb on uint8 pixels (the pipeline of
  * README.md:77-98 in one pass, 6 bytes of memory traffic per pixel).
  * A pixel is selected when H lies on the arc [h_lo, h_hi] (h_lo > h_hi: the arc

@@ -626,3 +626,26 @@ def test_lut_mode_with_other_table_sizes(cu):
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
     with pytest.raises(cu.CudaError):
         cu._rgb_to_husl(rgb.astype(np.float32) / 255, mode="lut")      # LUT modes take uint8, like _simd.c
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_channels_first_images(cu, dtype):
+    """(3, H, W) uint8 planes (torch / vision layout) <-> (3, H, W) HUSL planes:
+    same values as the interleaved path, exact round trip, ragged sizes."""
+    rng = np.random.default_rng(18)
+    for hw in ((7, 13), (37, 129), (1080, 1920)):
+        chw = rng.integers(0, 256, (3,) + hw, dtype=np.uint8)
+        hwc = np.ascontiguousarray(np.moveaxis(chw, 0, -1))
+        planes = cu.rgb_to_husl_planar(chw, dtype=dtype, channels_first=True)
+        assert planes.shape == (3,) + hw and planes.dtype == dtype
+        assert np.array_equal(planes, np.moveaxis(cu._rgb_to_husl(hwc, dtype=dtype), -1, 0))
+        back = cu.husl_planar_to_rgb(planes, channels_first=True)
+        assert back.shape == chw.shape and np.array_equal(back, chw)
+    torch = pytest.importorskip("torch")
+    t = torch.from_numpy(chw).cuda()
+    out = torch.empty(chw.shape, dtype=torch.float32 if dtype == np.float32 else torch.float64, device="cuda")
+    cu.rgb_to_husl_planar(t, out=out, channels_first=True)
+    back = torch.empty_like(t)
+    cu.husl_planar_to_rgb(out, out=back, channels_first=True)
+    torch.cuda.synchronize()
+    assert torch.equal(back, t)
