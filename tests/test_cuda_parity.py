@@ -649,3 +649,19 @@ def test_channels_first_images(cu, dtype):
     cu.husl_planar_to_rgb(out, out=back, channels_first=True)
     torch.cuda.synchronize()
     assert torch.equal(back, t)
+
+
+def test_cube_through_planar_chw_and_fused_paths(cu, cube, cube_oracle):
+    """All 2^24 colours through the other layouts: planar HUSL, channels-first
+    planes and the fused identity edit must reproduce the interleaved result /
+    the input exactly."""
+    inter = cu._rgb_to_husl(cube, dtype=np.float32)
+    planar = cu.rgb_to_husl_planar(cube, dtype=np.float32)
+    assert np.array_equal(planar, np.moveaxis(inter, -1, 0))
+    assert np.array_equal(cu.husl_planar_to_rgb(planar), cube)
+    chw = np.ascontiguousarray(np.moveaxis(cube, -1, 0))
+    p2 = cu.rgb_to_husl_planar(chw, dtype=np.float32, channels_first=True)
+    assert np.array_equal(p2, planar)
+    assert np.array_equal(cu.husl_planar_to_rgb(p2, channels_first=True), chw)
+    assert np.array_equal(cu.edit_rgb(cube), cube)
+    check_husl(np.moveaxis(planar, 0, -1), cube_oracle, ~_grey(cube))
