@@ -64,8 +64,12 @@ __device__ __forceinline__ float mufu_cos(float x) {
 // ---- hue: atan2 in degrees, [0, 360] -------------------------------------------
 // reference: H = degrees(arctan2(V, U)), +360 if negative (nphusl.py:231-239,
 // _cython_opt.pyx:75-79).  U, V share the positive factor 13L/D, so the hue is
-// atan2(Nv, Nu).  atan2(0,0) = 0 like libm.
-__device__ __forceinline__ float hue_deg(float nv, float nu) {
+// atan2(Nv, Nu).  Exact greys have Nu = Nv = 0: the float64 reference evaluates
+// atan2 of its own rounding noise there and lands within 2.4 degrees of the hue
+// of white (17.6 .. 21.1 over the 255 non-black greys; _simd.c:79 hard-codes
+// 19.916 for white); `grey_hue` is what to return instead -- WHITE_HUE, or 0 for
+// black where the reference's U = V = 0 gives atan2(0, 0) = 0.
+__device__ __forceinline__ float hue_deg(float nv, float nu, float grey_hue) {
     const float ax = fabsf(nu), ay = fabsf(nv);
     const float a = fminf(ax, ay);
     const float b = fmaxf(fmaxf(ax, ay), 1e-37f);
@@ -83,7 +87,7 @@ __device__ __forceinline__ float hue_deg(float nv, float nu) {
     r = (ay > ax) ? 90.0f - r : r;         // [0, 90]
     r = (nu < 0.0f) ? 180.0f - r : r;      // [0, 180]
     r = (nv < 0.0f) ? 360.0f - r : r;      // [0, 360]
-    return r;
+    return (fmaxf(ax, ay) == 0.0f) ? grey_hue : r;
 }
 
 // ---- sRGB linearisation of a FLOAT channel ------------------------------------------
@@ -129,9 +133,11 @@ __device__ __forceinline__ Diff make_diff(const LinPx &p) {
     return d;
 }
 
-// IS_U8: lightness clamps can only fire for pure black / pure white (nearest
-// neighbours (0,0,1) -> L = 0.0198, (255,255,254) -> L = 99.975), where the
-// float64 path yields H = 0 / H = WHITE_HUE (reference _simd.c:79-81, 205-212).
+// IS_U8 (kept for the callers' documentation value): with uint8 input the
+// lightness clamps can only fire for pure black / pure white (nearest neighbours
+// (0,0,1) -> L = 0.0198, (255,255,254) -> L = 99.975), where the float64 path
+// yields H = 0 / H = WHITE_HUE (reference _simd.c:79-81, 205-212) -- both are
+// exact greys and get their hue from hue_deg's grey rule.
 template <bool IS_U8>
 __device__ __forceinline__ void husl_from_diff(const Diff &d, float &H, float &S, float &L) {
     const float t = fmaf(Y_DR, d.dr, Y_DB * d.db);
@@ -141,7 +147,7 @@ __device__ __forceinline__ void husl_from_diff(const Diff &d, float &H, float &S
     const float D = fmaf(D_S, d.g, Dp);                    // X + 15Y + 3Z
     const float nu = fmaf(U_DR, d.dr, U_DB * d.db);        // 4X - REF_U*D
     const float nv = fmaf(V_DR, d.dr, V_DB * d.db);        // 9Y - REF_V*D
-    float h = hue_deg(nv, nu);
+    float h = hue_deg(nv, nu, (d.g > 0.0f) ? WHITE_HUE : 0.0f);
 
     // saturation: channel-hits-0 and channel-hits-1 gamut faces
     const float mnd = fminf(fminf(d.dr, d.db), 0.0f);      // min(r,g,b) - g
@@ -164,18 +170,13 @@ __device__ __forceinline__ void husl_from_diff(const Diff &d, float &H, float &S
     s = (white || black) ? 0.0f : s;
     l = white ? 100.0f : l;
     l = black ? 0.0f : l;
-    if (IS_U8) {
-        h = white ? WHITE_HUE : h;
-    } else {
-        h = (white && nu == 0.0f && nv == 0.0f) ? WHITE_HUE : h;
-    }
     H = h; S = s; L = l;
 }
 
 __device__ __forceinline__ float hue_from_diff(const Diff &d) {
     const float nu = fmaf(U_DR, d.dr, U_DB * d.db);
     const float nv = fmaf(V_DR, d.dr, V_DB * d.db);
-    return hue_deg(nv, nu);
+    return hue_deg(nv, nu, (d.g > 0.0f) ? WHITE_HUE : 0.0f);
 }
 
 // ---- inverse core --------------------------------------------------------------

@@ -51,9 +51,12 @@ def test_to_husl_golden(cu, golden, dtype):
     got = cu._rgb_to_husl(rgb, dtype=dtype)
     assert got.dtype == dtype and got.shape == ref.shape
     check_husl(got, ref, ~_grey(rgb))
-    # greys: S ~ 0 and the same lightness
+    # greys: S ~ 0, the same lightness, and a hue next to the reference's (which is atan2 of
+    # float64 rounding noise there: 17.6 .. 21.1 degrees; reference tests allow 5 degrees
+    # at low saturation, tests/test.py:130,147)
     g = _grey(rgb)
     assert np.abs(got[g, 1]).max() < TOL
+    assert hue_diff(got[g, 0], ref[g, 0]).max() < 2.5
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
