@@ -68,6 +68,13 @@ def derive():
     c["D_DR"], c["D_DB"], c["D_S"] = Df[0], Df[2], Df.sum()
     c["U_DR"], c["U_DB"], c["U_S"] = Nu[0], Nu[2], Nu.sum()
     c["V_DR"], c["V_DB"], c["V_S"] = Nv[0], Nv[2], Nv.sum()
+    # exact greys: the float64 reference evaluates atan2 of the residue of its white point,
+    # (U_S, V_S)*g ~ 1e-14, plus rounding noise, and lands at 17.6 .. 21.1 degrees (19.916 for
+    # white).  The kernels add a vanishing g-term pointing exactly at WHITE_HUE instead: greys
+    # get the hue of white, black (g = 0) gets atan2(0, 0) = 0, and any pixel with a real
+    # colour difference is unaffected (1e-13 is far below float32 resolution of Nu, Nv there).
+    c["GREY_U"] = 1e-13 * np.cos(np.radians(WHITE_HUE))
+    c["GREY_V"] = 1e-13 * np.sin(np.radians(WHITE_HUE))
     c["Y_HI"] = ((L_MAX + 16) / 116) ** 3        # L > 99.99  <=>  Y > Y_HI
     c["Y_LO"] = L_MIN / KAPPA                    # L < 0.01   <=>  Y < Y_LO
     # inverse: lin_i = Y * A_i(u', v') / (4 v'),  A_i = AU_i u' + AV_i v' + A0_i

@@ -64,12 +64,9 @@ __device__ __forceinline__ float mufu_cos(float x) {
 // ---- hue: atan2 in degrees, [0, 360] -------------------------------------------
 // reference: H = degrees(arctan2(V, U)), +360 if negative (nphusl.py:231-239,
 // _cython_opt.pyx:75-79).  U, V share the positive factor 13L/D, so the hue is
-// atan2(Nv, Nu).  Exact greys have Nu = Nv = 0: the float64 reference evaluates
-// atan2 of its own rounding noise there and lands within 2.4 degrees of the hue
-// of white (17.6 .. 21.1 over the 255 non-black greys; _simd.c:79 hard-codes
-// 19.916 for white); `grey_hue` is what to return instead -- WHITE_HUE, or 0 for
-// black where the reference's U = V = 0 gives atan2(0, 0) = 0.
-__device__ __forceinline__ float hue_deg(float nv, float nu, float grey_hue) {
+// atan2(Nv, Nu).  atan2(0,0) = 0 like libm.  (Exact greys never arrive here with
+// Nu = Nv = 0 unless they are black: see GREY_U / GREY_V in the callers.)
+__device__ __forceinline__ float hue_deg(float nv, float nu) {
     const float ax = fabsf(nu), ay = fabsf(nv);
     const float a = fminf(ax, ay);
     const float b = fmaxf(fmaxf(ax, ay), 1e-37f);
@@ -87,7 +84,7 @@ __device__ __forceinline__ float hue_deg(float nv, float nu, float grey_hue) {
     r = (ay > ax) ? 90.0f - r : r;         // [0, 90]
     r = (nu < 0.0f) ? 180.0f - r : r;      // [0, 180]
     r = (nv < 0.0f) ? 360.0f - r : r;      // [0, 360]
-    return (fmaxf(ax, ay) == 0.0f) ? grey_hue : r;
+    return r;
 }
 
 // ---- sRGB linearisation of a FLOAT channel ------------------------------------------
@@ -145,9 +142,11 @@ __device__ __forceinline__ void husl_from_diff(const Diff &d, float &H, float &S
     const float omY = fmaf(Y_S, d.cg, ONE_M_SY - t);       // 1 - Y, cancellation-free
     const float Dp = fmaf(D_DR, d.dr, D_DB * d.db);
     const float D = fmaf(D_S, d.g, Dp);                    // X + 15Y + 3Z
-    const float nu = fmaf(U_DR, d.dr, U_DB * d.db);        // 4X - REF_U*D
-    const float nv = fmaf(V_DR, d.dr, V_DB * d.db);        // 9Y - REF_V*D
-    float h = hue_deg(nv, nu, (d.g > 0.0f) ? WHITE_HUE : 0.0f);
+    // 4X - REF_U*D and 9Y - REF_V*D; the vanishing g-term gives exact greys the
+    // reference-like hue (WHITE_HUE; 0 for black) without a select (gen_coeffs.py)
+    const float nu = fmaf(GREY_U, d.g, fmaf(U_DR, d.dr, U_DB * d.db));
+    const float nv = fmaf(GREY_V, d.g, fmaf(V_DR, d.dr, V_DB * d.db));
+    const float h = hue_deg(nv, nu);
 
     // saturation: channel-hits-0 and channel-hits-1 gamut faces
     const float mnd = fminf(fminf(d.dr, d.db), 0.0f);      // min(r,g,b) - g
@@ -174,9 +173,9 @@ __device__ __forceinline__ void husl_from_diff(const Diff &d, float &H, float &S
 }
 
 __device__ __forceinline__ float hue_from_diff(const Diff &d) {
-    const float nu = fmaf(U_DR, d.dr, U_DB * d.db);
-    const float nv = fmaf(V_DR, d.dr, V_DB * d.db);
-    return hue_deg(nv, nu, (d.g > 0.0f) ? WHITE_HUE : 0.0f);
+    const float nu = fmaf(GREY_U, d.g, fmaf(U_DR, d.dr, U_DB * d.db));
+    const float nv = fmaf(GREY_V, d.g, fmaf(V_DR, d.dr, V_DB * d.db));
+    return hue_deg(nv, nu);
 }
 
 // ---- inverse core --------------------------------------------------------------
