@@ -348,4 +348,59 @@ k_inv_chw_any(const T *__restrict__ H, const T *__restrict__ S, const T *__restr
     }
 }
 
+// fused edit on channels-first uint8 planes (what nvJPEG / video decoders hand out)
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_edit_chw(const uint32_t *__restrict__ R, const uint32_t *__restrict__ G, const uint32_t *__restrict__ B,
+           uint32_t *__restrict__ Ro, uint32_t *__restrict__ Go, uint32_t *__restrict__ Bo,
+           long long n_tiles, const nphusl_edit e) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    fill_table(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane8 = lane * 8;
+    const long long nw = (long long)gridDim.x * (BLOCK / 32);
+    for (long long tile = (long long)blockIdx.x * (BLOCK / 32) + warp; tile < n_tiles; tile += nw) {
+        const long long w = tile * 32 + lane;
+        const uint32_t wr = ldg_u32(R + w), wg = ldg_u32(G + w), wb = ldg_u32(B + w);
+        LinPx px[4];
+        float2 v;
+#define CHW_PX(J)                                                                  \
+        v = lut_lin<J>(smem, wr, lane8); px[J].hr = v.x; px[J].lr = v.y;           \
+        v = lut_lin<J>(smem, wg, lane8); px[J].hg = v.x; px[J].lg = v.y;           \
+        v = lut_lin<J>(smem, wb, lane8); px[J].hb = v.x; px[J].lb = v.y;
+        CHW_PX(0) CHW_PX(1) CHW_PX(2) CHW_PX(3)
+#undef CHW_PX
+        uint32_t q[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float h, s, l, r, g, b;
+            husl_from_diff<true>(make_diff(px[j]), h, s, l);
+            apply_edit(e, h, s, l);
+            rgb255_from_husl(h, s, l, r, g, b);
+            q[3 * j] = round_u8_bits(r); q[3 * j + 1] = round_u8_bits(g); q[3 * j + 2] = round_u8_bits(b);
+        }
+        Ro[w] = __byte_perm(__byte_perm(q[0], q[3], 0x0040), __byte_perm(q[6], q[9], 0x0040), 0x5410);
+        Go[w] = __byte_perm(__byte_perm(q[1], q[4], 0x0040), __byte_perm(q[7], q[10], 0x0040), 0x5410);
+        Bo[w] = __byte_perm(__byte_perm(q[2], q[5], 0x0040), __byte_perm(q[8], q[11], 0x0040), 0x5410);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_edit_chw_any(const uint8_t *__restrict__ R, const uint8_t *__restrict__ G, const uint8_t *__restrict__ B,
+               uint8_t *__restrict__ Ro, uint8_t *__restrict__ Go, uint8_t *__restrict__ Bo, long long n, const nphusl_edit e) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float2 r = g_lin_tab[R[i]], g = g_lin_tab[G[i]], b = g_lin_tab[B[i]];
+        LinPx p;
+        p.hr = r.x; p.lr = r.y; p.hg = g.x; p.lg = g.y; p.hb = b.x; p.lb = b.y;
+        float h, s, l, fr, fg, fb;
+        husl_from_diff<true>(make_diff(p), h, s, l);
+        apply_edit(e, h, s, l);
+        rgb255_from_husl(h, s, l, fr, fg, fb);
+        Ro[i] = (uint8_t)(round_u8_bits(fr) & 0xFF);
+        Go[i] = (uint8_t)(round_u8_bits(fg) & 0xFF);
+        Bo[i] = (uint8_t)(round_u8_bits(fb) & 0xFF);
+    }
+}
+
 }  // namespace husl

@@ -166,6 +166,7 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_edit<512, 2>, TAB_BYTES + 16 * 384))) return rc;
+    if ((rc = set_smem(k_edit_chw<512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_chw<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_chw<double, 512, 2>, TAB_BYTES))) return rc;
 
@@ -799,6 +800,38 @@ int nphusl_cuda_rgb_edit_rgb(const void *rgb_in, int in_loc, void *rgb_out, int 
         return NPHUSL_OK;
     };
     return run_streamed(*c, rgb_in, in_loc, 3, rgb_out, out_loc, 3, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,
+                                void *r_out, void *g_out, void *b_out,
+                                size_t n_pixels, const nphusl_edit *edit, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!r || !g || !b || !r_out || !g_out || !b_out || !edit) return fail(NPHUSL_ERR_ARG, "rgb_planes_edit: null argument");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)n_pixels;
+    long long done = 0;
+    if (aligned(r, 4) && aligned(g, 4) && aligned(b, 4) && aligned(r_out, 4) && aligned(g_out, 4) && aligned(b_out, 4) && n >= TILE_PX) {
+        if ((rc = set_attrs(*c))) return rc;
+        const long long tiles = n / TILE_PX;
+        k_edit_chw<512, 2><<<grid_for(tiles, 16, c->sms * 2), 512, TAB_BYTES, st>>>(
+            (const uint32_t *)r, (const uint32_t *)g, (const uint32_t *)b, (uint32_t *)r_out, (uint32_t *)g_out, (uint32_t *)b_out, tiles, *edit);
+        g_launches++;
+        if ((rc = check_launch("k_edit_chw"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    if (n > done) {
+        const long long rest = n - done;
+        k_edit_chw_any<<<grid_for(rest, 256, c->sms * 8), 256, 0, st>>>(
+            (const uint8_t *)r + done, (const uint8_t *)g + done, (const uint8_t *)b + done,
+            (uint8_t *)r_out + done, (uint8_t *)g_out + done, (uint8_t *)b_out + done, rest, *edit);
+        g_launches++;
+        if ((rc = check_launch("k_edit_chw_any"))) return rc;
+    }
+    return NPHUSL_OK;
 }
 
 // ---- lookup tables ---------------------------------------------------------------------

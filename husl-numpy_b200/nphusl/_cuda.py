@@ -71,6 +71,7 @@ SIGNATURES = {
     "nphusl_cuda_rgb_planes_to_husl_planes": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _sz, _i, _vp]),
     "nphusl_cuda_husl_planes_to_rgb_planes": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "nphusl_cuda_rgb_edit_rgb": (_i, [_vp, _i, _vp, _i, _sz, _vp, _i, _vp]),
+    "nphusl_cuda_rgb_planes_edit": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "nphusl_cuda_lut_generate": (_i, [_i, _i, _i, _i]),
     "nphusl_cuda_lut_upload": (_i, [_i, _u16p, _i, _dp, _dp, _u16p, _i, _i,
                                     ctypes.c_double, ctypes.c_double, _dp]),
@@ -662,8 +663,11 @@ class Edit(ctypes.Structure):
                          h[0], h[1], s[0], s[1], l[0], l[1])
 
 
-def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, **edit_args):
+def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, channels_first=False, **edit_args):
     """Fused ``to_rgb(edit(to_husl(rgb)))`` on uint8 pixels in one kernel pass.
+
+    ``channels_first=True``: ``rgb`` (a device array) is ``(3, ...)`` planes, the
+    layout nvJPEG / torchvision decoders produce; so is the result.
 
     ``edit`` is an ``Edit`` (or pass its fields as keywords):
     ``edit_rgb(img, hue=(250, 290), invert=True, l=(0.5, 0))`` darkens every
@@ -675,6 +679,20 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
         edit = Edit(**edit_args)
     elif edit_args:
         raise TypeError("pass either an Edit or its fields as keywords, not both")
+    if channels_first:
+        if not _is_device(rgb):
+            raise ValueError("channels_first edit takes device arrays")
+        src = _describe_device(rgb, "rgb")
+        if src.dtype != np.uint8 or not src.shape or src.shape[0] != 3:
+            raise ValueError("channels_first edit takes uint8 (3, ...) planes, got {} {}".format(src.dtype, src.shape))
+        dev = _pick_device(device, src)
+        dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out")
+        if dst.loc != DEVICE:
+            raise ValueError("channels_first edit writes device arrays")
+        n = int(np.prod(src.shape[1:]))
+        _check(lib.nphusl_cuda_rgb_planes_edit(src.ptr, src.ptr + n, src.ptr + 2 * n, dst.ptr, dst.ptr + n, dst.ptr + 2 * n,
+                                               n, ctypes.byref(edit), dev, _stream_ptr(stream)), "rgb_planes_edit")
+        return ret
     src = _describe_rgb_in(rgb)
     if src.dtype != np.uint8 or src.channels != 3 or not src.shape or src.shape[-1] != 3:
         raise ValueError("edit_rgb takes uint8 RGB (..., 3), got {} {}".format(src.dtype, src.shape))

@@ -149,6 +149,12 @@ typedef struct nphusl_edit {
 int nphusl_cuda_rgb_edit_rgb(const void *rgb_in, int in_loc, void *rgb_out, int out_loc,
                              size_t n_pixels, const nphusl_edit *edit, int device, void *stream);
 
+/* The same fused edit on channels-first uint8 planes (what nvJPEG and video
+ * decoders hand out); DEVICE pointers only; outputs may alias the inputs. */
+int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,
+                                void *r_out, void *g_out, void *b_out,
+                                size_t n_pixels, const nphusl_edit *edit, int device, void *stream);
+
 /* ---- lookup tables (optional LUT mode) -------------------------------------- */
 
 /* Generate, ON THE DEVICE, the tables make_lookup_tables:8-9 produces with

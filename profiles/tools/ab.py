@@ -76,7 +76,9 @@ for name, fn, b in (("pipeline_f64", pipe64, 54), ("pipeline_f32", pipe32, 30),
                     ("planar_inv_f64", lambda: _cuda.husl_planar_to_rgb(pl64, out=back), 27),
                     ("chw_fwd_f32", lambda: _cuda.rgb_to_husl_planar(rgb.view(3, -1), out=pl32, channels_first=True), 15),
                     ("chw_inv_f32", lambda: _cuda.husl_planar_to_rgb(pl32, out=back.view(3, -1), channels_first=True), 15),
-                    ("fused_edit_u8", lambda: _cuda.edit_rgb(rgb, out=back, hue=(250, 290), invert=True, l=(0.5, 0)), 6)):
+                    ("fused_edit_u8", lambda: _cuda.edit_rgb(rgb, out=back, hue=(250, 290), invert=True, l=(0.5, 0)), 6),
+                    ("fused_edit_chw_u8", lambda: _cuda.edit_rgb(rgb.view(3, -1), out=back.view(3, -1), channels_first=True,
+                                                                hue=(250, 290), invert=True, l=(0.5, 0)), 6)):
     ms = timed(fn)
     res[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 1), "hbm_frac": round(px * b / ms / 1e6 / 6547.2, 3)}
 # float RGB inputs / float RGB outputs (generic one-pixel-per-thread kernels), 2 frames

@@ -668,3 +668,22 @@ def test_cube_through_planar_chw_and_fused_paths(cu, cube, cube_oracle):
     assert np.array_equal(cu.husl_planar_to_rgb(p2, channels_first=True), chw)
     assert np.array_equal(cu.edit_rgb(cube), cube)
     check_husl(np.moveaxis(planar, 0, -1), cube_oracle, ~_grey(cube))
+
+
+def test_fused_edit_on_channels_first_planes(cu):
+    """edit_rgb(channels_first=True) on (3, H, W) uint8 device planes equals the
+    interleaved fused edit pixel for pixel, also in place and at ragged sizes."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(19)
+    for hw in ((5, 9), (61, 131), (1080, 1920)):
+        hwc = rng.integers(0, 256, hw + (3,), dtype=np.uint8)
+        want = cu.edit_rgb(hwc, hue=(250, 290), invert=True, l=(0.5, 0))
+        t = torch.from_numpy(np.ascontiguousarray(np.moveaxis(hwc, -1, 0))).cuda()
+        got = cu.edit_rgb(t, channels_first=True, hue=(250, 290), invert=True, l=(0.5, 0))
+        assert isinstance(got, cu.DeviceArray) and got.shape == (3,) + hw
+        assert np.array_equal(np.moveaxis(got.copy_to_host(), 0, -1), want)
+        r = cu.edit_rgb(t, out=t, channels_first=True, hue=(250, 290), invert=True, l=(0.5, 0))
+        torch.cuda.synchronize()
+        assert r is t and np.array_equal(np.moveaxis(t.cpu().numpy(), 0, -1), want)
+    with pytest.raises(ValueError):
+        cu.edit_rgb(hwc, channels_first=True)                      # host arrays: interleaved only
