@@ -21,6 +21,7 @@
 #include "husl_stream.cuh"
 #include "husl_lut.cuh"
 #include "husl_fused.cuh"
+#include "husl_strided.cuh"
 
 namespace {
 
@@ -832,6 +833,102 @@ int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,
         if ((rc = check_launch("k_edit_chw_any"))) return rc;
     }
     return NPHUSL_OK;
+}
+
+// ---- strided device images ------------------------------------------------------------
+static int view_check(const nphusl_view *v, const char *what, bool want_u8, bool want_float) {
+    if (!v || !v->ptr) return fail(NPHUSL_ERR_ARG, std::string(what) + ": null view");
+    if (v->frames < 0 || v->rows < 0 || v->cols < 0) return fail(NPHUSL_ERR_ARG, std::string(what) + ": negative extent");
+    const bool is_u8 = v->dtype == NPHUSL_U8, is_f = v->dtype == NPHUSL_F32 || v->dtype == NPHUSL_F64;
+    if (!((want_u8 && is_u8) || (want_float && is_f))) return fail(NPHUSL_ERR_ARG, std::string(what) + ": dtype not allowed here");
+    const long long a = (long long)dsize(v->dtype);
+    if ((reinterpret_cast<uintptr_t>(v->ptr) % a) || (v->frame_stride % a) || (v->row_stride % a) || (v->col_stride % a) || (v->ch_stride % a))
+        return fail(NPHUSL_ERR_ARG, std::string(what) + ": pointer and strides must be multiples of the element size");
+    return NPHUSL_OK;
+}
+
+static View2 view_dev(const nphusl_view *v) {
+    return View2{(char *)v->ptr, v->frames, v->rows, v->cols, v->frame_stride, v->row_stride, v->col_stride, v->ch_stride};
+}
+
+static dim3 grid_3d(const DevCtx &c, const View2 &v) {
+    // enough CTAs to fill the GPU; rows / frames beyond that are grid-strided
+    const long long cap = (long long)c.sms * 16;
+    long long gx = (v.cols + 255) / 256, gy = v.rows, gz = v.frames;
+    if (gx > cap) gx = cap;
+    if (gx * gy > cap) gy = cap / gx > 0 ? cap / gx : 1;
+    if (gx * gy * gz > cap) gz = cap / (gx * gy) > 0 ? cap / (gx * gy) : 1;
+    if (gy > 65535) gy = 65535;
+    if (gz > 65535) gz = 65535;
+    return dim3((unsigned)gx, (unsigned)gy, (unsigned)gz);
+}
+static bool same_extent(const nphusl_view *a, const nphusl_view *b) {
+    return a->frames == b->frames && a->rows == b->rows && a->cols == b->cols;
+}
+static bool empty_view(const nphusl_view *a) { return a->frames == 0 || a->rows == 0 || a->cols == 0; }
+
+int nphusl_cuda_rgb_to_husl_strided(const nphusl_view *rgb, const nphusl_view *hsl, int hue_only,
+                                    int device, void *stream) {
+    DeviceGuard guard;
+    int rc;
+    if ((rc = view_check(rgb, "rgb_to_husl_strided: rgb", true, true))) return rc;
+    if ((rc = view_check(hsl, "rgb_to_husl_strided: hsl", false, true))) return rc;
+    if (!same_extent(rgb, hsl)) return fail(NPHUSL_ERR_ARG, "rgb_to_husl_strided: extents differ");
+    if (empty_view(rgb)) return NPHUSL_OK;
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    const View2 i = view_dev(rgb), o = view_dev(hsl);
+    const dim3 grid = grid_3d(*c, i);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GO(TI, TO) do { if (hue_only) k_fwd_strided<TI, TO, true><<<grid, 256, 0, st>>>(i, o); \
+                        else k_fwd_strided<TI, TO, false><<<grid, 256, 0, st>>>(i, o); } while (0)
+    const bool o32 = hsl->dtype == NPHUSL_F32;
+    if (rgb->dtype == NPHUSL_U8) { if (o32) GO(uint8_t, float); else GO(uint8_t, double); }
+    else if (rgb->dtype == NPHUSL_F32) { if (o32) GO(float, float); else GO(float, double); }
+    else { if (o32) GO(double, float); else GO(double, double); }
+#undef GO
+    g_launches++;
+    return check_launch("k_fwd_strided");
+}
+
+int nphusl_cuda_husl_to_rgb_strided(const nphusl_view *hsl, const nphusl_view *rgb, int device, void *stream) {
+    DeviceGuard guard;
+    int rc;
+    if ((rc = view_check(hsl, "husl_to_rgb_strided: hsl", false, true))) return rc;
+    if ((rc = view_check(rgb, "husl_to_rgb_strided: rgb", true, true))) return rc;
+    if (!same_extent(rgb, hsl)) return fail(NPHUSL_ERR_ARG, "husl_to_rgb_strided: extents differ");
+    if (empty_view(rgb)) return NPHUSL_OK;
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    const View2 i = view_dev(hsl), o = view_dev(rgb);
+    const dim3 grid = grid_3d(*c, i);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GO(TI, TO) k_inv_strided<TI, TO><<<grid, 256, 0, st>>>(i, o)
+    if (hsl->dtype == NPHUSL_F32) {
+        if (rgb->dtype == NPHUSL_U8) GO(float, uint8_t); else if (rgb->dtype == NPHUSL_F32) GO(float, float); else GO(float, double);
+    } else {
+        if (rgb->dtype == NPHUSL_U8) GO(double, uint8_t); else if (rgb->dtype == NPHUSL_F32) GO(double, float); else GO(double, double);
+    }
+#undef GO
+    g_launches++;
+    return check_launch("k_inv_strided");
+}
+
+int nphusl_cuda_rgb_edit_rgb_strided(const nphusl_view *rgb_in, const nphusl_view *rgb_out,
+                                     const nphusl_edit *edit, int device, void *stream) {
+    DeviceGuard guard;
+    int rc;
+    if (!edit) return fail(NPHUSL_ERR_ARG, "rgb_edit_rgb_strided: null edit");
+    if ((rc = view_check(rgb_in, "rgb_edit_rgb_strided: in", true, false))) return rc;
+    if ((rc = view_check(rgb_out, "rgb_edit_rgb_strided: out", true, false))) return rc;
+    if (!same_extent(rgb_in, rgb_out)) return fail(NPHUSL_ERR_ARG, "rgb_edit_rgb_strided: extents differ");
+    if (empty_view(rgb_in)) return NPHUSL_OK;
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    const View2 i = view_dev(rgb_in), o = view_dev(rgb_out);
+    k_edit_strided<<<grid_3d(*c, i), 256, 0, (cudaStream_t)stream>>>(i, o, *edit);
+    g_launches++;
+    return check_launch("k_edit_strided");
 }
 
 // ---- lookup tables ---------------------------------------------------------------------

@@ -72,6 +72,9 @@ SIGNATURES = {
     "nphusl_cuda_husl_planes_to_rgb_planes": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "nphusl_cuda_rgb_edit_rgb": (_i, [_vp, _i, _vp, _i, _sz, _vp, _i, _vp]),
     "nphusl_cuda_rgb_planes_edit": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "nphusl_cuda_rgb_to_husl_strided": (_i, [_vp, _vp, _i, _i, _vp]),
+    "nphusl_cuda_husl_to_rgb_strided": (_i, [_vp, _vp, _i, _vp]),
+    "nphusl_cuda_rgb_edit_rgb_strided": (_i, [_vp, _vp, _vp, _i, _vp]),
     "nphusl_cuda_lut_generate": (_i, [_i, _i, _i, _i]),
     "nphusl_cuda_lut_upload": (_i, [_i, _u16p, _i, _dp, _dp, _u16p, _i, _i,
                                     ctypes.c_double, ctypes.c_double, _dp]),
@@ -332,7 +335,14 @@ def pinned_empty(shape, dtype):
 # ---------------------------------------------------------------------------
 
 class _Buf:
-    __slots__ = ("ptr", "shape", "dtype", "loc", "device", "keep", "channels")
+    ptr = 0
+    shape = ()
+    dtype = None
+    loc = HOST
+    device = None
+    keep = None
+    channels = 3
+    strides = None          # byte strides of a NON-contiguous device array (else None)
 
 
 def _is_device(obj):
@@ -345,7 +355,7 @@ def _device_of_ptr(ptr):
     return dev.value if loc.value == DEVICE and dev.value >= 0 else None
 
 
-def _describe_device(obj, what, allow_gray=False):
+def _describe_device(obj, what, allow_gray=False, strided_ok=False):
     cai = obj.__cuda_array_interface__
     shape = tuple(cai["shape"])
     dtype = np.dtype(cai["typestr"])
@@ -362,8 +372,15 @@ def _describe_device(obj, what, allow_gray=False):
             expect.append(acc)
             acc *= s
         if any(s != e for s, e, n in zip(strides, reversed(expect), shape) if n > 1):
-            raise ValueError("{}: device arrays must be C-contiguous (got strides {})".format(what, strides))
+            if not strided_ok or channels == 1:
+                raise ValueError("{}: device arrays must be C-contiguous here (got strides {})".format(what, strides))
+            keep_strides = tuple(int(x) for x in strides)
+        else:
+            keep_strides = None
+    else:
+        keep_strides = None
     b = _Buf()
+    b.strides = keep_strides
     b.ptr = int(cai["data"][0]) if cai["data"][0] else 0
     b.shape, b.dtype, b.loc, b.keep, b.channels = shape, dtype, DEVICE, obj, channels
     if channels == 1:
@@ -384,10 +401,12 @@ def _describe_rgb_in(rgb):
     a zero-stride last axis (transform.from_grayscale's broadcast view) is sent
     as ONE channel and broadcast in registers."""
     if _is_device(rgb):
-        b = _describe_device(rgb, "rgb", allow_gray=True)
+        b = _describe_device(rgb, "rgb", allow_gray=True, strided_ok=True)
         if b.dtype not in _DT:
             raise ValueError("rgb device array dtype {} unsupported (uint8/float32/float64)".format(b.dtype))
         if getattr(rgb, "rgba", False):          # transform.RgbaDevice: 4 stored channels, premultiplied on load
+            if b.strides is not None:
+                raise ValueError("rgb: RGBA device arrays must be C-contiguous")
             b.channels = 4
             b.shape = tuple(b.shape[:-1]) + (3,)
         return b
@@ -408,10 +427,12 @@ def _describe_rgb_in(rgb):
     return b
 
 
-def _describe_out(out, shape, dtype, allowed, what):
+def _describe_out(out, shape, dtype, allowed, what, strided_ok=False):
     """Validate a caller-provided ``out`` (host ndarray or device array)."""
     if _is_device(out):
-        b = _describe_device(out, what)
+        b = _describe_device(out, what, strided_ok=strided_ok)
+        if b.strides is not None and tuple(b.shape) != tuple(shape):
+            raise ValueError("{}: a strided device array must have exactly the result's shape {}".format(what, tuple(shape)))
     else:
         if not isinstance(out, np.ndarray):
             raise TypeError("{} must be a numpy array or a device array".format(what))
@@ -435,10 +456,10 @@ def _pick_device(device, *bufs):
     return _default_device
 
 
-def _make_out(src, out, shape, dtype, allowed, device, what):
+def _make_out(src, out, shape, dtype, allowed, device, what, strided_ok=False):
     """-> (_Buf, object to return)"""
     if out is not None:
-        b = _describe_out(out, shape, dtype, allowed, what)
+        b = _describe_out(out, shape, dtype, allowed, what, strided_ok)
         return b, out
     if src.loc == DEVICE:
         d = DeviceArray(shape, dtype, device)
@@ -453,6 +474,58 @@ def _make_out(src, out, shape, dtype, allowed, device, what):
 
 _FLOATS = (np.dtype(np.float32), np.dtype(np.float64))
 _ANY = (np.dtype(np.uint8),) + _FLOATS
+
+
+# ---------------------------------------------------------------------------
+# strided device images (cropped views, channel slices, pitched frames)
+# ---------------------------------------------------------------------------
+
+class View(ctypes.Structure):
+    """``nphusl_view`` of include/nphusl_cuda.h"""
+    _fields_ = [("ptr", ctypes.c_void_p), ("dtype", ctypes.c_int),
+                ("frames", ctypes.c_longlong), ("rows", ctypes.c_longlong), ("cols", ctypes.c_longlong),
+                ("frame_stride", ctypes.c_longlong), ("row_stride", ctypes.c_longlong),
+                ("col_stride", ctypes.c_longlong), ("ch_stride", ctypes.c_longlong)]
+
+
+def _c_strides(shape, itemsize):
+    out, acc = [], itemsize
+    for n in reversed(shape):
+        out.append(acc)
+        acc *= n
+    return tuple(reversed(out))
+
+
+def _views(bufs, pixel_ndim):
+    """Collapse the pixel axes of several same-shaped buffers JOINTLY into
+    (frames, rows, cols): neighbouring axes merge when they are mergeable in
+    every buffer (stride[i] == stride[i+1] * shape[i+1]).  -> list of View.
+    Raises ValueError when more than three axes remain (make the array contiguous)."""
+    shape = tuple(bufs[0].shape[:pixel_ndim])
+    strides = []
+    for b in bufs:
+        st = b.strides if b.strides is not None else _c_strides(b.shape, b.dtype.itemsize)
+        strides.append(list(st))
+    axes = [i for i, n in enumerate(shape) if n != 1]
+    dims = [[shape[i]] + [st[i] for st in strides] for i in axes]          # [n, stride_buf0, stride_buf1, ...]
+    merged = []
+    for d in dims:
+        if merged and all(merged[-1][k] == d[k] * d[0] for k in range(1, len(d))):
+            merged[-1] = [merged[-1][0] * d[0]] + d[1:]
+        else:
+            merged.append(list(d))
+    if len(merged) > 3:
+        raise ValueError("strided device array with {} non-mergeable pixel axes: at most 3 are supported "
+                         "(call .contiguous() first)".format(len(merged)))
+    while len(merged) < 3:
+        merged.insert(0, [1] + [0] * len(bufs))
+    views = []
+    for k, b in enumerate(bufs):
+        st = strides[k]
+        es = st[pixel_ndim] if len(b.shape) > pixel_ndim else 0
+        views.append(View(b.ptr, _DT[b.dtype], merged[0][0], merged[1][0], merged[2][0],
+                          merged[0][k + 1], merged[1][k + 1], merged[2][k + 1], es))
+    return views
 
 
 # ---------------------------------------------------------------------------
@@ -476,6 +549,16 @@ class _host_async:
             self.lib.nphusl_cuda_set_host_async(0)
 
 
+
+def _strided_call(fn_name, src, dst, pixel_ndim, extra, dev, stream):
+    """Either side is a non-contiguous device array: both go to the strided entry points."""
+    if src.loc != DEVICE or dst.loc != DEVICE:
+        raise ValueError("strided device arrays convert device -> device only (pass a device `out` or none)")
+    vin, vout = _views([src, dst], pixel_ndim)
+    args = [ctypes.byref(vin), ctypes.byref(vout)] + list(extra) + [dev, _stream_ptr(stream)]
+    _check(getattr(load(), fn_name)(*args), fn_name[len("nphusl_cuda_"):])
+
+
 def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, device=None, blocking=True):
     """RGB -> HUSL on the GPU (kernel (a) husl_from_rgb).  Replaces
     ``_simd_opt._rgb_to_husl`` (_simd_opt.pyx:20-33) / ``_cython_opt._rgb_to_husl``
@@ -486,9 +569,14 @@ def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, dev
         raise ValueError("expected (..., 3) RGB, got shape {}".format(src.shape))
     dev = _pick_device(device, src)
     if out is not None:
-        dtype = _describe_out(out, src.shape, dtype, _FLOATS, "out").dtype
-    dst, ret = _make_out(src, out, src.shape, np.dtype(dtype), _FLOATS, dev, "out")
+        dtype = _describe_out(out, src.shape, dtype, _FLOATS, "out", True).dtype
+    dst, ret = _make_out(src, out, src.shape, np.dtype(dtype), _FLOATS, dev, "out", True)
     n = int(np.prod(src.shape[:-1]))
+    if src.strides is not None or dst.strides is not None:
+        if mode != "exact":
+            raise ValueError("LUT modes take C-contiguous arrays")
+        _strided_call("nphusl_cuda_rgb_to_husl_strided", src, dst, len(src.shape) - 1, [0], dev, stream)
+        return ret
     with _host_async(lib, blocking):
         rc = lib.nphusl_cuda_rgb_to_husl(src.ptr, _DT[src.dtype], src.loc, src.channels,
                                          dst.ptr, _DT[dst.dtype], dst.loc, n, MODES[mode], dev,
@@ -507,9 +595,12 @@ def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None, block
     dev = _pick_device(device, src)
     shape = src.shape[:-1]
     if out is not None:
-        dtype = _describe_out(out, shape, dtype, _FLOATS, "out").dtype
-    dst, ret = _make_out(src, out, shape, np.dtype(dtype), _FLOATS, dev, "out")
+        dtype = _describe_out(out, shape, dtype, _FLOATS, "out", True).dtype
+    dst, ret = _make_out(src, out, shape, np.dtype(dtype), _FLOATS, dev, "out", True)
     n = int(np.prod(shape))
+    if src.strides is not None or dst.strides is not None:
+        _strided_call("nphusl_cuda_rgb_to_husl_strided", src, dst, len(shape), [1], dev, stream)
+        return ret
     with _host_async(lib, blocking):
         rc = lib.nphusl_cuda_rgb_to_hue(src.ptr, _DT[src.dtype], src.loc, src.channels,
                                         dst.ptr, _DT[dst.dtype], dst.loc, n, dev, _stream_ptr(stream))
@@ -524,7 +615,7 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
     dtypes return RGB in [0, 1] like the reference callable."""
     lib = load()
     if _is_device(hsl):
-        src = _describe_device(hsl, "hsl")
+        src = _describe_device(hsl, "hsl", strided_ok=True)
         if src.dtype not in _FLOATS:
             raise ValueError("hsl device array must be float32/float64, got {}".format(src.dtype))
     else:
@@ -538,9 +629,12 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
         raise ValueError("expected (..., 3) HUSL, got shape {}".format(src.shape))
     dev = _pick_device(device, src)
     if out is not None:
-        dtype = _describe_out(out, src.shape, dtype, _ANY, "out").dtype
-    dst, ret = _make_out(src, out, src.shape, np.dtype(dtype), _ANY, dev, "out")
+        dtype = _describe_out(out, src.shape, dtype, _ANY, "out", True).dtype
+    dst, ret = _make_out(src, out, src.shape, np.dtype(dtype), _ANY, dev, "out", True)
     n = int(np.prod(src.shape[:-1]))
+    if src.strides is not None or dst.strides is not None:
+        _strided_call("nphusl_cuda_husl_to_rgb_strided", src, dst, len(src.shape) - 1, [], dev, stream)
+        return ret
     with _host_async(lib, blocking):
         rc = lib.nphusl_cuda_husl_to_rgb(src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
                                          n, dev, _stream_ptr(stream))
@@ -697,8 +791,11 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
     if src.dtype != np.uint8 or src.channels != 3 or not src.shape or src.shape[-1] != 3:
         raise ValueError("edit_rgb takes uint8 RGB (..., 3), got {} {}".format(src.dtype, src.shape))
     dev = _pick_device(device, src)
-    dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out")
+    dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out", True)
     n = int(np.prod(src.shape[:-1]))
+    if src.strides is not None or dst.strides is not None:
+        _strided_call("nphusl_cuda_rgb_edit_rgb_strided", src, dst, len(src.shape) - 1, [ctypes.byref(edit)], dev, stream)
+        return ret
     with _host_async(lib, blocking):
         rc = lib.nphusl_cuda_rgb_edit_rgb(src.ptr, src.loc, dst.ptr, dst.loc, n, ctypes.byref(edit), dev, _stream_ptr(stream))
     _check(rc, "rgb_edit_rgb")

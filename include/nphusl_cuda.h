@@ -155,6 +155,34 @@ int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,
                                 void *r_out, void *g_out, void *b_out,
                                 size_t n_pixels, const nphusl_edit *edit, int device, void *stream);
 
+/* ---- strided device images ---------------------------------------------------- */
+
+/* A batch of `frames` (rows x cols) images of 3-element pixels in DEVICE memory,
+ * described by BYTE strides (any sign): element c of pixel (y, x) of frame f is at
+ *     ptr + f*frame_stride + y*row_stride + x*col_stride + c*ch_stride.
+ * Covers cropped views img[y0:y1, x0:x1], channel slices rgba[..., :3], BGR seen
+ * as RGB (negative ch_stride), row-padded (pitched) decoder frames and (3, H, W)
+ * planes seen as (H, W, 3).  The reference makes such arrays contiguous with a
+ * host copy before a backend sees them (the C-contiguous memoryview casts of
+ * _simd_opt.pyx:36 and _cython_opt.pyx:22); here the kernels walk the view.
+ * For a hue image (rgb_to_husl_strided with hue_only != 0) ch_stride is unused. */
+typedef struct nphusl_view {
+    void *ptr;
+    int dtype;                       /* NPHUSL_U8 | NPHUSL_F32 | NPHUSL_F64 */
+    long long frames, rows, cols;
+    long long frame_stride, row_stride, col_stride, ch_stride;
+} nphusl_view;
+
+/* rgb: U8 (0..255) or F32/F64 ([0,1]); hsl (or hue): F32/F64; same frames x rows x cols */
+int nphusl_cuda_rgb_to_husl_strided(const nphusl_view *rgb, const nphusl_view *hsl, int hue_only,
+                                    int device, void *stream);
+/* hsl: F32/F64; rgb: U8 (to_rgb_int tail fused, transform.py:16-20) or F32/F64 in [0,1] */
+int nphusl_cuda_husl_to_rgb_strided(const nphusl_view *hsl, const nphusl_view *rgb,
+                                    int device, void *stream);
+/* fused edit on a U8 view, e.g. one region of a frame, in place when in == out */
+int nphusl_cuda_rgb_edit_rgb_strided(const nphusl_view *rgb_in, const nphusl_view *rgb_out,
+                                     const nphusl_edit *edit, int device, void *stream);
+
 /* ---- lookup tables (optional LUT mode) -------------------------------------- */
 
 /* Generate, ON THE DEVICE, the tables make_lookup_tables:8-9 produces with

@@ -101,3 +101,39 @@ def test_stream_pointer_forms():
     assert _cuda._stream_ptr(None) is None
     assert _cuda._stream_ptr(TorchLike()).value == 1234
     assert _cuda._stream_ptr(77).value == 77
+
+
+def test_strided_views_collapse_to_three_axes():
+    """_views: joint collapse of the pixel axes of (src, dst) into frames x rows x
+    cols with byte strides (include/nphusl_cuda.h nphusl_view); pure host logic."""
+    from nphusl import _cuda
+
+    def buf(shape, dtype, strides=None, ptr=4096):
+        b = _cuda._Buf()
+        b.ptr, b.shape, b.dtype, b.strides = ptr, tuple(shape), np.dtype(dtype), strides
+        return b
+
+    def dims(v):
+        return (v.frames, v.rows, v.cols, v.frame_stride, v.row_stride, v.col_stride, v.ch_stride)
+
+    # batch of cropped frames: (B, h, w, 3) view of (B, H, W, 4) uint8 -> float32 contiguous result
+    B, H, W, h, w = 5, 40, 60, 30, 20
+    src = buf((B, h, w, 3), np.uint8, (H * W * 4, W * 4, 4, 1))
+    dst = buf((B, h, w, 3), np.float32)
+    vi, vo = _cuda._views([src, dst], 3)
+    assert dims(vi) == (B, h, w, H * W * 4, W * 4, 4, 1)
+    assert dims(vo) == (B, h, w, h * w * 12, w * 12, 12, 4)
+    # single cropped frame: frames = 1
+    vi, vo = _cuda._views([buf((h, w, 3), np.uint8, (W * 4, 4, 1)), buf((h, w, 3), np.float64)], 2)
+    assert dims(vi)[:3] == (1, h, w) and dims(vi)[4:] == (W * 4, 4, 1)
+    assert dims(vo)[:3] == (1, h, w) and dims(vo)[4:] == (w * 24, 24, 8)
+    # channel slice of full frames: every pixel axis merges -> one row; hue image has no channel axis
+    vi, vo = _cuda._views([buf((B, H, W, 3), np.uint8, (H * W * 4, W * 4, 4, 1)), buf((B, H, W), np.float32)], 3)
+    assert dims(vi)[:3] == (1, 1, B * H * W) and vi.col_stride == 4
+    assert dims(vo)[:3] == (1, 1, B * H * W) and vo.col_stride == 4 and vo.ch_stride == 0
+    # size-1 axes never get in the way
+    vi, _ = _cuda._views([buf((1, h, 1, w, 3), np.uint8, (999, W * 4, 777, 4, 1)), buf((1, h, 1, w, 3), np.float32)], 4)
+    assert dims(vi)[:3] == (1, h, w) and (vi.row_stride, vi.col_stride) == (W * 4, 4)
+    # four independent pixel axes cannot be expressed
+    with pytest.raises(ValueError):
+        _cuda._views([buf((4, 3, 4, 5, 3), np.uint8, (10000, 2000, 200, 8, 1)), buf((4, 3, 4, 5, 3), np.float32)], 4)

@@ -304,11 +304,75 @@ def test_device_arrays_never_touch_the_host(cu):
     assert np.array_equal(o.cpu().numpy(), ref)
 
 
-def test_device_non_contiguous_rejected(cu):
+def test_strided_device_views(cu):
+    """Cropped views, channel slices, BGR-as-RGB, pitched rows and permuted planes
+    of device tensors are converted where they lie (strided kernels): same values
+    as the contiguous copy, nothing outside the view is written."""
     torch = pytest.importorskip("torch")
-    t = torch.zeros((8, 8, 3), dtype=torch.uint8, device="cuda")[:, ::2]
+    import nphusl
+    rng = np.random.default_rng(20)
+    frame = rng.integers(0, 256, (97, 203, 4), dtype=np.uint8)
+    t = torch.from_numpy(frame).cuda()
+    views = {
+        "crop": (t[10:80, 33:150, :3], frame[10:80, 33:150, :3]),
+        "rgba[..., :3]": (t[..., :3], frame[..., :3]),
+        "every other column": (t[:, ::2, :3], frame[:, ::2, :3]),
+        "planes permuted": (t[..., :3].permute(2, 0, 1).contiguous().permute(1, 2, 0), frame[..., :3]),
+    }
+    for name, (v, host) in views.items():
+        host = np.ascontiguousarray(host)
+        assert not v.is_contiguous(), name
+        want = cu._rgb_to_husl(host, dtype=np.float32)
+        got = cu._rgb_to_husl(v, dtype=np.float32)
+        assert isinstance(got, cu.DeviceArray) and got.shape == host.shape, name
+        assert np.array_equal(got.copy_to_host(), want), name
+        assert np.array_equal(cu._rgb_to_hue(v, dtype=np.float64).copy_to_host(), cu._rgb_to_hue(host)), name
+        with nphusl.cuda_enabled():                                   # and through the public API
+            assert np.array_equal(nphusl.to_husl(v).copy_to_host(), cu._rgb_to_husl(host)), name
+    # BGR memory presented as RGB: negative channel stride (torch has none; raw __cuda_array_interface__)
+    bgr = torch.from_numpy(np.ascontiguousarray(frame[..., 2::-1])).cuda()
+
+    class Raw:
+        device = 0
+        __cuda_array_interface__ = {"shape": (97, 203, 3), "typestr": "|u1", "data": (bgr.data_ptr() + 2, False),
+                                    "version": 3, "strides": (203 * 3, 3, -1)}
+    assert np.array_equal(cu._rgb_to_husl(Raw(), dtype=np.float32).copy_to_host(),
+                          cu._rgb_to_husl(np.ascontiguousarray(frame[..., :3]), dtype=np.float32))
+    # float RGB view
+    f = torch.from_numpy(frame[..., :3] / 255.0).cuda()
+    assert np.array_equal(cu._rgb_to_husl(f[5:50, 7:99]).copy_to_host(), cu._rgb_to_husl(np.ascontiguousarray(frame[5:50, 7:99, :3] / 255.0)))
+    # strided HUSL in, strided uint8 out: write a region of a larger frame, the rest stays untouched
+    hsl = torch.from_numpy(cu._rgb_to_husl(np.ascontiguousarray(frame[..., :3]), dtype=np.float32)).cuda()
+    canvas = torch.full((97, 203, 4), 0xA5, dtype=torch.uint8, device="cuda")
+    cu._husl_to_rgb(hsl[10:80, 33:150], out=canvas[10:80, 33:150, :3])
+    torch.cuda.synchronize()
+    c = canvas.cpu().numpy()
+    assert np.array_equal(c[10:80, 33:150, :3], frame[10:80, 33:150, :3])
+    c[10:80, 33:150, :3] = 0xA5
+    assert (c == 0xA5).all()
+    # fused edit of a region of interest, in place
+    work = t.clone()
+    roi = work[20:60, 40:140, :3]
+    r = cu.edit_rgb(roi, out=roi, lightness=(0, 50), l=(1, 20))
+    torch.cuda.synchronize()
+    w = work.cpu().numpy()
+    assert r is roi
+    assert np.array_equal(w[20:60, 40:140, :3], cu.edit_rgb(np.ascontiguousarray(frame[20:60, 40:140, :3]), lightness=(0, 50), l=(1, 20)))
+    w[20:60, 40:140, :3] = frame[20:60, 40:140, :3]
+    assert np.array_equal(w, frame)
+    # a batch of cropped frames (three strided pixel axes)
+    vid = torch.from_numpy(rng.integers(0, 256, (4, 50, 70, 3), dtype=np.uint8)).cuda()
+    crop = vid[:, 5:45, 10:61]
+    assert np.array_equal(cu._rgb_to_husl(crop, dtype=np.float32).copy_to_host(),
+                          cu._rgb_to_husl(crop.contiguous().cpu().numpy(), dtype=np.float32))
+    # what cannot be expressed as frames x rows x cols is refused, not copied behind the caller's back
+    five = torch.zeros((4, 6, 8, 10, 12, 3), dtype=torch.uint8, device="cuda")[:, ::2, ::2, ::2, ::2]
     with pytest.raises(ValueError):
-        cu._rgb_to_husl(t)
+        cu._rgb_to_husl(five)
+    with pytest.raises(ValueError):
+        cu._rgb_to_husl(t[:, ::2, :3], mode="lut")
+    with pytest.raises(ValueError):
+        cu.rgb_to_husl_planar(t[:, ::2, :3])                          # planar entry points: contiguous only
 
 
 # ---- BASELINE full-size workloads: size-independent properties -----------------------
