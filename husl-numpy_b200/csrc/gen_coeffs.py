@@ -57,6 +57,37 @@ def fit_atan(nterms, npts=6000, iters=80):
     return coef, err.max()
 
 
+ATAN_TERMS = 7
+ATAN_SHRINK = 6e-7
+
+
+def atan_first_quadrant_f32(c32, q):
+    """float32 emulation of hue_deg's `fmaf(P(q*q), q, 45)` (Horner with FFMA), q in [-1, 1]"""
+    q = q.astype(np.float32)
+    s = (q.astype(np.float64) ** 2).astype(np.float32)
+    p = np.full_like(s, np.float32(c32[-1]))
+    for c in c32[-2::-1]:
+        p = (p.astype(np.float64) * s.astype(np.float64) + np.float64(c)).astype(np.float32)
+    return (p.astype(np.float64) * q.astype(np.float64) + 45.0).astype(np.float32)
+
+
+def atan_coeffs():
+    """Degrees-valued coefficients of hue_deg, shrunk by ATAN_SHRINK so that the
+    first-quadrant angle 45 + q*P(q^2) stays inside [0, 90] for EVERY float q in
+    [-1 - 4 ulp, 1 + 4 ulp] (checked exhaustively near the ends, where the minimax error and the
+    Horner rounding could otherwise push it to -1.5e-5 / 90.000015 and the hue out
+    of [0, 360]).  Returns (float32 coefficients, max abs error in degrees)."""
+    coef, _ = fit_atan(ATAN_TERMS)
+    c32 = (np.degrees(coef) * (1.0 - ATAN_SHRINK)).astype(np.float32)
+    # all floats in [0.5, 1 + 4 ulp]: q = (y-x)*rcp(y+x) can overshoot 1 by the MUFU.RCP error (1 ulp)
+    ends = np.arange(0x3F000000, 0x3F800005, dtype=np.uint32).view(np.float32)
+    lo, hi = atan_first_quadrant_f32(c32, -ends), atan_first_quadrant_f32(c32, ends)
+    assert lo.min() >= 0.0 and hi.max() <= 90.0, (lo.min(), hi.max())
+    q = np.linspace(-1, 1, 2000001).astype(np.float32)
+    err = atan_first_quadrant_f32(c32, q).astype(np.float64) - (45.0 + np.degrees(np.arctan(q.astype(np.float64))))
+    return c32, np.abs(err).max()
+
+
 def derive():
     c = {}
     Yf = M_INV[1]
@@ -86,6 +117,7 @@ def derive():
         c["AU%d" % i], c["AV%d" % i], c["AN%d" % i] = Au[i], Av[i], An[i]
     c["AN"] = An.mean()
     c["REF_V4"] = 4 * REF_V
+    assert np.float32(c["AN"]) == np.float32(c["REF_V4"])     # the inverse uses AN*den for both
     return c
 
 
@@ -131,13 +163,15 @@ def verify(c, n=2000, seed=0):
         th = np.radians(H)
         gi = np.array([c["AU%d" % i] * np.cos(th) + c["AV%d" % i] * np.sin(th) for i in range(3)])
         inv_tau = max(-gi.min() / c["AN"], (Y * gi.max() - 4 * np.sin(th)) / (c["REF_V4"] * (1 - Y)))
+        # the kernel works with g_i/4 and den/4: 1/(4 tau) = max(-(gi/4).min()/AN, (Y*(gi/4).max() - sin)/(REF_V4 (1-Y)))
+        inv_tau4 = max(-(gi / 4).min() / c["AN"], (Y * (gi / 4).max() - np.sin(th)) / (c["REF_V4"] * (1 - Y)))
+        assert abs(inv_tau4 * 4 - inv_tau) <= 1e-12 * abs(inv_tau)
         worst_t = max(worst_t, abs(1 / inv_tau - six_line_max_chroma(L, H) / (13 * L)) * 13 * L)
     return worst_s, worst_t
 
 
 def emit(c, out):
-    atan_terms = 8
-    coef, err = fit_atan(atan_terms)
+    coef, err = atan_coeffs()
     p = lambda *a: print(*a, file=out)  # noqa: E731
     p("// husl_coeffs.h -- GENERATED by csrc/gen_coeffs.py, do not edit.")
     p("// float64-derived coefficients of the cancellation-free HUSL formulation")
@@ -152,10 +186,11 @@ def emit(c, out):
     p("constexpr float EPSILON = %.9ef;" % EPSILON)
     p("constexpr float WHITE_HUE = %.9ef;" % WHITE_HUE)
     p("constexpr double WHITE_HUE_D = %.17e;" % WHITE_HUE)
-    p("// atan(q) ~ q*P(q^2) on [0,1], result in DEGREES; max abs error %.3e deg" % np.degrees(err))
-    p("constexpr int ATAN_TERMS = %d;" % atan_terms)
+    p("// atan(q) ~ q*P(q^2) on [-1,1], result in DEGREES; 45 + q*P(q^2) evaluated in float32 stays in")
+    p("// [0, 90] for every float q and is within %.3e deg of 45 + atan(q)" % err)
+    p("constexpr int ATAN_TERMS = %d;" % ATAN_TERMS)
     for i, v in enumerate(coef):
-        p("constexpr float ATAN_C%d = %.9ef;" % (i, np.degrees(v)))
+        p("constexpr float ATAN_C%d = %.9ef;" % (i, v))
     p("}  // namespace husl")
 
 

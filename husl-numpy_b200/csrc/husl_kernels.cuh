@@ -302,7 +302,7 @@ k_inv_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float R, G, B;
-        rgb255_from_husl((float)in[3 * i], (float)in[3 * i + 1], (float)in[3 * i + 2], R, G, B);
+        rgb255_from_husl<sizeof(TOut) != 1>((float)in[3 * i], (float)in[3 * i + 1], (float)in[3 * i + 2], R, G, B);
         if (sizeof(TOut) == 1) {
             out[3 * i] = (TOut)(round_u8_bits(R) & 0xFF);
             out[3 * i + 1] = (TOut)(round_u8_bits(G) & 0xFF);

@@ -33,6 +33,7 @@ __device__ __forceinline__ float mufu_ex2(float x) { return emul_noise(exp2f(x))
 __device__ __forceinline__ float mufu_sin(float x) { return emul_noise(sinf(x)); }
 __device__ __forceinline__ float mufu_cos(float x) { return emul_noise(cosf(x)); }
 __device__ __forceinline__ uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+__device__ __forceinline__ float __saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }   // NaN -> 0 like the .SAT modifier
 #else
 __device__ __forceinline__ float mufu_rcp(float x) {
     float r;
@@ -64,24 +65,22 @@ __device__ __forceinline__ float mufu_cos(float x) {
 // ---- hue: atan2 in degrees, [0, 360] -------------------------------------------
 // reference: H = degrees(arctan2(V, U)), +360 if negative (nphusl.py:231-239,
 // _cython_opt.pyx:75-79).  U, V share the positive factor 13L/D, so the hue is
-// atan2(Nv, Nu).  atan2(0,0) = 0 like libm.  (Exact greys never arrive here with
-// Nu = Nv = 0 unless they are black: see GREY_U / GREY_V in the callers.)
+// atan2(Nv, Nu).  First-quadrant angle of (|Nu|, |Nv|) without the usual
+// min/max swap: atan(y/x) = 45 + atan((y-x)/(y+x)), (y-x)/(y+x) in [-1, 1] where
+// the odd minimax polynomial is valid on both signs; then two reflections.
+// Callers never pass (0, 0): Nu, Nv carry the GREY_U / GREY_V offsets.
 __device__ __forceinline__ float hue_deg(float nv, float nu) {
     const float ax = fabsf(nu), ay = fabsf(nv);
-    const float a = fminf(ax, ay);
-    const float b = fmaxf(fmaxf(ax, ay), 1e-37f);
-    const float q = a * mufu_rcp(b);
+    const float q = (ay - ax) * mufu_rcp(ay + ax);
     const float s = q * q;
-    static_assert(ATAN_TERMS == 8, "Horner chain below is written for 8 terms");
-    float p = fmaf(ATAN_C7, s, ATAN_C6);
-    p = fmaf(p, s, ATAN_C5);
+    static_assert(ATAN_TERMS == 7, "Horner chain below is written for 7 terms");
+    float p = fmaf(ATAN_C6, s, ATAN_C5);
     p = fmaf(p, s, ATAN_C4);
     p = fmaf(p, s, ATAN_C3);
     p = fmaf(p, s, ATAN_C2);
     p = fmaf(p, s, ATAN_C1);
     p = fmaf(p, s, ATAN_C0);
-    float r = p * q;                       // [0, 45]
-    r = (ay > ax) ? 90.0f - r : r;         // [0, 90]
+    float r = fmaf(p, q, 45.0f);           // [0, 90]
     r = (nu < 0.0f) ? 180.0f - r : r;      // [0, 180]
     r = (nv < 0.0f) ? 360.0f - r : r;      // [0, 360]
     return r;
@@ -130,23 +129,38 @@ __device__ __forceinline__ Diff make_diff(const LinPx &p) {
     return d;
 }
 
-// IS_U8 (kept for the callers' documentation value): with uint8 input the
-// lightness clamps can only fire for pure black / pure white (nearest neighbours
-// (0,0,1) -> L = 0.0198, (255,255,254) -> L = 99.975), where the float64 path
-// yields H = 0 / H = WHITE_HUE (reference _simd.c:79-81, 205-212) -- both are
-// exact greys and get their hue from hue_deg's grey rule.
+// 4X - REF_U*D and 9Y - REF_V*D as linear forms of the differences.  Their
+// g-coefficients vanish (white point), so exact greys would give atan2(0, 0);
+// the float64 reference evaluates atan2 of its own rounding residue there and
+// lands at 17.6 .. 21.1 degrees (19.916 for white, 0 for black).  The constant
+// offsets 1e-13*(cos, sin)(WHITE_HUE) -- nine orders of magnitude below the
+// smallest non-grey |Nu|, |Nv| -- give every grey the hue of white with no
+// select; black is handled by the callers (H = 0, like the reference).
+__device__ __forceinline__ void hue_forms(const Diff &d, float &nu, float &nv) {
+    nu = fmaf(U_DR, d.dr, fmaf(U_DB, d.db, GREY_U));
+    nv = fmaf(V_DR, d.dr, fmaf(V_DB, d.db, GREY_V));
+}
+
+// IS_U8: with uint8 input the lightness clamps (L > 99.99 -> S = 0, L = 100;
+// L < 0.01 -> S = 0, L = 0; nphusl.py:146-152) can only fire for pure white and
+// pure black (nearest neighbours (255,255,254) -> L = 99.975, (0,0,1) -> L =
+// 0.0198).  For those two colours D*(1-Y) is exactly 0, both saturation
+// candidates evaluate to 0*inf = NaN and the three-input max with 0 (FMNMX3
+// returns the non-NaN operand) yields S = 0; L = 116*ex2(lg2(1)/3) - 16 = 100 and
+// KAPPA*0 = 0 exactly.  So the uint8 kernels need no clamp instructions at all.
+// Float inputs keep the explicit clamps, expressed on Y.
 template <bool IS_U8>
 __device__ __forceinline__ void husl_from_diff(const Diff &d, float &H, float &S, float &L) {
+    static_assert(Y_S == 1.0f, "Y = g + t and 1 - Y = (1-g) - t below rely on the Y row summing to 1 in float32");
     const float t = fmaf(Y_DR, d.dr, Y_DB * d.db);
-    const float Y = fmaf(Y_S, d.g, t);                     // luminance
-    const float omY = fmaf(Y_S, d.cg, ONE_M_SY - t);       // 1 - Y, cancellation-free
+    const float Y = d.g + t;                               // luminance
+    const float omY = d.cg - t;                            // 1 - Y, cancellation-free
     const float Dp = fmaf(D_DR, d.dr, D_DB * d.db);
     const float D = fmaf(D_S, d.g, Dp);                    // X + 15Y + 3Z
-    // 4X - REF_U*D and 9Y - REF_V*D; the vanishing g-term gives exact greys the
-    // reference-like hue (WHITE_HUE; 0 for black) without a select (gen_coeffs.py)
-    const float nu = fmaf(GREY_U, d.g, fmaf(U_DR, d.dr, U_DB * d.db));
-    const float nv = fmaf(GREY_V, d.g, fmaf(V_DR, d.dr, V_DB * d.db));
-    const float h = hue_deg(nv, nu);
+    float nu, nv;
+    hue_forms(d, nu, nv);
+    float h = hue_deg(nv, nu);
+    h = (D > 0.0f) ? h : 0.0f;                             // black
 
     // saturation: channel-hits-0 and channel-hits-1 gamut faces
     const float mnd = fminf(fminf(d.dr, d.db), 0.0f);      // min(r,g,b) - g
@@ -156,26 +170,29 @@ __device__ __forceinline__ void husl_from_diff(const Diff &d, float &H, float &S
     const float R100 = 100.0f * mufu_rcp(D * omY);
     const float s0 = (T0 * omY) * R100;
     const float s1 = fmaf((-D_S * Y) * omx, R100, 100.0f);
-    float s = fmaxf(s0, s1);
+    float s = fmaxf(fmaxf(s0, s1), 0.0f);                  // one FMNMX3; NaN (black, white) -> 0
 
     // lightness: 116*cbrt(Y)-16 above EPSILON, KAPPA*Y below (nphusl.py:268-275)
     const float cb = mufu_ex2(mufu_lg2(Y) * (1.0f / 3.0f));
     float l = (Y > EPSILON) ? fmaf(116.0f, cb, -16.0f) : KAPPA * Y;
 
-    // L > 99.99 -> (S,L) = (0,100); L < 0.01 -> (0,0)  (nphusl.py:146-152),
-    // expressed on Y so the clamp does not depend on the cbrt approximation
-    const bool white = Y > Y_HI;
-    const bool black = Y < Y_LO;
-    s = (white || black) ? 0.0f : s;
-    l = white ? 100.0f : l;
-    l = black ? 0.0f : l;
+    if (!IS_U8) {
+        // L > 99.99 -> (S,L) = (0,100); L < 0.01 -> (0,0), expressed on Y so the
+        // clamp does not depend on the cbrt approximation
+        const bool white = Y > Y_HI;
+        const bool black = Y < Y_LO;
+        s = (white || black) ? 0.0f : s;
+        l = white ? 100.0f : l;
+        l = black ? 0.0f : l;
+    }
     H = h; S = s; L = l;
 }
 
 __device__ __forceinline__ float hue_from_diff(const Diff &d) {
-    const float nu = fmaf(GREY_U, d.g, fmaf(U_DR, d.dr, U_DB * d.db));
-    const float nv = fmaf(GREY_V, d.g, fmaf(V_DR, d.dr, V_DB * d.db));
-    return hue_deg(nv, nu);
+    float nu, nv;
+    hue_forms(d, nu, nv);
+    const float h = hue_deg(nv, nu);
+    return (fmaxf(fmaxf(d.dr, d.db), d.g) > 0.0f) ? h : 0.0f;   // black <=> r = g = b = 0
 }
 
 // ---- inverse core --------------------------------------------------------------
@@ -185,38 +202,41 @@ __device__ __forceinline__ float from_linear_255(float v) {
     return (v <= 0.0031308f) ? (12.92f * 255.0f) * v : fmaf(1.055f * 255.0f, pw, -0.055f * 255.0f);
 }
 
-// (H,S,L) -> companded RGB scaled to 0..255 (not rounded)
+// (H,S,L) -> companded RGB scaled to 0..255 (not rounded).
+// EXACT_EXT = false (uint8 output): the lightness clamps (L > 99.99 -> white,
+// L < 0.01 -> black, nphusl.py:351-357) cost one select: S is zeroed there, Y is
+// saturated to [0, 1] by the .SAT modifier of the multiply that produces it, and
+// what is left of Y between the clamp threshold and the end point (>= 0.99974 /
+// <= 1.1e-5) rounds to 255 / 0 in every channel.  EXACT_EXT = true (float RGB
+// output) returns exactly 1 / 0 there like the reference.
+template <bool EXACT_EXT = false>
 __device__ __forceinline__ void rgb255_from_husl(float H, float S, float L,
                                                  float &R, float &G, float &B) {
     const float th = H * 0.017453292519943295f;
     const float sn = mufu_sin(th), cs = mufu_cos(th);
-    // Y and 1-Y from L (nphusl.py:385-392); 1-Y = (1-w)(1+w+w^2), w = (L+16)/116
+    // Y from L (nphusl.py:385-392); near white 1-Y only scales a chroma that vanishes with it
     const float w = fmaf(L, 1.0f / 116.0f, 16.0f / 116.0f);
-    const float omw = fmaf(L, -1.0f / 116.0f, 100.0f / 116.0f);
-    const bool big = L > 8.0f;
-    float Y = big ? w * w * w : L * INV_KAPPA;
-    const float omY = big ? omw * fmaf(w, w, 1.0f + w) : 1.0f - Y;
-    // directional derivatives of the three channel forms along the hue ray
-    const float g0 = fmaf(AU0, cs, AV0 * sn);
-    const float g1 = fmaf(AU1, cs, AV1 * sn);
-    const float g2 = fmaf(AU2, cs, AV2 * sn);
+    float Y = (L > 8.0f) ? __saturatef(w * w * w) : __saturatef(L * INV_KAPPA);
+    // L outside [0.01, 99.99] (or NaN): one compare on |L - 50| for the uint8 path (the +-2e-6
+    // it blurs the lower threshold by is far inside the band that rounds to black anyway)
+    const bool ext = EXACT_EXT ? !(L >= 0.01f && L <= 99.99f) : !(fabsf(L - 50.0f) <= (99.99f - 50.0f));
+    if (EXACT_EXT) Y = (L > 99.99f) ? 1.0f : ((L < 0.01f) ? 0.0f : Y);
+    const float omY = 1.0f - Y;
+    // directional derivatives (a quarter of them) of the three channel forms along the hue ray
+    const float g0 = fmaf(0.25f * AU0, cs, (0.25f * AV0) * sn);
+    const float g1 = fmaf(0.25f * AU1, cs, (0.25f * AV1) * sn);
+    const float g2 = fmaf(0.25f * AU2, cs, (0.25f * AV2) * sn);
     const float gmin = fminf(fminf(g0, g1), g2);
     const float gmax = fmaxf(fmaxf(g0, g1), g2);
-    // 1/tau_max = max(-gmin/AN, (Y*gmax - 4 sin)/(4 REF_V (1-Y)))  (six lines)
-    const float c = REF_V4 * omY;
-    float den = fmaxf((gmin * (-1.0f / AN)) * c, fmaf(Y, gmax, -4.0f * sn));
-    float N = (S * 0.01f) * c;                              // tau = N / den
-    // L > 99.99 -> white, L < 0.01 -> black (nphusl.py:351-357)
-    const bool white = L > 99.99f;
-    const bool black = L < 0.01f;
-    const bool ext = white || black;
-    N = ext ? 0.0f : N;
-    den = ext ? 1.0f : den;
-    Y = white ? 1.0f : Y;
-    Y = black ? 0.0f : Y;
-    // lin_i = Y*(AN*den + N*g_i) / (4*(REF_V*den + N*sin))
-    const float yr = Y * mufu_rcp(fmaf(4.0f * N, sn, REF_V4 * den));
+    // 1/(4 tau_max) = max(-gmin/AN, (Y*gmax - sin)/(4 REF_V (1-Y)))  (six lines), both sides times
+    // 4 REF_V (1-Y) with AN == 4 REF_V: den = max(-gmin*(1-Y), Y*gmax - sin); > 0 inside the gamut,
+    // the tiny floor keeps 0/0 out when L is at or beyond an end point
+    static_assert(AN == REF_V4, "the inverse folds AN and 4*REF_V into one constant");
+    const float den = fmaxf(fmaxf(-gmin * omY, fmaf(Y, gmax, -sn)), 1e-30f);
+    const float N = ((ext ? 0.0f : S) * (0.01f * REF_V4)) * omY;   // tau = N / (4 den)
+    // lin_i = Y*(AN*den + N*g_i) / (4 REF_V*den + N*sin)   (AN == 4 REF_V)
     const float base = AN * den;
+    const float yr = Y * mufu_rcp(fmaf(N, sn, base));
     R = from_linear_255(fmaf(N, g0, base) * yr);
     G = from_linear_255(fmaf(N, g1, base) * yr);
     B = from_linear_255(fmaf(N, g2, base) * yr);

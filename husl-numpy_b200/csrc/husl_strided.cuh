@@ -81,8 +81,8 @@ k_inv_strided(const View2 in, const View2 out) {
         for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < in.cols; x += xstep) {
             const char *p = irow + x * in.cs;
             float R, G, B;
-            rgb255_from_husl((float)*reinterpret_cast<const TIn *>(p), (float)*reinterpret_cast<const TIn *>(p + in.es),
-                             (float)*reinterpret_cast<const TIn *>(p + 2 * in.es), R, G, B);
+            rgb255_from_husl<sizeof(TOut) != 1>((float)*reinterpret_cast<const TIn *>(p), (float)*reinterpret_cast<const TIn *>(p + in.es),
+                                                (float)*reinterpret_cast<const TIn *>(p + 2 * in.es), R, G, B);
             char *o = orow + x * out.cs;
             if (sizeof(TOut) == 1) {
                 *reinterpret_cast<uint8_t *>(o) = (uint8_t)(round_u8_bits(R) & 0xFF);

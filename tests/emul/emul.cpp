@@ -71,9 +71,12 @@ void emul_inv(const float *hsl, float *rgb255, uint8_t *u8, long long n) {
 #pragma omp parallel for
     for (long long i = 0; i < n; ++i) {
         float R, G, B;
-        rgb255_from_husl(hsl[3 * i], hsl[3 * i + 1], hsl[3 * i + 2], R, G, B);
-        if (rgb255) { rgb255[3 * i] = R; rgb255[3 * i + 1] = G; rgb255[3 * i + 2] = B; }
-        if (u8) {
+        if (rgb255) {      // float RGB output: exact end points (EXACT_EXT), as k_inv_any<T, float/double>
+            rgb255_from_husl<true>(hsl[3 * i], hsl[3 * i + 1], hsl[3 * i + 2], R, G, B);
+            rgb255[3 * i] = R; rgb255[3 * i + 1] = G; rgb255[3 * i + 2] = B;
+        }
+        if (u8) {          // uint8 output: the streaming kernels' variant
+            rgb255_from_husl<false>(hsl[3 * i], hsl[3 * i + 1], hsl[3 * i + 2], R, G, B);
             u8[3 * i] = (uint8_t)(round_u8_bits(R) & 0xFF);
             u8[3 * i + 1] = (uint8_t)(round_u8_bits(G) & 0xFF);
             u8[3 * i + 2] = (uint8_t)(round_u8_bits(B) & 0xFF);
