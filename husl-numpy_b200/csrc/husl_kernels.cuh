@@ -217,7 +217,7 @@ k_inv_u8(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_til
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
-            rgb255_from_husl(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
+            rgb255_from_husl<false, sizeof(TIn) == 8>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }
         // pack 12 low bytes into 3 words (PRMT), lane-contiguous 12 B -> staging -> coalesced
@@ -302,7 +302,7 @@ k_inv_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float R, G, B;
-        rgb255_from_husl<sizeof(TOut) != 1>((float)in[3 * i], (float)in[3 * i + 1], (float)in[3 * i + 2], R, G, B);
+        rgb255_from_husl<sizeof(TOut) != 1, sizeof(TIn) == 8>((float)in[3 * i], (float)in[3 * i + 1], (float)in[3 * i + 2], R, G, B);
         if (sizeof(TOut) == 1) {
             out[3 * i] = (TOut)(round_u8_bits(R) & 0xFF);
             out[3 * i + 1] = (TOut)(round_u8_bits(G) & 0xFF);

@@ -209,7 +209,14 @@ __device__ __forceinline__ float from_linear_255(float v) {
 // what is left of Y between the clamp threshold and the end point (>= 0.99974 /
 // <= 1.1e-5) rounds to 255 / 0 in every channel.  EXACT_EXT = true (float RGB
 // output) returns exactly 1 / 0 there like the reference.
-template <bool EXACT_EXT = false>
+// FACTORED_OMY: 1-Y as (1-w)(1+w+w^2) instead of 1 - w^3.  Numerically irrelevant
+// here (1-Y only scales a chroma that vanishes with it); it is a scheduling knob:
+// the float64 TMA kernel runs 16 warps/SM and is sensitive to the instruction-level
+// parallelism ptxas finds -- with the factored form it allocates 55 instead of 48
+// registers and the kernel goes from 0.290 to 0.277 ms per 66 Mpx, while the
+// float32 kernels (48 warps/SM) are faster with the shorter form (0.170 vs 0.196 ms;
+// profiles/r01_ab_variants.txt, run 22).
+template <bool EXACT_EXT = false, bool FACTORED_OMY = false>
 __device__ __forceinline__ void rgb255_from_husl(float H, float S, float L,
                                                  float &R, float &G, float &B) {
     const float th = H * 0.017453292519943295f;
@@ -221,7 +228,11 @@ __device__ __forceinline__ void rgb255_from_husl(float H, float S, float L,
     // it blurs the lower threshold by is far inside the band that rounds to black anyway)
     const bool ext = EXACT_EXT ? !(L >= 0.01f && L <= 99.99f) : !(fabsf(L - 50.0f) <= (99.99f - 50.0f));
     if (EXACT_EXT) Y = (L > 99.99f) ? 1.0f : ((L < 0.01f) ? 0.0f : Y);
-    const float omY = 1.0f - Y;
+    float omY = 1.0f - Y;
+    if (FACTORED_OMY) {      // (1-w)(1+w+w^2): same value to ~1e-7, five more instructions, more ILP (see above)
+        const float omw = fmaf(L, -1.0f / 116.0f, 100.0f / 116.0f);
+        omY = (L > 8.0f) ? omw * fmaf(w, w, 1.0f + w) : omY;
+    }
     // directional derivatives (a quarter of them) of the three channel forms along the hue ray
     const float g0 = fmaf(0.25f * AU0, cs, (0.25f * AV0) * sn);
     const float g1 = fmaf(0.25f * AU1, cs, (0.25f * AV1) * sn);

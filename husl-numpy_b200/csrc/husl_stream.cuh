@@ -241,7 +241,7 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
-            rgb255_from_husl(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
+            rgb255_from_husl<false, sizeof(TIn) == 8>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }
         const uint32_t o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);

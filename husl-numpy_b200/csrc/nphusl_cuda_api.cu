@@ -146,6 +146,48 @@ int ctx_get(int device, DevCtx **out) {
 // ---- kernel dispatch --------------------------------------------------------------
 constexpr int FWD_BLOCK = 512;
 constexpr int INV_BLOCK = 256;
+// launch shapes of the float32 streaming kernels (threads per CTA, CTAs per SM), tuned on B200
+// (profiles/r01_ab_variants.txt); overridable at build time for A/B runs
+#ifndef NPHUSL_FWD32_BLOCK
+#define NPHUSL_FWD32_BLOCK 1024      // one CTA of 32 warps (64 registers) beat 2 x 512 (48) by 2.8 %
+#define NPHUSL_FWD32_MINB 1
+#endif
+#ifndef NPHUSL_HUE32_BLOCK
+#define NPHUSL_HUE32_BLOCK 1024
+#define NPHUSL_HUE32_MINB 2
+#endif
+#ifndef NPHUSL_INV32_BLOCK
+#define NPHUSL_INV32_BLOCK 384
+#define NPHUSL_INV32_MINB 4
+#endif
+#ifndef NPHUSL_INV32_IST
+#define NPHUSL_INV32_IST 3
+#endif
+#ifndef NPHUSL_FWD32_TMA
+#define NPHUSL_FWD32_TMA 0          // 1: float32 results leave through TMA bulk stores as well
+#endif
+#ifndef NPHUSL_FWD32_OST
+#define NPHUSL_FWD32_OST 2
+#endif
+#ifndef NPHUSL_FWD64_BLOCK
+#define NPHUSL_FWD64_BLOCK 512
+#endif
+#ifndef NPHUSL_FWD64_OST
+#define NPHUSL_FWD64_OST 2
+#endif
+#ifndef NPHUSL_INV64_BLOCK
+#define NPHUSL_INV64_BLOCK 256
+#define NPHUSL_INV64_MINB 2
+#endif
+#ifndef NPHUSL_INV64_IST
+#define NPHUSL_INV64_IST 3
+#endif
+constexpr int FWD64_BLOCK = NPHUSL_FWD64_BLOCK, FWD64_OST = NPHUSL_FWD64_OST;
+constexpr int INV64_BLOCK = NPHUSL_INV64_BLOCK, INV64_MINB = NPHUSL_INV64_MINB, INV64_IST = NPHUSL_INV64_IST;
+[[maybe_unused]] constexpr int FWD32_OST = NPHUSL_FWD32_OST;
+constexpr int FWD32_BLOCK = NPHUSL_FWD32_BLOCK, FWD32_MINB = NPHUSL_FWD32_MINB;
+constexpr int HUE32_BLOCK = NPHUSL_HUE32_BLOCK, HUE32_MINB = NPHUSL_HUE32_MINB;
+constexpr int INV32_BLOCK = NPHUSL_INV32_BLOCK, INV32_MINB = NPHUSL_INV32_MINB, INV32_IST = NPHUSL_INV32_IST;
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
@@ -157,13 +199,16 @@ int set_attrs(DevCtx &c) {
     if (c.attr_set) return NPHUSL_OK;
     int rc;
     constexpr int W = FWD_BLOCK / 32;
-    if ((rc = set_smem(k_fwd_u8<float, false, FWD_BLOCK, 2>, TAB_BYTES + W * Pack<float>::STAGE))) return rc;
+    if ((rc = set_smem(k_fwd_u8<float, false, FWD32_BLOCK, FWD32_MINB>, TAB_BYTES + (FWD32_BLOCK / 32) * Pack<float>::STAGE))) return rc;
+#if NPHUSL_FWD32_TMA
+    if ((rc = set_smem(k_fwd_tma<float, FWD32_BLOCK, FWD32_MINB, FWD32_OST>, TAB_BYTES + (FWD32_BLOCK / 32) * FWD32_OST * Tile<float>::BYTES))) return rc;
+#endif
     if ((rc = set_smem(k_fwd_u8<double, false, FWD_BLOCK, 1>, TAB_BYTES + W * Pack<double>::STAGE))) return rc;
     if ((rc = set_smem(k_fwd_u8<double, true, FWD_BLOCK, 3>, TAB_BYTES))) return rc;
-    if ((rc = set_smem(k_fwd_tma<double, 512, 1, 2>, TAB_BYTES + 16 * 2 * Tile<double>::BYTES))) return rc;
-    if ((rc = set_smem(k_inv_tma<double, INV_BLOCK, 2, 3>, (INV_BLOCK / 32) * InvSmem<double, 3>::PER_WARP))) return rc;
-    if ((rc = set_smem(k_fwd_u8<float, true, 1024, 2>, TAB_BYTES))) return rc;
-    if ((rc = set_smem(k_inv_cp<384, 4, 3>, 12 * InvCpSmem<3>::PER_WARP))) return rc;
+    if ((rc = set_smem(k_fwd_tma<double, FWD64_BLOCK, 1, FWD64_OST>, TAB_BYTES + (FWD64_BLOCK / 32) * FWD64_OST * Tile<double>::BYTES))) return rc;
+    if ((rc = set_smem(k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST>, (INV64_BLOCK / 32) * InvSmem<double, INV64_IST>::PER_WARP))) return rc;
+    if ((rc = set_smem(k_fwd_u8<float, true, HUE32_BLOCK, HUE32_MINB>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST>, (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP))) return rc;
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_edit<512, 2>, TAB_BYTES + 16 * 384))) return rc;
@@ -234,19 +279,27 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
         if (!HUE && use_tma() && out_dt == NPHUSL_F64) {
             // float64 output is HBM-bound: results leave through TMA bulk stores;
             // float32 output is issue-bound and keeps the leaner LDS/STG transposition
-            const int grid = grid_for(tiles, 16, c.sms);
-            k_fwd_tma<double, 512, 1, 2><<<grid, 512, TAB_BYTES + 16 * 2 * Tile<double>::BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
+            const int grid = grid_for(tiles, FWD64_BLOCK / 32, c.sms);
+            k_fwd_tma<double, FWD64_BLOCK, 1, FWD64_OST><<<grid, FWD64_BLOCK, TAB_BYTES + (FWD64_BLOCK / 32) * FWD64_OST * Tile<double>::BYTES, s>>>(
+                (const uint32_t *)in, (double *)out, tiles);
         } else if (HUE) {
             // hue only: no staging buffer, 64 KB of table per CTA -> 3 CTAs (48 warps) per SM
             const int grid = grid_for(tiles, W, c.sms * 3);
             if (out_dt == NPHUSL_F32)   // float32 hue: 2 x 1024 threads (64 warps/SM, 32 registers) measured best
-                k_fwd_u8<float, true, 1024, 2><<<grid_for(tiles, 32, c.sms * 2), 1024, TAB_BYTES, s>>>((const uint32_t *)in, (float *)out, tiles);
+                k_fwd_u8<float, true, HUE32_BLOCK, HUE32_MINB><<<grid_for(tiles, HUE32_BLOCK / 32, c.sms * HUE32_MINB), HUE32_BLOCK, TAB_BYTES, s>>>(
+                    (const uint32_t *)in, (float *)out, tiles);
             else
                 k_fwd_u8<double, true, FWD_BLOCK, 3><<<grid, FWD_BLOCK, TAB_BYTES, s>>>((const uint32_t *)in, (double *)out, tiles);
         } else if (out_dt == NPHUSL_F32) {
-            const size_t sm = TAB_BYTES + W * Pack<float>::STAGE;
-            const int grid = grid_for(tiles, W, c.sms * 2);
-            k_fwd_u8<float, false, FWD_BLOCK, 2><<<grid, FWD_BLOCK, sm, s>>>((const uint32_t *)in, (float *)out, tiles);
+            constexpr int W32 = FWD32_BLOCK / 32;
+            const int grid = grid_for(tiles, W32, c.sms * FWD32_MINB);
+#if NPHUSL_FWD32_TMA
+            k_fwd_tma<float, FWD32_BLOCK, FWD32_MINB, FWD32_OST><<<grid, FWD32_BLOCK, TAB_BYTES + W32 * FWD32_OST * Tile<float>::BYTES, s>>>(
+                (const uint32_t *)in, (float *)out, tiles);
+#else
+            const size_t sm = TAB_BYTES + W32 * Pack<float>::STAGE;
+            k_fwd_u8<float, false, FWD32_BLOCK, FWD32_MINB><<<grid, FWD32_BLOCK, sm, s>>>((const uint32_t *)in, (float *)out, tiles);
+#endif
         } else {
             const size_t sm = TAB_BYTES + W * Pack<double>::STAGE;
             const int grid = grid_for(tiles, W, c.sms);
@@ -275,17 +328,17 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
         constexpr int W = INV_BLOCK / 32;
         if (use_tma() && aligned(out, 16)) {
             if ((rc = set_attrs(c))) return rc;
-#define INV_GO(T, MINB, IST) \
-    k_inv_tma<T, INV_BLOCK, MINB, IST><<<grid_for(tiles, W, c.sms * MINB), INV_BLOCK, W * InvSmem<T, IST>::PER_WARP, s>>>( \
-        (const T *)in, (uint32_t *)out, tiles)
             // tuned on B200 (profiles/r01_ab_variants.txt).  float32 input is bound by the math
             // pipes: 3-stage LDGSTS ring; float64 input is HBM-bound: 3-stage bulk-copy (TMA)
             // ring with mbarriers, 2 CTAs/SM
             if (in_dt == NPHUSL_F32)   // 4 CTAs x 384 threads = 48 warps/SM at 40 registers
-                k_inv_cp<384, 4, 3><<<grid_for(tiles, 12, c.sms * 4), 384, 12 * InvCpSmem<3>::PER_WARP, s>>>(
+                k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK,
+                                                               (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP, s>>>(
                     (const float *)in, (uint32_t *)out, tiles);
-            else INV_GO(double, 2, 3);
-#undef INV_GO
+            else
+                k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST><<<grid_for(tiles, INV64_BLOCK / 32, c.sms * INV64_MINB), INV64_BLOCK,
+                                                                        (INV64_BLOCK / 32) * InvSmem<double, INV64_IST>::PER_WARP, s>>>(
+                    (const double *)in, (uint32_t *)out, tiles);
         } else if (in_dt == NPHUSL_F32) {
             const int grid = grid_for(tiles, W, c.sms * 4);
             k_inv_u8<float, INV_BLOCK, 4><<<grid, INV_BLOCK, W * Pack<float>::STAGE, s>>>((const float *)in, (uint32_t *)out, tiles);
