@@ -214,7 +214,16 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(0.001)
+
+    def mark(self):
+        """-> index of the next sample (to cut the value region out of the whole run)"""
+        return len(self.samples)
+
+    def stats(self, lo=0, hi=None):
+        part = self.samples[lo:hi]
+        return {"sm_mhz": float(np.median(part)) if part else None, "sm_mhz_min": min(part) if part else None,
+                "samples": len(part)}
 
     def stop(self):
         self._stop_evt.set()
@@ -300,22 +309,35 @@ def run_cuda(args):
     for _ in range(W):
         step_dev()
     barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    # The K steps are bracketed by one pair of events; every PROBE-th step additionally carries
+    # events around each of its two kernels (the live per-launch durations of `roofline`).  An event
+    # between two kernels costs ~3.5 us of lost launch overlap, so not every step is instrumented.
+    PROBE = 4
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for k in range(0, K, PROBE)}
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
     n0 = _cuda.launch_count()
     barrier()
+    m0 = sampler.mark()
+    t_beg.record(stream)
     for k in range(K):
-        ev[k][0].record(stream)
+        e = ev.get(k)
+        if e:
+            e[0].record(stream)
         nphusl.to_husl(dev_in, out=dev_hsl, stream=stream)
-        ev[k][1].record(stream)
+        if e:
+            e[1].record(stream)
         nphusl.to_rgb(dev_hsl, out=dev_out, stream=stream)
-        ev[k][2].record(stream)
+        if e:
+            e[2].record(stream)
+    t_end.record(stream)
     torch.cuda.synchronize()
+    m1 = sampler.mark()
     launches = _cuda.launch_count() - n0
-    total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
-    t_fwd = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    t_inv = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    total_ms = t_beg.elapsed_time(t_end)
+    t_fwd = float(np.mean([e[0].elapsed_time(e[1]) for e in ev.values()]))
+    t_inv = float(np.mean([e[1].elapsed_time(e[2]) for e in ev.values()]))
     if not torch.equal(dev_out, dev_in):
         raise SystemExit("bench.py: round trip is not exact -- refusing to report a number")
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -373,6 +395,26 @@ def run_cuda(args):
     torch.cuda.synchronize()
     e2e_blocking = px * 5 / (time.perf_counter() - tb) / 1e6
 
+    # the reference's own data flow: the HUSL array comes back to the HOST (to_husl returns a
+    # float64 ndarray, 24 B/px) and goes up again for to_rgb -- 27 B/px over the link each way
+    e2e_host_husl = None
+    if rank == 0 and not args.no_variants:
+        try:
+            host_hsl = _cuda.pinned_empty((B,) + FRAME, hdt)
+            def step_host_husl():
+                nphusl.to_husl(host_in, out=host_hsl)
+                nphusl.to_rgb(host_hsl, out=host_out)
+            step_host_husl()
+            torch.cuda.synchronize()
+            th = time.perf_counter()
+            for _ in range(3):
+                step_host_husl()
+            torch.cuda.synchronize()
+            e2e_host_husl = px * 3 / (time.perf_counter() - th) / 1e6
+            del host_hsl
+        except Exception as e:                         # not enough pinned memory on this box
+            e2e_host_husl = repr(e)
+
     Ke = max(4, min(K, 20))
     for k in range(4):
         step_e2e(k)
@@ -383,6 +425,7 @@ def run_cuda(args):
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3         # wall clock around submit + drain of Ke steps
     clocks = sampler.stop()                           # sampled across the value and e2e timed regions
+    clocks["value_region"] = sampler.stats(m0, m1)    # the device-resident K steps alone
     if not np.array_equal(np.asarray(host_out), np.asarray(host_in)):
         raise SystemExit("bench.py: e2e round trip is not exact")
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
@@ -444,7 +487,8 @@ def run_cuda(args):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config(args, world, B),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px * 3,
-                    "steps": Ke, "link_gbs": link, "blocking_calls_mpix_s_this_rank": e2e_blocking, "path": "nphusl.to_husl(pinned host u8 -> device HUSL) + nphusl.to_rgb(device HUSL -> pinned host u8), "
+                    "steps": Ke, "link_gbs": link, "blocking_calls_mpix_s_this_rank": e2e_blocking,
+                    "host_husl_mpix_s_this_rank": e2e_host_husl, "path": "nphusl.to_husl(pinned host u8 -> device HUSL) + nphusl.to_rgb(device HUSL -> pinned host u8), "
                             "blocking=False on two alternating streams; wall clock incl. final synchronize"},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -209,30 +209,59 @@ __device__ __forceinline__ float from_linear_255(float v) {
 // what is left of Y between the clamp threshold and the end point (>= 0.99974 /
 // <= 1.1e-5) rounds to 255 / 0 in every channel.  EXACT_EXT = true (float RGB
 // output) returns exactly 1 / 0 there like the reference.
-// FACTORED_OMY: 1-Y as (1-w)(1+w+w^2) instead of 1 - w^3.  Numerically irrelevant
-// here (1-Y only scales a chroma that vanishes with it); it is a scheduling knob:
-// the float64 TMA kernel runs 16 warps/SM and is sensitive to the instruction-level
-// parallelism ptxas finds -- with the factored form it allocates 55 instead of 48
-// registers and the kernel goes from 0.290 to 0.277 ms per 66 Mpx, while the
-// float32 kernels (48 warps/SM) are faster with the shorter form (0.170 vs 0.196 ms;
-// profiles/r01_ab_variants.txt, run 22).
-template <bool EXACT_EXT = false, bool FACTORED_OMY = false>
+// WIDE selects the long-hand formulation below instead (explicit selects for the
+// end points, factored 1-Y, unfolded constants: 100 instead of 92 instructions per
+// pixel in k_inv_tma, same values to float32 rounding).  It is a scheduling choice
+// for float64 HUSL input: that kernel is HBM-bound at 16 warps/SM and, inside the
+// to_husl -> to_rgb pipeline where it starts on the producer's dirty L2 lines, the
+// step takes 0.594 ms with the long form against 0.600 - 0.608 ms with every
+// shorter form tried, although the short forms are faster stand-alone (0.280 vs
+// 0.284 ms).  The float32 kernels (48 warps/SM, issue-bound) gain 7 % from the
+// short form (profiles/r01_ab_variants.txt, runs 22-27).
+template <bool EXACT_EXT = false, bool WIDE = false>
 __device__ __forceinline__ void rgb255_from_husl(float H, float S, float L,
                                                  float &R, float &G, float &B) {
     const float th = H * 0.017453292519943295f;
     const float sn = mufu_sin(th), cs = mufu_cos(th);
-    // Y from L (nphusl.py:385-392); near white 1-Y only scales a chroma that vanishes with it
     const float w = fmaf(L, 1.0f / 116.0f, 16.0f / 116.0f);
+    if (WIDE) {
+        // Y and 1-Y from L (nphusl.py:385-392); 1-Y = (1-w)(1+w+w^2), w = (L+16)/116
+        const float omw = fmaf(L, -1.0f / 116.0f, 100.0f / 116.0f);
+        const bool big = L > 8.0f;
+        float Y = big ? w * w * w : L * INV_KAPPA;
+        const float omY = big ? omw * fmaf(w, w, 1.0f + w) : 1.0f - Y;
+        const float g0 = fmaf(AU0, cs, AV0 * sn);
+        const float g1 = fmaf(AU1, cs, AV1 * sn);
+        const float g2 = fmaf(AU2, cs, AV2 * sn);
+        const float gmin = fminf(fminf(g0, g1), g2);
+        const float gmax = fmaxf(fmaxf(g0, g1), g2);
+        // 1/tau_max = max(-gmin/AN, (Y*gmax - 4 sin)/(4 REF_V (1-Y)))  (six lines)
+        const float c = REF_V4 * omY;
+        float den = fmaxf((gmin * (-1.0f / AN)) * c, fmaf(Y, gmax, -4.0f * sn));
+        float N = (S * 0.01f) * c;                              // tau = N / den
+        // L > 99.99 -> white, L < 0.01 -> black (nphusl.py:351-357)
+        const bool white = L > 99.99f;
+        const bool black = L < 0.01f;
+        const bool ext = white || black;
+        N = ext ? 0.0f : N;
+        den = ext ? 1.0f : den;
+        Y = white ? 1.0f : Y;
+        Y = black ? 0.0f : Y;
+        // lin_i = Y*(AN*den + N*g_i) / (4*(REF_V*den + N*sin))
+        const float yr = Y * mufu_rcp(fmaf(4.0f * N, sn, REF_V4 * den));
+        const float base = AN * den;
+        R = from_linear_255(fmaf(N, g0, base) * yr);
+        G = from_linear_255(fmaf(N, g1, base) * yr);
+        B = from_linear_255(fmaf(N, g2, base) * yr);
+        return;
+    }
+    // Y from L (nphusl.py:385-392); near white 1-Y only scales a chroma that vanishes with it
     float Y = (L > 8.0f) ? __saturatef(w * w * w) : __saturatef(L * INV_KAPPA);
     // L outside [0.01, 99.99] (or NaN): one compare on |L - 50| for the uint8 path (the +-2e-6
     // it blurs the lower threshold by is far inside the band that rounds to black anyway)
     const bool ext = EXACT_EXT ? !(L >= 0.01f && L <= 99.99f) : !(fabsf(L - 50.0f) <= (99.99f - 50.0f));
     if (EXACT_EXT) Y = (L > 99.99f) ? 1.0f : ((L < 0.01f) ? 0.0f : Y);
-    float omY = 1.0f - Y;
-    if (FACTORED_OMY) {      // (1-w)(1+w+w^2): same value to ~1e-7, five more instructions, more ILP (see above)
-        const float omw = fmaf(L, -1.0f / 116.0f, 100.0f / 116.0f);
-        omY = (L > 8.0f) ? omw * fmaf(w, w, 1.0f + w) : omY;
-    }
+    const float omY = 1.0f - Y;
     // directional derivatives (a quarter of them) of the three channel forms along the hue ray
     const float g0 = fmaf(0.25f * AU0, cs, (0.25f * AV0) * sn);
     const float g1 = fmaf(0.25f * AU1, cs, (0.25f * AV1) * sn);

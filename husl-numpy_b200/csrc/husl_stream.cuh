@@ -59,6 +59,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// L2 eviction-priority policies for the bulk copies (A/B knobs, see nphusl_cuda_api.cu)
+#ifndef HUSL_FWD_ST_HINT
+#define HUSL_FWD_ST_HINT 0      // 0 none | 1 evict_first | 2 evict_last | 3 no_allocate-like (evict_first, fraction 1)
+#endif
+#ifndef HUSL_INV_LD_HINT
+#define HUSL_INV_LD_HINT 0
+#endif
+#ifndef HUSL_INV_ST_HINT
+#define HUSL_INV_ST_HINT 0
+#endif
+template <int KIND>
+__device__ __forceinline__ uint64_t l2_policy() {
+    uint64_t p = 0;
+    if (KIND == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    if (KIND == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    if (KIND == 3) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void *dst, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes), "l"(pol)
+                 : "memory");
+}
 // global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
@@ -157,7 +184,8 @@ k_fwd_tma(const uint32_t *__restrict__ in, TOut *__restrict__ out, long long n_t
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            bulk_store(reinterpret_cast<unsigned char *>(out) + tile * TB, obuf_s + st * TB, TB);
+            if (HUSL_FWD_ST_HINT) bulk_store_hint(reinterpret_cast<unsigned char *>(out) + tile * TB, obuf_s + st * TB, TB, l2_policy<HUSL_FWD_ST_HINT>());
+            else bulk_store(reinterpret_cast<unsigned char *>(out) + tile * TB, obuf_s + st * TB, TB);
             bulk_commit();
         }
         st = (st + 1 == OST) ? 0 : st + 1;
@@ -204,7 +232,8 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
             const long long t = first + s * nw;
             if (t < n_tiles) {
                 mbar_expect_tx(bar_s + 8 * s, TB);
-                bulk_load(ibuf_s + s * TB, src - t * TB, TB, bar_s + 8 * s);
+                if (HUSL_INV_LD_HINT) bulk_load_hint(ibuf_s + s * TB, src - t * TB, TB, bar_s + 8 * s, l2_policy<HUSL_INV_LD_HINT>());
+                else bulk_load(ibuf_s + s * TB, src - t * TB, TB, bar_s + 8 * s);
             }
         }
     }
@@ -234,7 +263,8 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
             const long long t = tile + (long long)IST * nw;
             if (t < n_tiles) {
                 mbar_expect_tx(bar_s + 8 * st, TB);
-                bulk_load(ibuf_s + st * TB, src - t * TB, TB, bar_s + 8 * st);
+                if (HUSL_INV_LD_HINT) bulk_load_hint(ibuf_s + st * TB, src - t * TB, TB, bar_s + 8 * st, l2_policy<HUSL_INV_LD_HINT>());
+                else bulk_load(ibuf_s + st * TB, src - t * TB, TB, bar_s + 8 * st);
             }
         }
         uint32_t q[12];
@@ -254,7 +284,8 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            bulk_store(dstb - tile * U8_TILE, obuf_s + ost * U8_TILE, U8_TILE);
+            if (HUSL_INV_ST_HINT) bulk_store_hint(dstb - tile * U8_TILE, obuf_s + ost * U8_TILE, U8_TILE, l2_policy<HUSL_INV_ST_HINT>());
+            else bulk_store(dstb - tile * U8_TILE, obuf_s + ost * U8_TILE, U8_TILE);
             bulk_commit();
         }
         ost ^= 1;

@@ -14,7 +14,10 @@ import sys
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "launch__registers_per_thread",
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.avg.per_second",
