@@ -755,3 +755,43 @@ def test_fused_edit_on_channels_first_planes(cu):
         assert r is t and np.array_equal(np.moveaxis(t.cpu().numpy(), 0, -1), want)
     with pytest.raises(ValueError):
         cu.edit_rgb(hwc, channels_first=True)                      # host arrays: interleaved only
+
+
+def test_decoder_adjacent_frames_never_touch_the_host(cu):
+    """a JPEG decoded ON the GPU (torchvision.io.decode_jpeg(device="cuda"), nvJPEG)
+    arrives as (3, H, W) uint8 planes; the channels-first kernels convert / edit it in place of the
+    reference's imageio -> numpy -> to_husl path and the result is re-encoded on the GPU.  Checked
+    against the host path on the same decoded pixels."""
+    torch = pytest.importorskip("torch")
+    tvio = pytest.importorskip("torchvision.io")
+    rng = np.random.default_rng(21)
+    # a smooth synthetic picture (JPEG-friendly), encoded on the CPU
+    yy, xx = np.mgrid[0:360, 0:640]
+    pic = np.stack([(127 + 120 * np.sin(xx / 40.0)), (127 + 120 * np.cos(yy / 30.0)), (xx + yy) % 256], 0).astype(np.uint8)
+    pic[:, 100:140, 200:300] = rng.integers(0, 256, (3, 40, 100), dtype=np.uint8)
+    jpeg = tvio.encode_jpeg(torch.from_numpy(pic), quality=92)
+    try:
+        frame = tvio.decode_jpeg(jpeg, device="cuda")                  # (3, H, W) uint8 on the device
+    except Exception as e:                                             # torchvision built without nvJPEG
+        pytest.skip("GPU JPEG decode unavailable: %r" % (e,))
+    assert frame.is_cuda and frame.dtype == torch.uint8 and tuple(frame.shape) == pic.shape
+    host = np.ascontiguousarray(np.moveaxis(frame.cpu().numpy(), 0, -1))   # the same decoded pixels, HWC on the host
+    # planes -> HUSL planes -> planes: exact round trip, values equal to the interleaved host path
+    planes = cu.rgb_to_husl_planar(frame, dtype=np.float32, channels_first=True)
+    assert np.array_equal(np.moveaxis(planes.copy_to_host(), 0, -1), cu._rgb_to_husl(host, dtype=np.float32))
+    back = torch.empty_like(frame)
+    cu.husl_planar_to_rgb(planes, out=back, channels_first=True)
+    torch.cuda.synchronize()
+    assert torch.equal(back, frame)
+    # fused edit on the decoded planes, in place, then re-encode on the GPU
+    want = cu.edit_rgb(host, hue=(250, 290), invert=True, l=(0.5, 0))
+    cu.edit_rgb(frame, out=frame, channels_first=True, hue=(250, 290), invert=True, l=(0.5, 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(np.moveaxis(frame.cpu().numpy(), 0, -1), want)
+    try:
+        out_jpeg = tvio.encode_jpeg(frame, quality=92)
+    except Exception as e:
+        pytest.skip("GPU JPEG encode unavailable: %r" % (e,))
+    redecoded = tvio.decode_jpeg(out_jpeg.cpu())
+    assert tuple(redecoded.shape) == pic.shape
+    assert np.abs(redecoded.numpy().astype(int) - np.moveaxis(want, -1, 0).astype(int)).mean() < 6.0
