@@ -331,6 +331,121 @@ def pinned_empty(shape, dtype):
 
 
 # ---------------------------------------------------------------------------
+# page-locked results for host-array calls
+# ---------------------------------------------------------------------------
+# `to_husl(numpy_image)` returns a NEW float64 array: 50 MB for a 1080p frame.  As
+# a fresh pageable allocation that costs more than the conversion itself --
+# 12 000 first-touch page faults plus a bounce copy out of the pinned staging
+# slot (numpy's own `hsl.copy()` of that array runs at 213 Mpix/s on the B200
+# hosts).  Results are therefore carved out of a small recycling pool of
+# page-locked blocks: the D2H copy lands in the returned array directly, and when
+# the caller drops the array the block goes back to the pool.  The returned object
+# is a plain numpy.ndarray whose `.base` keeps the block alive; passing it back
+# into `to_rgb` is a direct DMA as well.  `set_pinned_results(False)` restores
+# plain `np.empty` results.
+
+class _PinnedBlock:
+    """Owner of one page-locked block, exposed through __array_interface__."""
+    __slots__ = ("ptr", "cap", "shape", "typestr")
+
+    def __init__(self, ptr, cap, shape, dtype):
+        self.ptr, self.cap, self.shape, self.typestr = ptr, cap, tuple(shape), np.dtype(dtype).str
+
+    @property
+    def __array_interface__(self):
+        return {"shape": self.shape, "typestr": self.typestr, "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            _pinned_pool.release(self.ptr, self.cap)
+        except Exception:
+            pass
+
+
+class _PinnedPool:
+    GRAIN = 2 << 20                      # size classes of 2 MiB
+
+    def __init__(self):
+        self.enabled = os.environ.get("NPHUSL_PINNED_RESULTS", "1") != "0"
+        self.min_bytes = 1 << 20         # smaller results: np.empty
+        self.max_cached = int(os.environ.get("NPHUSL_PINNED_CACHE_MB", "1024")) << 20
+        self.max_outstanding = int(os.environ.get("NPHUSL_PINNED_MAX_MB", "8192")) << 20
+        self.free = {}                   # cap -> [ptr, ...]
+        self.cached = 0
+        self.outstanding = 0
+        self.lock = threading.Lock()
+        self.hits = self.misses = 0
+
+    def empty(self, shape, dtype):
+        """-> ndarray backed by a pooled pinned block, or None (disabled / too small / over budget)"""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        if not self.enabled or n < self.min_bytes:
+            return None
+        cap = (n + self.GRAIN - 1) // self.GRAIN * self.GRAIN
+        ptr = None
+        with self.lock:
+            if self.outstanding + cap > self.max_outstanding:
+                return None
+            lst = self.free.get(cap)
+            if lst:
+                ptr = lst.pop()
+                self.cached -= cap
+                self.hits += 1
+            self.outstanding += cap
+        if ptr is None:
+            p = ctypes.c_void_p()
+            if load().nphusl_cuda_host_alloc(ctypes.byref(p), cap) != 0 or not p.value:
+                with self.lock:
+                    self.outstanding -= cap
+                return None              # the host refuses more pinned memory: pageable result
+            ptr = p.value
+            with self.lock:
+                self.misses += 1
+        return np.asarray(_PinnedBlock(ptr, cap, shape, dtype))
+
+    def release(self, ptr, cap):
+        keep = False
+        with self.lock:
+            self.outstanding -= cap
+            if self.enabled and self.cached + cap <= self.max_cached:
+                self.free.setdefault(cap, []).append(ptr)
+                self.cached += cap
+                keep = True
+        if not keep and _lib is not None:
+            _lib.nphusl_cuda_host_free(ctypes.c_void_p(ptr))
+
+    def trim(self):
+        with self.lock:
+            blocks = [p for lst in self.free.values() for p in lst]
+            self.free.clear()
+            self.cached = 0
+        for p in blocks:
+            if _lib is not None:
+                _lib.nphusl_cuda_host_free(ctypes.c_void_p(p))
+
+
+_pinned_pool = _PinnedPool()
+
+
+def set_pinned_results(enabled=True, max_cached_mb=None, max_outstanding_mb=None):
+    """Host-array calls return page-locked (pooled) arrays when enabled (default)."""
+    _pinned_pool.enabled = bool(enabled)
+    if max_cached_mb is not None:
+        _pinned_pool.max_cached = int(max_cached_mb) << 20
+    if max_outstanding_mb is not None:
+        _pinned_pool.max_outstanding = int(max_outstanding_mb) << 20
+    if not enabled:
+        _pinned_pool.trim()
+
+
+def pinned_pool_stats():
+    p = _pinned_pool
+    return {"enabled": p.enabled, "cached_bytes": p.cached, "outstanding_bytes": p.outstanding,
+            "hits": p.hits, "misses": p.misses}
+
+
+# ---------------------------------------------------------------------------
 # buffer description
 # ---------------------------------------------------------------------------
 
@@ -466,7 +581,9 @@ def _make_out(src, out, shape, dtype, allowed, device, what, strided_ok=False):
         b = _Buf()
         b.ptr, b.shape, b.dtype, b.loc, b.device, b.keep, b.channels = d.ptr, d.shape, d.dtype, DEVICE, d.device, d, 3
         return b, d
-    a = np.empty(shape, dtype)
+    a = _pinned_pool.empty(shape, dtype)
+    if a is None:
+        a = np.empty(shape, dtype)
     b = _Buf()
     b.ptr, b.shape, b.dtype, b.loc, b.device, b.keep, b.channels = a.ctypes.data, a.shape, a.dtype, HOST, None, a, 3
     return b, a

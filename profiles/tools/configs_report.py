@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--devices", default="0")
     ap.add_argument("--video-frames", type=int, default=1000)
     ap.add_argument("--only-video", action="store_true", help="run config 5 only")
+    ap.add_argument("--skip-video", action="store_true", help="skip config 5")
     args = ap.parse_args()
     devices = [int(d) for d in args.devices.split(",")]
     nphusl.enable_cuda()
@@ -75,7 +76,8 @@ def main():
 
     if not args.only_video:
         run_configs_1_to_4(out, ref, rng)
-    run_config_5(out, ref, rng, args, devices)
+    if not args.skip_video:
+        run_config_5(out, ref, rng, args, devices)
     print(json.dumps(out, indent=1))
 
 
@@ -89,6 +91,15 @@ def run_configs_1_to_4(out, ref, rng):
           "round_trip_exact": bool(np.array_equal(nphusl.to_rgb(hsl), img)),
           "cpu_ref_to_husl": mpix(px, best(lambda: ref.to_husl(img), 3)),
           "cpu_ref_to_rgb": mpix(px, best(lambda: ref.to_rgb(hsl), 3))}
+    # the same with plain pageable np.empty results (what every call paid before the pinned result pool)
+    _cuda.set_pinned_results(False)
+    hsl_pageable = nphusl.to_husl(img)
+    c1["gpu_to_husl_host_f64_pageable_result"] = mpix(px, best(lambda: nphusl.to_husl(img)))
+    c1["gpu_to_rgb_host_f64_pageable_input"] = mpix(px, best(lambda: nphusl.to_rgb(hsl_pageable)))
+    _cuda.set_pinned_results(True)
+    c1["gpu_round_trip_host"] = mpix(px, best(lambda: nphusl.to_rgb(nphusl.to_husl(img))))
+    c1["gpu_round_trip_host_f32"] = mpix(px, best(lambda: nphusl.to_rgb(nphusl.to_husl(img, dtype=np.float32))))
+    c1["pinned_pool"] = _cuda.pinned_pool_stats()
     d_img = torch.from_numpy(img).cuda()
     d_hsl = torch.empty(img.shape, dtype=torch.float64, device="cuda")
     d_back = torch.empty_like(d_img)

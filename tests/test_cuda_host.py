@@ -137,3 +137,59 @@ def test_strided_views_collapse_to_three_axes():
     # four independent pixel axes cannot be expressed
     with pytest.raises(ValueError):
         _cuda._views([buf((4, 3, 4, 5, 3), np.uint8, (10000, 2000, 200, 8, 1)), buf((4, 3, 4, 5, 3), np.float32)], 4)
+
+
+def test_pinned_result_pool_recycles_blocks(monkeypatch):
+    """_PinnedPool (page-locked results of host-array calls): block reuse, budgets and the
+    plain-ndarray contract, with malloc/free standing in for cudaHostAlloc on this CPU-only box."""
+    import ctypes
+    import gc
+    from nphusl import _cuda
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes = ctypes.c_void_p, [ctypes.c_size_t]
+    libc.free.argtypes = [ctypes.c_void_p]
+    live = set()
+
+    class FakeLib:
+        @staticmethod
+        def nphusl_cuda_host_alloc(pp, n):
+            p = libc.malloc(n)
+            pp._obj.value = p
+            live.add(p)
+            return 0
+
+        @staticmethod
+        def nphusl_cuda_host_free(p):
+            live.discard(p.value)
+            libc.free(p)
+            return 0
+
+    monkeypatch.setattr(_cuda, "load", lambda: FakeLib)
+    monkeypatch.setattr(_cuda, "_lib", FakeLib)
+    pool = _cuda._PinnedPool()
+    monkeypatch.setattr(_cuda, "_pinned_pool", pool)
+    pool.enabled, pool.max_cached, pool.max_outstanding = True, 64 << 20, 96 << 20
+    shape = (1080, 1920, 3)
+    a = pool.empty(shape, np.float64)
+    assert type(a) is np.ndarray and a.shape == shape and a.dtype == np.float64 and a.flags.writeable and a.flags.c_contiguous
+    a[...] = 1.5
+    view = a[..., 0]                                           # views keep the block alive
+    ptr = a.ctypes.data
+    del a
+    gc.collect()
+    assert pool.cached == 0 and pool.outstanding > 0 and view[5, 5] == 1.5
+    del view
+    gc.collect()
+    assert pool.outstanding == 0 and pool.cached == (1080 * 1920 * 24 + pool.GRAIN - 1) // pool.GRAIN * pool.GRAIN
+    b = pool.empty(shape, np.float64)                          # same size class: the block comes back
+    assert b.ctypes.data == ptr and pool.hits == 1 and pool.misses == 1 and pool.cached == 0
+    assert pool.empty((100, 3), np.float64) is None            # small results stay pageable
+    c = pool.empty(shape, np.float64)
+    assert pool.empty(shape, np.float64) is None               # outstanding budget (96 MiB) exhausted
+    del b, c
+    gc.collect()
+    assert pool.cached <= pool.max_cached and len(live) == 1   # only one 48 MiB block fits the 64 MiB cache
+    pool.trim()
+    assert not live and pool.cached == 0
+    pool.enabled = False
+    assert pool.empty(shape, np.float64) is None

@@ -795,3 +795,40 @@ def test_decoder_adjacent_frames_never_touch_the_host(cu):
     redecoded = tvio.decode_jpeg(out_jpeg.cpu())
     assert tuple(redecoded.shape) == pic.shape
     assert np.abs(redecoded.numpy().astype(int) - np.moveaxis(want, -1, 0).astype(int)).mean() < 6.0
+
+
+def test_host_results_are_pooled_page_locked_arrays(cu):
+    """Host-array calls return plain ndarrays carved out of the page-locked result pool: the D2H
+    copy lands in them directly, dropping them recycles the block, and feeding one back into
+    to_rgb is a direct DMA.  Values are those of the pageable path."""
+    import ctypes
+    import gc
+    import nphusl
+    rng = np.random.default_rng(22)
+    img = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+
+    def pinned(a):
+        loc, dev, pin = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        cu.load().nphusl_cuda_pointer_info(ctypes.c_void_p(a.ctypes.data), ctypes.byref(loc), ctypes.byref(dev), ctypes.byref(pin))
+        return loc.value == cu.HOST and pin.value == 1
+
+    cu.set_pinned_results(False)
+    want = nphusl.to_husl(img)
+    assert not pinned(want)
+    cu.set_pinned_results(True)
+    s0 = cu.pinned_pool_stats()
+    with nphusl.cuda_enabled():
+        hsl = nphusl.to_husl(img)
+        assert type(hsl) is np.ndarray and pinned(hsl) and np.array_equal(hsl, want)
+        ptr = hsl.ctypes.data
+        assert np.array_equal(nphusl.to_rgb(hsl), img)            # pinned in, (small) result out
+        hue = nphusl.to_hue(img)
+        assert np.array_equal(hue, want[..., 0])
+        del hsl
+        gc.collect()
+        again = nphusl.to_husl(img)                               # the block is recycled
+    s1 = cu.pinned_pool_stats()
+    assert again.ctypes.data == ptr and s1["hits"] > s0["hits"]
+    assert np.array_equal(again, want)
+    tiny = nphusl.to_husl(img[:4, :4])                            # small results stay pageable
+    assert not pinned(tiny) and np.array_equal(tiny, want[:4, :4])
