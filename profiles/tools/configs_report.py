@@ -239,18 +239,24 @@ def run_config_5(out, ref, rng, args, devices):
     for ndev in sorted({1, len(devices)}):
         devs = devices[:ndev]
         bounds = nphusl._shard.shard_bounds(n_frames // B, ndev)      # batches per GPU
-        res = {"barrier": threading.Barrier(ndev + 1)}
-        ths = [threading.Thread(target=run_device, args=(d, b - a, res)) for d, (a, b) in zip(devs, bounds)]
-        for t in ths:
-            t.start()
-        res["barrier"].wait()
-        t0 = time.perf_counter()
-        for t in ths:
-            t.join()
-        dt = time.perf_counter() - t0
         done = (n_frames // B) * B
+        runs = []
+        # the virtualised hosts place pinned memory differently from run to run (the same binary gives
+        # 1380 or 810 frames/s on the same box): two passes, all of them reported, the best one headlined
+        for _ in range(2):
+            res = {"barrier": threading.Barrier(ndev + 1)}
+            ths = [threading.Thread(target=run_device, args=(d, b - a, res)) for d, (a, b) in zip(devs, bounds)]
+            for t in ths:
+                t.start()
+            res["barrier"].wait()
+            t0 = time.perf_counter()
+            for t in ths:
+                t.join()
+            runs.append((time.perf_counter() - t0, all(res[d] for d in devs)))
+        dt = min(r[0] for r in runs)
         c5["%d_gpu" % ndev] = {"frames": done, "seconds": round(dt, 3), "mpix_s": mpix(done * 2160 * 3840, dt),
-                               "fps_4k": round(done / dt, 1), "last_batch_exact": all(res[d] for d in devs)}
+                               "fps_4k": round(done / dt, 1), "all_passes_fps_4k": [round(done / r[0], 1) for r in runs],
+                               "last_batch_exact": all(r[1] for r in runs)}
     frame = np.asarray(rng.integers(0, 256, (2160, 3840, 3), dtype=np.uint8))
     c5["cpu_ref_round_trip_mpix"] = mpix(2160 * 3840, best(lambda: ref.step(frame), 2))
     out["config5_video_e2e"] = c5
