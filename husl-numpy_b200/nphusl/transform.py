@@ -37,6 +37,11 @@ from numpy import ndarray
 def is_device_array(obj) -> bool:
     """True for anything that lives in GPU memory (torch CUDA tensors, our own
     ``DeviceArray``, ...) -- recognised by ``__cuda_array_interface__``."""
+    if isinstance(obj, ndarray):
+        return False
+    is_cuda = getattr(obj, "is_cuda", None)      # torch answers this without building the interface dict
+    if isinstance(is_cuda, bool):
+        return is_cuda
     return hasattr(obj, "__cuda_array_interface__")
 
 

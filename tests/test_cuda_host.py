@@ -193,3 +193,28 @@ def test_pinned_result_pool_recycles_blocks(monkeypatch):
     assert not live and pool.cached == 0
     pool.enabled = False
     assert pool.empty(shape, np.float64) is None
+
+
+def test_device_pool_size_classes_and_cheap_device_check():
+    from nphusl import _cuda
+    sc = _cuda._DevicePool.size_class
+    assert sc(1) == 512 and sc(512) == 512 and sc(513) == 1024 and sc(100000) == 131072
+    assert sc((1 << 20) - 1) == 1 << 20 and sc(1 << 20) == 2 << 20 and sc((2 << 20) + 1) == 4 << 20
+    assert sc(1080 * 1920 * 24) % (2 << 20) == 0 and sc(1080 * 1920 * 24) >= 1080 * 1920 * 24
+
+    class FakeTorchCpu:
+        is_cuda = False
+
+        @property
+        def __cuda_array_interface__(self):
+            raise AssertionError("must not be evaluated for a host tensor")
+
+    class FakeTorchCuda(FakeTorchCpu):
+        is_cuda = True
+
+    class Other:
+        __cuda_array_interface__ = {"shape": (1,), "typestr": "|u1", "data": (0, False), "version": 3}
+
+    assert not _cuda._is_device(np.zeros(3)) and not _cuda._is_device(FakeTorchCpu()) and not _cuda._is_device([1, 2, 3])
+    assert _cuda._is_device(FakeTorchCuda()) and _cuda._is_device(Other())
+    assert _cuda._prod((2, 3, 4)) == 24 and _cuda._prod(()) == 1 and _cuda._prod(7) == 7

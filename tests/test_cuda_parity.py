@@ -832,3 +832,38 @@ def test_host_results_are_pooled_page_locked_arrays(cu):
     assert np.array_equal(again, want)
     tiny = nphusl.to_husl(img[:4, :4])                            # small results stay pageable
     assert not pinned(tiny) and np.array_equal(tiny, want[:4, :4])
+
+
+def test_device_results_come_from_a_recycling_pool(cu):
+    """A call that returns a NEW DeviceArray must not pay cudaMalloc + cudaFree (0.6 ms and a device
+    synchronisation): dropped results go back to a pool and the next result reuses the block."""
+    import gc
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(23)
+    img = rng.integers(0, 256, (540, 960, 3), dtype=np.uint8)
+    t = torch.from_numpy(img).cuda()
+    want = cu._rgb_to_husl(img, dtype=np.float32)
+    a = cu._rgb_to_husl(t, dtype=np.float32)
+    ptr = a.ptr
+    assert np.array_equal(a.copy_to_host(), want)
+    del a
+    gc.collect()
+    s0 = cu.device_pool_stats()
+    b = cu._rgb_to_husl(t, dtype=np.float32)
+    s1 = cu.device_pool_stats()
+    assert b.ptr == ptr and s1["hits"] == s0["hits"] + 1 and s1["misses"] == s0["misses"]
+    assert np.array_equal(b.copy_to_host(), want)
+    c = cu._rgb_to_husl(t, dtype=np.float32)                      # b is still alive: a different block
+    assert c.ptr != b.ptr and np.array_equal(c.copy_to_host(), want)
+    hue = cu._rgb_to_hue(t)                                       # other size class
+    assert np.array_equal(hue.copy_to_host(), cu._rgb_to_hue(img))
+    view = b[10:20]                                               # views keep the owner alive, never release
+    del b
+    gc.collect()
+    assert np.array_equal(view.copy_to_host(), want[10:20])
+    del view, c, hue
+    gc.collect()
+    assert cu.device_pool_stats()["cached_bytes"] > 0
+    cu.empty_cache()
+    assert cu.device_pool_stats()["cached_bytes"] == 0
+    assert np.array_equal(cu._rgb_to_husl(t, dtype=np.float32).copy_to_host(), want)
