@@ -383,4 +383,83 @@ k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_t
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------
+// (b'') rgb_from_husl, float32 HUSL PLANES H[], S[], L[] (planar / channels-first callers)
+// ---------------------------------------------------------------------------------
+// The same LDGSTS ring as k_inv_cp; a stage holds the three 512-byte plane segments of
+// one 128-pixel tile.  Every lane copies and later reads the SAME 16 bytes of each plane
+// (its 4 pixels), so the ring needs no warp synchronisation at all.  CHW = true writes
+// uint8 planes R[], G[], B[] (one word = the lane's 4 pixels), CHW = false interleaved
+// RGB through the 384-byte staging transposition.
+template <int BLOCK, int MINB, int IST, bool CHW>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_inv_planes_cp(const float *__restrict__ H, const float *__restrict__ S, const float *__restrict__ L,
+                uint32_t *__restrict__ o0p, uint32_t *__restrict__ o1p, uint32_t *__restrict__ o2p, long long n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TB = Tile<float>::BYTES;                       // 3 x 512
+    unsigned char *ibuf = smem + warp * InvCpSmem<IST>::PER_WARP;
+    uint32_t *sw = reinterpret_cast<uint32_t *>(ibuf + IST * TB);
+    const uint32_t ld_s = smem_addr(ibuf) + lane * 16;
+    const long long nw = (long long)gridDim.x * (BLOCK / 32);
+    const long long first = (long long)blockIdx.x * (BLOCK / 32) + warp;
+    // walked from the end of the image (see k_inv_tma)
+    const long long last_px = (n_tiles - 1) * (long long)TILE_PX + lane * 4;
+    const float *hp = H + last_px, *sp = S + last_px, *lp = L + last_px;
+
+#pragma unroll
+    for (int s = 0; s < IST; ++s) {
+        const long long t = first + s * nw;
+        if (t < n_tiles) {
+            cp_async16(ld_s + s * TB, hp - t * TILE_PX);
+            cp_async16(ld_s + s * TB + 512, sp - t * TILE_PX);
+            cp_async16(ld_s + s * TB + 1024, lp - t * TILE_PX);
+        }
+        cp_async_commit();
+    }
+    int st = 0;
+    for (long long tile = first; tile < n_tiles; tile += nw) {
+        cp_async_wait<IST - 1>();
+        const unsigned char *rd = ibuf + st * TB + lane * 16;
+        const float4 h = *reinterpret_cast<const float4 *>(rd);
+        const float4 s = *reinterpret_cast<const float4 *>(rd + 512);
+        const float4 l = *reinterpret_cast<const float4 *>(rd + 1024);
+        {
+            const long long t = tile + (long long)IST * nw;
+            if (t < n_tiles) {
+                cp_async16(ld_s + st * TB, hp - t * TILE_PX);
+                cp_async16(ld_s + st * TB + 512, sp - t * TILE_PX);
+                cp_async16(ld_s + st * TB + 1024, lp - t * TILE_PX);
+            }
+            cp_async_commit();
+        }
+        const float hh[4] = {h.x, h.y, h.z, h.w}, ss[4] = {s.x, s.y, s.z, s.w}, ll[4] = {l.x, l.y, l.z, l.w};
+        uint32_t q[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float R, G, B;
+            rgb255_from_husl(hh[j], ss[j], ll[j], R, G, B);
+            q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
+        }
+        const long long rt = n_tiles - 1 - tile;                 // the tile this iteration really holds
+        if (CHW) {
+            const long long w = rt * 32 + lane;
+            o0p[w] = __byte_perm(__byte_perm(q[0], q[3], 0x0040), __byte_perm(q[6], q[9], 0x0040), 0x5410);
+            o1p[w] = __byte_perm(__byte_perm(q[1], q[4], 0x0040), __byte_perm(q[7], q[10], 0x0040), 0x5410);
+            o2p[w] = __byte_perm(__byte_perm(q[2], q[5], 0x0040), __byte_perm(q[8], q[11], 0x0040), 0x5410);
+        } else {
+            const uint32_t a = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+            const uint32_t b = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+            const uint32_t c = __byte_perm(__byte_perm(q[8], q[9], 0x0040), __byte_perm(q[10], q[11], 0x0040), 0x5410);
+            sw[lane * 3] = a; sw[lane * 3 + 1] = b; sw[lane * 3 + 2] = c;
+            __syncwarp();
+            uint32_t *d = o0p + rt * 96 + lane;
+            d[0] = sw[lane]; d[32] = sw[lane + 32]; d[64] = sw[lane + 64];
+            __syncwarp();
+        }
+        st = (st + 1 == IST) ? 0 : st + 1;
+    }
+    cp_async_wait<0>();
+}
+
 }  // namespace husl

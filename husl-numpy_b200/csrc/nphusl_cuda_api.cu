@@ -209,6 +209,8 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST>, (INV64_BLOCK / 32) * InvSmem<double, INV64_IST>::PER_WARP))) return rc;
     if ((rc = set_smem(k_fwd_u8<float, true, HUE32_BLOCK, HUE32_MINB>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST>, (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP))) return rc;
+    if ((rc = set_smem(k_inv_planes_cp<INV32_BLOCK, INV32_MINB, INV32_IST, false>, (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP))) return rc;
+    if ((rc = set_smem(k_inv_planes_cp<INV32_BLOCK, INV32_MINB, INV32_IST, true>, (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP))) return rc;
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_edit<512, 2>, TAB_BYTES + 16 * 384))) return rc;
@@ -724,8 +726,12 @@ int nphusl_cuda_husl_planar_to_rgb(const void *h, const void *s, const void *l, 
     if (aligned(rgb, 4) && aligned(h, va) && aligned(s, va) && aligned(l, va) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
         const int grid = grid_for(tiles, 8, c->sms * 4);
-        if (hsl_dtype == NPHUSL_F32)
-            k_inv_planar<float, 384, 4><<<grid_for(tiles, 12, c->sms * 4), 384, 12 * 384, st>>>((const float *)h, (const float *)s, (const float *)l, (uint32_t *)rgb, tiles);
+        if (hsl_dtype == NPHUSL_F32) {
+            if ((rc = set_attrs(*c))) return rc;
+            k_inv_planes_cp<INV32_BLOCK, INV32_MINB, INV32_IST, false><<<grid_for(tiles, INV32_BLOCK / 32, c->sms * INV32_MINB), INV32_BLOCK,
+                                                                         (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP, st>>>(
+                (const float *)h, (const float *)s, (const float *)l, (uint32_t *)rgb, nullptr, nullptr, tiles);
+        }
         else
             k_inv_planar<double, 256, 4><<<grid, 256, 8 * 384, st>>>((const double *)h, (const double *)s, (const double *)l, (uint32_t *)rgb, tiles);
         g_launches++;
@@ -803,8 +809,12 @@ int nphusl_cuda_husl_planes_to_rgb_planes(const void *h, const void *s, const vo
     if (aligned(r, 4) && aligned(g, 4) && aligned(b, 4) && aligned(h, va) && aligned(s, va) && aligned(l, va) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
         const int grid = grid_for(tiles, 12, c->sms * 4);
-        if (hsl_dtype == NPHUSL_F32)
-            k_inv_chw<float, 384, 4><<<grid, 384, 0, st>>>((const float *)h, (const float *)s, (const float *)l, (uint32_t *)r, (uint32_t *)g, (uint32_t *)b, tiles);
+        if (hsl_dtype == NPHUSL_F32) {
+            if ((rc = set_attrs(*c))) return rc;
+            k_inv_planes_cp<INV32_BLOCK, INV32_MINB, INV32_IST, true><<<grid_for(tiles, INV32_BLOCK / 32, c->sms * INV32_MINB), INV32_BLOCK,
+                                                                        (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP, st>>>(
+                (const float *)h, (const float *)s, (const float *)l, (uint32_t *)r, (uint32_t *)g, (uint32_t *)b, tiles);
+        }
         else
             k_inv_chw<double, 384, 4><<<grid, 384, 0, st>>>((const double *)h, (const double *)s, (const double *)l, (uint32_t *)r, (uint32_t *)g, (uint32_t *)b, tiles);
         g_launches++;
