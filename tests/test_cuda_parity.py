@@ -867,3 +867,39 @@ def test_device_results_come_from_a_recycling_pool(cu):
     cu.empty_cache()
     assert cu.device_pool_stats()["cached_bytes"] == 0
     assert np.array_equal(cu._rgb_to_husl(t, dtype=np.float32).copy_to_host(), want)
+
+
+def test_past_the_reference_size_limit(cu):
+    """The reference's C path indexes with `int size` (elements, _simd.c:128,195) and overflows past
+    715 Mpx.  750 Mpx here: element offsets beyond 2^31 in every kernel family on the
+    path (TMA / cp.async streaming kernels, hue, fused edit), exact round trip, spot checks vs the oracle."""
+    torch = pytest.importorskip("torch")
+    n = 750_000_128                                           # > 2^31 / 3 pixels, a multiple of the 128-px tile plus nothing
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~32 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rgb = torch.randint(0, 256, (n, 3), dtype=torch.uint8, device="cuda", generator=g)
+    back = torch.empty_like(rgb)
+    for tdt, ndt in ((torch.float32, np.float32), (torch.float64, np.float64)):
+        hsl = torch.empty((n, 3), dtype=tdt, device="cuda")
+        cu._rgb_to_husl(rgb, out=hsl)
+        cu._husl_to_rgb(hsl, out=back)
+        torch.cuda.synchronize()
+        assert torch.equal(back, rgb)
+        for lo in (0, n // 2 + 77, n - 1000):                 # first, middle and the very last pixels
+            want = orc.rgb_to_husl(rgb[lo:lo + 1000].cpu().numpy())
+            got = hsl[lo:lo + 1000].cpu().numpy().astype(np.float64)
+            assert hue_diff(got[:, 0], want[:, 0])[want[:, 1] > 0.1].max() < TOL
+            assert np.abs(got[:, 1:] - want[:, 1:]).max() < TOL
+        del hsl
+    hue = torch.empty((n,), dtype=torch.float32, device="cuda")
+    cu._rgb_to_hue(rgb, out=hue)
+    torch.cuda.synchronize()
+    want = orc.rgb_to_husl(rgb[n - 1000:].cpu().numpy())
+    assert hue_diff(hue[n - 1000:].cpu().numpy().astype(np.float64), want[:, 0])[want[:, 1] > 0.1].max() < TOL
+    del hue
+    back.zero_()
+    cu.edit_rgb(rgb, out=back)                                # identity edit: the fused kernel at the same offsets
+    torch.cuda.synchronize()
+    assert torch.equal(back, rgb)
