@@ -95,4 +95,16 @@ for name, fn, b in (("frgb32_to_husl32", lambda: _cuda._rgb_to_husl(rf32, out=o3
                     ("husl32_to_frgb32", lambda: _cuda._husl_to_rgb(o32, out=rf32), 24)):
     ms = timed(fn)
     res[name] = {"ms": round(ms, 4), "gpix_s": round(px2 / ms / 1e6, 1), "hbm_frac": round(px2 * b / ms / 1e6 / 6547.2, 3)}
+# strided device views (one-pixel-per-thread kernels): a crop of every frame, and RGBA seen as RGB
+crop = rgb[:, 100:2060, 200:3640]
+cpx = crop.numel() // 3
+crop32 = torch.empty(crop.shape, dtype=torch.float32, device="cuda")
+rgba = torch.empty(rgb.shape[:-1] + (4,), dtype=torch.uint8, device="cuda")
+rgba[..., :3] = rgb
+for name, fn, b, npx in (("strided_crop_to_husl32", lambda: _cuda._rgb_to_husl(crop, out=crop32), 15, cpx),
+                         ("strided_crop_to_rgb", lambda: _cuda._husl_to_rgb(crop32, out=back[:, 100:2060, 200:3640]), 15, cpx),
+                         ("strided_rgba3_to_husl32", lambda: _cuda._rgb_to_husl(rgba[..., :3], out=h32), 16, px),
+                         ("strided_crop_edit", lambda: _cuda.edit_rgb(crop, out=crop, lightness=(0, 50), l=(1, 20)), 6, cpx)):
+    ms = timed(fn)
+    res[name] = {"ms": round(ms, 4), "gpix_s": round(npx / ms / 1e6, 1), "hbm_frac": round(npx * b / ms / 1e6 / 6547.2, 3)}
 print(json.dumps(res))
