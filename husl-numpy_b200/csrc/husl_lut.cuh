@@ -15,12 +15,19 @@
 
 namespace husl {
 
+// Tables keep the element type the reference generator was asked for
+// (make_lookup_tables:4 `table_type`, LUT/light.py:21-32): uint16 holding the value
+// times the int scale (the default, LIGHT_SCALE = CHROMA_SCALE = 100), or float /
+// double holding the 4- / 3-decimal literal itself (scales 1).  The kernels are
+// templated on the element type; the arithmetic on the promoted double is the same.
 struct LutParams {
     const double *linear;     // 256, 6-decimal values (_linear_lookup.c:9-42)
-    const uint16_t *light;    // 3*seg, L*100 (light_table_big)
-    const uint16_t *chroma;   // nh*nl, max chroma * 100 (chroma_table)
+    const void *light;        // 3*seg entries (light_table_big)
+    const void *chroma;       // nh*nl entries (chroma_table)
     int seg, nh, nl;
     double ystep[3], ythresh[2], hstep, lstep;
+    double light_scale;       // LIGHT_SCALE
+    double sat_scale;         // 100 * CHROMA_SCALE (_simd.c:334)
 };
 
 __device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
@@ -29,13 +36,14 @@ __device__ __forceinline__ double ds(double a, double b) { return __dsub_rn(a, b
 __device__ __forceinline__ double dd(double a, double b) { return __ddiv_rn(a, b); }
 
 // _simd.c:485-496
+template <typename TT>
 __device__ __forceinline__ double lut_light(const LutParams &t, double y) {
     double idx;
     if (y < t.ythresh[0]) idx = dd(y, t.ystep[0]);
     else if (y < t.ythresh[1]) idx = da(dd(ds(y, t.ythresh[0]), t.ystep[1]), (double)t.seg);
     else idx = da(dd(ds(y, t.ythresh[1]), t.ystep[2]), (double)(t.seg * 2));
     const double r = fmax(0.0, fmin((double)(3 * t.seg - 1), (double)roundf(__double2float_rn(idx))));
-    return dd((double)t.light[(unsigned short)r], 100.0);
+    return dd((double)static_cast<const TT *>(t.light)[(unsigned short)r], t.light_scale);
 }
 
 // _simd.c:279-281
@@ -81,20 +89,21 @@ __device__ __forceinline__ double lut_hue(double u, double v) {
 }
 
 // _simd.c:399-406 / :360-387
-template <bool INTERP>
+template <bool INTERP, typename TT>
 __device__ __forceinline__ double lut_chroma(const LutParams &t, double l, double h) {
+    const TT *chroma = static_cast<const TT *>(t.chroma);
     const double hs = dd(h, t.hstep), ls = dd(l, t.lstep);
     if (!INTERP) {
         const unsigned short hi = (unsigned short)fmax(0.0, fmin((double)(t.nh - 1), (double)roundf(__double2float_rn(hs))));
         const unsigned short li = (unsigned short)fmax(0.0, fmin((double)(t.nl - 1), (double)roundf(__double2float_rn(ls))));
-        return fmax(1e-10, (double)t.chroma[(size_t)hi * t.nl + li]);
+        return fmax(1e-10, (double)chroma[(size_t)hi * t.nl + li]);
     }
     const unsigned short hf = (unsigned short)fmax(0.0, fmin((double)(t.nh - 2), (double)floorf(__double2float_rn(hs))));
     const unsigned short lf = (unsigned short)fmax(0.0, fmin((double)(t.nl - 2), (double)floorf(__double2float_rn(ls))));
-    const double c00 = t.chroma[(size_t)hf * t.nl + lf];
-    const double c10 = t.chroma[(size_t)(hf + 1) * t.nl + lf];
-    const double c01 = t.chroma[(size_t)hf * t.nl + lf + 1];
-    const double c11 = t.chroma[(size_t)(hf + 1) * t.nl + lf + 1];
+    const double c00 = chroma[(size_t)hf * t.nl + lf];
+    const double c10 = chroma[(size_t)(hf + 1) * t.nl + lf];
+    const double c01 = chroma[(size_t)hf * t.nl + lf + 1];
+    const double c11 = chroma[(size_t)(hf + 1) * t.nl + lf + 1];
     const double hn = ds(hs, (double)hf), ln = ds(ls, (double)lf);
     const double hv = ds(1.0, hn), lv = ds(1.0, ln);
     const double c = da(da(da(dm(dm(c00, hv), lv), dm(dm(c10, hn), lv)), dm(dm(c01, hv), ln)), dm(dm(c11, hn), ln));
@@ -102,7 +111,7 @@ __device__ __forceinline__ double lut_chroma(const LutParams &t, double l, doubl
 }
 
 // rgb_to_husl_nd, default build: _simd.c:87-225
-template <bool INTERP>
+template <bool INTERP, typename TT>
 __global__ void __launch_bounds__(256)
 k_fwd_lut(const uint8_t *__restrict__ rgb, double *__restrict__ hsl, long long n, LutParams t) {
     const double REF_U = 0.19783000664283, REF_V = 0.46831999493879;
@@ -118,12 +127,12 @@ k_fwd_lut(const uint8_t *__restrict__ rgb, double *__restrict__ hsl, long long n
         const double z = da(da(dm(0.019331, rl), dm(0.119195, gl)), dm(0.950532, bl));
         const double vs = da(da(x, dm(15.0, y)), dm(3.0, z));
         const double var_u = dd(dm(4.0, x), vs), var_v = dd(dm(9.0, y), vs);
-        const double l = lut_light(t, y);
+        const double l = lut_light<TT>(t, y);
         const double l13 = dm(l, 13.0);
         const double u = dm(l13, ds(var_u, REF_U)), v = dm(l13, ds(var_v, REF_V));
         const double h = lut_hue(u, v);
-        const double mc = lut_chroma<INTERP>(t, l, h);
-        const double sat = dd(dm(10000.0, __dsqrt_rn(da(dm(u, u), dm(v, v)))), mc);
+        const double mc = lut_chroma<INTERP, TT>(t, l, h);
+        const double sat = dd(dm(t.sat_scale, __dsqrt_rn(da(dm(u, u), dm(v, v)))), mc);
         o[0] = h;
         o[1] = fmin(sat, 100.0);
         o[2] = l;
@@ -171,24 +180,35 @@ __global__ void k_gen_linear(double *out) {
     out[j] = x > 0.04045 ? pow((x + 0.055) / (1.0 + 0.055), 2.4) : x / 12.92;
 }
 
-// LUT/light.py:62-80, 100-107: entry k of segment i = round(to_light(start_i + k*step_i) * 100)
-__global__ void k_gen_light(uint16_t *table, int seg, double s0, double s1, double s2,
-                            double st0, double st1, double st2) {
+// One table entry as the generated C source holds it (LUT/light.py:86-97, LUT/chroma.py:60-70):
+// integer types: int(round(v * int_scale)); float / double: the "{:7.Nf}" literal, i.e. v rounded
+// to N decimals (rint(v * 10^N) / 10^N is the double nearest to that decimal), narrowed for float.
+template <typename TT>
+__device__ __forceinline__ TT lut_entry(double v, double int_scale, double pow10) {
+    if (sizeof(TT) == 2) return (TT)(long long)rint(v * int_scale);
+    return (TT)(rint(v * pow10) / pow10);
+}
+
+// LUT/light.py:62-80, 100-107: entry k of segment i = to_light(start_i + k*step_i)
+template <typename TT>
+__global__ void k_gen_light(TT *table, int seg, double s0, double s1, double s2,
+                            double st0, double st1, double st2, double int_scale) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 3 * seg) return;
     const int i = idx / seg, k = idx % seg;
     const double start = i == 0 ? s0 : (i == 1 ? s1 : s2);
     const double step = i == 0 ? st0 : (i == 1 ? st1 : st2);
-    table[idx] = (uint16_t)(long long)rint(gen_to_light(start + k * step) * 100);
+    table[idx] = lut_entry<TT>(gen_to_light(start + k * step), int_scale, 1e4);
 }
 
-// LUT/chroma.py:73-84: entry [h][l] = round(max_chroma(l*lstep, h*hstep) * 100), column l = 0 left 0
-__global__ void k_gen_chroma(uint16_t *table, int nh, int nl, double hstep, double lstep) {
+// LUT/chroma.py:73-84: entry [h][l] = max_chroma(l*lstep, h*hstep), column l = 0 left 0
+template <typename TT>
+__global__ void k_gen_chroma(TT *table, int nh, int nl, double hstep, double lstep, double int_scale) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)nh * nl) return;
     const int i = (int)(idx / nl), j = (int)(idx % nl);
-    uint16_t v = 0;
-    if (j > 0) v = (uint16_t)(long long)rint(gen_max_chroma(0.0 + j * lstep, 0.0 + i * hstep) * 100);
+    TT v = 0;
+    if (j > 0) v = lut_entry<TT>(gen_max_chroma(0.0 + j * lstep, 0.0 + i * hstep), int_scale, 1e3);
     table[idx] = v;
 }
 

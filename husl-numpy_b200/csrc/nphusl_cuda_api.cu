@@ -71,10 +71,13 @@ size_t dsize(int dt) { return dt == NPHUSL_U8 ? 1 : dt == NPHUSL_F32 ? 4 : dt ==
 struct Lut {
     bool ready = false;
     int seg = 0, nh = 0, nl = 0;
-    uint16_t *light = nullptr, *chroma = nullptr;
+    int type = NPHUSL_LUT_U16;           // element type of light / chroma
+    void *light = nullptr, *chroma = nullptr;
     double *linear = nullptr;
+    double light_scale = 100, chroma_scale = 100;
     LutParams p{};
 };
+size_t lut_esize(int type) { return type == NPHUSL_LUT_U16 ? 2 : type == NPHUSL_LUT_F32 ? 4 : type == NPHUSL_LUT_F64 ? 8 : 0; }
 
 // One staging set = NSLOT streams, each with a device-side chunk buffer per
 // direction and (for pageable callers) a pinned bounce buffer.  A device owns
@@ -372,10 +375,12 @@ int run_lut_dev(DevCtx &c, const void *in, void *out, long long n, int mode, cud
     if (!c.lut.ready) return fail(NPHUSL_ERR_NO_LUT, "LUT mode: call nphusl_cuda_lut_generate or nphusl_cuda_lut_upload first");
     if (n <= 0) return NPHUSL_OK;
     const int grid = grid_for(n, 256, c.sms * 8);
-    if (mode == NPHUSL_LUT)
-        k_fwd_lut<false><<<grid, 256, 0, s>>>((const uint8_t *)in, (double *)out, n, c.lut.p);
-    else
-        k_fwd_lut<true><<<grid, 256, 0, s>>>((const uint8_t *)in, (double *)out, n, c.lut.p);
+#define LUT_GO(TT) do { if (mode == NPHUSL_LUT) k_fwd_lut<false, TT><<<grid, 256, 0, s>>>((const uint8_t *)in, (double *)out, n, c.lut.p); \
+                        else k_fwd_lut<true, TT><<<grid, 256, 0, s>>>((const uint8_t *)in, (double *)out, n, c.lut.p); } while (0)
+    if (c.lut.type == NPHUSL_LUT_U16) LUT_GO(uint16_t);
+    else if (c.lut.type == NPHUSL_LUT_F32) LUT_GO(float);
+    else LUT_GO(double);
+#undef LUT_GO
     g_launches++;
     return check_launch("k_fwd_lut");
 }
@@ -995,30 +1000,38 @@ int nphusl_cuda_rgb_edit_rgb_strided(const nphusl_view *rgb_in, const nphusl_vie
 }
 
 // ---- lookup tables ---------------------------------------------------------------------
-static int lut_alloc(DevCtx &c, int seg, int nh, int nl) {
+static int lut_alloc(DevCtx &c, int seg, int nh, int nl, int type, double light_scale, double chroma_scale) {
     Lut &l = c.lut;
     if (l.light) cudaFree(l.light);
     if (l.chroma) cudaFree(l.chroma);
     if (!l.linear) CU(cudaMalloc(&l.linear, 256 * sizeof(double)));
     l.light = l.chroma = nullptr;
     l.ready = false;
-    CU(cudaMalloc(&l.light, sizeof(uint16_t) * 3 * seg));
-    CU(cudaMalloc(&l.chroma, sizeof(uint16_t) * (size_t)nh * nl));
-    l.seg = seg; l.nh = nh; l.nl = nl;
+    CU(cudaMalloc(&l.light, lut_esize(type) * 3 * seg));
+    CU(cudaMalloc(&l.chroma, lut_esize(type) * (size_t)nh * nl));
+    l.seg = seg; l.nh = nh; l.nl = nl; l.type = type;
+    l.light_scale = light_scale; l.chroma_scale = chroma_scale;
     l.p.linear = l.linear; l.p.light = l.light; l.p.chroma = l.chroma;
     l.p.seg = seg; l.p.nh = nh; l.p.nl = nl;
+    l.p.light_scale = light_scale;
+    l.p.sat_scale = 100 * chroma_scale;
     return NPHUSL_OK;
 }
 
-int nphusl_cuda_lut_generate(int device, int light_seg, int nh, int nl) {
+int nphusl_cuda_lut_generate_typed(int device, int light_seg, int nh, int nl, int table_type, int int_scale) {
     DeviceGuard guard;
     if (light_seg < 2 || nh < 2 || nl < 2 || light_seg > 21845 || nh > 65535 || nl > 65535)
         return fail(NPHUSL_ERR_ARG, "lut_generate: table sizes must fit 16 bits (LUT/light.py:27, LUT/chroma.py:27-28)");
+    if (!lut_esize(table_type)) return fail(NPHUSL_ERR_ARG, "lut_generate: table_type must be NPHUSL_LUT_U16 / _F32 / _F64");
+    if (table_type == NPHUSL_LUT_U16 && (int_scale < 1 || int_scale > 655))
+        return fail(NPHUSL_ERR_ARG, "lut_generate: int_scale must keep 100 * int_scale inside uint16");
+    // LUT/light.py:31-32: the int scale applies to integer table types only
+    const double scale = table_type == NPHUSL_LUT_U16 ? (double)int_scale : 1.0;
     DevCtx *c;
     int rc = ctx_get(device, &c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    if ((rc = lut_alloc(*c, light_seg, nh, nl))) return rc;
+    if ((rc = lut_alloc(*c, light_seg, nh, nl, table_type, scale, scale))) return rc;
     Lut &l = c->lut;
     // index steps exactly as LUT/light.py:62-80 and LUT/chroma.py:63-65 compute them
     const double ysteps[3] = {0.070, 0.350, 1.0};
@@ -1056,34 +1069,45 @@ int nphusl_cuda_lut_generate(int device, int light_seg, int nh, int nl) {
         lin[j] = std::strtod(buf, nullptr);
     }
     CU(cudaMemcpy(l.linear, lin, sizeof lin, cudaMemcpyHostToDevice));
-    k_gen_light<<<(3 * light_seg + 255) / 256, 256>>>(l.light, light_seg, seg_start[0], seg_start[1], seg_start[2],
-                                                        l.p.ystep[0], l.p.ystep[1], l.p.ystep[2]);
-    g_launches++;
-    if ((rc = check_launch("k_gen_light"))) return rc;
     const long long total = (long long)nh * nl;
-    k_gen_chroma<<<(int)((total + 255) / 256), 256>>>(l.chroma, nh, nl, l.p.hstep, l.p.lstep);
-    g_launches++;
-    if ((rc = check_launch("k_gen_chroma"))) return rc;
+#define GEN_GO(TT) do { \
+        k_gen_light<TT><<<(3 * light_seg + 255) / 256, 256>>>((TT *)l.light, light_seg, seg_start[0], seg_start[1], seg_start[2], \
+                                                             l.p.ystep[0], l.p.ystep[1], l.p.ystep[2], scale); \
+        k_gen_chroma<TT><<<(int)((total + 255) / 256), 256>>>((TT *)l.chroma, nh, nl, l.p.hstep, l.p.lstep, scale); } while (0)
+    if (table_type == NPHUSL_LUT_U16) GEN_GO(uint16_t);
+    else if (table_type == NPHUSL_LUT_F32) GEN_GO(float);
+    else GEN_GO(double);
+#undef GEN_GO
+    g_launches += 2;
+    if ((rc = check_launch("k_gen_light / k_gen_chroma"))) return rc;
     CU(cudaDeviceSynchronize());
     l.ready = true;
     return NPHUSL_OK;
 }
 
-int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
-                           const double *y_idx_step3, const double *y_thresh2,
-                           const uint16_t *chroma, int nh, int nl,
-                           double h_idx_step, double l_idx_step, const double *linear256) {
+int nphusl_cuda_lut_generate(int device, int light_seg, int nh, int nl) {
+    return nphusl_cuda_lut_generate_typed(device, light_seg, nh, nl, NPHUSL_LUT_U16, 100);
+}
+
+int nphusl_cuda_lut_upload_typed(int device, int table_type, double light_scale, double chroma_scale,
+                                 const void *light, int light_seg,
+                                 const double *y_idx_step3, const double *y_thresh2,
+                                 const void *chroma, int nh, int nl,
+                                 double h_idx_step, double l_idx_step, const double *linear256) {
     DeviceGuard guard;
     if (!light || !chroma || !y_idx_step3 || !y_thresh2 || !linear256 || light_seg < 2 || nh < 2 || nl < 2)
         return fail(NPHUSL_ERR_ARG, "lut_upload: null table or bad size");
+    if (!lut_esize(table_type)) return fail(NPHUSL_ERR_ARG, "lut_upload: table_type must be NPHUSL_LUT_U16 / _F32 / _F64");
+    if (!(light_scale > 0) || !(chroma_scale > 0)) return fail(NPHUSL_ERR_ARG, "lut_upload: scales must be positive");
     DevCtx *c;
     int rc = ctx_get(device, &c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    if ((rc = lut_alloc(*c, light_seg, nh, nl))) return rc;
+    if ((rc = lut_alloc(*c, light_seg, nh, nl, table_type, light_scale, chroma_scale))) return rc;
     Lut &l = c->lut;
-    CU(cudaMemcpy(l.light, light, sizeof(uint16_t) * 3 * light_seg, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(l.chroma, chroma, sizeof(uint16_t) * (size_t)nh * nl, cudaMemcpyHostToDevice));
+    const size_t es = lut_esize(table_type);
+    CU(cudaMemcpy(l.light, light, es * 3 * light_seg, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(l.chroma, chroma, es * (size_t)nh * nl, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(l.linear, linear256, 256 * sizeof(double), cudaMemcpyHostToDevice));
     for (int i = 0; i < 3; ++i) l.p.ystep[i] = y_idx_step3[i];
     for (int i = 0; i < 2; ++i) l.p.ythresh[i] = y_thresh2[i];
@@ -1093,8 +1117,16 @@ int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
     return NPHUSL_OK;
 }
 
-int nphusl_cuda_lut_download(int device, uint16_t *light, uint16_t *chroma, double *linear256,
-                             int *dims4, double *steps7) {
+int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
+                           const double *y_idx_step3, const double *y_thresh2,
+                           const uint16_t *chroma, int nh, int nl,
+                           double h_idx_step, double l_idx_step, const double *linear256) {
+    return nphusl_cuda_lut_upload_typed(device, NPHUSL_LUT_U16, 100, 100, light, light_seg, y_idx_step3, y_thresh2,
+                                        chroma, nh, nl, h_idx_step, l_idx_step, linear256);
+}
+
+int nphusl_cuda_lut_download_typed(int device, void *light, void *chroma, double *linear256,
+                                   int *dims4, double *steps7, double *scales2) {
     DeviceGuard guard;
     DevCtx *c;
     int rc = ctx_get(device, &c);
@@ -1102,16 +1134,30 @@ int nphusl_cuda_lut_download(int device, uint16_t *light, uint16_t *chroma, doub
     std::lock_guard<std::mutex> lk(c->mu);
     Lut &l = c->lut;
     if (!l.ready) return fail(NPHUSL_ERR_NO_LUT, "lut_download: no tables installed");
-    if (light) CU(cudaMemcpy(light, l.light, sizeof(uint16_t) * 3 * l.seg, cudaMemcpyDeviceToHost));
-    if (chroma) CU(cudaMemcpy(chroma, l.chroma, sizeof(uint16_t) * (size_t)l.nh * l.nl, cudaMemcpyDeviceToHost));
+    const size_t es = lut_esize(l.type);
+    if (light) CU(cudaMemcpy(light, l.light, es * 3 * l.seg, cudaMemcpyDeviceToHost));
+    if (chroma) CU(cudaMemcpy(chroma, l.chroma, es * (size_t)l.nh * l.nl, cudaMemcpyDeviceToHost));
     if (linear256) CU(cudaMemcpy(linear256, l.linear, 256 * sizeof(double), cudaMemcpyDeviceToHost));
-    if (dims4) { dims4[0] = l.seg; dims4[1] = l.nh; dims4[2] = l.nl; dims4[3] = 0; }
+    if (dims4) { dims4[0] = l.seg; dims4[1] = l.nh; dims4[2] = l.nl; dims4[3] = l.type; }
     if (steps7) {
         for (int i = 0; i < 3; ++i) steps7[i] = l.p.ystep[i];
         steps7[3] = l.p.ythresh[0]; steps7[4] = l.p.ythresh[1];
         steps7[5] = l.p.hstep; steps7[6] = l.p.lstep;
     }
+    if (scales2) { scales2[0] = l.light_scale; scales2[1] = l.chroma_scale; }
     return NPHUSL_OK;
+}
+
+int nphusl_cuda_lut_download(int device, uint16_t *light, uint16_t *chroma, double *linear256,
+                             int *dims4, double *steps7) {
+    if (light || chroma) {
+        DevCtx *c;
+        int rc = ctx_get(device, &c);
+        if (rc) return rc;
+        if (c->lut.ready && c->lut.type != NPHUSL_LUT_U16)
+            return fail(NPHUSL_ERR_ARG, "lut_download: the installed tables are not uint16; use nphusl_cuda_lut_download_typed");
+    }
+    return nphusl_cuda_lut_download_typed(device, light, chroma, linear256, dims4, steps7, nullptr);
 }
 
 // ---- memory / stream helpers --------------------------------------------------------------

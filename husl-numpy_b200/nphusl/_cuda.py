@@ -85,6 +85,10 @@ SIGNATURES = {
     "nphusl_cuda_lut_upload": (_i, [_i, _u16p, _i, _dp, _dp, _u16p, _i, _i,
                                     ctypes.c_double, ctypes.c_double, _dp]),
     "nphusl_cuda_lut_download": (_i, [_i, _u16p, _u16p, _dp, _ip, _dp]),
+    "nphusl_cuda_lut_generate_typed": (_i, [_i, _i, _i, _i, _i, _i]),
+    "nphusl_cuda_lut_upload_typed": (_i, [_i, _i, ctypes.c_double, ctypes.c_double, _vp, _i, _dp, _dp, _vp, _i, _i,
+                                          ctypes.c_double, ctypes.c_double, _dp]),
+    "nphusl_cuda_lut_download_typed": (_i, [_i, _vp, _vp, _dp, _ip, _dp, _dp]),
     "nphusl_cuda_malloc": (_i, [ctypes.POINTER(_vp), _sz, _i]),
     "nphusl_cuda_free": (_i, [_vp, _i]),
     "nphusl_cuda_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
@@ -1002,39 +1006,63 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
 # lookup tables (optional LUT mode)
 # ---------------------------------------------------------------------------
 
-def lut_generate(light_seg=1024, nh=1024, nl=1024, device=None):
+LUT_TYPES = {"uint16": 0, "float": 1, "double": 2}
+_LUT_DTYPES = {0: np.dtype(np.uint16), 1: np.dtype(np.float32), 2: np.dtype(np.float64)}
+
+
+def lut_generate(light_seg=1024, nh=1024, nl=1024, device=None, table_type="uint16", int_scale=100):
     """Build the reference's light / chroma / linear tables ON THE DEVICE
-    (make_lookup_tables:8-9, LUT/light.py, LUT/chroma.py, _linear_lookup.c)."""
+    (make_lookup_tables:4-9, LUT/light.py, LUT/chroma.py, _linear_lookup.c).
+    ``table_type``: "uint16" (the default build: round(value * int_scale)), "float"
+    or "double" (the value to 4 / 3 decimals, scales 1), as `make_lookup_tables
+    <table_type> <light size> <chroma size>` would bake them into _simd.c."""
     dev = _default_device if device is None else device
-    _check(load().nphusl_cuda_lut_generate(dev, light_seg, nh, nl), "lut_generate")
+    _check(load().nphusl_cuda_lut_generate_typed(dev, light_seg, nh, nl, LUT_TYPES[table_type], int(int_scale)), "lut_generate")
 
 
-def lut_upload(light, y_idx_step, y_thresh, chroma, h_idx_step, l_idx_step, linear, device=None):
+def lut_upload(light, y_idx_step, y_thresh, chroma, h_idx_step, l_idx_step, linear, device=None,
+               light_scale=None, chroma_scale=None):
+    """Install caller-made tables (e.g. the reference's own).  uint16, float32 or float64
+    tables; the scales default to 100 for integer tables and 1 for float tables."""
     dev = _default_device if device is None else device
-    light = np.ascontiguousarray(light, np.uint16)
-    chroma = np.ascontiguousarray(chroma, np.uint16)
+    light, chroma = np.asarray(light), np.asarray(chroma)
+    if np.issubdtype(chroma.dtype, np.integer):
+        dt, kind, default_scale = np.uint16, 0, 100.0
+    elif chroma.dtype == np.float32:
+        dt, kind, default_scale = np.float32, 1, 1.0
+    else:
+        dt, kind, default_scale = np.float64, 2, 1.0
+    light = np.ascontiguousarray(light, dt)
+    chroma = np.ascontiguousarray(chroma, dt)
     st = np.ascontiguousarray(y_idx_step, np.float64)
     th = np.ascontiguousarray(y_thresh, np.float64)
     lin = np.ascontiguousarray(linear, np.float64)
     assert chroma.ndim == 2 and light.size % 3 == 0 and lin.size == 256
-    _check(load().nphusl_cuda_lut_upload(
-        dev, light.ctypes.data_as(_u16p), light.size // 3, st.ctypes.data_as(_dp), th.ctypes.data_as(_dp),
-        chroma.ctypes.data_as(_u16p), chroma.shape[0], chroma.shape[1], float(h_idx_step), float(l_idx_step),
+    _check(load().nphusl_cuda_lut_upload_typed(
+        dev, kind, float(default_scale if light_scale is None else light_scale),
+        float(default_scale if chroma_scale is None else chroma_scale),
+        light.ctypes.data, light.size // 3, st.ctypes.data_as(_dp), th.ctypes.data_as(_dp),
+        chroma.ctypes.data, chroma.shape[0], chroma.shape[1], float(h_idx_step), float(l_idx_step),
         lin.ctypes.data_as(_dp)), "lut_upload")
 
 
 def lut_download(device=None):
-    """-> dict(light, chroma, linear, y_idx_step, y_thresh, h_idx_step, l_idx_step)"""
+    """-> dict(light, chroma, linear, y_idx_step, y_thresh, h_idx_step, l_idx_step, table_type,
+    light_scale, chroma_scale); the tables come back in their element type"""
     dev = _default_device if device is None else device
     dims = (ctypes.c_int * 4)()
     steps = (ctypes.c_double * 7)()
-    _check(load().nphusl_cuda_lut_download(dev, None, None, None, dims, steps), "lut_download")
-    seg, nh, nl = dims[0], dims[1], dims[2]
-    light = np.empty(3 * seg, np.uint16)
-    chroma = np.empty((nh, nl), np.uint16)
+    scales = (ctypes.c_double * 2)()
+    _check(load().nphusl_cuda_lut_download_typed(dev, None, None, None, dims, steps, scales), "lut_download")
+    seg, nh, nl, kind = dims[0], dims[1], dims[2], dims[3]
+    dt = _LUT_DTYPES[kind]
+    light = np.empty(3 * seg, dt)
+    chroma = np.empty((nh, nl), dt)
     lin = np.empty(256, np.float64)
-    _check(load().nphusl_cuda_lut_download(dev, light.ctypes.data_as(_u16p), chroma.ctypes.data_as(_u16p),
-                                           lin.ctypes.data_as(_dp), dims, steps), "lut_download")
+    _check(load().nphusl_cuda_lut_download_typed(dev, light.ctypes.data, chroma.ctypes.data,
+                                                 lin.ctypes.data_as(_dp), dims, steps, scales), "lut_download")
     s = list(steps)
     return {"light": light, "chroma": chroma, "linear": lin, "y_idx_step": np.array(s[0:3]),
-            "y_thresh": np.array(s[3:5]), "h_idx_step": s[5], "l_idx_step": s[6]}
+            "y_thresh": np.array(s[3:5]), "h_idx_step": s[5], "l_idx_step": s[6],
+            "table_type": {v: k for k, v in LUT_TYPES.items()}[kind],
+            "light_scale": scales[0], "chroma_scale": scales[1]}

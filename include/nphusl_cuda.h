@@ -202,6 +202,25 @@ int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
 int nphusl_cuda_lut_download(int device, uint16_t *light, uint16_t *chroma,
                              double *linear256, int *dims4, double *steps7);
 
+/* The same three with the table element type the reference generator takes as its first
+ * argument (make_lookup_tables:4 `table_type`, LUT/light.py:21-32, LUT/chroma.py:20-33):
+ *   NPHUSL_LUT_U16  integer tables holding round(value * int_scale) (default: uint16_t, scale 100)
+ *   NPHUSL_LUT_F32 / _F64  float / double tables holding the value as the generated source spells
+ *                   it ("{:7.4f}" light, "{:7.3f}" chroma), LIGHT_SCALE = CHROMA_SCALE = 1
+ * LUT / LUT_INTERP modes are bit-exact against _simd.c built (strictly) with those tables. */
+enum { NPHUSL_LUT_U16 = 0, NPHUSL_LUT_F32 = 1, NPHUSL_LUT_F64 = 2 };
+int nphusl_cuda_lut_generate_typed(int device, int light_seg, int nh, int nl, int table_type, int int_scale);
+/* light / chroma: arrays of the element type; light_scale / chroma_scale: LIGHT_SCALE / CHROMA_SCALE */
+int nphusl_cuda_lut_upload_typed(int device, int table_type, double light_scale, double chroma_scale,
+                                 const void *light, int light_seg,
+                                 const double *y_idx_step3, const double *y_thresh2,
+                                 const void *chroma, int nh, int nl,
+                                 double h_idx_step, double l_idx_step,
+                                 const double *linear256);
+/* dims4 = {light_seg, nh, nl, table_type}; scales2 = {LIGHT_SCALE, CHROMA_SCALE} */
+int nphusl_cuda_lut_download_typed(int device, void *light, void *chroma, double *linear256,
+                                   int *dims4, double *steps7, double *scales2);
+
 /* ---- memory / stream helpers (so a host needs no other CUDA binding) -------- */
 int nphusl_cuda_malloc(void **ptr, size_t bytes, int device);
 int nphusl_cuda_free(void *ptr, int device);

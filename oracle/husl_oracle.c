@@ -262,7 +262,19 @@ void oracle_linear_table6(double *t256) {
  * three Y segments [0,.07) [.07,.35) [.35,1+step]; entries round(L*100) as
  * uint16; steps3/thresh2 receive Y_IDX_STEP_{0,1,2} and Y_THRESH_{0,1}.
  * np.arange(start, stop, step)[k] = start + k*step. */
-void oracle_light_table(uint16_t *table, int seg, double *steps3, double *thresh2) {
+/* One table entry as the generated C source holds it (LUT/light.py:86-97, LUT/chroma.py:60-70):
+ * kind 0 = integer types: int(round(v * int_scale)); kind 1 / 2 = `float` / `double` tables: the
+ * "{:7.Nf}" literal (N = 4 for light, 3 for chroma), which the C compiler reads as a double and,
+ * for a float table, narrows to float. */
+static double table_entry(double v, int kind, double int_scale, int decimals) {
+    if (kind == 0) return (double)(long)nearbyint(v * int_scale);
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.*f", decimals, v);
+    const double d = strtod(buf, NULL);
+    return kind == 1 ? (double)(float)d : d;
+}
+
+void oracle_light_table_typed(double *table, int seg, double *steps3, double *thresh2, int kind, double int_scale) {
     double ysteps[3] = {0.070, 0.350, 1.0};
     double start = 0.0;
     for (int i = 0; i < 3; i++) {
@@ -280,29 +292,39 @@ void oracle_light_table(uint16_t *table, int seg, double *steps3, double *thresh
             snprintf(buf, sizeof buf, "%0.4f", stop);
             thresh2[i] = strtod(buf, NULL);
         }
-        for (int k = 0; k < seg; k++) {
-            double l = to_light(start + k * step);
-            table[i * seg + k] = (uint16_t)(long)nearbyint(l * 100);
-        }
+        for (int k = 0; k < seg; k++)
+            table[i * seg + k] = table_entry(to_light(start + k * step), kind, int_scale, 4);
         start = stop;
     }
+}
+
+void oracle_light_table(uint16_t *table, int seg, double *steps3, double *thresh2) {
+    double *t = (double *)malloc(sizeof(double) * 3 * (size_t)seg);
+    oracle_light_table_typed(t, seg, steps3, thresh2, 0, 100);
+    for (int i = 0; i < 3 * seg; i++) table[i] = (uint16_t)t[i];
+    free(t);
 }
 
 /* LUT/chroma.py:73-84, 63-65: hues = arange(0, 360+hstep, hstep), lights =
  * arange(0, 100+lstep, lstep), entry [h][l] = round(max_chroma(L,H)*100), L=0
  * column left 0 */
-void oracle_chroma_table(uint16_t *table, int nh, int nl, double *h_step, double *l_step) {
+void oracle_chroma_table_typed(double *table, int nh, int nl, double *h_step, double *l_step, int kind, double int_scale) {
     double hs = 360.0 / (nh - 1), ls = 100.0 / (nl - 1);
     *h_step = hs; *l_step = ls;
     long i;
 #pragma omp parallel for schedule(static)
     for (i = 0; i < nh; i++) {
         table[i * nl] = 0;
-        for (int j = 1; j < nl; j++) {
-            double c = oracle_max_chroma(0.0 + j * ls, 0.0 + i * hs);
-            table[i * nl + j] = (uint16_t)(long)nearbyint(c * 100);
-        }
+        for (int j = 1; j < nl; j++)
+            table[i * nl + j] = table_entry(oracle_max_chroma(0.0 + j * ls, 0.0 + i * hs), kind, int_scale, 3);
     }
+}
+
+void oracle_chroma_table(uint16_t *table, int nh, int nl, double *h_step, double *l_step) {
+    double *t = (double *)malloc(sizeof(double) * (size_t)nh * nl);
+    oracle_chroma_table_typed(t, nh, nl, h_step, l_step, 0, 100);
+    for (size_t i = 0; i < (size_t)nh * nl; i++) table[i] = (uint16_t)t[i];
+    free(t);
 }
 
 /* ======================================================================== */
@@ -311,8 +333,9 @@ void oracle_chroma_table(uint16_t *table, int nh, int nl, double *h_step, double
 
 typedef struct {
     const double *linear;       /* 256, 6-decimal (_linear_lookup.c:9-42) */
-    const uint16_t *light;      /* 3*seg  (light_table_big) */
-    const uint16_t *chroma;     /* nh*nl  (chroma_table) */
+    const double *light;        /* 3*seg  (light_table_big), the entries of any l_table_t as doubles */
+    const double *chroma;       /* nh*nl  (chroma_table), the entries of any c_table_t as doubles */
+    double light_scale, chroma_scale;   /* LIGHT_SCALE, CHROMA_SCALE: the int scale, 1 for float tables */
     int seg, nh, nl;
     double ystep[3], ythresh[2], hstep, lstep;
 } simd_tables;
@@ -331,7 +354,7 @@ static double simd_light_lut(const simd_tables *t, double y) {
     else idx = ((y - t->ythresh[1]) / t->ystep[2]) + t->seg * 2;
     /* roundf takes a float: idx is narrowed first */
     const unsigned short r = fmax(0, fmin(3 * t->seg - 1, roundf(idx)));
-    return (double)t->light[r] / 100;
+    return (double)t->light[r] / t->light_scale;
 }
 
 /* _simd.c:503-509 (no LUT) */
@@ -400,10 +423,10 @@ static double simd_chroma_interp(const simd_tables *t, double l, double h) {
     const double hidx = h / t->hstep, lidx = l / t->lstep;
     const unsigned short hf = fmax(0.0, fmin(t->nh - 2, floorf(hidx)));
     const unsigned short lf = fmax(0.0, fmin(t->nl - 2, floorf(lidx)));
-    const uint16_t c00 = t->chroma[(size_t)hf * t->nl + lf];
-    const uint16_t c10 = t->chroma[(size_t)(hf + 1) * t->nl + lf];
-    const uint16_t c01 = t->chroma[(size_t)hf * t->nl + lf + 1];
-    const uint16_t c11 = t->chroma[(size_t)(hf + 1) * t->nl + lf + 1];
+    const double c00 = t->chroma[(size_t)hf * t->nl + lf];        /* c_table_t promoted to double by the products below */
+    const double c10 = t->chroma[(size_t)(hf + 1) * t->nl + lf];
+    const double c01 = t->chroma[(size_t)hf * t->nl + lf + 1];
+    const double c11 = t->chroma[(size_t)(hf + 1) * t->nl + lf + 1];
     const double hn = hidx - hf, ln = lidx - lf, hv = 1 - hn, lv = 1 - ln;
     const double c = c00 * hv * lv + c10 * hn * lv + c01 * hv * ln + c11 * hn * ln;
     return fmax(1e-10f, c);
@@ -436,19 +459,20 @@ static double simd_chroma_exact(double l, double h) {
  * approx), 2 = LUT + INTERPOLATE_CHROMA.  _simd.c:87-225 */
 void oracle_simd_rgb_to_husl(const uint8_t *rgb, double *hsl, size_t n_pixels,
                              int variant, const double *linear256,
-                             const uint16_t *light, int seg,
+                             const double *light, int seg, double light_scale,
                              const double *ystep3, const double *ythresh2,
-                             const uint16_t *chroma, int nh, int nl,
+                             const double *chroma, int nh, int nl, double chroma_scale_in,
                              double hstep, double lstep) {
     simd_tables t;
     memset(&t, 0, sizeof t);
     t.linear = linear256; t.light = light; t.chroma = chroma;
     t.seg = seg; t.nh = nh; t.nl = nl; t.hstep = hstep; t.lstep = lstep;
+    t.light_scale = light_scale; t.chroma_scale = chroma_scale_in;
     if (variant) {
         memcpy(t.ystep, ystep3, sizeof t.ystep);
         memcpy(t.ythresh, ythresh2, sizeof t.ythresh);
     }
-    const double chroma_scale = variant ? 100 : 1;     /* CHROMA_SCALE */
+    const double chroma_scale = variant ? chroma_scale_in : 1;     /* CHROMA_SCALE (_simd.c:64 without the LUT) */
     long i;
 #pragma omp parallel for schedule(static)
     for (i = 0; i < (long)n_pixels; i++) {

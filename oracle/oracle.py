@@ -112,33 +112,46 @@ def linear_table6():
     return t
 
 
-def light_table(seg=1024):
-    """-> (uint16[3*seg], Y_IDX_STEP[3], Y_THRESH[2])"""
-    t = np.empty(3 * seg, dtype=np.uint16)
+_KINDS = {"uint16": (0, np.uint16, 100.0), "float": (1, np.float32, 1.0), "double": (2, np.float64, 1.0)}
+
+
+def light_table(seg=1024, table_type="uint16"):
+    """-> (table[3*seg], Y_IDX_STEP[3], Y_THRESH[2]); table dtype uint16 (L*100), float32 or float64
+    (L to 4 decimals) as `LUT/light.py -t <table_type>` writes it"""
+    kind, dt, scale = _KINDS[table_type]
+    t = np.empty(3 * seg, dtype=np.float64)
     steps = np.empty(3, dtype=np.float64)
     thresh = np.empty(2, dtype=np.float64)
-    lib().oracle_light_table(_p(t, _c_u16p), ctypes.c_int(seg), _p(steps, _c_f64p), _p(thresh, _c_f64p))
-    return t, steps, thresh
+    lib().oracle_light_table_typed(_p(t, _c_f64p), ctypes.c_int(seg), _p(steps, _c_f64p), _p(thresh, _c_f64p),
+                                   ctypes.c_int(kind), ctypes.c_double(scale))
+    return t.astype(dt), steps, thresh
 
 
-def chroma_table(nh=1024, nl=1024):
-    """-> (uint16[nh, nl], H_IDX_STEP, L_IDX_STEP)"""
-    t = np.empty((nh, nl), dtype=np.uint16)
-    hs = ctypes.c_double()
-    ls = ctypes.c_double()
-    lib().oracle_chroma_table(_p(t, _c_u16p), ctypes.c_int(nh), ctypes.c_int(nl),
-                              ctypes.byref(hs), ctypes.byref(ls))
-    return t, hs.value, ls.value
+def chroma_table(nh=1024, nl=1024, table_type="uint16"):
+    """-> (table[nh, nl], H_IDX_STEP, L_IDX_STEP); dtype as light_table (chroma to 3 decimals)"""
+    kind, dt, scale = _KINDS[table_type]
+    t = np.empty((nh, nl), dtype=np.float64)
+    hs, ls = ctypes.c_double(), ctypes.c_double()
+    lib().oracle_chroma_table_typed(_p(t, _c_f64p), ctypes.c_int(nh), ctypes.c_int(nl),
+                                    ctypes.byref(hs), ctypes.byref(ls), ctypes.c_int(kind), ctypes.c_double(scale))
+    return t.astype(dt), hs.value, ls.value
 
 
 _TABLE_CACHE = {}
 
 
+def table_scale(table):
+    """LIGHT_SCALE / CHROMA_SCALE of a table: 100 for the integer types, 1 for float / double
+    (LUT/light.py:31-32 with the default --int-scale)"""
+    return 100.0 if np.issubdtype(np.asarray(table).dtype, np.integer) else 1.0
+
+
 def simd_rgb_to_husl(rgb, variant="lut", tables=None):
     """Restatement of nphusl/_simd.c::rgb_to_husl_nd.  variant: "exact" (no -D
     flags), "lut" (setup.py default), "lut_interp" (+INTERPOLATE_CHROMA).
-    ``tables`` = (light_u16, ystep3, ythresh2, chroma_u16, hstep, lstep); made
-    by the oracle's own generators when omitted."""
+    ``tables`` = (light, ystep3, ythresh2, chroma, hstep, lstep) with uint16,
+    float32 or float64 tables; made by the oracle's own uint16 generators when
+    omitted."""
     v = {"exact": 0, "lut": 1, "lut_interp": 2}[variant]
     a = np.ascontiguousarray(rgb, dtype=np.uint8)
     out = np.empty(a.shape, dtype=np.float64)
@@ -150,15 +163,18 @@ def simd_rgb_to_husl(rgb, variant="lut", tables=None):
             _TABLE_CACHE["tab"] = (lt, st, th, ct, hs, ls)
         tables = _TABLE_CACHE["tab"]
     lt, st, th, ct, hs, ls = tables
-    lt = np.ascontiguousarray(lt, dtype=np.uint16)
-    ct = np.ascontiguousarray(ct, dtype=np.uint16)
+    lsc, csc = table_scale(lt), table_scale(ct)
+    ct = np.asarray(ct)
+    nh, nl = ct.shape
+    lt = np.ascontiguousarray(lt, dtype=np.float64)          # every table type is exact in a double
+    ct = np.ascontiguousarray(ct, dtype=np.float64)
     st = np.ascontiguousarray(st, dtype=np.float64)
     th = np.ascontiguousarray(th, dtype=np.float64)
     lib().oracle_simd_rgb_to_husl(
         _p(a, _c_u8p), _p(out, _c_f64p), ctypes.c_size_t(a.size // 3), ctypes.c_int(v),
-        _p(lin, _c_f64p), _p(lt, _c_u16p), ctypes.c_int(lt.size // 3),
-        _p(st, _c_f64p), _p(th, _c_f64p), _p(ct, _c_u16p),
-        ctypes.c_int(ct.shape[0]), ctypes.c_int(ct.shape[1]),
+        _p(lin, _c_f64p), _p(lt, _c_f64p), ctypes.c_int(lt.size // 3), ctypes.c_double(lsc),
+        _p(st, _c_f64p), _p(th, _c_f64p), _p(ct, _c_f64p),
+        ctypes.c_int(nh), ctypes.c_int(nl), ctypes.c_double(csc),
         ctypes.c_double(hs), ctypes.c_double(ls))
     return out
 
@@ -202,15 +218,17 @@ def ref_simd(rgb, build="lut", copy=True):
         _LIBC.free(ptr)
 
 
-def ref_tables():
-    """Tables baked into the reference build (generated by its own
-    LUT/light.py and LUT/chroma.py) -> same tuple as simd_rgb_to_husl(tables=)."""
-    l = _ref_lib("lut_strict")
+def ref_tables(build="lut_strict"):
+    """Tables baked into a reference build (generated by its own LUT/light.py and
+    LUT/chroma.py) -> same tuple as simd_rgb_to_husl(tables=).  build "lutf_strict":
+    the float-table build (`make_lookup_tables float`)."""
+    l = _ref_lib(build)
+    ctype, dt = (ctypes.c_float, np.float32) if build.startswith("lutf") else (ctypes.c_uint16, np.uint16)
     seg = ctypes.c_ushort.in_dll(l, "L_SEGMENT_SIZE").value
     nh = ctypes.c_ushort.in_dll(l, "CH_TABLE_SIZE").value
     nl = ctypes.c_ushort.in_dll(l, "CL_TABLE_SIZE").value
-    lt = np.frombuffer((ctypes.c_uint16 * (3 * seg)).in_dll(l, "light_table_big"), dtype=np.uint16).copy()
-    ct = np.frombuffer((ctypes.c_uint16 * (nh * nl)).in_dll(l, "chroma_table"), dtype=np.uint16).reshape(nh, nl).copy()
+    lt = np.frombuffer((ctype * (3 * seg)).in_dll(l, "light_table_big"), dtype=dt).copy()
+    ct = np.frombuffer((ctype * (nh * nl)).in_dll(l, "chroma_table"), dtype=dt).reshape(nh, nl).copy()
     st = np.array([ctypes.c_double.in_dll(l, "Y_IDX_STEP_%d" % i).value for i in range(3)])
     th = np.array([ctypes.c_double.in_dll(l, "Y_THRESH_%d" % i).value for i in range(2)])
     hs = ctypes.c_double.in_dll(l, "H_IDX_STEP").value

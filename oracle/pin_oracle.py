@@ -138,6 +138,22 @@ def main():
                                    "max_abs": [float(np.nanmax(d[:, k])) for k in range(3)]}
         res["simd_" + variant] = entry
 
+    # ---- 3b. _simd.c built with FLOAT lookup tables (make_lookup_tables float) --------
+    try:
+        ftabs = oracle.ref_tables("lutf_strict")
+        flt, fst, fth = oracle.light_table(1024, "float")
+        fct, fhs, fls = oracle.chroma_table(1024, 1024, "float")
+        entry = {"light_equal_ref": bool(np.array_equal(flt, ftabs[0])),
+                 "chroma_entries_differing": int((fct != ftabs[3]).sum())}
+        for variant, build in (("lut", "lutf_strict"), ("lut_interp", "lutf_interp_strict")):
+            mine = oracle.simd_rgb_to_husl(rgb, variant, tables=ftabs).reshape(-1, 3)
+            theirs = oracle.ref_simd(rgb, build).reshape(-1, 3)
+            same = (mine.view(np.uint64) == theirs.view(np.uint64)) | (np.isnan(mine) & np.isnan(theirs))
+            entry[variant + "_mismatching_values_vs_strict_O2"] = int((~same).sum())
+        res["simd_float_tables"] = entry
+    except OSError as e:  # pragma: no cover
+        res["simd_float_tables"] = "unavailable: %r" % (e,)
+
     # ---- 4. tables -------------------------------------------------------
     lt, st, th = oracle.light_table()
     ct, hs, ls = oracle.chroma_table()

@@ -30,6 +30,12 @@ def simd_golden():
 
 
 @pytest.fixture(scope="session")
+def simd_float_golden():
+    """the reference built with FLOAT lookup tables (`make_lookup_tables float 1024 1024`)"""
+    return dict(np.load(os.path.join(GOLDEN, "simd_float_golden.npz")))
+
+
+@pytest.fixture(scope="session")
 def cube_slices():
     return dict(np.load(os.path.join(GOLDEN, "cube_numpy_slices.npz")))
 

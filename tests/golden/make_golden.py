@@ -45,7 +45,34 @@ def cube():
     return np.stack([r, g, b], axis=-1).reshape(4096, 4096, 3)
 
 
+def float_lut_fixtures(rgb, meta):
+    """The float-table build of the reference (`make_lookup_tables float 1024 1024`,
+    oracle/_ref/libsimd_lutf*_strict.so): sampled outputs, its tables, full-cube digests."""
+    lt, st, th, ct, hs, ls = _o.ref_tables("lutf_strict")
+    np.savez_compressed(
+        os.path.join(HERE, "simd_float_golden.npz"),
+        rgb=rgb,
+        hsl_lutf_strict=_o.ref_simd(rgb, "lutf_strict"),
+        hsl_lutf_interp_strict=_o.ref_simd(rgb, "lutf_interp_strict"),
+        light_table=lt, y_idx_step=st, y_thresh=th, h_idx_step=hs, l_idx_step=ls,
+        chroma_rows_every_64=ct[::64].copy())
+    c = cube()
+    meta["lutf_strict_cube_sha256"] = hashlib.sha256(_o.ref_simd(c, "lutf_strict").tobytes()).hexdigest()
+    meta["lutf_interp_strict_cube_sha256"] = hashlib.sha256(_o.ref_simd(c, "lutf_interp_strict").tobytes()).hexdigest()
+    meta["light_table_float_sha256"] = hashlib.sha256(lt.tobytes()).hexdigest()
+    meta["chroma_table_float_sha256"] = hashlib.sha256(ct.tobytes()).hexdigest()
+
+
 def main():
+    if "--float-lut-only" in sys.argv:       # add the float-table fixtures to an existing set
+        rgb = np.load(os.path.join(HERE, "simd_golden.npz"))["rgb"]
+        with open(os.path.join(HERE, "golden_meta.json")) as f:
+            meta = json.load(f)
+        float_lut_fixtures(rgb, meta)
+        with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
+            json.dump(meta, f, indent=1)
+        print(json.dumps({k: v for k, v in meta.items() if "float" in k or "lutf" in k}, indent=1))
+        return
     ref = import_reference()
     rng = np.random.default_rng(20261019)
     warnings.simplefilter("ignore")
@@ -136,6 +163,7 @@ def main():
                         # every 4099th colour, full precision, for spot checks
                         sample_idx=np.arange(0, 1 << 24, 4099),
                         sample_hsl=ch.reshape(-1, 3)[::4099].copy())
+    float_lut_fixtures(rgb, meta)
     with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print(json.dumps(meta, indent=1))

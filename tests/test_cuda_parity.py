@@ -903,3 +903,39 @@ def test_past_the_reference_size_limit(cu):
     cu.edit_rgb(rgb, out=back)                                # identity edit: the fused kernel at the same offsets
     torch.cuda.synchronize()
     assert torch.equal(back, rgb)
+
+
+def test_lut_mode_with_float_and_double_tables(cu, cube, golden_meta):
+    """The reference generator's table element type (make_lookup_tables:4): float tables built ON
+    THE DEVICE equal the reference generator's, and LUT / LUT+interp modes with them are bit-exact
+    against the reference C build that bakes them in (sha256 over the 2^24 cube); double tables and
+    another int scale against the oracle."""
+    cu.lut_generate(1024, 1024, 1024, table_type="float")
+    t = cu.lut_download()
+    assert t["table_type"] == "float" and t["light"].dtype == np.float32 and t["light_scale"] == 1.0
+    lt, st, th = orc.light_table(1024, "float")
+    ct, hs, ls = orc.chroma_table(1024, 1024, "float")
+    assert hashlib.sha256(t["light"].tobytes()).hexdigest() == golden_meta["light_table_float_sha256"]
+    assert np.array_equal(t["y_idx_step"], st) and np.array_equal(t["y_thresh"], th)
+    # device pow / sin / cos vs glibc: a handful of entries may sit on the other side of a decimal
+    assert np.abs(t["chroma"] - ct).max() <= 0.0011 and np.count_nonzero(t["chroma"] != ct) <= 64
+    cu.lut_upload(lt, st, th, ct, hs, ls, orc.linear_table6())            # the reference's exact tables
+    for mode, key in (("lut", "lutf_strict_cube_sha256"), ("lut_interp", "lutf_interp_strict_cube_sha256")):
+        got = cu._rgb_to_husl(cube, mode=mode)
+        assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == golden_meta[key]
+    rng = np.random.default_rng(24)
+    rgb = rng.integers(0, 256, (60000, 3), dtype=np.uint8)
+    # double tables, odd sizes
+    ltd, std_, thd = orc.light_table(300, "double")
+    ctd, hsd, lsd = orc.chroma_table(200, 260, "double")
+    cu.lut_upload(ltd, std_, thd, ctd, hsd, lsd, orc.linear_table6())
+    assert cu.lut_download()["table_type"] == "double"
+    for mode in ("lut", "lut_interp"):
+        want = orc.simd_rgb_to_husl(rgb, mode, tables=(ltd, std_, thd, ctd, hsd, lsd))
+        assert np.array_equal(cu._rgb_to_husl(rgb, mode=mode).view(np.uint64), want.view(np.uint64))
+    cu.lut_generate(300, 200, 260, table_type="double")
+    td = cu.lut_download()
+    assert np.abs(td["light"] - ltd).max() <= 1.1e-4 and np.abs(td["chroma"] - ctd).max() <= 1.1e-3
+    # back to the default build for whoever comes next
+    cu.lut_generate()
+    assert cu.lut_download()["table_type"] == "uint16"
