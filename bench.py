@@ -466,6 +466,16 @@ def run_cuda(args):
             variants[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 2),
                               "gb_s": round(px * nbytes / ms / 1e6, 1), "hbm_frac": round(px * nbytes / ms / 1e6 / hbm, 3)}
         del h32, hue64, hue32
+        # configs[3] as its callers write it (README.md:77-81): to_husl -> lightness edit -> to_rgb, with the
+        # edit as the caller's own device op between the two conversions, and the same result from the fused kernel
+        def with_edit():
+            nphusl.to_husl(dev_in, out=dev_hsl, stream=stream)
+            dev_hsl[..., 2] *= 0.5
+            nphusl.to_rgb(dev_hsl, out=dev_out, stream=stream)
+        ms = timed(with_edit, 10)
+        variants["to_husl_edit_to_rgb_3_calls"] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 2)}
+        ms = timed(lambda: _cuda.edit_rgb(dev_in, out=dev_out, stream=stream, l=(0.5, 0)), 10)
+        variants["to_husl_edit_to_rgb_fused"] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 2)}
 
     # ---- cpu baseline (rank 0, N=1 only) ---------------------------------------------
     cpu = None

@@ -161,24 +161,44 @@ k_inv_planar_any(const T *__restrict__ H, const T *__restrict__ S, const T *__re
 // Selection: a pixel is selected when H lies on the arc [h_lo, h_hi] (h_lo > h_hi
 // means the arc through 360/0) AND S in [s_lo, s_hi] AND L in [l_lo, l_hi];
 // `invert` selects the complement.  Selected pixels get H' = H*h_mul + h_add
-// (wrapped to [0, 360)), S' = clamp(S*s_mul + s_add, 0, 100), L' likewise.  Every
-// pixel -- selected or not -- goes through the float32 HUSL round trip, exactly
-// as to_rgb(edit(to_husl(rgb, dtype=float32))) does.
+// (wrapped to [0, 360)), S' = clamp(S*s_mul + s_add, 0, 100), L' likewise; a
+// channel whose (mul, add) is (1, 0) is left exactly as it is, like the channels a
+// caller's `hsl[..., 2][mask] *= 0.5` never touches.  Every pixel -- selected or
+// not -- goes through the float32 HUSL round trip, exactly as
+// to_rgb(edit(to_husl(rgb, dtype=float32))) does.
+// EH / ES / RSL are compile-time promises of the dispatcher ("the hue / saturation
+// channel may be edited", "a saturation or lightness range may be bounded"): the
+// streaming kernels are instantiated per combination so that an edit which only
+// scales L inside a hue arc (README.md:77-81) carries no hue-wrap, saturation or
+// range arithmetic at all.  <true, true, true> is valid for every descriptor.
+template <bool EH = true, bool ES = true, bool RSL = true>
 __device__ __forceinline__ void apply_edit(const nphusl_edit &e, float &h, float &s, float &l) {
-    const bool arc = (e.h_lo <= e.h_hi) ? (h >= e.h_lo && h <= e.h_hi) : (h >= e.h_lo || h <= e.h_hi);
-    bool sel = arc && s >= e.s_lo && s <= e.s_hi && l >= e.l_lo && l <= e.l_hi;
+    bool sel = (e.h_lo <= e.h_hi) ? (h >= e.h_lo && h <= e.h_hi) : (h >= e.h_lo || h <= e.h_hi);
+    if (RSL) sel = sel && s >= e.s_lo && s <= e.s_hi && l >= e.l_lo && l <= e.l_hi;
     sel = e.invert ? !sel : sel;
-    if (sel) {
+    if (EH) {
         float hn = __fadd_rn(__fmul_rn(h, e.h_mul), e.h_add);
         hn = hn - 360.0f * floorf(hn * (1.0f / 360.0f));
         hn = (hn >= 360.0f || hn < 0.0f) ? 0.0f : hn;
-        h = hn;
-        s = fminf(fmaxf(__fadd_rn(__fmul_rn(s, e.s_mul), e.s_add), 0.0f), 100.0f);
-        l = fminf(fmaxf(__fadd_rn(__fmul_rn(l, e.l_mul), e.l_add), 0.0f), 100.0f);
+        h = (sel && (e.h_mul != 1.0f || e.h_add != 0.0f)) ? hn : h;
     }
+    if (ES) {
+        const float sn = fminf(fmaxf(__fadd_rn(__fmul_rn(s, e.s_mul), e.s_add), 0.0f), 100.0f);
+        s = (sel && (e.s_mul != 1.0f || e.s_add != 0.0f)) ? sn : s;
+    }
+    const float ln = fminf(fmaxf(__fadd_rn(__fmul_rn(l, e.l_mul), e.l_add), 0.0f), 100.0f);
+    l = (sel && (e.l_mul != 1.0f || e.l_add != 0.0f)) ? ln : l;
 }
 
-template <int BLOCK, int MINB>
+// what the dispatcher may promise for a descriptor (host side)
+struct EditShape {
+    bool eh, es, rsl;
+    __host__ explicit EditShape(const nphusl_edit &e)
+        : eh(e.h_mul != 1.0f || e.h_add != 0.0f), es(e.s_mul != 1.0f || e.s_add != 0.0f),
+          rsl(!(e.s_lo == -INFINITY && e.s_hi == INFINITY && e.l_lo == -INFINITY && e.l_hi == INFINITY)) {}
+};
+
+template <int BLOCK, int MINB, bool EH, bool ES, bool RSL>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_edit(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const nphusl_edit e) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -206,7 +226,7 @@ k_edit(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n_
         for (int j = 0; j < 4; ++j) {
             float h, s, l, R, G, B;
             husl_from_diff<true>(make_diff(px[j]), h, s, l);
-            apply_edit(e, h, s, l);
+            apply_edit<EH, ES, RSL>(e, h, s, l);
             rgb255_from_husl(h, s, l, R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }
@@ -349,7 +369,7 @@ k_inv_chw_any(const T *__restrict__ H, const T *__restrict__ S, const T *__restr
 }
 
 // fused edit on channels-first uint8 planes (what nvJPEG / video decoders hand out)
-template <int BLOCK, int MINB>
+template <int BLOCK, int MINB, bool EH, bool ES, bool RSL>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_edit_chw(const uint32_t *__restrict__ R, const uint32_t *__restrict__ G, const uint32_t *__restrict__ B,
            uint32_t *__restrict__ Ro, uint32_t *__restrict__ Go, uint32_t *__restrict__ Bo,
@@ -375,7 +395,7 @@ k_edit_chw(const uint32_t *__restrict__ R, const uint32_t *__restrict__ G, const
         for (int j = 0; j < 4; ++j) {
             float h, s, l, r, g, b;
             husl_from_diff<true>(make_diff(px[j]), h, s, l);
-            apply_edit(e, h, s, l);
+            apply_edit<EH, ES, RSL>(e, h, s, l);
             rgb255_from_husl(h, s, l, r, g, b);
             q[3 * j] = round_u8_bits(r); q[3 * j + 1] = round_u8_bits(g); q[3 * j + 2] = round_u8_bits(b);
         }

@@ -216,8 +216,12 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_inv_planes_cp<INV32_BLOCK, INV32_MINB, INV32_IST, true>, (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP))) return rc;
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
-    if ((rc = set_smem(k_edit<512, 2>, TAB_BYTES + 16 * 384))) return rc;
-    if ((rc = set_smem(k_edit_chw<512, 2>, TAB_BYTES))) return rc;
+#define EDIT_ATTRS(EH, ES, RSL) \
+    if ((rc = set_smem(k_edit<512, 2, EH, ES, RSL>, TAB_BYTES + 16 * 384))) return rc; \
+    if ((rc = set_smem(k_edit_chw<512, 2, EH, ES, RSL>, TAB_BYTES))) return rc;
+    EDIT_ATTRS(false, false, false) EDIT_ATTRS(false, false, true) EDIT_ATTRS(false, true, false) EDIT_ATTRS(false, true, true)
+    EDIT_ATTRS(true, false, false) EDIT_ATTRS(true, false, true) EDIT_ATTRS(true, true, false) EDIT_ATTRS(true, true, true)
+#undef EDIT_ATTRS
     if ((rc = set_smem(k_fwd_chw<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_chw<double, 512, 2>, TAB_BYTES))) return rc;
 
@@ -856,7 +860,14 @@ int nphusl_cuda_rgb_edit_rgb(const void *rgb_in, int in_loc, void *rgb_out, int 
         if (aligned(i, 4) && aligned(o, 4) && n >= TILE_PX) {
             if ((r = set_attrs(*c))) return r;
             const long long tiles = n / TILE_PX;
-            k_edit<512, 2><<<grid_for(tiles, 16, c->sms * 2), 512, TAB_BYTES + 16 * 384, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, e);
+            const EditShape sh(e);
+            const int grid = grid_for(tiles, 16, c->sms * 2);
+#define EDIT_GO(EH, ES, RSL) \
+    if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) \
+        k_edit<512, 2, EH, ES, RSL><<<grid, 512, TAB_BYTES + 16 * 384, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, e);
+            EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
+            EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
+#undef EDIT_GO
             g_launches++;
             if ((r = check_launch("k_edit"))) return r;
             done = tiles * TILE_PX;
@@ -886,8 +897,15 @@ int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,
     if (aligned(r, 4) && aligned(g, 4) && aligned(b, 4) && aligned(r_out, 4) && aligned(g_out, 4) && aligned(b_out, 4) && n >= TILE_PX) {
         if ((rc = set_attrs(*c))) return rc;
         const long long tiles = n / TILE_PX;
-        k_edit_chw<512, 2><<<grid_for(tiles, 16, c->sms * 2), 512, TAB_BYTES, st>>>(
-            (const uint32_t *)r, (const uint32_t *)g, (const uint32_t *)b, (uint32_t *)r_out, (uint32_t *)g_out, (uint32_t *)b_out, tiles, *edit);
+        const EditShape sh(*edit);
+        const int grid = grid_for(tiles, 16, c->sms * 2);
+#define EDIT_GO(EH, ES, RSL) \
+    if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) \
+        k_edit_chw<512, 2, EH, ES, RSL><<<grid, 512, TAB_BYTES, st>>>((const uint32_t *)r, (const uint32_t *)g, (const uint32_t *)b, \
+                                                                      (uint32_t *)r_out, (uint32_t *)g_out, (uint32_t *)b_out, tiles, *edit);
+        EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
+        EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
+#undef EDIT_GO
         g_launches++;
         if ((rc = check_launch("k_edit_chw"))) return rc;
         done = tiles * TILE_PX;

@@ -138,7 +138,8 @@ int nphusl_cuda_husl_planes_to_rgb_planes(const void *h, const void *s, const vo
  * through 0), S in [s_lo, s_hi] and L in [l_lo, l_hi]; invert != 0 selects the
  * complement (use -INFINITY / +INFINITY for an unbounded range: S may exceed
  * 100 by an ulp on the gamut boundary).  Selected pixels get H' = H*h_mul + h_add wrapped to [0, 360),
- * S' = clamp(S*s_mul + s_add, 0, 100), L' = clamp(L*l_mul + l_add, 0, 100).
+ * S' = clamp(S*s_mul + s_add, 0, 100), L' = clamp(L*l_mul + l_add, 0, 100); a channel whose
+ * (mul, add) is (1, 0) is left untouched (not clamped).
  * Results equal husl_to_rgb(edit(rgb_to_husl(rgb -> F32))) bit for bit. */
 typedef struct nphusl_edit {
     float h_lo, h_hi, s_lo, s_hi, l_lo, l_hi;
