@@ -775,6 +775,7 @@ def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, dev
         raise ValueError("expected (..., 3) RGB, got shape {}".format(src.shape))
     dev = _pick_device(device, src)
     dst, ret = _make_out(src, out, src.shape, dtype, _FLOATS, dev, "out", True)
+    dev = _pick_device(device, src, dst)                  # host input, `out` on another GPU: go where `out` lives
     n = _prod(src.shape[:-1])
     if src.strides is not None or dst.strides is not None:
         if mode != "exact":
@@ -799,6 +800,7 @@ def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None, block
     dev = _pick_device(device, src)
     shape = src.shape[:-1]
     dst, ret = _make_out(src, out, shape, dtype, _FLOATS, dev, "out", True)
+    dev = _pick_device(device, src, dst)
     n = _prod(shape)
     if src.strides is not None or dst.strides is not None:
         _strided_call("nphusl_cuda_rgb_to_husl_strided", src, dst, len(shape), [1], dev, stream)
@@ -831,6 +833,7 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
         raise ValueError("expected (..., 3) HUSL, got shape {}".format(src.shape))
     dev = _pick_device(device, src)
     dst, ret = _make_out(src, out, src.shape, dtype, _ANY, dev, "out", True)
+    dev = _pick_device(device, src, dst)
     n = _prod(src.shape[:-1])
     if src.strides is not None or dst.strides is not None:
         _strided_call("nphusl_cuda_husl_to_rgb_strided", src, dst, len(src.shape) - 1, [], dev, stream)
@@ -992,6 +995,7 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
         raise ValueError("edit_rgb takes uint8 RGB (..., 3), got {} {}".format(src.dtype, src.shape))
     dev = _pick_device(device, src)
     dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out", True)
+    dev = _pick_device(device, src, dst)
     n = _prod(src.shape[:-1])
     if src.strides is not None or dst.strides is not None:
         _strided_call("nphusl_cuda_rgb_edit_rgb_strided", src, dst, len(src.shape) - 1, [ctypes.byref(edit)], dev, stream)

@@ -615,6 +615,11 @@ def test_shard_over_devices(cu):
     d = cu._rgb_to_husl(t, dtype=np.float32)
     assert d.device == 1 and torch.cuda.current_device() == 0
     assert np.array_equal(d.copy_to_host(), hsl[0])
+    # a host array converted INTO a tensor that lives on GPU 1: the call goes where `out` lives
+    o1 = torch.empty(frames[0].shape, dtype=torch.float32, device="cuda:1")
+    cu._rgb_to_husl(frames[0], out=o1)
+    torch.cuda.synchronize(1)
+    assert np.array_equal(o1.cpu().numpy(), hsl[0]) and torch.cuda.current_device() == 0
 
 
 def test_out_of_gamut_husl_wraps_like_the_reference(cu):
