@@ -588,10 +588,21 @@ def test_guard_bands_stay_untouched(cu):
             assert intact(raw, n * 3 * isz) and intact(rawb, n * 3) and intact(rawh, n * isz)
             assert intact(rawp, n * 3 * isz) and intact(rawq, n * 3)
             assert torch.equal(back.view(n, 3), rgb) and torch.equal(back2.view(n, 3), rgb)
+            # channels-first planes both ways (cp.async ring kernel for float32 planes)
+            chw = rgb.t().contiguous()
+            rawc, cplanes = guarded(n * 3 * isz, tdt)
+            cu.rgb_to_husl_planar(chw, out=cplanes.view(3, n), channels_first=True)
+            rawd, cback = guarded(n * 3, torch.uint8)
+            cu.husl_planar_to_rgb(cplanes.view(3, n), out=cback.view(3, n), channels_first=True)
+            torch.cuda.synchronize()
+            assert intact(rawc, n * 3 * isz) and intact(rawd, n * 3) and torch.equal(cback.view(3, n), chw)
         rawe, ed = guarded(n * 3, torch.uint8)
         cu.edit_rgb(rgb, out=ed.view(n, 3))
+        rawf, edc = guarded(n * 3, torch.uint8)
+        cu.edit_rgb(rgb.t().contiguous(), out=edc.view(3, n), channels_first=True)
         torch.cuda.synchronize()
         assert intact(rawe, n * 3) and torch.equal(ed.view(n, 3), rgb)
+        assert intact(rawf, n * 3) and torch.equal(edc.view(3, n), rgb.t())
 
 
 def test_shard_over_devices(cu):
