@@ -172,6 +172,11 @@ constexpr int INV_BLOCK = 256;
 #ifndef NPHUSL_FWD32_OST
 #define NPHUSL_FWD32_OST 2
 #endif
+#ifndef NPHUSL_EDIT_BLOCK
+#define NPHUSL_EDIT_BLOCK 512
+#define NPHUSL_EDIT_MINB 2
+#endif
+constexpr int EDIT_BLOCK = NPHUSL_EDIT_BLOCK, EDIT_MINB = NPHUSL_EDIT_MINB, EDIT_W = NPHUSL_EDIT_BLOCK / 32;
 #ifndef NPHUSL_FWD64_BLOCK
 #define NPHUSL_FWD64_BLOCK 512
 #endif
@@ -217,8 +222,8 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
 #define EDIT_ATTRS(EH, ES, RSL) \
-    if ((rc = set_smem(k_edit<512, 2, EH, ES, RSL>, TAB_BYTES + 16 * 384))) return rc; \
-    if ((rc = set_smem(k_edit_chw<512, 2, EH, ES, RSL>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES + EDIT_W * 384))) return rc; \
+    if ((rc = set_smem(k_edit_chw<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES))) return rc;
     EDIT_ATTRS(false, false, false) EDIT_ATTRS(false, false, true) EDIT_ATTRS(false, true, false) EDIT_ATTRS(false, true, true)
     EDIT_ATTRS(true, false, false) EDIT_ATTRS(true, false, true) EDIT_ATTRS(true, true, false) EDIT_ATTRS(true, true, true)
 #undef EDIT_ATTRS
@@ -861,10 +866,10 @@ int nphusl_cuda_rgb_edit_rgb(const void *rgb_in, int in_loc, void *rgb_out, int 
             if ((r = set_attrs(*c))) return r;
             const long long tiles = n / TILE_PX;
             const EditShape sh(e);
-            const int grid = grid_for(tiles, 16, c->sms * 2);
+            const int grid = grid_for(tiles, EDIT_W, c->sms * EDIT_MINB);
 #define EDIT_GO(EH, ES, RSL) \
     if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) \
-        k_edit<512, 2, EH, ES, RSL><<<grid, 512, TAB_BYTES + 16 * 384, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, e);
+        k_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL><<<grid, EDIT_BLOCK, TAB_BYTES + EDIT_W * 384, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, e);
             EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
             EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
 #undef EDIT_GO
@@ -898,10 +903,10 @@ int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,
         if ((rc = set_attrs(*c))) return rc;
         const long long tiles = n / TILE_PX;
         const EditShape sh(*edit);
-        const int grid = grid_for(tiles, 16, c->sms * 2);
+        const int grid = grid_for(tiles, EDIT_W, c->sms * EDIT_MINB);
 #define EDIT_GO(EH, ES, RSL) \
     if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) \
-        k_edit_chw<512, 2, EH, ES, RSL><<<grid, 512, TAB_BYTES, st>>>((const uint32_t *)r, (const uint32_t *)g, (const uint32_t *)b, \
+        k_edit_chw<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL><<<grid, EDIT_BLOCK, TAB_BYTES, st>>>((const uint32_t *)r, (const uint32_t *)g, (const uint32_t *)b, \
                                                                       (uint32_t *)r_out, (uint32_t *)g_out, (uint32_t *)b_out, tiles, *edit);
         EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
         EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
