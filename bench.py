@@ -263,6 +263,15 @@ def traffic_for(kernel):
         return None
 
 
+def warp_inst_for(kernel):
+    """warp instructions per 66 355 200-px launch from the committed ncu capture (None when not recorded)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("warp_inst", {}).get(kernel)
+    except Exception:
+        return None
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -451,20 +460,30 @@ def run_cuda(args):
         hue64 = torch.empty((B,) + FRAME[:2], dtype=torch.float64, device="cuda")
         hue32 = torch.empty((B,) + FRAME[:2], dtype=torch.float32, device="cuda")
         _cuda._rgb_to_husl(dev_in, out=h32, stream=stream)
-        for name, fn, nbytes in (
-                ("to_husl_u8_f64", lambda: _cuda._rgb_to_husl(dev_in, out=dev_hsl, stream=stream), 27),
-                ("to_rgb_f64_u8", lambda: _cuda._husl_to_rgb(dev_hsl, out=dev_out, stream=stream), 27),
-                ("to_husl_u8_f32", lambda: _cuda._rgb_to_husl(dev_in, out=h32, stream=stream), 15),
-                ("to_rgb_f32_u8", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream), 15),
-                ("to_hue_u8_f64", lambda: _cuda._rgb_to_hue(dev_in, out=hue64, stream=stream), 11),
-                ("to_hue_u8_f32", lambda: _cuda._rgb_to_hue(dev_in, out=hue32, stream=stream), 7),
-                ("fused_edit_u8_u8", lambda: _cuda.edit_rgb(dev_in, out=dev_out, stream=stream, hue=(250, 290),
-                                                            invert=True, l=(0.5, 0)), 6)):
+        # each kernel against the SLOWER of its two limits: HBM bytes at the measured copy peak, or
+        # instruction issue (warp instructions of the ncu capture, profiles/traffic.json, scaled to this launch,
+        # over SMs x 4 schedulers x max SM clock)
+        issue_rate = _cuda.device_info()["sm_count"] * 4 * float(clocks.get("sm_max_mhz") or 1965) * 1e6
+        for name, kern, fn, nbytes in (
+                ("to_husl_u8_f64", "k_fwd_tma<double>", lambda: _cuda._rgb_to_husl(dev_in, out=dev_hsl, stream=stream), 27),
+                ("to_rgb_f64_u8", "k_inv_tma<double>", lambda: _cuda._husl_to_rgb(dev_hsl, out=dev_out, stream=stream), 27),
+                ("to_husl_u8_f32", "k_fwd_u8<float>", lambda: _cuda._rgb_to_husl(dev_in, out=h32, stream=stream), 15),
+                ("to_rgb_f32_u8", "k_inv_cp<float>", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream), 15),
+                ("to_hue_u8_f64", "k_fwd_u8<double,hue>", lambda: _cuda._rgb_to_hue(dev_in, out=hue64, stream=stream), 11),
+                ("to_hue_u8_f32", "k_fwd_u8<float,hue>", lambda: _cuda._rgb_to_hue(dev_in, out=hue32, stream=stream), 7),
+                ("fused_edit_u8_u8", "k_edit", lambda: _cuda.edit_rgb(dev_in, out=dev_out, stream=stream, hue=(250, 290),
+                                                                      invert=True, l=(0.5, 0)), 6)):
             if hdt != np.float64 and "f64" in name and "hue" not in name:
                 continue
             ms = timed(fn)
             variants[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 2),
                               "gb_s": round(px * nbytes / ms / 1e6, 1), "hbm_frac": round(px * nbytes / ms / 1e6 / hbm, 3)}
+            winst = warp_inst_for(kern)
+            if winst:
+                hbm_ms = px * nbytes / hbm / 1e6
+                issue_ms = winst * (px / 66355200.0) / issue_rate * 1e3
+                variants[name].update({"issue_frac": round(issue_ms / ms, 3), "bound": "issue" if issue_ms > hbm_ms else "hbm",
+                                       "roofline_frac": round(max(hbm_ms, issue_ms) / ms, 3)})
         del h32, hue64, hue32
         # configs[3] as its callers write it (README.md:77-81): to_husl -> lightness edit -> to_rgb, with the
         # edit as the caller's own device op between the two conversions, and the same result from the fused kernel

@@ -656,6 +656,27 @@ def test_out_of_gamut_husl_wraps_like_the_reference(cu):
     assert (np.abs(gf - f)[sane] / np.maximum(1.0, np.abs(f[sane]))).max() < 5e-4
 
 
+def test_hue_outside_0_360_is_periodic(cu, cube):
+    """Callers rotate hues without wrapping (`hsl[..., 0] += 120`): the reference feeds
+    the angle to sin / cos (_cython_opt.pyx:219-221, nphusl.py:170-171), so to_rgb is
+    periodic in H.  Every colour of a cube slice must come back to the same uint8 RGB
+    when its hue is given one or two turns up or down."""
+    rgb = np.ascontiguousarray(cube.reshape(-1, 3)[::17])  # ~1 M colours spread over the cube
+    for dt in (np.float64, np.float32):
+        hsl = np.asarray(cu._rgb_to_husl(rgb, dtype=dt))
+        for turns in (-2, -1, 1, 2):
+            h2 = hsl.copy()
+            h2[:, 0] += 360.0 * turns
+            back = np.asarray(cu._husl_to_rgb(h2))
+            if dt == np.float64:
+                assert np.array_equal(back, rgb), "turns=%d" % turns
+            else:                                         # float32 H + 720 has lost 2 bits of the angle itself
+                d = np.abs(back.astype(int) - rgb.astype(int))
+                assert d.max() <= 1 and (d != 0).mean() < 1e-3, "turns=%d" % turns
+        want = orc.husl_to_rgb(np.asarray(hsl, np.float64) + np.array([720.0, 0, 0]))
+        assert np.array_equal(want, rgb)                  # the oracle (reference math) is periodic too
+
+
 def test_rgba_device_arrays_are_premultiplied_on_load(cu):
     """4-channel device input: rgb * alpha in the load stage of the kernel
     (reference transform.py:221-230 does it as a host pass).  Float RGBA follows
