@@ -20,6 +20,7 @@
 #include "husl_kernels.cuh"
 #include "husl_stream.cuh"
 #include "husl_lut.cuh"
+#include "husl_nv12.cuh"
 #include "husl_fused.cuh"
 #include "husl_strided.cuh"
 
@@ -586,6 +587,59 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
 
 bool ok_loc(int l) { return l == NPHUSL_HOST || l == NPHUSL_DEVICE; }
 
+// ---- NV12 decoder surfaces ------------------------------------------------------------
+int nv12_src(const nphusl_nv12 *src, const char *what, Nv12Src *out) {
+    if (!src || !src->y || !src->uv) return fail(NPHUSL_ERR_ARG, std::string(what) + ": null surface");
+    if (src->width <= 0 || src->height <= 0) return fail(NPHUSL_ERR_ARG, std::string(what) + ": width and height must be positive");
+    if (src->y_pitch < src->width || src->uv_pitch < ((src->width + 1) / 2) * 2)
+        return fail(NPHUSL_ERR_ARG, std::string(what) + ": pitch smaller than a row");
+    if (src->matrix != NPHUSL_BT601 && src->matrix != NPHUSL_BT709) return fail(NPHUSL_ERR_ARG, std::string(what) + ": matrix must be BT601 or BT709");
+    const double kr = src->matrix == NPHUSL_BT601 ? 0.299 : 0.2126, kb = src->matrix == NPHUSL_BT601 ? 0.114 : 0.0722;
+    const double kg = 1.0 - kr - kb;
+    const double ys = src->full_range ? 1.0 : 255.0 / 219.0, cs = src->full_range ? 1.0 : 255.0 / 224.0;
+    Nv12Src o;
+    o.y = (const uint8_t *)src->y; o.uv = (const uint8_t *)src->uv;
+    o.y_pitch = src->y_pitch; o.uv_pitch = src->uv_pitch;
+    o.width = src->width; o.height = src->height;
+    o.k.ky = (int)std::lround(65536.0 * ys);
+    o.k.rv = (int)std::lround(65536.0 * cs * 2.0 * (1.0 - kr));
+    o.k.gu = (int)std::lround(65536.0 * cs * 2.0 * kb * (1.0 - kb) / kg);
+    o.k.gv = (int)std::lround(65536.0 * cs * 2.0 * kr * (1.0 - kr) / kg);
+    o.k.bu = (int)std::lround(65536.0 * cs * 2.0 * (1.0 - kb));
+    o.k.y_off = src->full_range ? 0 : 16;
+    *out = o;
+    return NPHUSL_OK;
+}
+
+// whole groups of 4 pixels per lane: width % 4 == 0, word-aligned planes and pitches
+bool nv12_vector_ok(const Nv12Src &s) {
+    return s.width % 4 == 0 && aligned(s.y, 4) && aligned(s.uv, 4) && s.y_pitch % 4 == 0 && s.uv_pitch % 4 == 0;
+}
+
+template <int MODE, typename TOut, int BLOCK, int MINB>
+int nv12_launch(DevCtx &c, const Nv12Src &s, void *out, size_t out_align, const nphusl_edit &e, cudaStream_t st) {
+    int rc;
+    if (nv12_vector_ok(s) && aligned(out, out_align)) {
+        static bool attr[MAX_DEV] = {};
+        const int smem = Nv12Smem<MODE, TOut>::bytes(BLOCK);
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            if (!attr[c.dev]) {
+                if ((rc = set_smem(k_nv12<MODE, TOut, BLOCK, MINB>, smem))) return rc;
+                attr[c.dev] = true;
+            }
+        }
+        const long long tiles = (long long)((s.width + TILE_PX - 1) / TILE_PX) * s.height;
+        k_nv12<MODE, TOut, BLOCK, MINB><<<grid_for(tiles, BLOCK / 32, c.sms * MINB), BLOCK, smem, st>>>(s, (TOut *)out, e);
+        g_launches++;
+        return check_launch("k_nv12");
+    }
+    const long long n = (long long)s.width * s.height;
+    k_nv12_any<MODE, TOut><<<grid_for(n, 256, c.sms * 8), 256, 0, st>>>(s, (TOut *)out, e);
+    g_launches++;
+    return check_launch("k_nv12_any");
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -924,6 +978,47 @@ int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,
         if ((rc = check_launch("k_edit_chw_any"))) return rc;
     }
     return NPHUSL_OK;
+}
+
+// ---- NV12 decoder surfaces ------------------------------------------------------------
+int nphusl_cuda_nv12_to_rgb(const nphusl_nv12 *src, void *rgb, int device, void *stream) {
+    DeviceGuard guard;
+    Nv12Src s;
+    int rc = nv12_src(src, "nv12_to_rgb", &s);
+    if (rc) return rc;
+    if (!rgb) return fail(NPHUSL_ERR_ARG, "nv12_to_rgb: null output");
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    return nv12_launch<NV12_RGB, uint8_t, 512, 4>(*c, s, rgb, 4, nphusl_edit{}, (cudaStream_t)stream);
+}
+
+int nphusl_cuda_nv12_to_husl(const nphusl_nv12 *src, void *hsl, int hsl_dtype, int hue_only, int device, void *stream) {
+    DeviceGuard guard;
+    Nv12Src s;
+    int rc = nv12_src(src, "nv12_to_husl", &s);
+    if (rc) return rc;
+    if (!hsl) return fail(NPHUSL_ERR_ARG, "nv12_to_husl: null output");
+    if (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) return fail(NPHUSL_ERR_ARG, "nv12_to_husl: output must be f32/f64");
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const nphusl_edit none{};
+    if (hue_only)
+        return hsl_dtype == NPHUSL_F32 ? nv12_launch<NV12_HUE, float, 1024, 2>(*c, s, hsl, 16, none, st)
+                                       : nv12_launch<NV12_HUE, double, 512, 3>(*c, s, hsl, 32, none, st);
+    return hsl_dtype == NPHUSL_F32 ? nv12_launch<NV12_HUSL, float, 1024, 1>(*c, s, hsl, 16, none, st)
+                                   : nv12_launch<NV12_HUSL, double, 512, 1>(*c, s, hsl, 16, none, st);
+}
+
+int nphusl_cuda_nv12_edit_rgb(const nphusl_nv12 *src, const nphusl_edit *edit, void *rgb, int device, void *stream) {
+    DeviceGuard guard;
+    Nv12Src s;
+    int rc = nv12_src(src, "nv12_edit_rgb", &s);
+    if (rc) return rc;
+    if (!rgb || !edit) return fail(NPHUSL_ERR_ARG, "nv12_edit_rgb: null argument");
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    return nv12_launch<NV12_EDIT, uint8_t, 512, 2>(*c, s, rgb, 4, *edit, (cudaStream_t)stream);
 }
 
 // ---- strided device images ------------------------------------------------------------

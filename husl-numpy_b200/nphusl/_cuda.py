@@ -34,7 +34,7 @@ import threading
 import numpy as np
 
 __all__ = ["_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue", "rgb_to_husl_planar", "husl_planar_to_rgb",
-           "edit_rgb", "Edit", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
+           "edit_rgb", "Edit", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
 
 def _prod(shape):
     """Number of elements of a shape (np.prod on a tuple costs 3 us and runs several times per call)."""
@@ -81,6 +81,9 @@ SIGNATURES = {
     "nphusl_cuda_rgb_to_husl_strided": (_i, [_vp, _vp, _i, _i, _vp]),
     "nphusl_cuda_husl_to_rgb_strided": (_i, [_vp, _vp, _i, _vp]),
     "nphusl_cuda_rgb_edit_rgb_strided": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "nphusl_cuda_nv12_to_rgb": (_i, [_vp, _vp, _i, _vp]),
+    "nphusl_cuda_nv12_to_husl": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "nphusl_cuda_nv12_edit_rgb": (_i, [_vp, _vp, _vp, _i, _vp]),
     "nphusl_cuda_lut_generate": (_i, [_i, _i, _i, _i]),
     "nphusl_cuda_lut_upload": (_i, [_i, _u16p, _i, _dp, _dp, _u16p, _i, _i,
                                     ctypes.c_double, ctypes.c_double, _dp]),
@@ -1003,6 +1006,114 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
     with _host_async(lib, blocking):
         rc = lib.nphusl_cuda_rgb_edit_rgb(src.ptr, src.loc, dst.ptr, dst.loc, n, ctypes.byref(edit), dev, _stream_ptr(stream))
     _check(rc, "rgb_edit_rgb")
+    return ret
+
+
+# ---------------------------------------------------------------------------
+# video-decoder surfaces (NV12) as the load stage
+# ---------------------------------------------------------------------------
+
+MATRICES = {"bt601": 0, "bt709": 1}
+
+
+class Nv12(ctypes.Structure):
+    """``nphusl_nv12`` of include/nphusl_cuda.h"""
+    _fields_ = [("y", ctypes.c_void_p), ("uv", ctypes.c_void_p),
+                ("y_pitch", ctypes.c_longlong), ("uv_pitch", ctypes.c_longlong),
+                ("width", ctypes.c_int), ("height", ctypes.c_int),
+                ("matrix", ctypes.c_int), ("full_range", ctypes.c_int)]
+
+
+def _plane(obj, what):
+    """-> (ptr, shape, row pitch in bytes, device, keep-alive) of a uint8 device plane whose rows are dense"""
+    if not _is_device(obj):
+        raise ValueError("{}: NV12 planes are device arrays (decoder surfaces); upload host frames with "
+                         "DeviceArray.from_host".format(what))
+    cai = obj.__cuda_array_interface__
+    shape, dtype, strides = tuple(cai["shape"]), np.dtype(cai["typestr"]), cai.get("strides")
+    if dtype != np.uint8 or len(shape) not in (2, 3):
+        raise ValueError("{}: expected a 2-D (or (rows, pairs, 2)) uint8 plane, got {} {}".format(what, dtype, shape))
+    row = _prod(shape[1:])
+    if strides is None:
+        pitch = row
+    else:
+        if tuple(strides[1:]) != _c_strides(shape, 1)[1:]:
+            raise ValueError("{}: rows must be dense (only the row pitch may be padded), got strides {}".format(what, strides))
+        pitch = int(strides[0]) if shape[0] > 1 else row
+    dev = getattr(obj, "device", None)
+    if not isinstance(dev, int):
+        dev = int(dev.index) if dev is not None and getattr(dev, "index", None) is not None else _device_of_ptr(int(cai["data"][0]))
+    return int(cai["data"][0]), shape, pitch, dev, obj
+
+
+def _nv12_surface(y, uv, matrix, full_range):
+    """``y``: (H, W) uint8 device plane; ``uv``: (ceil(H/2), 2*ceil(W/2)) or (ceil(H/2), ceil(W/2), 2)
+    interleaved chroma.  ``uv=None``: ``y`` is a whole (H*3/2, W) NVDEC surface, luma rows first."""
+    yp, ys, ypitch, dev, keep = _plane(y, "y")
+    if len(ys) != 2:
+        raise ValueError("y: expected a 2-D luma plane, got shape {}".format(ys))
+    if uv is None:
+        if ys[0] % 3:
+            raise ValueError("a whole NV12 surface has 3/2 * height rows, got {}".format(ys[0]))
+        h, w = ys[0] * 2 // 3, ys[1]
+        if h % 2 or w % 2:
+            raise ValueError("a whole NV12 surface needs even width and height, got {}x{}".format(w, h))
+        up, upitch, keep2 = yp + h * ypitch, ypitch, None
+    else:
+        h, w = ys
+        up, us, upitch, udev, keep2 = _plane(uv, "uv")
+        if us[0] != (h + 1) // 2 or _prod(us[1:]) != 2 * ((w + 1) // 2) or udev != dev:
+            raise ValueError("uv: expected {} rows of {} bytes on device {}, got shape {} on device {}".format(
+                (h + 1) // 2, 2 * ((w + 1) // 2), dev, us, udev))
+    if matrix not in MATRICES:
+        raise ValueError("matrix must be one of {}".format(sorted(MATRICES)))
+    return Nv12(yp, up, ypitch, upitch, w, h, MATRICES[matrix], int(bool(full_range))), (h, w), dev, (keep, keep2)
+
+
+def _nv12_out(out, shape, dtype, allowed, dev):
+    if out is None:
+        d = DeviceArray(shape, dtype, dev)
+        return d.ptr, d.dtype, d
+    b = _describe_out(out, shape, dtype, allowed, "out")
+    if b.loc != DEVICE:
+        raise ValueError("out: NV12 conversions write device arrays")
+    return b.ptr, b.dtype, out
+
+
+def nv12_to_rgb(y, uv=None, out=None, matrix="bt709", full_range=False, stream=None):
+    """NV12 decoder surface -> uint8 RGB ``(H, W, 3)`` on the device (integer BT.601 / BT.709
+    conversion documented in include/nphusl_cuda.h)."""
+    src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
+    ptr, _, ret = _nv12_out(out, (h, w, 3), np.uint8, (np.dtype(np.uint8),), dev)
+    _check(load().nphusl_cuda_nv12_to_rgb(ctypes.byref(src), ptr, dev, _stream_ptr(stream)), "nv12_to_rgb")
+    return ret
+
+
+def nv12_to_husl(y, uv=None, out=None, dtype=np.float32, matrix="bt709", full_range=False, stream=None, hue_only=False):
+    """NV12 decoder surface -> HUSL ``(H, W, 3)`` (or hue ``(H, W)``) on the device in ONE pass:
+    the colour conversion is the load stage of the to_husl kernel, the result equals
+    ``to_husl(nv12_to_rgb(...))`` bit for bit."""
+    src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
+    shape = (h, w) if hue_only else (h, w, 3)
+    ptr, dt, ret = _nv12_out(out, shape, dtype, _FLOATS, dev)
+    _check(load().nphusl_cuda_nv12_to_husl(ctypes.byref(src), ptr, _DT[dt], int(bool(hue_only)), dev, _stream_ptr(stream)),
+           "nv12_to_husl")
+    return ret
+
+
+def nv12_to_hue(y, uv=None, **kw):
+    return nv12_to_husl(y, uv, hue_only=True, **kw)
+
+
+def nv12_edit_rgb(y, uv=None, edit=None, out=None, matrix="bt709", full_range=False, stream=None, **edit_args):
+    """Fused NV12 -> HUSL -> select + edit -> uint8 RGB ``(H, W, 3)`` (see ``edit_rgb``)."""
+    if edit is None:
+        edit = Edit(**edit_args)
+    elif edit_args:
+        raise TypeError("pass either an Edit or its fields as keywords, not both")
+    src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
+    ptr, _, ret = _nv12_out(out, (h, w, 3), np.uint8, (np.dtype(np.uint8),), dev)
+    _check(load().nphusl_cuda_nv12_edit_rgb(ctypes.byref(src), ctypes.byref(edit), ptr, dev, _stream_ptr(stream)), "nv12_edit_rgb")
     return ret
 
 

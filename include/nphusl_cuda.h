@@ -184,6 +184,42 @@ int nphusl_cuda_husl_to_rgb_strided(const nphusl_view *hsl, const nphusl_view *r
 int nphusl_cuda_rgb_edit_rgb_strided(const nphusl_view *rgb_in, const nphusl_view *rgb_out,
                                      const nphusl_edit *edit, int device, void *stream);
 
+/* ---- video-decoder surfaces (NV12) as the load stage ------------------------------ */
+
+/* The reference's callers decode video on the CPU and hand RGB arrays to to_husl
+ * (examples.py:117-134, moviepy / imageio readers).  A hardware decoder (NVDEC)
+ * leaves NV12 in DEVICE memory: a pitched luma plane and a pitched plane of
+ * interleaved half-resolution U,V pairs (one pair per 2 x 2 luma block).  These
+ * entry points make the YUV -> RGB step the load stage of the HUSL kernels, so a
+ * decoded frame is read once (1.5 B/px) instead of being converted to an RGB copy
+ * first.  Colour conversion: integer, 16.16 fixed-point coefficients of the
+ * BT.601 / BT.709 matrix, round half up, clamp to 0..255, chroma replicated over
+ * its 2 x 2 block:
+ *     R = clamp8((ky*(Y-yoff)              + rv*(V-128) + 32768) >> 16)
+ *     G = clamp8((ky*(Y-yoff) - gu*(U-128) - gv*(V-128) + 32768) >> 16)
+ *     B = clamp8((ky*(Y-yoff) + bu*(U-128)              + 32768) >> 16)
+ * ky = round(65536*ys), rv = round(65536*cs*2(1-Kr)), gu = round(65536*cs*2Kb(1-Kb)/Kg),
+ * gv = round(65536*cs*2Kr(1-Kr)/Kg), bu = round(65536*cs*2(1-Kb)); limited range:
+ * ys = 255/219, cs = 255/224, yoff = 16; full range: ys = cs = 1, yoff = 0.
+ * HUSL results equal rgb_to_husl(nv12_to_rgb(frame)) bit for bit. */
+enum { NPHUSL_BT601 = 0, NPHUSL_BT709 = 1 };
+typedef struct nphusl_nv12 {
+    const void *y;                   /* DEVICE: height rows of width luma bytes, y_pitch apart */
+    const void *uv;                  /* DEVICE: ceil(height/2) rows of ceil(width/2) U,V byte pairs, uv_pitch apart */
+    long long y_pitch, uv_pitch;     /* bytes */
+    int width, height;               /* luma size in pixels */
+    int matrix;                      /* NPHUSL_BT601 | NPHUSL_BT709 */
+    int full_range;                  /* 0: 16..235 / 16..240 (video), 1: 0..255 (JPEG) */
+} nphusl_nv12;
+/* rgb: DEVICE, height*width*3 uint8, C-contiguous */
+int nphusl_cuda_nv12_to_rgb(const nphusl_nv12 *src, void *rgb, int device, void *stream);
+/* hsl: DEVICE, height*width*3 (or height*width when hue_only) F32 / F64, C-contiguous */
+int nphusl_cuda_nv12_to_husl(const nphusl_nv12 *src, void *hsl, int hsl_dtype, int hue_only,
+                             int device, void *stream);
+/* fused NV12 -> HUSL -> select + edit -> uint8 RGB (DEVICE, height*width*3) */
+int nphusl_cuda_nv12_edit_rgb(const nphusl_nv12 *src, const nphusl_edit *edit, void *rgb,
+                              int device, void *stream);
+
 /* ---- lookup tables (optional LUT mode) -------------------------------------- */
 
 /* Generate, ON THE DEVICE, the tables make_lookup_tables:8-9 produces with

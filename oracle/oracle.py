@@ -10,6 +10,10 @@ package never imports this module and has no CPU fallback.
 * ``simd_rgb_to_husl(variant=...)`` -- restatement of nphusl/_simd.c;
 * ``light_table / chroma_table / linear_table6`` -- restatement of
   LUT/light.py, LUT/chroma.py and nphusl/_linear_lookup.c:45-75;
+* ``nv12_to_rgb`` -- numpy statement of the integer BT.601 / BT.709 conversion that
+  include/nphusl_cuda.h specifies for decoder surfaces (not reference code: the
+  reference's callers decode with imageio / moviepy, examples.py:117-134), plus
+  ``nv12_to_rgb_float`` (the textbook float matrix, to bound the integer one);
 * ``ref_simd(...)``, ``ref_tables()``, ``ref_cython()`` -- the reference's own
   compiled code (``oracle/_ref``, built by ``oracle/build_ref.sh`` from the
   sources under /root/reference; present on the GPU box as prebuilt files).
@@ -98,6 +102,40 @@ def husl_to_rgb(hsl):
     out = np.empty(a.shape, dtype=np.uint8)
     lib().oracle_husl_to_rgb_u8(_p(a, _c_f64p), _p(out, _c_u8p), ctypes.c_size_t(a.size // 3))
     return out
+
+
+def _nv12_k(matrix, full_range):
+    kr, kb = {"bt601": (0.299, 0.114), "bt709": (0.2126, 0.0722)}[matrix]
+    kg = 1.0 - kr - kb
+    ys, cs, yoff = (1.0, 1.0, 0) if full_range else (255.0 / 219.0, 255.0 / 224.0, 16)
+    return ys, cs * 2 * (1 - kr), cs * 2 * kb * (1 - kb) / kg, cs * 2 * kr * (1 - kr) / kg, cs * 2 * (1 - kb), yoff
+
+
+def _nv12_planes(y, uv):
+    y = np.asarray(y).astype(np.int64)
+    h, w = y.shape
+    uv = np.asarray(uv).reshape((h + 1) // 2, (w + 1) // 2, 2).astype(np.int64)
+    up = np.repeat(np.repeat(uv, 2, axis=0), 2, axis=1)[:h, :w]      # chroma replicated over its 2 x 2 block
+    return y, up[..., 0] - 128, up[..., 1] - 128
+
+
+def nv12_to_rgb(y, uv, matrix="bt709", full_range=False):
+    """NV12 planes -> uint8 RGB (H, W, 3), the integer conversion of include/nphusl_cuda.h:
+    16.16 fixed-point coefficients, round half up, clamp."""
+    ys, rv, gu, gv, bu, yoff = _nv12_k(matrix, full_range)
+    ky, rv, gu, gv, bu = (int(np.floor(65536.0 * v + 0.5)) for v in (ys, rv, gu, gv, bu))
+    yv, d, e = _nv12_planes(y, uv)
+    yv = ky * (yv - yoff) + 32768
+    rgb = np.stack([(yv + rv * e) >> 16, (yv - (gu * d + gv * e)) >> 16, (yv + bu * d) >> 16], axis=-1)
+    return np.clip(rgb, 0, 255).astype(np.uint8)
+
+
+def nv12_to_rgb_float(y, uv, matrix="bt709", full_range=False):
+    """The same conversion with the real-valued matrix, unrounded and unclamped (0..255 scale)."""
+    ys, rv, gu, gv, bu, yoff = _nv12_k(matrix, full_range)
+    yv, d, e = _nv12_planes(y, uv)
+    yv = ys * (yv - yoff)
+    return np.stack([yv + rv * e, yv - gu * d - gv * e, yv + bu * d], axis=-1)
 
 
 def max_chroma(l, h):

@@ -972,3 +972,56 @@ def test_lut_mode_with_float_and_double_tables(cu, cube, golden_meta):
     # back to the default build for whoever comes next
     cu.lut_generate()
     assert cu.lut_download()["table_type"] == "uint16"
+
+
+@pytest.mark.parametrize("shape,pitch_pad", [((2160, 3840), 0), ((270, 484), 28), ((66, 130), 0), ((7, 9), 3)])
+def test_nv12_decoder_surfaces(cu, shape, pitch_pad):
+    """NV12 as the load stage: uint8 RGB bit-exact against the numpy
+    statement of the integer colour conversion, HUSL / hue equal to to_husl of that RGB bit
+    for bit (and within 1e-3 of the oracle), fused edit equal to edit_rgb of that RGB;
+    pitched planes, widths that are not a multiple of 128 / 4, odd sizes; nothing written
+    past the outputs."""
+    import torch
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + w)
+    hc, wc = (h + 1) // 2, (w + 1) // 2
+    y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    uv = rng.integers(0, 256, (hc, 2 * wc), dtype=np.uint8)
+    ybuf = torch.zeros((h, w + pitch_pad), dtype=torch.uint8, device="cuda")
+    uvbuf = torch.zeros((hc, 2 * wc + pitch_pad), dtype=torch.uint8, device="cuda")
+    ybuf[:, :w] = torch.from_numpy(y).cuda()
+    uvbuf[:, :2 * wc] = torch.from_numpy(uv).cuda()
+    yd, uvd = ybuf[:, :w], uvbuf[:, :2 * wc]
+    for matrix, full in (("bt709", False), ("bt601", True)):
+        want_rgb = orc.nv12_to_rgb(y, uv, matrix, full)
+        guard = torch.full((h * w * 3 + 256,), 0xA5, dtype=torch.uint8, device="cuda")
+        out = guard[128:128 + h * w * 3].view(h, w, 3)
+        cu.nv12_to_rgb(yd, uvd, out=out, matrix=matrix, full_range=full)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want_rgb)
+        assert bool((guard[:128] == 0xA5).all()) and bool((guard[128 + h * w * 3:] == 0xA5).all())
+        rgb_d = torch.from_numpy(want_rgb).cuda()
+        for dt in (np.float32, np.float64):
+            hsl = np.asarray(cu.nv12_to_husl(yd, uvd, dtype=dt, matrix=matrix, full_range=full))
+            assert np.array_equal(hsl, np.asarray(cu._rgb_to_husl(rgb_d, dtype=dt)))
+            hue = np.asarray(cu.nv12_to_hue(yd, uvd, dtype=dt, matrix=matrix, full_range=full))
+            assert hue.shape == (h, w) and np.array_equal(hue, hsl[..., 0])
+        check_husl(hsl, orc.rgb_to_husl(want_rgb), ~_grey(want_rgb))
+        ed = dict(hue=(200, 320), lightness=(10, 90), l=(0.5, 5.0), s=(1.2, 0.0))
+        got = np.asarray(cu.nv12_edit_rgb(yd, uvd, matrix=matrix, full_range=full, **ed))
+        assert np.array_equal(got, np.asarray(cu.edit_rgb(rgb_d, **ed)))
+    if h % 2 == 0 and w % 2 == 0 and pitch_pad == 0:
+        # one NVDEC-style allocation: luma rows, then the chroma rows, same pitch
+        surf = torch.cat([torch.from_numpy(y), torch.from_numpy(uv)]).cuda()
+        assert np.array_equal(np.asarray(cu.nv12_to_rgb(surf)), orc.nv12_to_rgb(y, uv))
+
+
+def test_nv12_argument_errors(cu):
+    import torch
+    y = torch.zeros((4, 8), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        cu.nv12_to_rgb(y, torch.zeros((2, 6), dtype=torch.uint8, device="cuda"))      # chroma plane too narrow
+    with pytest.raises(ValueError):
+        cu.nv12_to_rgb(np.zeros((4, 8), np.uint8), np.zeros((2, 8), np.uint8))         # host planes
+    with pytest.raises(ValueError):
+        cu.nv12_to_husl(y, torch.zeros((2, 8), dtype=torch.uint8, device="cuda"), matrix="bt2020")
