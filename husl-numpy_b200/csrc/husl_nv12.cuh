@@ -39,8 +39,12 @@ template <> struct Pack<uint8_t> {          // uint8 RGB tile: 384 B, no padding
     static constexpr int STAGE = 384;
 };
 
+// ky, rv, gu, gv, bu: 16.16 coefficients; cr, cg, cb: everything constant folded into one
+// term per channel (rounding 32768, -ky*y_off, -+128*chroma coefficients), so that
+//     R = clamp8((ky*Y + rv*V + cr) >> 16), G = clamp8((ky*Y - gu*U - gv*V + cg) >> 16), ...
+// is the documented formula with no subtraction left per pixel (all integers: bit-identical).
 struct Nv12Coef {
-    int ky, rv, gu, gv, bu, y_off;
+    int ky, rv, gu, gv, bu, cr, cg, cb;
 };
 
 struct Nv12Src {
@@ -52,33 +56,34 @@ struct Nv12Src {
 
 enum { NV12_HUSL = 0, NV12_HUE = 1, NV12_RGB = 2, NV12_EDIT = 3 };
 
-__device__ __forceinline__ uint32_t clamp8(int v) { return (uint32_t)min(max(v, 0), 255); }
+// max(min(v, 255), 0) is one VIMNMX.RELU on sm_100
+__device__ __forceinline__ uint32_t clamp8(int v) { return (uint32_t)__vimin_s32_relu(v, 255); }
 
 // one pixel: luma byte + the three chroma terms of its 2 x 2 block -> R, G, B in 0..255
 __device__ __forceinline__ void yuv_px(const Nv12Coef &k, int yb, int cr, int cg, int cb,
                                        uint32_t &R, uint32_t &G, uint32_t &B) {
-    const int yv = k.ky * (yb - k.y_off) + 32768;
+    const int yv = k.ky * yb;
     R = clamp8((yv + cr) >> 16);
     G = clamp8((yv + cg) >> 16);
     B = clamp8((yv + cb) >> 16);
 }
 
 __device__ __forceinline__ void chroma_terms(const Nv12Coef &k, int u, int v, int &cr, int &cg, int &cb) {
-    const int d = u - 128, e = v - 128;
-    cr = k.rv * e;
-    cg = -(k.gu * d + k.gv * e);
-    cb = k.bu * d;
+    cr = k.rv * v + k.cr;
+    cg = k.cg - k.gu * u - k.gv * v;
+    cb = k.bu * u + k.cb;
 }
 
 // 4 pixels of a lane: y4 = Y0 Y1 Y2 Y3, uv4 = U0 V0 U1 V1 (little endian bytes) -> 12 channel values
 __device__ __forceinline__ void yuv4(const Nv12Coef &k, uint32_t y4, uint32_t uv4, uint32_t (&c)[12]) {
     int cr0, cg0, cb0, cr1, cg1, cb1;
-    chroma_terms(k, uv4 & 0xFF, (uv4 >> 8) & 0xFF, cr0, cg0, cb0);
-    chroma_terms(k, (uv4 >> 16) & 0xFF, uv4 >> 24, cr1, cg1, cb1);
-    yuv_px(k, y4 & 0xFF, cr0, cg0, cb0, c[0], c[1], c[2]);
-    yuv_px(k, (y4 >> 8) & 0xFF, cr0, cg0, cb0, c[3], c[4], c[5]);
-    yuv_px(k, (y4 >> 16) & 0xFF, cr1, cg1, cb1, c[6], c[7], c[8]);
-    yuv_px(k, y4 >> 24, cr1, cg1, cb1, c[9], c[10], c[11]);
+    // byte K zero-extended: one PRMT each
+    chroma_terms(k, __byte_perm(uv4, 0, 0x4440), __byte_perm(uv4, 0, 0x4441), cr0, cg0, cb0);
+    chroma_terms(k, __byte_perm(uv4, 0, 0x4442), __byte_perm(uv4, 0, 0x4443), cr1, cg1, cb1);
+    yuv_px(k, __byte_perm(y4, 0, 0x4440), cr0, cg0, cb0, c[0], c[1], c[2]);
+    yuv_px(k, __byte_perm(y4, 0, 0x4441), cr0, cg0, cb0, c[3], c[4], c[5]);
+    yuv_px(k, __byte_perm(y4, 0, 0x4442), cr1, cg1, cb1, c[6], c[7], c[8]);
+    yuv_px(k, __byte_perm(y4, 0, 0x4443), cr1, cg1, cb1, c[9], c[10], c[11]);
 }
 
 __device__ __forceinline__ LinPx lin_px(const unsigned char *tab, uint32_t r, uint32_t g, uint32_t b, uint32_t lane8) {
@@ -108,11 +113,15 @@ k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane8 = lane * 8;
     unsigned char *stage = smem + TAB + warp * Nv12Smem<MODE, TOut>::STAGE;
-    const int W = src.width;
-    const long long segs = (W + TILE_PX - 1) / TILE_PX;
-    const long long n_tiles = segs * src.height;
-    const long long nw = (long long)gridDim.x * (BLOCK / 32);
-    long long tile = (long long)blockIdx.x * (BLOCK / 32) + warp;
+    const int W = src.width, H = src.height;
+    // Tiles are (row, 128-pixel segment) pairs.  A warp keeps ONE segment column and walks down the
+    // rows with an even row step, so every address advances by a constant (luma pointer by
+    // step*y_pitch, chroma pointer by step/2*uv_pitch, output by step*W pixels): no division and no
+    // 64-bit multiply per tile.  slot -> (segment, first row); slots beyond the grid loop again.
+    const int segs = (W + TILE_PX - 1) / TILE_PX;
+    const long long n_warps = (long long)gridDim.x * (BLOCK / 32);
+    const int step = 2 * (int)max(1LL, min(n_warps / (2LL * segs), (long long)((H + 1) / 2)));
+    const long long n_slots = (long long)segs * step;
 
     constexpr int CH = MODE == NV12_HUSL ? Pack<TOut>::CHUNKS : 1;
     uint32_t rd_off[CH];
@@ -123,28 +132,32 @@ k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
             rd_off[k] = (p / CH) * Pack<TOut>::LANE_STRIDE + (p % CH) * 16;
         }
     }
+    constexpr int OUT_PX_BYTES = (MODE == NV12_HUE ? 1 : 3) * (int)sizeof(TOut);
 
-    // words of a tile: luma word of this lane's 4 pixels, chroma word of the row pair
-    auto fetch = [&](long long t, uint32_t &y4, uint32_t &uv4) {
-        y4 = 0; uv4 = 0x80808080u;
-        if (t < n_tiles) {
-            const long long row = t / segs;
-            const int x = (int)(t - row * segs) * TILE_PX + lane * 4;
-            if (x < W) {
-                y4 = ldg_u32(reinterpret_cast<const uint32_t *>(src.y + row * src.y_pitch + x));
-                uv4 = ldg_u32(reinterpret_cast<const uint32_t *>(src.uv + (row >> 1) * src.uv_pitch + x));
-            }
+    for (long long slot = (long long)blockIdx.x * (BLOCK / 32) + warp; slot < n_slots; slot += n_warps) {
+    const int seg = (int)(slot % segs);
+    int row = (int)(slot / segs);
+    const int x0 = seg * TILE_PX;
+    const int valid = min(TILE_PX, W - x0);                       // pixels of this column's tiles, a multiple of 4
+    const bool lane_on = lane * 4 < valid;
+    const uint8_t *yp = src.y + (long long)row * src.y_pitch + x0 + lane * 4;
+    const uint8_t *uvp = src.uv + (long long)(row >> 1) * src.uv_pitch + x0 + lane * 4;
+    unsigned char *op = reinterpret_cast<unsigned char *>(out) + ((long long)row * W + x0) * OUT_PX_BYTES;
+    const long long y_step = (long long)step * src.y_pitch, uv_step = (long long)(step / 2) * src.uv_pitch;
+    const long long o_step = (long long)step * W * OUT_PX_BYTES;
+
+    uint32_t y4 = 0, uv4 = 0x80808080u;
+    if (row < H && lane_on) {
+        y4 = ldg_u32(reinterpret_cast<const uint32_t *>(yp));
+        uv4 = ldg_u32(reinterpret_cast<const uint32_t *>(uvp));
+    }
+    for (; row < H; row += step, op += o_step) {
+        yp += y_step; uvp += uv_step;
+        uint32_t ny = 0, nuv = 0x80808080u;
+        if (row + step < H && lane_on) {
+            ny = ldg_u32(reinterpret_cast<const uint32_t *>(yp));
+            nuv = ldg_u32(reinterpret_cast<const uint32_t *>(uvp));
         }
-    };
-    uint32_t y4, uv4;
-    fetch(tile, y4, uv4);
-    for (; tile < n_tiles; tile += nw) {
-        uint32_t ny, nuv;
-        fetch(tile + nw, ny, nuv);
-        const long long row = tile / segs;
-        const int x0 = (int)(tile - row * segs) * TILE_PX;
-        const int valid = min(TILE_PX, W - x0);                   // pixels of this tile, a multiple of 4
-        const long long px0 = row * W + x0;                       // first pixel of the tile in the output
 
         uint32_t c[12];
         yuv4(src.k, y4, uv4, c);
@@ -168,7 +181,7 @@ k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
             uint32_t *sw = reinterpret_cast<uint32_t *>(stage);
             sw[lane * 3] = o0; sw[lane * 3 + 1] = o1; sw[lane * 3 + 2] = o2;
             __syncwarp();
-            uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(out) + px0 * 3) + lane;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(op) + lane;
             const int words = valid * 3 / 4;
 #pragma unroll
             for (int k = 0; k < 3; ++k)
@@ -179,11 +192,11 @@ k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 h[j] = hue_from_diff(make_diff(lin_px(tab, c[3 * j], c[3 * j + 1], c[3 * j + 2], lane8)));
-            if (lane * 4 < valid) {
+            if (lane_on) {
                 if (sizeof(TOut) == 4)
-                    *reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + px0 + lane * 4) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4 *>(reinterpret_cast<float *>(op) + lane * 4) = make_float4(h[0], h[1], h[2], h[3]);
                 else
-                    stg_f64x4(reinterpret_cast<double *>(out) + px0 + lane * 4, (double)h[0], (double)h[1], (double)h[2], (double)h[3]);
+                    stg_f64x4(reinterpret_cast<double *>(op) + lane * 4, (double)h[0], (double)h[1], (double)h[2], (double)h[3]);
             }
         } else {
             float r[12];
@@ -202,7 +215,7 @@ k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
                     *reinterpret_cast<double2 *>(wr + 16 * k) = make_double2((double)r[2 * k], (double)r[2 * k + 1]);
             }
             __syncwarp();
-            float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<TOut *>(out) + px0 * 3) + lane;
+            float4 *o = reinterpret_cast<float4 *>(op) + lane;
             const int chunks = valid / 4 * CH;                    // 16-byte chunks of this tile
 #pragma unroll
             for (int k = 0; k < CH; ++k)
@@ -210,6 +223,7 @@ k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
             __syncwarp();
         }
         y4 = ny; uv4 = nuv;
+    }
     }
 }
 

@@ -606,7 +606,10 @@ int nv12_src(const nphusl_nv12 *src, const char *what, Nv12Src *out) {
     o.k.gu = (int)std::lround(65536.0 * cs * 2.0 * kb * (1.0 - kb) / kg);
     o.k.gv = (int)std::lround(65536.0 * cs * 2.0 * kr * (1.0 - kr) / kg);
     o.k.bu = (int)std::lround(65536.0 * cs * 2.0 * (1.0 - kb));
-    o.k.y_off = src->full_range ? 0 : 16;
+    const int y_off = src->full_range ? 0 : 16;
+    o.k.cr = 32768 - o.k.ky * y_off - 128 * o.k.rv;
+    o.k.cg = 32768 - o.k.ky * y_off + 128 * (o.k.gu + o.k.gv);
+    o.k.cb = 32768 - o.k.ky * y_off - 128 * o.k.bu;
     *out = o;
     return NPHUSL_OK;
 }
