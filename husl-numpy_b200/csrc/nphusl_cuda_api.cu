@@ -21,6 +21,7 @@
 #include "husl_stream.cuh"
 #include "husl_lut.cuh"
 #include "husl_nv12.cuh"
+#include "husl_float.cuh"
 #include "husl_fused.cuh"
 #include "husl_strided.cuh"
 
@@ -178,6 +179,12 @@ constexpr int INV_BLOCK = 256;
 #define NPHUSL_EDIT_MINB 2
 #endif
 constexpr int EDIT_BLOCK = NPHUSL_EDIT_BLOCK, EDIT_MINB = NPHUSL_EDIT_MINB, EDIT_W = NPHUSL_EDIT_BLOCK / 32;
+#ifndef NPHUSL_FLT_BLOCK
+#define NPHUSL_FLT_BLOCK 256        // tiled float-RGB kernels (husl_float.cuh)
+#define NPHUSL_FLT_MINB 2
+#define NPHUSL_FLT_IST 2
+#endif
+constexpr int FLT_BLOCK = NPHUSL_FLT_BLOCK, FLT_MINB = NPHUSL_FLT_MINB, FLT_IST = NPHUSL_FLT_IST;
 #ifndef NPHUSL_FWD64_BLOCK
 #define NPHUSL_FWD64_BLOCK 512
 #endif
@@ -232,6 +239,17 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_chw<double, 512, 2>, TAB_BYTES))) return rc;
 
     c.attr_set = true;
+    return NPHUSL_OK;
+}
+
+// opt-in dynamic shared memory, once per device; `done` is a static of the CALL SITE (one per kernel
+// instantiation -- kernels of equal signature share a function-pointer type, so it cannot live here)
+template <typename K>
+int flt_attr(std::atomic<bool> *done, DevCtx &c, K kernel, int bytes) {
+    if (done[c.dev].load(std::memory_order_acquire)) return NPHUSL_OK;
+    int rc = set_smem(kernel, (size_t)bytes);
+    if (rc) return rc;
+    done[c.dev].store(true, std::memory_order_release);
     return NPHUSL_OK;
 }
 
@@ -324,6 +342,22 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
         if ((rc = check_launch("k_fwd_u8"))) return rc;
         done = tiles * TILE_PX;
     }
+    if (in_dt != NPHUSL_U8 && channels == 3 && aligned(in, 16) && aligned(out, HUE ? 32 : 16) && n >= TILE_PX) {
+        // float RGB in [0,1] (the Cython backend's own input type): cp.async input ring + staged stores
+        const long long tiles = n / TILE_PX;
+        const int grid = grid_for(tiles, FLT_BLOCK / 32, c.sms * FLT_MINB);
+#define FLT_GO(TI, TO) do { \
+        constexpr int sm = (FLT_BLOCK / 32) * (HUE ? FltHueSmem<TI, FLT_IST>::PER_WARP : FltSmem<TI, TO, FLT_IST>::PER_WARP); \
+        static std::atomic<bool> attr_done[MAX_DEV]; \
+        if ((rc = flt_attr(attr_done, c, k_fwd_flt<TI, TO, HUE, FLT_BLOCK, FLT_MINB, FLT_IST>, sm))) return rc; \
+        k_fwd_flt<TI, TO, HUE, FLT_BLOCK, FLT_MINB, FLT_IST><<<grid, FLT_BLOCK, sm, s>>>((const TI *)in, (TO *)out, tiles); } while (0)
+        if (in_dt == NPHUSL_F32) { if (out_dt == NPHUSL_F32) FLT_GO(float, float); else FLT_GO(float, double); }
+        else { if (out_dt == NPHUSL_F32) FLT_GO(double, float); else FLT_GO(double, double); }
+#undef FLT_GO
+        g_launches++;
+        if ((rc = check_launch("k_fwd_flt"))) return rc;
+        done = tiles * TILE_PX;
+    }
     const long long rest = n - done;
     if (rest <= 0) return NPHUSL_OK;
     const char *ip = (const char *)in + done * channels * dsize(in_dt);
@@ -363,6 +397,22 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
         }
         g_launches++;
         if ((rc = check_launch("k_inv_u8"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    if (out_dt != NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
+        // float RGB in [0,1] out (what the reference's _husl_to_rgb returns, _cython_opt.pyx:177-192)
+        const long long tiles = n / TILE_PX;
+        const int grid = grid_for(tiles, FLT_BLOCK / 32, c.sms * FLT_MINB);
+#define FLT_GO(TI, TO) do { \
+        constexpr int sm = (FLT_BLOCK / 32) * FltSmem<TI, TO, FLT_IST>::PER_WARP; \
+        static std::atomic<bool> attr_done[MAX_DEV]; \
+        if ((rc = flt_attr(attr_done, c, k_inv_flt<TI, TO, FLT_BLOCK, FLT_MINB, FLT_IST>, sm))) return rc; \
+        k_inv_flt<TI, TO, FLT_BLOCK, FLT_MINB, FLT_IST><<<grid, FLT_BLOCK, sm, s>>>((const TI *)in, (TO *)out, tiles); } while (0)
+        if (in_dt == NPHUSL_F32) { if (out_dt == NPHUSL_F32) FLT_GO(float, float); else FLT_GO(float, double); }
+        else { if (out_dt == NPHUSL_F32) FLT_GO(double, float); else FLT_GO(double, double); }
+#undef FLT_GO
+        g_launches++;
+        if ((rc = check_launch("k_inv_flt"))) return rc;
         done = tiles * TILE_PX;
     }
     const long long rest = n - done;
@@ -623,15 +673,9 @@ template <int MODE, typename TOut, int BLOCK, int MINB>
 int nv12_launch(DevCtx &c, const Nv12Src &s, void *out, size_t out_align, const nphusl_edit &e, cudaStream_t st) {
     int rc;
     if (nv12_vector_ok(s) && aligned(out, out_align)) {
-        static bool attr[MAX_DEV] = {};
+        static std::atomic<bool> attr_done[MAX_DEV];
         const int smem = Nv12Smem<MODE, TOut>::bytes(BLOCK);
-        {
-            std::lock_guard<std::mutex> lk(c.mu);
-            if (!attr[c.dev]) {
-                if ((rc = set_smem(k_nv12<MODE, TOut, BLOCK, MINB>, smem))) return rc;
-                attr[c.dev] = true;
-            }
-        }
+        if ((rc = flt_attr(attr_done, c, k_nv12<MODE, TOut, BLOCK, MINB>, smem))) return rc;
         const long long tiles = (long long)((s.width + TILE_PX - 1) / TILE_PX) * s.height;
         k_nv12<MODE, TOut, BLOCK, MINB><<<grid_for(tiles, BLOCK / 32, c.sms * MINB), BLOCK, smem, st>>>(s, (TOut *)out, e);
         g_launches++;

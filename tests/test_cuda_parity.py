@@ -1025,3 +1025,43 @@ def test_nv12_argument_errors(cu):
         cu.nv12_to_rgb(np.zeros((4, 8), np.uint8), np.zeros((2, 8), np.uint8))         # host planes
     with pytest.raises(ValueError):
         cu.nv12_to_husl(y, torch.zeros((2, 8), dtype=torch.uint8, device="cuda"), matrix="bt2020")
+
+
+@pytest.mark.parametrize("n", [128 * 37 + 5, 1 << 20])
+def test_tiled_float_rgb_kernels_equal_the_generic_ones(cu, n):
+    """float RGB in [0,1] <-> HUSL (the Cython backend's own signatures, _cython_opt.pyx:22,177):
+    the tiled kernels (aligned buffers) give bit for bit what the one-pixel-per-thread kernels
+    give (a misaligned view of the same data forces those), and both sit within 1e-3 of the oracle."""
+    import torch
+    rng = np.random.default_rng(n)
+    frgb = rng.random((n, 3))
+    frgb[:64] = np.repeat(rng.random((64, 1)), 3, axis=1)          # greys
+    frgb[64:70] = [[0, 0, 0], [1, 1, 1], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1e-4, 0, 0]]
+    want = orc.rgb_to_husl(frgb)
+    sat = want[:, 1] > 0.5
+    for tin in (torch.float32, torch.float64):
+        pad = torch.zeros(3 * n + 16, dtype=tin, device="cuda")
+        src = torch.from_numpy(frgb).to("cuda", tin)
+        pad[1:3 * n + 1] = src.reshape(-1)
+        off = pad[1:3 * n + 1].view(n, 3)                          # 4 / 8 bytes off a 16-byte boundary
+        for tout in (np.float32, np.float64):
+            a = np.asarray(cu._rgb_to_husl(src, dtype=tout))
+            b = np.asarray(cu._rgb_to_husl(off, dtype=tout))
+            assert np.array_equal(a, b)
+            if tin == torch.float64:
+                check_husl(a, want, sat)
+            assert np.array_equal(np.asarray(cu._rgb_to_hue(src, dtype=tout)), np.asarray(cu._rgb_to_hue(off, dtype=tout)))
+    hsl = np.stack([rng.uniform(0, 360, n), rng.uniform(0, 100, n), rng.uniform(0, 100, n)], -1)
+    hsl[:4] = [[10, 50, 0], [10, 50, 100], [200, 0, 50], [359.9, 100, 99.995]]
+    wantf = orc.husl_to_rgb_float(hsl)
+    for tin in (torch.float32, torch.float64):
+        pad = torch.zeros(3 * n + 16, dtype=tin, device="cuda")
+        src = torch.from_numpy(hsl).to("cuda", tin)
+        pad[1:3 * n + 1] = src.reshape(-1)
+        off = pad[1:3 * n + 1].view(n, 3)
+        for tout in (np.float32, np.float64):
+            a = np.asarray(cu._husl_to_rgb(src, dtype=tout))
+            b = np.asarray(cu._husl_to_rgb(off, dtype=tout))
+            assert np.array_equal(a, b)
+            if tin == torch.float64:
+                assert np.abs(a - wantf).max() < 2e-5
