@@ -175,13 +175,13 @@ constexpr int INV_BLOCK = 256;
 #define NPHUSL_FWD32_OST 2
 #endif
 #ifndef NPHUSL_EDIT_BLOCK
-#define NPHUSL_EDIT_BLOCK 512
-#define NPHUSL_EDIT_MINB 2
+#define NPHUSL_EDIT_BLOCK 1024      // one CTA of 32 warps: interleaved A/B (ab_interleaved.py) 0.3002 -> 0.2956 ms, planes 0.3176 -> 0.3000
+#define NPHUSL_EDIT_MINB 1
 #endif
 constexpr int EDIT_BLOCK = NPHUSL_EDIT_BLOCK, EDIT_MINB = NPHUSL_EDIT_MINB, EDIT_W = NPHUSL_EDIT_BLOCK / 32;
 #ifndef NPHUSL_FLT_BLOCK
-#define NPHUSL_FLT_BLOCK 256        // tiled float-RGB kernels (husl_float.cuh)
-#define NPHUSL_FLT_MINB 2
+#define NPHUSL_FLT_BLOCK 512        // tiled float-RGB kernels (husl_float.cuh); 512 x 1 best of 5 shapes for 3 of the 4 dtype pairs
+#define NPHUSL_FLT_MINB 1
 #define NPHUSL_FLT_IST 2
 #endif
 constexpr int FLT_BLOCK = NPHUSL_FLT_BLOCK, FLT_MINB = NPHUSL_FLT_MINB, FLT_IST = NPHUSL_FLT_IST;
@@ -1065,7 +1065,7 @@ int nphusl_cuda_nv12_edit_rgb(const nphusl_nv12 *src, const nphusl_edit *edit, v
     if (!rgb || !edit) return fail(NPHUSL_ERR_ARG, "nv12_edit_rgb: null argument");
     DevCtx *c;
     if ((rc = ctx_get(device, &c))) return rc;
-    return nv12_launch<NV12_EDIT, uint8_t, 512, 2>(*c, s, rgb, 4, *edit, (cudaStream_t)stream);
+    return nv12_launch<NV12_EDIT, uint8_t, EDIT_BLOCK, EDIT_MINB>(*c, s, rgb, 4, *edit, (cudaStream_t)stream);
 }
 
 // ---- strided device images ------------------------------------------------------------
