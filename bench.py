@@ -484,7 +484,32 @@ def run_cuda(args):
                 issue_ms = winst * (px / 66355200.0) / issue_rate * 1e3
                 variants[name].update({"issue_frac": round(issue_ms / ms, 3), "bound": "issue" if issue_ms > hbm_ms else "hbm",
                                        "roofline_frac": round(max(hbm_ms, issue_ms) / ms, 3)})
-        del h32, hue64, hue32
+        # decoder surfaces and float images as inputs (8 frames as one tall NV12 surface; 2 frames of float64 RGB)
+        ysurf = torch.randint(0, 256, (B * FRAME[0], FRAME[1]), dtype=torch.uint8, device="cuda")
+        uvsurf = torch.randint(0, 256, (B * FRAME[0] // 2, FRAME[1]), dtype=torch.uint8, device="cuda")
+        hv64 = dev_hsl.view(B * FRAME[0], FRAME[1], 3) if hdt == np.float64 else None
+        hv32 = h32.view(B * FRAME[0], FRAME[1], 3)
+        f64in = (dev_in[:2].to(torch.float64) / 255.0).contiguous()
+        f64out = torch.empty(f64in.shape, dtype=torch.float64, device="cuda")
+        px2 = f64in.numel() // 3
+        extra = [("nv12_to_husl_f32", "k_nv12<husl,float>", lambda: _cuda.nv12_to_husl(ysurf, uvsurf, out=hv32, stream=stream), 13.5, px),
+                 ("frgb_f64_to_husl_f64", "k_fwd_flt<double,double>", lambda: _cuda._rgb_to_husl(f64in, out=f64out, stream=stream), 48, px2),
+                 ("husl_f64_to_frgb_f64", "k_inv_flt<double,double>",
+                  lambda: _cuda._husl_to_rgb(f64out, out=f64in, dtype=np.float64, stream=stream), 48, px2)]
+        if hv64 is not None:
+            extra.insert(0, ("nv12_to_husl_f64", "k_nv12<husl,double>",
+                             lambda: _cuda.nv12_to_husl(ysurf, uvsurf, out=hv64, stream=stream), 25.5, px))
+        for name, kern, fn, nbytes, npx in extra:
+            ms = timed(fn)
+            variants[name] = {"ms": round(ms, 4), "gpix_s": round(npx / ms / 1e6, 2),
+                              "gb_s": round(npx * nbytes / ms / 1e6, 1), "hbm_frac": round(npx * nbytes / ms / 1e6 / hbm, 3)}
+            winst = warp_inst_for(kern)
+            if winst:
+                hbm_ms = npx * nbytes / hbm / 1e6
+                issue_ms = winst * (npx / 66355200.0) / issue_rate * 1e3
+                variants[name].update({"issue_frac": round(issue_ms / ms, 3), "bound": "issue" if issue_ms > hbm_ms else "hbm",
+                                       "roofline_frac": round(max(hbm_ms, issue_ms) / ms, 3)})
+        del h32, hue64, hue32, ysurf, uvsurf, f64in, f64out
         # configs[3] as its callers write it (README.md:77-81): to_husl -> lightness edit -> to_rgb, with the
         # edit as the caller's own device op between the two conversions, and the same result from the fused kernel
         def with_edit():

@@ -3,7 +3,7 @@
 device-resident 4K frames) a few times -- the command ncu wraps:
 
   python profiles/prof_kernels.py > gpurun_out/plain.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'k_(fwd|inv|edit)' \
+  ncu --set full --clock-control none --import-source on -k regex:'k_(fwd|inv|edit|nv12)' \
       -o gpurun_out/prof python profiles/prof_kernels.py
 """
 import os
@@ -26,6 +26,10 @@ hue64 = torch.empty(rgb.shape[:-1], dtype=torch.float64, device="cuda")
 hue32 = torch.empty(rgb.shape[:-1], dtype=torch.float32, device="cuda")
 back = torch.empty_like(rgb)
 planes = torch.empty((3,) + tuple(rgb.shape[:-1]), dtype=torch.float32, device="cuda")
+ysurf = torch.randint(0, 256, (frames * 2160, 3840), dtype=torch.uint8, device="cuda", generator=g)
+uvsurf = torch.randint(0, 256, (frames * 1080, 3840), dtype=torch.uint8, device="cuda", generator=g)
+f64in = (rgb[:2].to(torch.float64) / 255.0).contiguous()
+f64out = torch.empty_like(f64in)
 for _ in range(reps):
     _cuda._rgb_to_husl(rgb, out=h64)
     _cuda._husl_to_rgb(h64, out=back)
@@ -35,6 +39,11 @@ for _ in range(reps):
     _cuda._rgb_to_hue(rgb, out=hue32)
     _cuda.rgb_to_husl_planar(rgb, out=planes)
     _cuda.husl_planar_to_rgb(planes, out=back)
+    _cuda.nv12_to_husl(ysurf, uvsurf, out=h64.view(-1, 3840, 3))
+    _cuda.nv12_to_husl(ysurf, uvsurf, out=h32.view(-1, 3840, 3))
+    _cuda.nv12_edit_rgb(ysurf, uvsurf, out=back.view(-1, 3840, 3), l=(0.5, 0))
+    _cuda._rgb_to_husl(f64in, out=f64out)         # float64 RGB in [0,1] (2 frames), tiled float kernels
+    _cuda._husl_to_rgb(f64out, out=f64in, dtype=np.float64)
     _cuda.edit_rgb(rgb, out=back)                 # identity edit: exact round trip
 torch.cuda.synchronize()
 assert torch.equal(back, rgb)
