@@ -205,7 +205,6 @@ k_edit(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n_
     fill_table(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane8 = lane * 8;
-    uint32_t *sw = reinterpret_cast<uint32_t *>(smem + TAB_BYTES) + warp * 96;
     const long long nw = (long long)gridDim.x * (BLOCK / 32);
     long long tile = (long long)blockIdx.x * (BLOCK / 32) + warp;
     uint32_t w0 = 0, w1 = 0, w2 = 0;
@@ -232,11 +231,10 @@ k_edit(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n_
         }
         uint32_t o0, o1, o2;
         pack12(q, o0, o1, o2);
-        sw[lane * 3] = o0; sw[lane * 3 + 1] = o1; sw[lane * 3 + 2] = o2;
-        __syncwarp();
-        uint32_t *dst = out + tile * 96 + lane;
-        dst[0] = sw[lane]; dst[32] = sw[lane + 32]; dst[64] = sw[lane + 64];
-        __syncwarp();
+        // the lane's own 12 bytes straight to global: for this issue-bound kernel three strided 32-bit stores
+        // beat the staging transposition (6 shared-memory instructions + 2 warp syncs per tile) by 1 %
+        uint32_t *dst = out + tile * 96 + lane * 3;
+        dst[0] = o0; dst[1] = o1; dst[2] = o2;
         w0 = n0; w1 = n1; w2 = n2;
     }
 }

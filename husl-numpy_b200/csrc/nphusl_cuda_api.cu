@@ -230,7 +230,7 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_planar<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_planar<double, 512, 2>, TAB_BYTES))) return rc;
 #define EDIT_ATTRS(EH, ES, RSL) \
-    if ((rc = set_smem(k_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES + EDIT_W * 384))) return rc; \
+    if ((rc = set_smem(k_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES))) return rc; \
     if ((rc = set_smem(k_edit_chw<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES))) return rc;
     EDIT_ATTRS(false, false, false) EDIT_ATTRS(false, false, true) EDIT_ATTRS(false, true, false) EDIT_ATTRS(false, true, true)
     EDIT_ATTRS(true, false, false) EDIT_ATTRS(true, false, true) EDIT_ATTRS(true, true, false) EDIT_ATTRS(true, true, true)
@@ -970,7 +970,7 @@ int nphusl_cuda_rgb_edit_rgb(const void *rgb_in, int in_loc, void *rgb_out, int 
             const int grid = grid_for(tiles, EDIT_W, c->sms * EDIT_MINB);
 #define EDIT_GO(EH, ES, RSL) \
     if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) \
-        k_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL><<<grid, EDIT_BLOCK, TAB_BYTES + EDIT_W * 384, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, e);
+        k_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL><<<grid, EDIT_BLOCK, TAB_BYTES, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, e);
             EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
             EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
 #undef EDIT_GO
