@@ -56,16 +56,18 @@ struct Nv12Src {
 
 enum { NV12_HUSL = 0, NV12_HUE = 1, NV12_RGB = 2, NV12_EDIT = 3 };
 
-// max(min(v, 255), 0) is one VIMNMX.RELU on sm_100
-__device__ __forceinline__ uint32_t clamp8(int v) { return (uint32_t)__vimin_s32_relu(v, 255); }
+// Channel values stay in 16.16 form after the clamp -- max(min(v, 0xFFFFFF), 0) is one VIMNMX.RELU
+// on sm_100 -- so that byte 2 IS the 8-bit channel (floor(v / 65536) in 0..255): the table lookups
+// and the uint8 packing pick that byte with the PRMT they need anyway, and no shift is issued.
+__device__ __forceinline__ uint32_t clamp16_16(int v) { return (uint32_t)__vimin_s32_relu(v, 0xFFFFFF); }
 
-// one pixel: luma byte + the three chroma terms of its 2 x 2 block -> R, G, B in 0..255
+// one pixel: luma byte + the three chroma terms of its 2 x 2 block -> R, G, B as 16.16 values (byte 2 = 0..255)
 __device__ __forceinline__ void yuv_px(const Nv12Coef &k, int yb, int cr, int cg, int cb,
                                        uint32_t &R, uint32_t &G, uint32_t &B) {
     const int yv = k.ky * yb;
-    R = clamp8((yv + cr) >> 16);
-    G = clamp8((yv + cg) >> 16);
-    B = clamp8((yv + cb) >> 16);
+    R = clamp16_16(yv + cr);
+    G = clamp16_16(yv + cg);
+    B = clamp16_16(yv + cb);
 }
 
 __device__ __forceinline__ void chroma_terms(const Nv12Coef &k, int u, int v, int &cr, int &cg, int &cb) {
@@ -89,9 +91,9 @@ __device__ __forceinline__ void yuv4(const Nv12Coef &k, uint32_t y4, uint32_t uv
 __device__ __forceinline__ LinPx lin_px(const unsigned char *tab, uint32_t r, uint32_t g, uint32_t b, uint32_t lane8) {
     LinPx p;
     float2 v;
-    v = lut_lin<0>(tab, r, lane8); p.hr = v.x; p.lr = v.y;
-    v = lut_lin<0>(tab, g, lane8); p.hg = v.x; p.lg = v.y;
-    v = lut_lin<0>(tab, b, lane8); p.hb = v.x; p.lb = v.y;
+    v = lut_lin<2>(tab, r, lane8); p.hr = v.x; p.lr = v.y;      // byte 2 of a 16.16 channel value
+    v = lut_lin<2>(tab, g, lane8); p.hg = v.x; p.lg = v.y;
+    v = lut_lin<2>(tab, b, lane8); p.hb = v.x; p.lb = v.y;
     return p;
 }
 
@@ -177,7 +179,13 @@ k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
                 for (int j = 0; j < 12; ++j) q[j] = c[j];
             }
             uint32_t o0, o1, o2;
-            pack12(q, o0, o1, o2);
+            if constexpr (MODE == NV12_EDIT) {
+                pack12(q, o0, o1, o2);
+            } else {                                              // byte 2 of the 16.16 values
+                o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0062), __byte_perm(q[2], q[3], 0x0062), 0x5410);
+                o1 = __byte_perm(__byte_perm(q[4], q[5], 0x0062), __byte_perm(q[6], q[7], 0x0062), 0x5410);
+                o2 = __byte_perm(__byte_perm(q[8], q[9], 0x0062), __byte_perm(q[10], q[11], 0x0062), 0x5410);
+            }
             uint32_t *sw = reinterpret_cast<uint32_t *>(stage);
             sw[lane * 3] = o0; sw[lane * 3 + 1] = o1; sw[lane * 3 + 2] = o2;
             __syncwarp();
@@ -241,6 +249,7 @@ k_nv12_any(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
         chroma_terms(src.k, uvp[0], uvp[1], cr, cg, cb);
         uint32_t R, G, B;
         yuv_px(src.k, src.y[row * src.y_pitch + x], cr, cg, cb, R, G, B);
+        R >>= 16; G >>= 16; B >>= 16;
         if constexpr (MODE == NV12_RGB) {
             uint8_t *o = reinterpret_cast<uint8_t *>(out) + 3 * i;
             o[0] = (uint8_t)R; o[1] = (uint8_t)G; o[2] = (uint8_t)B;
