@@ -24,6 +24,7 @@
 #include "husl_float.cuh"
 #include "husl_fused.cuh"
 #include "husl_strided.cuh"
+#include "husl_rows.cuh"
 
 namespace {
 
@@ -1100,6 +1101,15 @@ static bool same_extent(const nphusl_view *a, const nphusl_view *b) {
 }
 static bool empty_view(const nphusl_view *a) { return a->frames == 0 || a->rows == 0 || a->cols == 0; }
 
+// Rows of contiguous pixels with aligned starts: the row-tiled kernels of husl_rows.cuh apply.
+// `unit` = elements per pixel in this view (3, or 1 for a hue image), `align` = bytes every row start must honour.
+static bool dense_rows(const nphusl_view *v, int unit, long long align) {
+    const long long a = (long long)dsize(v->dtype);
+    if (v->col_stride != unit * a || (unit == 3 && v->ch_stride != a) || v->cols % 4) return false;
+    return reinterpret_cast<uintptr_t>(v->ptr) % align == 0 && v->frame_stride % align == 0 && v->row_stride % align == 0;
+}
+static long long row_tiles(const nphusl_view *v) { return (v->cols + TILE_PX - 1) / TILE_PX * v->frames * v->rows; }
+
 int nphusl_cuda_rgb_to_husl_strided(const nphusl_view *rgb, const nphusl_view *hsl, int hue_only,
                                     int device, void *stream) {
     DeviceGuard guard;
@@ -1113,6 +1123,25 @@ int nphusl_cuda_rgb_to_husl_strided(const nphusl_view *rgb, const nphusl_view *h
     const View2 i = view_dev(rgb), o = view_dev(hsl);
     const dim3 grid = grid_3d(*c, i);
     cudaStream_t st = (cudaStream_t)stream;
+    if (rgb->dtype == NPHUSL_U8 && dense_rows(rgb, 3, 4) &&
+        dense_rows(hsl, hue_only ? 1 : 3, hue_only ? 4 * (long long)dsize(hsl->dtype) : 16)) {
+        // crops, pitched frames, batches of ROIs: 128-pixel row tiles (husl_rows.cuh)
+        const long long tiles = row_tiles(rgb);
+#define ROWS_GO(TO, HUE, BLK, MB, SM) do { \
+        static std::atomic<bool> attr_done[MAX_DEV]; \
+        if ((rc = flt_attr(attr_done, *c, k_rows_fwd<TO, HUE, BLK, MB>, SM))) return rc; \
+        k_rows_fwd<TO, HUE, BLK, MB><<<grid_for(tiles, BLK / 32, c->sms * MB), BLK, SM, st>>>(i, o); } while (0)
+        if (hsl->dtype == NPHUSL_F32) {
+            if (hue_only) ROWS_GO(float, true, 512, 3, TAB_BYTES);
+            else ROWS_GO(float, false, 512, 2, TAB_BYTES + 16 * Pack<float>::STAGE);
+        } else {
+            if (hue_only) ROWS_GO(double, true, 512, 3, TAB_BYTES);
+            else ROWS_GO(double, false, 512, 1, TAB_BYTES + 16 * Pack<double>::STAGE);
+        }
+#undef ROWS_GO
+        g_launches++;
+        return check_launch("k_rows_fwd");
+    }
 #define GO(TI, TO) do { if (hue_only) k_fwd_strided<TI, TO, true><<<grid, 256, 0, st>>>(i, o); \
                         else k_fwd_strided<TI, TO, false><<<grid, 256, 0, st>>>(i, o); } while (0)
     const bool o32 = hsl->dtype == NPHUSL_F32;
@@ -1136,6 +1165,13 @@ int nphusl_cuda_husl_to_rgb_strided(const nphusl_view *hsl, const nphusl_view *r
     const View2 i = view_dev(hsl), o = view_dev(rgb);
     const dim3 grid = grid_3d(*c, i);
     cudaStream_t st = (cudaStream_t)stream;
+    if (rgb->dtype == NPHUSL_U8 && dense_rows(rgb, 3, 4) && dense_rows(hsl, 3, hsl->dtype == NPHUSL_F32 ? 16 : 32)) {
+        const int g = grid_for(row_tiles(hsl), 8, c->sms * 4);
+        if (hsl->dtype == NPHUSL_F32) k_rows_inv<float, 256, 4><<<g, 256, 0, st>>>(i, o);
+        else k_rows_inv<double, 256, 4><<<g, 256, 0, st>>>(i, o);
+        g_launches++;
+        return check_launch("k_rows_inv");
+    }
 #define GO(TI, TO) k_inv_strided<TI, TO><<<grid, 256, 0, st>>>(i, o)
     if (hsl->dtype == NPHUSL_F32) {
         if (rgb->dtype == NPHUSL_U8) GO(float, uint8_t); else if (rgb->dtype == NPHUSL_F32) GO(float, float); else GO(float, double);
@@ -1159,6 +1195,20 @@ int nphusl_cuda_rgb_edit_rgb_strided(const nphusl_view *rgb_in, const nphusl_vie
     DevCtx *c;
     if ((rc = ctx_get(device, &c))) return rc;
     const View2 i = view_dev(rgb_in), o = view_dev(rgb_out);
+    if (dense_rows(rgb_in, 3, 4) && dense_rows(rgb_out, 3, 4)) {
+        const EditShape sh(*edit);
+        const int g = grid_for(row_tiles(rgb_in), EDIT_BLOCK / 32, c->sms * EDIT_MINB);
+#define EDIT_GO(EH, ES, RSL) \
+    if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) { \
+        static std::atomic<bool> attr_done[MAX_DEV]; \
+        if ((rc = flt_attr(attr_done, *c, k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES))) return rc; \
+        k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL><<<g, EDIT_BLOCK, TAB_BYTES, (cudaStream_t)stream>>>(i, o, *edit); }
+        EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
+        EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
+#undef EDIT_GO
+        g_launches++;
+        return check_launch("k_rows_edit");
+    }
     k_edit_strided<<<grid_3d(*c, i), 256, 0, (cudaStream_t)stream>>>(i, o, *edit);
     g_launches++;
     return check_launch("k_edit_strided");

@@ -1065,3 +1065,53 @@ def test_tiled_float_rgb_kernels_equal_the_generic_ones(cu, n):
             assert np.array_equal(a, b)
             if tin == torch.float64:
                 assert np.abs(a - wantf).max() < 2e-5
+
+
+@pytest.mark.parametrize("x0,x1", [(40, 300), (0, 384), (128, 132)])
+def test_dense_row_views_take_the_row_tiled_kernels(cu, x0, x1):
+    """Crops / pitched frames / batches of ROIs whose rows are dense and aligned go through
+    the row-tiled kernels (husl_rows.cuh): bit for bit what the contiguous copy gives, for
+    to_husl (f32 / f64), to_hue, to_rgb into a region of a larger canvas and the in-place
+    fused edit; nothing outside the views is written."""
+    import torch
+    rng = np.random.default_rng(x0 * 1000 + x1)
+    vid = rng.integers(0, 256, (3, 64, 400, 3), dtype=np.uint8)
+    t = torch.from_numpy(vid).cuda()
+    crop, hcrop = t[:, 5:61, x0:x1], np.ascontiguousarray(vid[:, 5:61, x0:x1])
+    assert not crop.is_contiguous() or x1 - x0 == 400
+    n0 = cu.launch_count()
+    for dt in (np.float32, np.float64):
+        got = np.asarray(cu._rgb_to_husl(crop, dtype=dt))
+        assert np.array_equal(got, np.asarray(cu._rgb_to_husl(hcrop, dtype=dt)))
+        assert np.array_equal(np.asarray(cu._rgb_to_hue(crop, dtype=dt)), got[..., 0])
+        # strided out= : a region of a larger HUSL canvas
+        canvas = torch.full((3, 64, 400, 3), -7.0, dtype=torch.float32 if dt == np.float32 else torch.float64, device="cuda")
+        cu._rgb_to_husl(crop, out=canvas[:, 5:61, x0:x1])
+        c = canvas.cpu().numpy()
+        assert np.array_equal(c[:, 5:61, x0:x1], got)
+        c[:, 5:61, x0:x1] = -7.0
+        assert (c == -7.0).all()
+        # and back: HUSL region -> uint8 region of a canvas
+        hsl_full = torch.from_numpy(np.asarray(cu._rgb_to_husl(vid, dtype=dt))).cuda()
+        out = torch.full((3, 64, 400, 3), 0xA5, dtype=torch.uint8, device="cuda")
+        cu._husl_to_rgb(hsl_full[:, 5:61, x0:x1], out=out[:, 5:61, x0:x1])
+        o = out.cpu().numpy()
+        assert np.array_equal(o[:, 5:61, x0:x1], hcrop)
+        o[:, 5:61, x0:x1] = 0xA5
+        assert (o == 0xA5).all()
+    assert cu.launch_count() - n0 >= 10
+    # fused edit of the regions, in place, for two edit shapes
+    for ed in (dict(lightness=(0, 50), l=(1, 20)), dict(hue=(250, 290), invert=True, l=(0.5, 0), s=(0.9, 1))):
+        work = t.clone()
+        roi = work[:, 5:61, x0:x1]
+        cu.edit_rgb(roi, out=roi, **ed)
+        w = work.cpu().numpy()
+        assert np.array_equal(w[:, 5:61, x0:x1], np.asarray(cu.edit_rgb(hcrop, **ed)))
+        w[:, 5:61, x0:x1] = vid[:, 5:61, x0:x1]
+        assert np.array_equal(w, vid)
+    # a pitched frame (row padding), one frame, rows = 1 .. many
+    pitched = torch.zeros((37, 300 + 20, 3), dtype=torch.uint8, device="cuda")
+    img = rng.integers(0, 256, (37, 300, 3), dtype=np.uint8)
+    pitched[:, :300] = torch.from_numpy(img).cuda()
+    assert np.array_equal(np.asarray(cu._rgb_to_husl(pitched[:, :300], dtype=np.float32)), np.asarray(cu._rgb_to_husl(img, dtype=np.float32)))
+    assert np.array_equal(np.asarray(cu._rgb_to_husl(pitched[:1, :300], dtype=np.float32)), np.asarray(cu._rgb_to_husl(img[:1], dtype=np.float32)))
