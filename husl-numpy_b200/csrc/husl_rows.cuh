@@ -35,7 +35,16 @@ struct RowWalk {
 };
 struct RowPos {
     long long f, y;
-    __device__ RowPos(const RowWalk &w, long long slot) { const long long r0 = slot / w.segs; f = r0 / w.rows; y = r0 % w.rows; }
+    // slot -> segment column `seg` and the first (frame, row); 32-bit divisions whenever the numbers allow,
+    // none at all for a view that collapsed to one long row (a fully dense image)
+    __device__ RowPos(const RowWalk &w, long long slot, int &seg) {
+        if (w.frames * w.rows == 1) { seg = (int)slot; f = 0; y = 0; return; }
+        long long r0;
+        if (slot < 0x7fffffffLL) { const unsigned s32 = (unsigned)slot, g = (unsigned)w.segs; r0 = s32 / g; seg = (int)(s32 - (unsigned)r0 * g); }
+        else { r0 = slot / w.segs; seg = (int)(slot - r0 * w.segs); }
+        if (r0 < 0x7fffffffLL && w.rows < 0x7fffffffLL) { const unsigned r32 = (unsigned)r0, n = (unsigned)w.rows; f = r32 / n; y = r32 - (unsigned)f * n; }
+        else { f = r0 / w.rows; y = r0 - f * w.rows; }
+    }
     __device__ RowPos next(const RowWalk &w) const {
         RowPos n = *this;
         n.y += w.dr; n.f += w.dq;
@@ -46,7 +55,10 @@ struct RowPos {
     __device__ long long off(const View2 &v) const { return f * v.fs + y * v.rs; }
 };
 
-template <typename TOut, bool HUE, int BLOCK, int MINB>
+// PXB = bytes per stored pixel of the uint8 view: 3 (RGB), or 4 (RGBA / RGBX memory seen through
+// rgba[..., :3]: one 128-bit load per lane, the fourth byte is ignored); BGR: the view's channel
+// stride is -1 (BGRA memory presented as RGB), in.base then points at the R byte = byte 2 of a pixel.
+template <typename TOut, bool HUE, int BLOCK, int MINB, int PXB = 3, bool BGR = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_rows_fwd(const View2 in, const View2 out) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -63,27 +75,41 @@ k_rows_fwd(const View2 in, const View2 out) {
         rd_off[k] = (p / CH) * Pack<TOut>::LANE_STRIDE + (p % CH) * 16;
     }
     for (long long slot = (long long)blockIdx.x * (BLOCK / 32) + warp; slot < w.n_slots; slot += w.n_warps) {
-        const int x0 = (int)(slot % w.segs) * TILE_PX;
+        int seg;
+        RowPos pos(w, slot, seg);
+        const long long x0 = (long long)seg * TILE_PX;
         const int valid = (int)min((long long)TILE_PX, in.cols - x0);
         const bool lane_on = lane * 4 < valid;
-        const long long in_off = (long long)x0 * 3 + lane * 12;
-        const long long out_off = (long long)x0 * (HUE ? 1 : 3) * (long long)sizeof(TOut);
-        RowPos pos(w, slot);
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
-        if (pos.in(w) && lane_on) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(in.base + pos.off(in) + in_off);
-            w0 = ldg_u32(p); w1 = ldg_u32(p + 1); w2 = ldg_u32(p + 2);
-        }
+        const long long in_off = x0 * PXB + lane * (4 * PXB) - (BGR ? 2 : 0);
+        const long long out_off = x0 * (HUE ? 1 : 3) * (long long)sizeof(TOut);
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        auto fetch = [&](const RowPos &p_, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+            a = b = c = d = 0;
+            if (p_.in(w) && lane_on) {
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(in.base + p_.off(in) + in_off);
+                if (PXB == 4) { const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p)); a = q.x; b = q.y; c = q.z; d = q.w; }
+                else { a = ldg_u32(p); b = ldg_u32(p + 1); c = ldg_u32(p + 2); }
+            }
+        };
+        fetch(pos, w0, w1, w2, w3);
         for (; pos.in(w);) {
             const RowPos nxt = pos.next(w);
-            uint32_t n0 = 0, n1 = 0, n2 = 0;
-            if (nxt.in(w) && lane_on) {
-                const uint32_t *p = reinterpret_cast<const uint32_t *>(in.base + nxt.off(in) + in_off);
-                n0 = ldg_u32(p); n1 = ldg_u32(p + 1); n2 = ldg_u32(p + 2);
-            }
+            uint32_t n0, n1, n2, n3;
+            fetch(nxt, n0, n1, n2, n3);
             unsigned char *op = reinterpret_cast<unsigned char *>(out.base) + pos.off(out) + out_off;
             LinPx px[4];
-            lookup4(smem, w0, w1, w2, lane8, px);
+            if (PXB == 4) {
+                const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 v;
+                    v = lut_lin<BGR ? 2 : 0>(smem, ww[j], lane8); px[j].hr = v.x; px[j].lr = v.y;
+                    v = lut_lin<1>(smem, ww[j], lane8); px[j].hg = v.x; px[j].lg = v.y;
+                    v = lut_lin<BGR ? 0 : 2>(smem, ww[j], lane8); px[j].hb = v.x; px[j].lb = v.y;
+                }
+            } else {
+                lookup4(smem, w0, w1, w2, lane8, px);
+            }
             if (HUE) {
                 float h[4];
 #pragma unroll
@@ -116,7 +142,7 @@ k_rows_fwd(const View2 in, const View2 out) {
                     if (32 * k + lane < chunks) o[32 * k] = *reinterpret_cast<const float4 *>(stage + rd_off[k]);
                 __syncwarp();
             }
-            w0 = n0; w1 = n1; w2 = n2;
+            w0 = n0; w1 = n1; w2 = n2; w3 = n3;
             pos = nxt;
         }
     }
@@ -128,12 +154,14 @@ k_rows_inv(const View2 in, const View2 out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const RowWalk w(in.cols, in.frames, in.rows, BLOCK / 32);
     for (long long slot = (long long)blockIdx.x * (BLOCK / 32) + warp; slot < w.n_slots; slot += w.n_warps) {
-        const int x0 = (int)(slot % w.segs) * TILE_PX;
+        int seg;
+        RowPos pos(w, slot, seg);
+        const long long x0 = (long long)seg * TILE_PX;
         const int valid = (int)min((long long)TILE_PX, in.cols - x0);
         if (lane * 4 >= valid) continue;                              // no warp-level synchronisation below
-        const long long in_off = ((long long)x0 + lane * 4) * 3 * (long long)sizeof(TIn);
-        const long long out_off = ((long long)x0 + lane * 4) * 3;
-        for (RowPos pos(w, slot); pos.in(w); pos = pos.next(w)) {
+        const long long in_off = (x0 + lane * 4) * 3 * (long long)sizeof(TIn);
+        const long long out_off = (x0 + lane * 4) * 3;
+        for (; pos.in(w); pos = pos.next(w)) {
             const unsigned char *ip = reinterpret_cast<const unsigned char *>(in.base) + pos.off(in) + in_off;
             float v[12];
             if (sizeof(TIn) == 4) {
@@ -174,11 +202,12 @@ k_rows_edit(const View2 in, const View2 out, const nphusl_edit e) {
     const uint32_t lane8 = lane * 8;
     const RowWalk w(in.cols, in.frames, in.rows, BLOCK / 32);
     for (long long slot = (long long)blockIdx.x * (BLOCK / 32) + warp; slot < w.n_slots; slot += w.n_warps) {
-        const int x0 = (int)(slot % w.segs) * TILE_PX;
+        int seg;
+        RowPos pos(w, slot, seg);
+        const long long x0 = (long long)seg * TILE_PX;
         const int valid = (int)min((long long)TILE_PX, in.cols - x0);
         if (lane * 4 >= valid) continue;                              // no warp-level synchronisation below
-        const long long off = ((long long)x0 + lane * 4) * 3;
-        RowPos pos(w, slot);
+        const long long off = (x0 + lane * 4) * 3;
         uint32_t w0 = 0, w1 = 0, w2 = 0;
         if (pos.in(w)) {
             const uint32_t *p = reinterpret_cast<const uint32_t *>(in.base + pos.off(in) + off);

@@ -688,6 +688,24 @@ int nv12_launch(DevCtx &c, const Nv12Src &s, void *out, size_t out_align, const 
     return check_launch("k_nv12_any");
 }
 
+// A dense view that collapsed to ONE long row (e.g. a whole contiguous RGBA batch seen through
+// rgba[..., :3]) gives the row walk nothing to step down: re-tile it as rows of FLAT_ROW pixels plus a
+// remainder row (row strides stay multiples of every alignment the row kernels need).
+template <typename F>
+int with_flat_split(const View2 &i, const View2 &o, F launch) {
+    constexpr long long FLAT_ROW = 8192;
+    if (i.frames * i.rows != 1 || i.cols < 2 * FLAT_ROW) return launch(i, o);
+    const long long R = i.cols / FLAT_ROW, rem = i.cols - R * FLAT_ROW;
+    View2 a = i, b = o;
+    a.rows = b.rows = R; a.cols = b.cols = FLAT_ROW; a.rs = FLAT_ROW * i.cs; b.rs = FLAT_ROW * o.cs;
+    const int rc = launch(a, b);
+    if (rc || !rem) return rc;
+    a = i; b = o;
+    a.base += R * FLAT_ROW * i.cs; b.base += R * FLAT_ROW * o.cs; a.cols = b.cols = rem;
+    return launch(a, b);
+}
+
+
 }  // namespace
 
 // =====================================================================================
@@ -1108,8 +1126,7 @@ static bool dense_rows(const nphusl_view *v, int unit, long long align) {
     if (v->col_stride != unit * a || (unit == 3 && v->ch_stride != a) || v->cols % 4) return false;
     return reinterpret_cast<uintptr_t>(v->ptr) % align == 0 && v->frame_stride % align == 0 && v->row_stride % align == 0;
 }
-static long long row_tiles(const nphusl_view *v) { return (v->cols + TILE_PX - 1) / TILE_PX * v->frames * v->rows; }
-
+static long long row_tiles(const View2 &v) { return (v.cols + TILE_PX - 1) / TILE_PX * v.frames * v.rows; }
 int nphusl_cuda_rgb_to_husl_strided(const nphusl_view *rgb, const nphusl_view *hsl, int hue_only,
                                     int device, void *stream) {
     DeviceGuard guard;
@@ -1123,24 +1140,41 @@ int nphusl_cuda_rgb_to_husl_strided(const nphusl_view *rgb, const nphusl_view *h
     const View2 i = view_dev(rgb), o = view_dev(hsl);
     const dim3 grid = grid_3d(*c, i);
     cudaStream_t st = (cudaStream_t)stream;
-    if (rgb->dtype == NPHUSL_U8 && dense_rows(rgb, 3, 4) &&
-        dense_rows(hsl, hue_only ? 1 : 3, hue_only ? 4 * (long long)dsize(hsl->dtype) : 16)) {
-        // crops, pitched frames, batches of ROIs: 128-pixel row tiles (husl_rows.cuh)
-        const long long tiles = row_tiles(rgb);
-#define ROWS_GO(TO, HUE, BLK, MB, SM) do { \
-        static std::atomic<bool> attr_done[MAX_DEV]; \
-        if ((rc = flt_attr(attr_done, *c, k_rows_fwd<TO, HUE, BLK, MB>, SM))) return rc; \
-        k_rows_fwd<TO, HUE, BLK, MB><<<grid_for(tiles, BLK / 32, c->sms * MB), BLK, SM, st>>>(i, o); } while (0)
-        if (hsl->dtype == NPHUSL_F32) {
-            if (hue_only) ROWS_GO(float, true, 512, 3, TAB_BYTES);
-            else ROWS_GO(float, false, 512, 2, TAB_BYTES + 16 * Pack<float>::STAGE);
-        } else {
-            if (hue_only) ROWS_GO(double, true, 512, 3, TAB_BYTES);
-            else ROWS_GO(double, false, 512, 1, TAB_BYTES + 16 * Pack<double>::STAGE);
+    // uint8 side: 3 = packed RGB rows; 4 = RGBA / RGBX memory seen through rgba[..., :3]; -4 = BGRA memory
+    // presented as RGB (channel stride -1, the view's pointer is the R byte of the first pixel)
+    int pxb = 0;
+    if (rgb->dtype == NPHUSL_U8) {
+        if (dense_rows(rgb, 3, 4)) pxb = 3;
+        else if (rgb->col_stride == 4 && rgb->cols % 4 == 0 && rgb->frame_stride % 16 == 0 && rgb->row_stride % 16 == 0) {
+            const uintptr_t p = reinterpret_cast<uintptr_t>(rgb->ptr);
+            if (rgb->ch_stride == 1 && p % 16 == 0) pxb = 4;
+            else if (rgb->ch_stride == -1 && p % 16 == 2) pxb = -4;
         }
+    }
+    if (pxb && dense_rows(hsl, hue_only ? 1 : 3, hue_only ? 4 * (long long)dsize(hsl->dtype) : 16)) {
+        // crops, pitched frames, batches of ROIs: 128-pixel row tiles (husl_rows.cuh)
+        return with_flat_split(i, o, [&](const View2 &vi, const View2 &vo) -> int {
+            const long long tiles = row_tiles(vi);
+#define ROWS_GO1(TO, HUE, BLK, MB, SM, PXB, BGR) do { \
+            static std::atomic<bool> attr_done[MAX_DEV]; \
+            if ((rc = flt_attr(attr_done, *c, k_rows_fwd<TO, HUE, BLK, MB, PXB, BGR>, SM))) return rc; \
+            k_rows_fwd<TO, HUE, BLK, MB, PXB, BGR><<<grid_for(tiles, BLK / 32, c->sms * MB), BLK, SM, st>>>(vi, vo); } while (0)
+#define ROWS_GO(TO, HUE, BLK, MB, SM) do { \
+            if (pxb == 3) ROWS_GO1(TO, HUE, BLK, MB, SM, 3, false); \
+            else if (pxb == 4) ROWS_GO1(TO, HUE, BLK, MB, SM, 4, false); \
+            else ROWS_GO1(TO, HUE, BLK, MB, SM, 4, true); } while (0)
+            if (hsl->dtype == NPHUSL_F32) {
+                if (hue_only) ROWS_GO(float, true, 512, 3, TAB_BYTES);
+                else ROWS_GO(float, false, 512, 2, TAB_BYTES + 16 * Pack<float>::STAGE);
+            } else {
+                if (hue_only) ROWS_GO(double, true, 512, 3, TAB_BYTES);
+                else ROWS_GO(double, false, 512, 1, TAB_BYTES + 16 * Pack<double>::STAGE);
+            }
 #undef ROWS_GO
-        g_launches++;
-        return check_launch("k_rows_fwd");
+#undef ROWS_GO1
+            g_launches++;
+            return check_launch("k_rows_fwd");
+        });
     }
 #define GO(TI, TO) do { if (hue_only) k_fwd_strided<TI, TO, true><<<grid, 256, 0, st>>>(i, o); \
                         else k_fwd_strided<TI, TO, false><<<grid, 256, 0, st>>>(i, o); } while (0)
@@ -1166,11 +1200,13 @@ int nphusl_cuda_husl_to_rgb_strided(const nphusl_view *hsl, const nphusl_view *r
     const dim3 grid = grid_3d(*c, i);
     cudaStream_t st = (cudaStream_t)stream;
     if (rgb->dtype == NPHUSL_U8 && dense_rows(rgb, 3, 4) && dense_rows(hsl, 3, hsl->dtype == NPHUSL_F32 ? 16 : 32)) {
-        const int g = grid_for(row_tiles(hsl), 8, c->sms * 4);
-        if (hsl->dtype == NPHUSL_F32) k_rows_inv<float, 256, 4><<<g, 256, 0, st>>>(i, o);
-        else k_rows_inv<double, 256, 4><<<g, 256, 0, st>>>(i, o);
-        g_launches++;
-        return check_launch("k_rows_inv");
+        return with_flat_split(i, o, [&](const View2 &vi, const View2 &vo) -> int {
+            const int g = grid_for(row_tiles(vi), 8, c->sms * 4);
+            if (hsl->dtype == NPHUSL_F32) k_rows_inv<float, 256, 4><<<g, 256, 0, st>>>(vi, vo);
+            else k_rows_inv<double, 256, 4><<<g, 256, 0, st>>>(vi, vo);
+            g_launches++;
+            return check_launch("k_rows_inv");
+        });
     }
 #define GO(TI, TO) k_inv_strided<TI, TO><<<grid, 256, 0, st>>>(i, o)
     if (hsl->dtype == NPHUSL_F32) {
@@ -1197,17 +1233,19 @@ int nphusl_cuda_rgb_edit_rgb_strided(const nphusl_view *rgb_in, const nphusl_vie
     const View2 i = view_dev(rgb_in), o = view_dev(rgb_out);
     if (dense_rows(rgb_in, 3, 4) && dense_rows(rgb_out, 3, 4)) {
         const EditShape sh(*edit);
-        const int g = grid_for(row_tiles(rgb_in), EDIT_BLOCK / 32, c->sms * EDIT_MINB);
+        return with_flat_split(i, o, [&](const View2 &vi, const View2 &vo) -> int {
+            const int g = grid_for(row_tiles(vi), EDIT_BLOCK / 32, c->sms * EDIT_MINB);
 #define EDIT_GO(EH, ES, RSL) \
-    if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) { \
-        static std::atomic<bool> attr_done[MAX_DEV]; \
-        if ((rc = flt_attr(attr_done, *c, k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES))) return rc; \
-        k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL><<<g, EDIT_BLOCK, TAB_BYTES, (cudaStream_t)stream>>>(i, o, *edit); }
-        EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
-        EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
+        if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) { \
+            static std::atomic<bool> attr_done[MAX_DEV]; \
+            if ((rc = flt_attr(attr_done, *c, k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES))) return rc; \
+            k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL><<<g, EDIT_BLOCK, TAB_BYTES, (cudaStream_t)stream>>>(vi, vo, *edit); }
+            EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
+            EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
 #undef EDIT_GO
-        g_launches++;
-        return check_launch("k_rows_edit");
+            g_launches++;
+            return check_launch("k_rows_edit");
+        });
     }
     k_edit_strided<<<grid_3d(*c, i), 256, 0, (cudaStream_t)stream>>>(i, o, *edit);
     g_launches++;

@@ -1115,3 +1115,25 @@ def test_dense_row_views_take_the_row_tiled_kernels(cu, x0, x1):
     pitched[:, :300] = torch.from_numpy(img).cuda()
     assert np.array_equal(np.asarray(cu._rgb_to_husl(pitched[:, :300], dtype=np.float32)), np.asarray(cu._rgb_to_husl(img, dtype=np.float32)))
     assert np.array_equal(np.asarray(cu._rgb_to_husl(pitched[:1, :300], dtype=np.float32)), np.asarray(cu._rgb_to_husl(img[:1], dtype=np.float32)))
+
+
+def test_rgba_and_bgra_memory_through_the_row_kernels(cu):
+    """rgba[..., :3] (4 stored bytes per pixel, alpha ignored) and BGRA memory presented as RGB
+    (channel stride -1) with aligned rows: one 128-bit load per lane, same values as the packed copy."""
+    import torch
+    rng = np.random.default_rng(44)
+    rgba = rng.integers(0, 256, (2, 33, 260, 4), dtype=np.uint8)
+    t = torch.from_numpy(rgba).cuda()
+    packed = np.ascontiguousarray(rgba[..., :3])
+    for dt in (np.float32, np.float64):
+        want = np.asarray(cu._rgb_to_husl(packed, dtype=dt))
+        assert np.array_equal(np.asarray(cu._rgb_to_husl(t[..., :3], dtype=dt)), want)
+        assert np.array_equal(np.asarray(cu._rgb_to_hue(t[..., :3], dtype=dt)), want[..., 0])
+        assert np.array_equal(np.asarray(cu._rgb_to_husl(t[:, 3:30, 8:200, :3], dtype=dt)), want[:, 3:30, 8:200])
+
+        class Bgra:                               # the same memory read as B, G, R, A: R is byte 2, channels run backwards
+            device = 0
+            __cuda_array_interface__ = {"shape": (2, 33, 260, 3), "typestr": "|u1", "data": (t.data_ptr() + 2, False),
+                                        "version": 3, "strides": (33 * 260 * 4, 260 * 4, 4, -1)}
+        swapped = np.ascontiguousarray(rgba[..., 2::-1])
+        assert np.array_equal(np.asarray(cu._rgb_to_husl(Bgra(), dtype=dt)), np.asarray(cu._rgb_to_husl(swapped, dtype=dt)))
