@@ -166,7 +166,11 @@ int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,
  * planes seen as (H, W, 3).  The reference makes such arrays contiguous with a
  * host copy before a backend sees them (the C-contiguous memoryview casts of
  * _simd_opt.pyx:36 and _cython_opt.pyx:22); here the kernels walk the view.
- * For a hue image (rgb_to_husl_strided with hue_only != 0) ch_stride is unused. */
+ * For a hue image (rgb_to_husl_strided with hue_only != 0) ch_stride is unused.
+ * Views whose rows are dense and aligned -- col_stride = 3 elements with ch_stride = 1 element (or uint8
+ * col_stride = 4 with ch_stride = +-1: RGBA / BGRA memory), cols % 4 == 0, pointer / row / frame strides
+ * multiples of 4 bytes (uint8 RGB), 16 bytes (RGBA, float HUSL; 32 for float64 HUSL input) or 4 elements
+ * (hue) -- run in 128-pixel row tiles; every other view one pixel per thread.  Same values either way. */
 typedef struct nphusl_view {
     void *ptr;
     int dtype;                       /* NPHUSL_U8 | NPHUSL_F32 | NPHUSL_F64 */
