@@ -193,7 +193,9 @@ k_rows_inv(const View2 in, const View2 out) {
     }
 }
 
-template <int BLOCK, int MINB, bool EH, bool ES, bool RSL>
+// PXB = 4: RGBA / BGRA memory edited IN PLACE through rgba[..., :3] (out aliases in): one 128-bit load
+// and one 128-bit store per lane, the fourth byte of every pixel is written back unchanged.
+template <int BLOCK, int MINB, bool EH, bool ES, bool RSL, int PXB = 3, bool BGR = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_rows_edit(const View2 in, const View2 out, const nphusl_edit e) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -207,21 +209,34 @@ k_rows_edit(const View2 in, const View2 out, const nphusl_edit e) {
         const long long x0 = (long long)seg * TILE_PX;
         const int valid = (int)min((long long)TILE_PX, in.cols - x0);
         if (lane * 4 >= valid) continue;                              // no warp-level synchronisation below
-        const long long off = (x0 + lane * 4) * 3;
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
-        if (pos.in(w)) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(in.base + pos.off(in) + off);
-            w0 = ldg_u32(p); w1 = ldg_u32(p + 1); w2 = ldg_u32(p + 2);
-        }
+        const long long off = (x0 + lane * 4) * PXB - (BGR ? 2 : 0);
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        auto fetch = [&](const RowPos &p_, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+            a = b = c = d = 0;
+            if (p_.in(w)) {
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(in.base + p_.off(in) + off);
+                if (PXB == 4) { const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p)); a = q.x; b = q.y; c = q.z; d = q.w; }
+                else { a = ldg_u32(p); b = ldg_u32(p + 1); c = ldg_u32(p + 2); }
+            }
+        };
+        fetch(pos, w0, w1, w2, w3);
         for (; pos.in(w);) {
             const RowPos nxt = pos.next(w);
-            uint32_t n0 = 0, n1 = 0, n2 = 0;
-            if (nxt.in(w)) {
-                const uint32_t *p = reinterpret_cast<const uint32_t *>(in.base + nxt.off(in) + off);
-                n0 = ldg_u32(p); n1 = ldg_u32(p + 1); n2 = ldg_u32(p + 2);
-            }
+            uint32_t n0, n1, n2, n3;
+            fetch(nxt, n0, n1, n2, n3);
             LinPx px[4];
-            lookup4(smem, w0, w1, w2, lane8, px);
+            const uint32_t ww[4] = {w0, w1, w2, w3};
+            if (PXB == 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 v;
+                    v = lut_lin<BGR ? 2 : 0>(smem, ww[j], lane8); px[j].hr = v.x; px[j].lr = v.y;
+                    v = lut_lin<1>(smem, ww[j], lane8); px[j].hg = v.x; px[j].lg = v.y;
+                    v = lut_lin<BGR ? 0 : 2>(smem, ww[j], lane8); px[j].hb = v.x; px[j].lb = v.y;
+                }
+            } else {
+                lookup4(smem, w0, w1, w2, lane8, px);
+            }
             uint32_t q[12];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -231,11 +246,24 @@ k_rows_edit(const View2 in, const View2 out, const nphusl_edit e) {
                 rgb255_from_husl(h, s, l, Rr, G, B);
                 q[3 * j] = round_u8_bits(Rr); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
             }
-            uint32_t o0, o1, o2;
-            pack12(q, o0, o1, o2);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(out.base + pos.off(out) + off);
-            dst[0] = o0; dst[1] = o1; dst[2] = o2;
-            w0 = n0; w1 = n1; w2 = n2;
+            if (PXB == 4) {
+                uint4 o;
+                uint32_t *ow = &o.x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // bytes: (first, G, last, untouched 4th byte of the input word)
+                    const uint32_t lo = __byte_perm(q[3 * j + (BGR ? 2 : 0)], q[3 * j + 1], 0x0040);
+                    const uint32_t hi = __byte_perm(q[3 * j + (BGR ? 0 : 2)], ww[j], 0x0070);
+                    ow[j] = __byte_perm(lo, hi, 0x5410);
+                }
+                *reinterpret_cast<uint4 *>(out.base + pos.off(out) + off) = o;
+            } else {
+                uint32_t o0, o1, o2;
+                pack12(q, o0, o1, o2);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(out.base + pos.off(out) + off);
+                dst[0] = o0; dst[1] = o1; dst[2] = o2;
+            }
+            w0 = n0; w1 = n1; w2 = n2; w3 = n3;
             pos = nxt;
         }
     }

@@ -1231,18 +1231,33 @@ int nphusl_cuda_rgb_edit_rgb_strided(const nphusl_view *rgb_in, const nphusl_vie
     DevCtx *c;
     if ((rc = ctx_get(device, &c))) return rc;
     const View2 i = view_dev(rgb_in), o = view_dev(rgb_out);
-    if (dense_rows(rgb_in, 3, 4) && dense_rows(rgb_out, 3, 4)) {
+    // 3: packed RGB rows on both sides; 4 / -4: RGBA / BGRA memory edited IN PLACE through rgba[..., :3]
+    // (the same view on both sides: the fourth byte of each pixel is carried over from the input word)
+    int pxb = 0;
+    if (dense_rows(rgb_in, 3, 4) && dense_rows(rgb_out, 3, 4)) pxb = 3;
+    else if (rgb_in->ptr == rgb_out->ptr && rgb_in->col_stride == 4 && rgb_out->col_stride == 4 &&
+             rgb_in->ch_stride == rgb_out->ch_stride && rgb_in->row_stride == rgb_out->row_stride &&
+             rgb_in->frame_stride == rgb_out->frame_stride && rgb_in->cols % 4 == 0 &&
+             rgb_in->frame_stride % 16 == 0 && rgb_in->row_stride % 16 == 0) {
+        const uintptr_t p = reinterpret_cast<uintptr_t>(rgb_in->ptr);
+        if (rgb_in->ch_stride == 1 && p % 16 == 0) pxb = 4;
+        else if (rgb_in->ch_stride == -1 && p % 16 == 2) pxb = -4;
+    }
+    if (pxb) {
         const EditShape sh(*edit);
         return with_flat_split(i, o, [&](const View2 &vi, const View2 &vo) -> int {
             const int g = grid_for(row_tiles(vi), EDIT_BLOCK / 32, c->sms * EDIT_MINB);
+#define EDIT_GO1(EH, ES, RSL, PXB, BGR) do { \
+            static std::atomic<bool> attr_done[MAX_DEV]; \
+            if ((rc = flt_attr(attr_done, *c, k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL, PXB, BGR>, TAB_BYTES))) return rc; \
+            k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL, PXB, BGR><<<g, EDIT_BLOCK, TAB_BYTES, (cudaStream_t)stream>>>(vi, vo, *edit); } while (0)
 #define EDIT_GO(EH, ES, RSL) \
         if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) { \
-            static std::atomic<bool> attr_done[MAX_DEV]; \
-            if ((rc = flt_attr(attr_done, *c, k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>, TAB_BYTES))) return rc; \
-            k_rows_edit<EDIT_BLOCK, EDIT_MINB, EH, ES, RSL><<<g, EDIT_BLOCK, TAB_BYTES, (cudaStream_t)stream>>>(vi, vo, *edit); }
+            if (pxb == 3) EDIT_GO1(EH, ES, RSL, 3, false); else if (pxb == 4) EDIT_GO1(EH, ES, RSL, 4, false); else EDIT_GO1(EH, ES, RSL, 4, true); }
             EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
             EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false) EDIT_GO(true, true, true)
 #undef EDIT_GO
+#undef EDIT_GO1
             g_launches++;
             return check_launch("k_rows_edit");
         });

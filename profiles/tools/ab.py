@@ -104,7 +104,8 @@ rgba[..., :3] = rgb
 for name, fn, b, npx in (("strided_crop_to_husl32", lambda: _cuda._rgb_to_husl(crop, out=crop32), 15, cpx),
                          ("strided_crop_to_rgb", lambda: _cuda._husl_to_rgb(crop32, out=back[:, 100:2060, 200:3640]), 15, cpx),
                          ("strided_rgba3_to_husl32", lambda: _cuda._rgb_to_husl(rgba[..., :3], out=h32), 16, px),
-                         ("strided_crop_edit", lambda: _cuda.edit_rgb(crop, out=crop, lightness=(0, 50), l=(1, 20)), 6, cpx)):
+                         ("strided_crop_edit", lambda: _cuda.edit_rgb(crop, out=crop, lightness=(0, 50), l=(1, 20)), 6, cpx),
+                         ("rgba_edit_in_place", lambda: _cuda.edit_rgb(rgba[..., :3], out=rgba[..., :3], lightness=(0, 50), l=(1, 20)), 8, px)):
     ms = timed(fn)
     res[name] = {"ms": round(ms, 4), "gpix_s": round(npx / ms / 1e6, 1), "hbm_frac": round(npx * b / ms / 1e6 / 6547.2, 3)}
 # NV12 decoder surfaces as the load stage (8 frames stacked as one tall 4K-wide surface)

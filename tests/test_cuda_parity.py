@@ -1137,3 +1137,38 @@ def test_rgba_and_bgra_memory_through_the_row_kernels(cu):
                                         "version": 3, "strides": (33 * 260 * 4, 260 * 4, 4, -1)}
         swapped = np.ascontiguousarray(rgba[..., 2::-1])
         assert np.array_equal(np.asarray(cu._rgb_to_husl(Bgra(), dtype=dt)), np.asarray(cu._rgb_to_husl(swapped, dtype=dt)))
+
+
+def test_in_place_edit_of_rgba_and_bgra_frames(cu):
+    """Fused edit of RGBA / BGRA frames in place through rgba[..., :3]: the colour bytes equal
+    edit_rgb of the packed copy, every alpha byte is left as it was."""
+    import torch
+    rng = np.random.default_rng(45)
+    rgba = rng.integers(0, 256, (2, 33, 260, 4), dtype=np.uint8)
+    for ed in (dict(lightness=(0, 50), l=(1, 20)), dict(hue=(250, 290), invert=True, l=(0.5, 0)), dict(h=(1, 90), s=(0.5, 0))):
+        t = torch.from_numpy(rgba).cuda()
+        roi = t[..., :3]
+        assert cu.edit_rgb(roi, out=roi, **ed) is roi
+        got = t.cpu().numpy()
+        assert np.array_equal(got[..., :3], np.asarray(cu.edit_rgb(np.ascontiguousarray(rgba[..., :3]), **ed)))
+        assert np.array_equal(got[..., 3], rgba[..., 3])
+        # a cropped region of the RGBA frames, in place: the rest of the frames untouched
+        t = torch.from_numpy(rgba).cuda()
+        roi = t[:, 4:30, 8:200, :3]
+        cu.edit_rgb(roi, out=roi, **ed)
+        got = t.cpu().numpy()
+        assert np.array_equal(got[:, 4:30, 8:200, :3], np.asarray(cu.edit_rgb(np.ascontiguousarray(rgba[:, 4:30, 8:200, :3]), **ed)))
+        got[:, 4:30, 8:200, :3] = rgba[:, 4:30, 8:200, :3]
+        assert np.array_equal(got, rgba)
+        # the same memory as BGRA: R is byte 2, channels run backwards
+        t = torch.from_numpy(rgba).cuda()
+
+        class Bgra:
+            device = 0
+            __cuda_array_interface__ = {"shape": (2, 33, 260, 3), "typestr": "|u1", "data": (t.data_ptr() + 2, False),
+                                        "version": 3, "strides": (33 * 260 * 4, 260 * 4, 4, -1)}
+        v = Bgra()
+        cu.edit_rgb(v, out=v, **ed)
+        got = t.cpu().numpy()
+        want = np.asarray(cu.edit_rgb(np.ascontiguousarray(rgba[..., 2::-1]), **ed))
+        assert np.array_equal(got[..., 2::-1], want) and np.array_equal(got[..., 3], rgba[..., 3])
