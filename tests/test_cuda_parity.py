@@ -1172,3 +1172,72 @@ def test_in_place_edit_of_rgba_and_bgra_frames(cu):
         got = t.cpu().numpy()
         want = np.asarray(cu.edit_rgb(np.ascontiguousarray(rgba[..., 2::-1]), **ed))
         assert np.array_equal(got[..., 2::-1], want) and np.array_equal(got[..., 3], rgba[..., 3])
+
+
+def test_strided_view_fuzz(cu):
+    """Random (frames, rows, cols) views over one device buffer -- aligned and unaligned offsets,
+    padded and NEGATIVE row / frame strides (flipped images), 3- and 4-byte pixels, tiny and wide
+    rows, single rows, many frames of few rows -- through to_husl, to_hue, to_rgb and the fused
+    edit: always what the packed copy of the same pixels gives, and never a byte outside the view."""
+    import torch
+    rng = np.random.default_rng(2024)
+    buf_np = rng.integers(0, 256, 1 << 22, dtype=np.uint8)
+    buf = torch.from_numpy(buf_np).cuda()
+    base = buf.data_ptr()
+
+    def raw(ptr, shape, strides, typestr="|u1"):
+        class V:
+            device = 0
+            __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3, "strides": strides}
+        return V()
+
+    cases = 0
+    for trial in range(60):
+        pxb = int(rng.choice([3, 3, 4]))
+        cols = int(rng.choice([4, 8, 12, 124, 128, 132, 256, 300, 301, 1000, 8192 * 2 + 4, 5]))
+        rows = int(rng.choice([1, 2, 3, 7, 40]))
+        frames = int(rng.choice([1, 1, 2, 5, 33]))
+        if frames * rows * cols > 400000:
+            frames, rows = 1, min(rows, 3)
+        pad = int(rng.choice([0, 0, 4, 16, 1, 7]))
+        rs = cols * pxb + pad
+        fs = rows * rs + int(rng.choice([0, 0, 16, 3]))
+        flip_rows, flip_frames = bool(rng.integers(0, 2)), bool(rng.integers(0, 4) == 0)
+        start = int(rng.choice([0, 16, 4, 2, 1, 64]))
+        span = frames * fs + 64
+        if start + span > buf_np.size:
+            continue
+        # element (f, y, x, c) lives at start + f*fs + y*rs + x*pxb + c of the buffer
+        idx = (start + np.arange(frames)[:, None, None, None] * fs + np.arange(rows)[None, :, None, None] * rs
+               + np.arange(cols)[None, None, :, None] * pxb + np.arange(3)[None, None, None, :])
+        if flip_rows:
+            idx = idx[:, ::-1]
+        if flip_frames:
+            idx = idx[::-1]
+        packed = np.ascontiguousarray(buf_np[idx])
+        p0 = base + int(idx[0, 0, 0, 0])
+        strides = (-fs if flip_frames else fs, -rs if flip_rows else rs, pxb, 1)
+        v = raw(p0, (frames, rows, cols, 3), strides)
+        want = np.asarray(cu._rgb_to_husl(packed, dtype=np.float32))
+        assert np.array_equal(np.asarray(cu._rgb_to_husl(v, dtype=np.float32)), want), (trial, pxb, cols, rows, frames, pad, start)
+        assert np.array_equal(np.asarray(cu._rgb_to_hue(v, dtype=np.float64)), np.asarray(cu._rgb_to_hue(packed)))
+        # inverse into the same view of a canvas, and the fused edit in place: bytes outside the view stay
+        canvas = torch.full((buf_np.size,), 0x5A, dtype=torch.uint8, device="cuda")
+        cv = raw(canvas.data_ptr() + int(idx[0, 0, 0, 0]), (frames, rows, cols, 3), strides)
+        cu._husl_to_rgb(torch.from_numpy(want).cuda(), out=cv)
+        torch.cuda.synchronize()
+        c = canvas.cpu().numpy()
+        assert np.array_equal(c[idx], packed), (trial, "to_rgb")
+        c[idx] = 0x5A
+        assert (c == 0x5A).all(), (trial, "to_rgb wrote outside the view")
+        work = buf.clone()
+        wv = raw(work.data_ptr() + int(idx[0, 0, 0, 0]), (frames, rows, cols, 3), strides)
+        ed = dict(lightness=(20, 80), l=(0.7, 3.0), h=(1, 30))
+        cu.edit_rgb(wv, out=wv, **ed)
+        torch.cuda.synchronize()
+        w = work.cpu().numpy()
+        assert np.array_equal(w[idx], np.asarray(cu.edit_rgb(packed, **ed))), (trial, "edit")
+        w[idx] = buf_np[idx]
+        assert np.array_equal(w, buf_np), (trial, "edit wrote outside the view")
+        cases += 1
+    assert cases >= 40
