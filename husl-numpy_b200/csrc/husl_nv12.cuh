@@ -105,7 +105,8 @@ struct Nv12Smem {
     static constexpr int bytes(int block) { return TAB + (block / 32) * STAGE; }
 };
 
-template <int MODE, typename TOut, int BLOCK, int MINB>
+// EH / ES / RSL: the edit-shape promises of husl_fused.cuh (NV12_EDIT only)
+template <int MODE, typename TOut, int BLOCK, int MINB, bool EH = true, bool ES = true, bool RSL = true>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -170,7 +171,7 @@ k_nv12(const Nv12Src src, TOut *__restrict__ out, const nphusl_edit e) {
                 for (int j = 0; j < 4; ++j) {
                     float h, s, l, R, G, B;
                     husl_from_diff<true>(make_diff(lin_px(tab, c[3 * j], c[3 * j + 1], c[3 * j + 2], lane8)), h, s, l);
-                    apply_edit<true, true, true>(e, h, s, l);
+                    apply_edit<EH, ES, RSL>(e, h, s, l);
                     rgb255_from_husl(h, s, l, R, G, B);
                     q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
                 }

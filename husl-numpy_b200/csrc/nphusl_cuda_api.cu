@@ -670,15 +670,15 @@ bool nv12_vector_ok(const Nv12Src &s) {
     return s.width % 4 == 0 && aligned(s.y, 4) && aligned(s.uv, 4) && s.y_pitch % 4 == 0 && s.uv_pitch % 4 == 0;
 }
 
-template <int MODE, typename TOut, int BLOCK, int MINB>
+template <int MODE, typename TOut, int BLOCK, int MINB, bool EH = true, bool ES = true, bool RSL = true>
 int nv12_launch(DevCtx &c, const Nv12Src &s, void *out, size_t out_align, const nphusl_edit &e, cudaStream_t st) {
     int rc;
     if (nv12_vector_ok(s) && aligned(out, out_align)) {
         static std::atomic<bool> attr_done[MAX_DEV];
         const int smem = Nv12Smem<MODE, TOut>::bytes(BLOCK);
-        if ((rc = flt_attr(attr_done, c, k_nv12<MODE, TOut, BLOCK, MINB>, smem))) return rc;
+        if ((rc = flt_attr(attr_done, c, k_nv12<MODE, TOut, BLOCK, MINB, EH, ES, RSL>, smem))) return rc;
         const long long tiles = (long long)((s.width + TILE_PX - 1) / TILE_PX) * s.height;
-        k_nv12<MODE, TOut, BLOCK, MINB><<<grid_for(tiles, BLOCK / 32, c.sms * MINB), BLOCK, smem, st>>>(s, (TOut *)out, e);
+        k_nv12<MODE, TOut, BLOCK, MINB, EH, ES, RSL><<<grid_for(tiles, BLOCK / 32, c.sms * MINB), BLOCK, smem, st>>>(s, (TOut *)out, e);
         g_launches++;
         return check_launch("k_nv12");
     }
@@ -1084,7 +1084,14 @@ int nphusl_cuda_nv12_edit_rgb(const nphusl_nv12 *src, const nphusl_edit *edit, v
     if (!rgb || !edit) return fail(NPHUSL_ERR_ARG, "nv12_edit_rgb: null argument");
     DevCtx *c;
     if ((rc = ctx_get(device, &c))) return rc;
-    return nv12_launch<NV12_EDIT, uint8_t, EDIT_BLOCK, EDIT_MINB>(*c, s, rgb, 4, *edit, (cudaStream_t)stream);
+    const EditShape sh(*edit);
+#define EDIT_GO(EH, ES, RSL) \
+    if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) \
+        return nv12_launch<NV12_EDIT, uint8_t, EDIT_BLOCK, EDIT_MINB, EH, ES, RSL>(*c, s, rgb, 4, *edit, (cudaStream_t)stream);
+    EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
+    EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false)
+#undef EDIT_GO
+    return nv12_launch<NV12_EDIT, uint8_t, EDIT_BLOCK, EDIT_MINB, true, true, true>(*c, s, rgb, 4, *edit, (cudaStream_t)stream);
 }
 
 // ---- strided device images ------------------------------------------------------------
