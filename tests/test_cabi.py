@@ -72,3 +72,26 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")) and f != "gen_coeffs.py":
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "husl_oracle" not in src and "libemul" not in src, f
+
+
+def _client():
+    import subprocess
+    d = os.path.join(ROOT, "tests", "cabi")
+    subprocess.run(["make", "-C", d, "-s"], check=True)
+    return os.path.join(d, "cabi_client")
+
+
+def test_plain_c_client_links_against_the_header_and_library():
+    """A C99 program that includes nothing but include/nphusl_cuda.h links and runs (no CUDA
+    headers, no Python): the boundary really is a C ABI."""
+    import subprocess
+    out = subprocess.run([_client()], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("abi 1 devices ")
+
+
+@pytest.mark.gpu
+def test_plain_c_client_round_trip_on_the_gpu():
+    import subprocess
+    r = subprocess.run([_client(), "roundtrip"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "roundtrip ok" in r.stdout
