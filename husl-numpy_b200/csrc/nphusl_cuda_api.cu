@@ -21,6 +21,7 @@
 #include "husl_stream.cuh"
 #include "husl_lut.cuh"
 #include "husl_nv12.cuh"
+#include "husl_nv12_out.cuh"
 #include "husl_float.cuh"
 #include "husl_fused.cuh"
 #include "husl_strided.cuh"
@@ -688,6 +689,51 @@ int nv12_launch(DevCtx &c, const Nv12Src &s, void *out, size_t out_align, const 
     return check_launch("k_nv12_any");
 }
 
+int nv12_dst(const nphusl_nv12 *d, const char *what, Nv12Dst *out) {
+    if (!d || !d->y || !d->uv) return fail(NPHUSL_ERR_ARG, std::string(what) + ": null destination surface");
+    if (d->width <= 0 || d->height <= 0 || (d->width & 1) || (d->height & 1))
+        return fail(NPHUSL_ERR_ARG, std::string(what) + ": destination width and height must be positive and even");
+    if (d->y_pitch < d->width || d->uv_pitch < d->width) return fail(NPHUSL_ERR_ARG, std::string(what) + ": pitch smaller than a row");
+    if (d->matrix != NPHUSL_BT601 && d->matrix != NPHUSL_BT709) return fail(NPHUSL_ERR_ARG, std::string(what) + ": matrix must be BT601 or BT709");
+    const double kr = d->matrix == NPHUSL_BT601 ? 0.299 : 0.2126, kb = d->matrix == NPHUSL_BT601 ? 0.114 : 0.0722;
+    const double kg = 1.0 - kr - kb;
+    const double ys = d->full_range ? 1.0 : 219.0 / 255.0, cs = d->full_range ? 1.0 : 224.0 / 255.0;
+    auto q = [](double v) { return (int)std::lround(65536.0 * v); };
+    Nv12Dst o;
+    o.y = (uint8_t *)d->y; o.uv = (uint8_t *)d->uv; o.y_pitch = d->y_pitch; o.uv_pitch = d->uv_pitch;
+    o.k.yr = q(ys * kr); o.k.yg = q(ys * kg); o.k.yb = q(ys * kb);
+    o.k.yc = 32768 + ((d->full_range ? 0 : 16) << 16);
+    o.k.ur = q(-cs * 0.5 * kr / (1.0 - kb)); o.k.ug = q(-cs * 0.5 * kg / (1.0 - kb)); o.k.ub = q(cs * 0.5);
+    o.k.vr = q(cs * 0.5); o.k.vg = q(-cs * 0.5 * kg / (1.0 - kr)); o.k.vb = q(-cs * 0.5 * kb / (1.0 - kr));
+    o.k.cc = 32768 + (128 << 16);
+    *out = o;
+    return NPHUSL_OK;
+}
+
+bool nv12_dst_vector_ok(const Nv12Dst &d, int width) {
+    return width % 4 == 0 && aligned(d.y, 4) && aligned(d.uv, 4) && d.y_pitch % 4 == 0 && d.uv_pitch % 4 == 0;
+}
+
+template <bool SRC_NV12, bool EH, bool ES, bool RSL>
+int to_nv12_launch(DevCtx &c, const Nv12Src &s, const void *rgb, int W, int H, const Nv12Dst &d, const nphusl_edit &e,
+                   bool vector_ok, cudaStream_t st) {
+    int rc;
+    if (vector_ok) {
+        constexpr int BLK = 512, MB = 2;
+        static std::atomic<bool> attr_done[MAX_DEV];
+        const int smem = SRC_NV12 ? TAB_BYTES : 0;
+        if (smem && (rc = flt_attr(attr_done, c, k_to_nv12<SRC_NV12, BLK, MB, EH, ES, RSL>, smem))) return rc;
+        const long long tiles = (long long)((W + TILE_PX - 1) / TILE_PX) * (H / 2);
+        k_to_nv12<SRC_NV12, BLK, MB, EH, ES, RSL><<<grid_for(tiles, BLK / 32, c.sms * MB), BLK, smem, st>>>(s, (const uint8_t *)rgb, W, H, d, e);
+        g_launches++;
+        return check_launch("k_to_nv12");
+    }
+    const long long n = (long long)(W / 2) * (H / 2);
+    k_to_nv12_any<SRC_NV12><<<grid_for(n, 256, c.sms * 8), 256, 0, st>>>(s, (const uint8_t *)rgb, W, H, d, e);
+    g_launches++;
+    return check_launch("k_to_nv12_any");
+}
+
 // A dense view that collapsed to ONE long row (e.g. a whole contiguous RGBA batch seen through
 // rgba[..., :3]) gives the row walk nothing to step down: re-tile it as rows of FLAT_ROW pixels plus a
 // remainder row (row strides stay multiples of every alignment the row kernels need).
@@ -1092,6 +1138,41 @@ int nphusl_cuda_nv12_edit_rgb(const nphusl_nv12 *src, const nphusl_edit *edit, v
     EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false)
 #undef EDIT_GO
     return nv12_launch<NV12_EDIT, uint8_t, EDIT_BLOCK, EDIT_MINB, true, true, true>(*c, s, rgb, 4, *edit, (cudaStream_t)stream);
+}
+
+int nphusl_cuda_rgb_to_nv12(const void *rgb, const nphusl_nv12 *dst, int device, void *stream) {
+    DeviceGuard guard;
+    Nv12Dst d;
+    int rc = nv12_dst(dst, "rgb_to_nv12", &d);
+    if (rc) return rc;
+    if (!rgb) return fail(NPHUSL_ERR_ARG, "rgb_to_nv12: null input");
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    const bool vec = nv12_dst_vector_ok(d, dst->width) && aligned(rgb, 4);
+    return to_nv12_launch<false, true, true, true>(*c, Nv12Src{}, rgb, dst->width, dst->height, d, nphusl_edit{}, vec, (cudaStream_t)stream);
+}
+
+int nphusl_cuda_nv12_edit_nv12(const nphusl_nv12 *src, const nphusl_edit *edit, const nphusl_nv12 *dst, int device, void *stream) {
+    DeviceGuard guard;
+    Nv12Src s;
+    Nv12Dst d;
+    int rc = nv12_src(src, "nv12_edit_nv12", &s);
+    if (rc) return rc;
+    if ((rc = nv12_dst(dst, "nv12_edit_nv12", &d))) return rc;
+    if (!edit) return fail(NPHUSL_ERR_ARG, "nv12_edit_nv12: null edit");
+    if (src->width != dst->width || src->height != dst->height) return fail(NPHUSL_ERR_ARG, "nv12_edit_nv12: source and destination sizes differ");
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    const bool vec = nv12_vector_ok(s) && nv12_dst_vector_ok(d, dst->width);
+    const EditShape sh(*edit);
+    cudaStream_t st = (cudaStream_t)stream;
+#define EDIT_GO(EH, ES, RSL) \
+    if (sh.eh == EH && sh.es == ES && sh.rsl == RSL) \
+        return to_nv12_launch<true, EH, ES, RSL>(*c, s, nullptr, src->width, src->height, d, *edit, vec, st);
+    EDIT_GO(false, false, false) EDIT_GO(false, false, true) EDIT_GO(false, true, false) EDIT_GO(false, true, true)
+    EDIT_GO(true, false, false) EDIT_GO(true, false, true) EDIT_GO(true, true, false)
+#undef EDIT_GO
+    return to_nv12_launch<true, true, true, true>(*c, s, nullptr, src->width, src->height, d, *edit, vec, st);
 }
 
 // ---- strided device images ------------------------------------------------------------

@@ -34,7 +34,7 @@ import threading
 import numpy as np
 
 __all__ = ["_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue", "rgb_to_husl_planar", "husl_planar_to_rgb",
-           "edit_rgb", "Edit", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
+           "edit_rgb", "Edit", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "rgb_to_nv12", "nv12_edit_nv12", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
 
 def _prod(shape):
     """Number of elements of a shape (np.prod on a tuple costs 3 us and runs several times per call)."""
@@ -84,6 +84,8 @@ SIGNATURES = {
     "nphusl_cuda_nv12_to_rgb": (_i, [_vp, _vp, _i, _vp]),
     "nphusl_cuda_nv12_to_husl": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nphusl_cuda_nv12_edit_rgb": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "nphusl_cuda_rgb_to_nv12": (_i, [_vp, _vp, _i, _vp]),
+    "nphusl_cuda_nv12_edit_nv12": (_i, [_vp, _vp, _vp, _i, _vp]),
     "nphusl_cuda_lut_generate": (_i, [_i, _i, _i, _i]),
     "nphusl_cuda_lut_upload": (_i, [_i, _u16p, _i, _dp, _dp, _u16p, _i, _i,
                                     ctypes.c_double, ctypes.c_double, _dp]),
@@ -1114,6 +1116,53 @@ def nv12_edit_rgb(y, uv=None, edit=None, out=None, matrix="bt709", full_range=Fa
     src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
     ptr, _, ret = _nv12_out(out, (h, w, 3), np.uint8, (np.dtype(np.uint8),), dev)
     _check(load().nphusl_cuda_nv12_edit_rgb(ctypes.byref(src), ctypes.byref(edit), ptr, dev, _stream_ptr(stream)), "nv12_edit_rgb")
+    return ret
+
+
+def _nv12_dest(h, w, out_y, out_uv, matrix, full_range, dev):
+    """-> (Nv12 descriptor of the destination, (y, uv) arrays to return)"""
+    if h % 2 or w % 2:
+        raise ValueError("an NV12 destination needs even width and height, got {}x{}".format(w, h))
+    if (out_y is None) != (out_uv is None):
+        raise ValueError("pass both out_y and out_uv, or neither")
+    if out_y is None:
+        out_y, out_uv = DeviceArray((h, w), np.uint8, dev), DeviceArray((h // 2, w), np.uint8, dev)
+    yp, ys, ypitch, ydev, _ = _plane(out_y, "out_y")
+    up, us, upitch, udev, _ = _plane(out_uv, "out_uv")
+    if tuple(ys) != (h, w) or us[0] != h // 2 or _prod(us[1:]) != w or ydev != dev or udev != dev:
+        raise ValueError("out_y / out_uv: expected ({}, {}) and ({}, {}) uint8 planes on device {}".format(h, w, h // 2, w, dev))
+    if matrix not in MATRICES:
+        raise ValueError("matrix must be one of {}".format(sorted(MATRICES)))
+    return Nv12(yp, up, ypitch, upitch, w, h, MATRICES[matrix], int(bool(full_range))), (out_y, out_uv)
+
+
+def rgb_to_nv12(rgb, out_y=None, out_uv=None, matrix="bt709", full_range=False, stream=None):
+    """uint8 RGB ``(H, W, 3)`` device array -> NV12 planes ``(y, uv)`` (what a hardware encoder takes);
+    the integer conversion documented in include/nphusl_cuda.h, chroma = rounded mean of each 2 x 2 block."""
+    if not _is_device(rgb):
+        raise ValueError("rgb_to_nv12 takes a device array")
+    src = _describe_device(rgb, "rgb")
+    if src.dtype != np.uint8 or len(src.shape) != 3 or src.shape[-1] != 3:
+        raise ValueError("rgb_to_nv12 takes uint8 (H, W, 3), got {} {}".format(src.dtype, src.shape))
+    dev = _pick_device(None, src)
+    dst, ret = _nv12_dest(src.shape[0], src.shape[1], out_y, out_uv, matrix, full_range, dev)
+    _check(load().nphusl_cuda_rgb_to_nv12(src.ptr, ctypes.byref(dst), dev, _stream_ptr(stream)), "rgb_to_nv12")
+    return ret
+
+
+def nv12_edit_nv12(y, uv=None, edit=None, out_y=None, out_uv=None, matrix="bt709", full_range=False,
+                   out_matrix=None, out_full_range=None, stream=None, **edit_args):
+    """The whole video loop in one pass: NV12 -> HUSL -> select + edit -> NV12 (3 bytes of memory
+    traffic per pixel).  Equals ``rgb_to_nv12(nv12_edit_rgb(...))`` bit for bit; ``out_y`` / ``out_uv``
+    may be the source planes themselves.  Returns ``(y, uv)``."""
+    if edit is None:
+        edit = Edit(**edit_args)
+    elif edit_args:
+        raise TypeError("pass either an Edit or its fields as keywords, not both")
+    src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
+    dst, ret = _nv12_dest(h, w, out_y, out_uv, out_matrix or matrix, full_range if out_full_range is None else out_full_range, dev)
+    _check(load().nphusl_cuda_nv12_edit_nv12(ctypes.byref(src), ctypes.byref(edit), ctypes.byref(dst), dev, _stream_ptr(stream)),
+           "nv12_edit_nv12")
     return ret
 
 

@@ -224,6 +224,21 @@ int nphusl_cuda_nv12_to_husl(const nphusl_nv12 *src, void *hsl, int hsl_dtype, i
 int nphusl_cuda_nv12_edit_rgb(const nphusl_nv12 *src, const nphusl_edit *edit, void *rgb,
                               int device, void *stream);
 
+/* The encode side (what a hardware encoder takes): uint8 RGB -> NV12, and the whole video loop
+ * NV12 -> HUSL -> select + edit -> NV12 in one pass (3 bytes of memory traffic per pixel).
+ * `dst` describes the destination surface (its y / uv planes are WRITTEN; width and height must
+ * be even; matrix and range may differ from the source's).  RGB -> YUV: integer, 16.16 coefficients,
+ *     Y = clamp8((yr*R + yg*G + yb*B + 32768 + (yoff << 16)) >> 16)
+ *     U = clamp8((ur*Ra + ug*Ga + ub*Ba + 32768 + (128 << 16)) >> 16), V likewise,
+ * (Ra, Ga, Ba) = (sum of the 2 x 2 block + 2) >> 2 per channel; yr = round(65536*ys*Kr) ...,
+ * ur = round(-65536*cs*0.5*Kr/(1-Kb)), ug = round(-65536*cs*0.5*Kg/(1-Kb)), ub = vr = round(65536*cs*0.5),
+ * vg = round(-65536*cs*0.5*Kg/(1-Kr)), vb = round(-65536*cs*0.5*Kb/(1-Kr)); video range: ys = 219/255,
+ * cs = 224/255, yoff = 16; full range: ys = cs = 1, yoff = 0.
+ * nv12_edit_nv12 equals rgb_to_nv12(nv12_edit_rgb(src)) bit for bit; dst may be src itself. */
+int nphusl_cuda_rgb_to_nv12(const void *rgb, const nphusl_nv12 *dst, int device, void *stream);
+int nphusl_cuda_nv12_edit_nv12(const nphusl_nv12 *src, const nphusl_edit *edit, const nphusl_nv12 *dst,
+                               int device, void *stream);
+
 /* ---- lookup tables (optional LUT mode) -------------------------------------- */
 
 /* Generate, ON THE DEVICE, the tables make_lookup_tables:8-9 produces with

@@ -13,7 +13,7 @@ package never imports this module and has no CPU fallback.
 * ``nv12_to_rgb`` -- numpy statement of the integer BT.601 / BT.709 conversion that
   include/nphusl_cuda.h specifies for decoder surfaces (not reference code: the
   reference's callers decode with imageio / moviepy, examples.py:117-134), plus
-  ``nv12_to_rgb_float`` (the textbook float matrix, to bound the integer one);
+  ``nv12_to_rgb_float`` (the textbook float matrix, to bound the integer one), ``rgb_to_nv12`` (the encode side);
 * ``ref_simd(...)``, ``ref_tables()``, ``ref_cython()`` -- the reference's own
   compiled code (``oracle/_ref``, built by ``oracle/build_ref.sh`` from the
   sources under /root/reference; present on the GPU box as prebuilt files).
@@ -136,6 +136,25 @@ def nv12_to_rgb_float(y, uv, matrix="bt709", full_range=False):
     yv, d, e = _nv12_planes(y, uv)
     yv = ys * (yv - yoff)
     return np.stack([yv + rv * e, yv - gu * d - gv * e, yv + bu * d], axis=-1)
+
+
+def rgb_to_nv12(rgb, matrix="bt709", full_range=False):
+    """uint8 RGB (H, W, 3), H and W even -> (y (H, W), uv (H/2, W)) uint8: the integer conversion of
+    include/nphusl_cuda.h (16.16 coefficients, round half up, clamp; chroma from the rounded 2 x 2 mean)."""
+    kr, kb = {"bt601": (0.299, 0.114), "bt709": (0.2126, 0.0722)}[matrix]
+    kg = 1.0 - kr - kb
+    ys, cs, yoff = (1.0, 1.0, 0) if full_range else (219.0 / 255.0, 224.0 / 255.0, 16)
+    q = lambda v: int(np.floor(65536.0 * abs(v) + 0.5)) * (1 if v >= 0 else -1)     # lround: half away from zero
+    yr, yg, yb = q(ys * kr), q(ys * kg), q(ys * kb)
+    ur, ug, ub = q(-cs * 0.5 * kr / (1 - kb)), q(-cs * 0.5 * kg / (1 - kb)), q(cs * 0.5)
+    vr, vg, vb = q(cs * 0.5), q(-cs * 0.5 * kg / (1 - kr)), q(-cs * 0.5 * kb / (1 - kr))
+    a = np.asarray(rgb).astype(np.int64)
+    h, w, _ = a.shape
+    y = np.clip((yr * a[..., 0] + yg * a[..., 1] + yb * a[..., 2] + 32768 + (yoff << 16)) >> 16, 0, 255)
+    m = (a.reshape(h // 2, 2, w // 2, 2, 3).sum(axis=(1, 3)) + 2) >> 2
+    u = np.clip((ur * m[..., 0] + ug * m[..., 1] + ub * m[..., 2] + 32768 + (128 << 16)) >> 16, 0, 255)
+    v = np.clip((vr * m[..., 0] + vg * m[..., 1] + vb * m[..., 2] + 32768 + (128 << 16)) >> 16, 0, 255)
+    return y.astype(np.uint8), np.stack([u, v], axis=-1).reshape(h // 2, w).astype(np.uint8)
 
 
 def max_chroma(l, h):

@@ -111,13 +111,16 @@ for name, fn, b, npx in (("strided_crop_to_husl32", lambda: _cuda._rgb_to_husl(c
 # NV12 decoder surfaces as the load stage (8 frames stacked as one tall 4K-wide surface)
 ysurf = torch.randint(0, 256, (frames * 2160, 3840), dtype=torch.uint8, device="cuda", generator=g)
 uvsurf = torch.randint(0, 256, (frames * 1080, 3840), dtype=torch.uint8, device="cuda", generator=g)
+ysurf2, uvsurf2 = torch.empty_like(ysurf), torch.empty_like(uvsurf)
 hv32, hv64 = h32.view(frames * 2160, 3840, 3), h64.view(frames * 2160, 3840, 3)
 bv = back.view(frames * 2160, 3840, 3)
 for name, fn, b in (("nv12_to_husl_f32", lambda: _cuda.nv12_to_husl(ysurf, uvsurf, out=hv32), 13.5),
                     ("nv12_to_husl_f64", lambda: _cuda.nv12_to_husl(ysurf, uvsurf, out=hv64), 25.5),
                     ("nv12_to_hue_f32", lambda: _cuda.nv12_to_hue(ysurf, uvsurf, out=hue32.view(frames * 2160, 3840)), 5.5),
                     ("nv12_to_rgb", lambda: _cuda.nv12_to_rgb(ysurf, uvsurf, out=bv), 4.5),
-                    ("nv12_edit_rgb", lambda: _cuda.nv12_edit_rgb(ysurf, uvsurf, out=bv, hue=(250, 290), invert=True, l=(0.5, 0)), 4.5)):
+                    ("nv12_edit_rgb", lambda: _cuda.nv12_edit_rgb(ysurf, uvsurf, out=bv, hue=(250, 290), invert=True, l=(0.5, 0)), 4.5),
+                    ("nv12_edit_nv12", lambda: _cuda.nv12_edit_nv12(ysurf, uvsurf, out_y=ysurf2, out_uv=uvsurf2, hue=(250, 290), invert=True, l=(0.5, 0)), 3.0),
+                    ("rgb_to_nv12", lambda: _cuda.rgb_to_nv12(bv, out_y=ysurf2, out_uv=uvsurf2), 4.5)):
     ms = timed(fn)
     res[name] = {"ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 1), "hbm_frac": round(px * b / ms / 1e6 / 6547.2, 3)}
 print(json.dumps(res))

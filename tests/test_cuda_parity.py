@@ -1241,3 +1241,41 @@ def test_strided_view_fuzz(cu):
         assert np.array_equal(w, buf_np), (trial, "edit wrote outside the view")
         cases += 1
     assert cases >= 40
+
+
+@pytest.mark.parametrize("shape,pad", [((2160, 3840), 0), ((66, 132), 12), ((10, 6), 2)])
+def test_nv12_encode_side(cu, shape, pad):
+    """uint8 RGB -> NV12 bit-exact against the numpy statement; the fused video loop NV12 -> edit -> NV12
+    equals rgb_to_nv12(nv12_edit_rgb(...)) bit for bit, also in place and into pitched destination planes
+    (whose padding stays untouched), and with a different output matrix / range."""
+    import torch
+    h, w = shape
+    rng = np.random.default_rng(h + w)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    rgb_d = torch.from_numpy(rgb).cuda()
+    for matrix, full in (("bt709", False), ("bt601", True)):
+        wy, wuv = orc.rgb_to_nv12(rgb, matrix, full)
+        ybuf = torch.full((h, w + pad), 0xA5, dtype=torch.uint8, device="cuda")
+        uvbuf = torch.full((h // 2, w + pad), 0xA5, dtype=torch.uint8, device="cuda")
+        gy, guv = cu.rgb_to_nv12(rgb_d, out_y=ybuf[:, :w], out_uv=uvbuf[:, :w], matrix=matrix, full_range=full)
+        torch.cuda.synchronize()
+        assert np.array_equal(ybuf.cpu().numpy()[:, :w], wy) and np.array_equal(uvbuf.cpu().numpy()[:, :w], wuv)
+        assert bool((ybuf[:, w:] == 0xA5).all()) and bool((uvbuf[:, w:] == 0xA5).all())
+    # the video loop
+    y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    uv = rng.integers(0, 256, (h // 2, w), dtype=np.uint8)
+    yd, uvd = torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()
+    for ed in (dict(l=(0.5, 0)), dict(hue=(250, 290), invert=True, l=(0.5, 0), s=(0.8, 0)), dict(lightness=(0, 62), l=(0, 0), h=(1, 40))):
+        edited = cu.nv12_edit_rgb(yd, uvd, **ed)                                   # fused NV12 -> edit -> RGB
+        wy, wuv = (np.asarray(a) for a in cu.rgb_to_nv12(edited))
+        gy, guv = cu.nv12_edit_nv12(yd, uvd, **ed)
+        assert np.array_equal(np.asarray(gy), wy) and np.array_equal(np.asarray(guv), wuv)
+        oy, ouv = orc.rgb_to_nv12(np.asarray(edited))
+        assert np.array_equal(wy, oy) and np.array_equal(wuv, ouv)
+        # other output matrix / range, in place
+        y2, uv2 = yd.clone(), uvd.clone()
+        cu.nv12_edit_nv12(y2, uv2, out_y=y2, out_uv=uv2, out_matrix="bt601", out_full_range=True, **ed)
+        oy, ouv = orc.rgb_to_nv12(np.asarray(edited), "bt601", True)
+        assert np.array_equal(y2.cpu().numpy(), oy) and np.array_equal(uv2.cpu().numpy(), ouv)
+    with pytest.raises(ValueError):
+        cu.rgb_to_nv12(torch.zeros((5, 8, 3), dtype=torch.uint8, device="cuda"))    # odd height
