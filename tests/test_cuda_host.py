@@ -218,3 +218,37 @@ def test_device_pool_size_classes_and_cheap_device_check():
     assert not _cuda._is_device(np.zeros(3)) and not _cuda._is_device(FakeTorchCpu()) and not _cuda._is_device([1, 2, 3])
     assert _cuda._is_device(FakeTorchCuda()) and _cuda._is_device(Other())
     assert _cuda._prod((2, 3, 4)) == 24 and _cuda._prod(()) == 1 and _cuda._prod(7) == 7
+
+
+def test_nv12_struct_matches_header_and_surface_description():
+    """nphusl_nv12 layout against the header, and the surface descriptor built from device planes
+    (pitched planes, (rows, pairs, 2) chroma, one whole NVDEC surface) -- no GPU needed."""
+    text = open(os.path.join(ROOT, "include", "nphusl_cuda.h")).read()
+    body = re.search(r"typedef struct nphusl_nv12 \{(.*?)\} nphusl_nv12;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = re.sub(r"\b(const|void|long|int)\b|\*", " ", decl)
+        names += [n.strip() for n in decl.split(",") if n.strip()]
+    assert names == [f[0] for f in _cuda.Nv12._fields_]
+    y = FakeDev((1080, 1920), "|u1", strides=(2048, 1), ptr=1 << 20, device=0)            # pitched luma
+    uv = FakeDev((540, 960, 2), "|u1", strides=(2048, 2, 1), ptr=1 << 23, device=0)       # pairs as a last axis
+    s, (h, w), dev, _ = _cuda._nv12_surface(y, uv, "bt709", False)
+    assert (s.y, s.uv, s.y_pitch, s.uv_pitch, s.width, s.height, s.matrix, s.full_range) == (1 << 20, 1 << 23, 2048, 2048, 1920, 1080, 1, 0)
+    assert (h, w, dev) == (1080, 1920, 0)
+    whole = FakeDev((1620, 1920), "|u1", strides=(2048, 1), ptr=1 << 20, device=1)       # luma rows, then chroma rows
+    s, (h, w), dev, _ = _cuda._nv12_surface(whole, None, "bt601", True)
+    assert (s.uv - s.y, s.uv_pitch, h, w, dev, s.matrix, s.full_range) == (1080 * 2048, 2048, 1080, 1920, 1, 0, 1)
+    odd = FakeDev((5, 7), "|u1", device=0)
+    s, (h, w), _, _ = _cuda._nv12_surface(odd, FakeDev((3, 8), "|u1", device=0), "bt709", False)   # odd sizes: ceil(h/2) x 2*ceil(w/2)
+    assert (h, w) == (5, 7)
+    for bad_uv in (FakeDev((540, 1918), "|u1", device=0), FakeDev((539, 1920), "|u1", device=0), FakeDev((540, 1920), "|u1", device=1),
+                   FakeDev((540, 1920), "<f4", device=0), FakeDev((540, 960, 2), "|u1", strides=(4096, 4, 1), device=0)):
+        with pytest.raises(ValueError):
+            _cuda._nv12_surface(FakeDev((1080, 1920), "|u1", device=0), bad_uv, "bt709", False)
+    with pytest.raises(ValueError):
+        _cuda._nv12_surface(y, uv, "bt2020", False)
+    with pytest.raises(ValueError):
+        _cuda._nv12_surface(np.zeros((4, 4), np.uint8), None, "bt709", False)             # host planes are refused
+    with pytest.raises(ValueError):
+        _cuda._nv12_surface(FakeDev((1621, 1920), "|u1", device=0), None, "bt709", False)  # not 3/2 * height rows
