@@ -1279,3 +1279,37 @@ def test_nv12_encode_side(cu, shape, pad):
         assert np.array_equal(y2.cpu().numpy(), oy) and np.array_equal(uv2.cpu().numpy(), ouv)
     with pytest.raises(ValueError):
         cu.rgb_to_nv12(torch.zeros((5, 8, 3), dtype=torch.uint8, device="cuda"))    # odd height
+
+
+def test_nv12_size_fuzz(cu):
+    """Random surface sizes and pitches (vector path, partial tiles, odd sizes -> one-pixel kernels):
+    NV12 -> RGB against the numpy statement, NV12 -> HUSL against to_husl of that RGB, and for even
+    sizes the encode side against the numpy statement."""
+    import torch
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        w = int(rng.choice([2, 4, 6, 8, 36, 124, 128, 130, 132, 256, 260, 1000, 1001, 37]))
+        h = int(rng.choice([1, 2, 3, 4, 10, 11, 64, 300]))
+        pad_y, pad_uv = int(rng.choice([0, 0, 4, 12, 3])), int(rng.choice([0, 0, 4, 8, 1]))
+        hc, wc2 = (h + 1) // 2, 2 * ((w + 1) // 2)
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        uv = rng.integers(0, 256, (hc, wc2), dtype=np.uint8)
+        yb = torch.zeros((h, w + pad_y), dtype=torch.uint8, device="cuda")
+        ub = torch.zeros((hc, wc2 + pad_uv), dtype=torch.uint8, device="cuda")
+        yb[:, :w] = torch.from_numpy(y).cuda()
+        ub[:, :wc2] = torch.from_numpy(uv).cuda()
+        yd, ud = yb[:, :w], ub[:, :wc2]
+        matrix, full = ("bt709", "bt601")[trial & 1], bool(trial & 2)
+        want = orc.nv12_to_rgb(y, uv, matrix, full)
+        got = np.asarray(cu.nv12_to_rgb(yd, ud, matrix=matrix, full_range=full))
+        assert np.array_equal(got, want), (trial, w, h, pad_y, pad_uv)
+        hsl = np.asarray(cu.nv12_to_husl(yd, ud, matrix=matrix, full_range=full))
+        assert np.array_equal(hsl, np.asarray(cu._rgb_to_husl(want, dtype=np.float32))), (trial, w, h)
+        if h % 2 == 0 and w % 2 == 0:
+            gy, guv = cu.rgb_to_nv12(torch.from_numpy(want).cuda(), matrix=matrix, full_range=full)
+            oy, ouv = orc.rgb_to_nv12(want, matrix, full)
+            assert np.array_equal(np.asarray(gy), oy) and np.array_equal(np.asarray(guv), ouv), (trial, w, h)
+            ed = dict(lightness=(10, 90), l=(0.8, 2.0))
+            ey, euv = cu.nv12_edit_nv12(yd, ud, matrix=matrix, full_range=full, **ed)
+            oy, ouv = orc.rgb_to_nv12(np.asarray(cu.edit_rgb(want, **ed)), matrix, full)
+            assert np.array_equal(np.asarray(ey), oy) and np.array_equal(np.asarray(euv), ouv), (trial, w, h, "loop")
