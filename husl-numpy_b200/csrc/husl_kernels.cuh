@@ -27,6 +27,10 @@
 #pragma once
 #include "husl_math.cuh"
 
+#ifndef HUSL_FWD_PF2
+#define HUSL_FWD_PF2 0      // A/B knob: register prefetch of k_fwd_u8 two tiles ahead instead of one
+#endif
+
 namespace husl {
 
 // 256 x {hi, lo}: hi = float(lin), lo = float(lin - hi); filled per device by
@@ -95,7 +99,7 @@ k_fwd_u8(const uint32_t *__restrict__ in, TOut *__restrict__ out, long long n_ti
     }
 
     // register prefetch of the next tile's words (PF2: two tiles ahead)
-    constexpr bool PF2 = false;   // measured: a second tile in flight does not pay (profiles/r01_ab_variants.txt)
+    constexpr bool PF2 = HUSL_FWD_PF2;   // measured: a second tile in flight does not pay (profiles/r01_ab_variants.txt)
     uint32_t w0 = 0, w1 = 0, w2 = 0, x0 = 0, x1 = 0, x2 = 0;
     if (tile < n_tiles) {
         const uint32_t *p = in + tile * 96 + lane * 3;
