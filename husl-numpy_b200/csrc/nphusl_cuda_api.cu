@@ -103,7 +103,7 @@ struct DevCtx {
     int dev = -1, sms = 0;
     Staging set[NSETS];
     cudaEvent_t gate = nullptr;
-    bool attr_set = false;
+    std::atomic<bool> attr_set{false};   // device-pointer calls reach set_attrs() from any thread without c.mu
     Lut lut;
 };
 
@@ -214,7 +214,7 @@ int set_smem(K kernel, size_t bytes) {
 }
 
 int set_attrs(DevCtx &c) {
-    if (c.attr_set) return NPHUSL_OK;
+    if (c.attr_set.load(std::memory_order_acquire)) return NPHUSL_OK;
     int rc;
     constexpr int W = FWD_BLOCK / 32;
     if ((rc = set_smem(k_fwd_u8<float, false, FWD32_BLOCK, FWD32_MINB>, TAB_BYTES + (FWD32_BLOCK / 32) * Pack<float>::STAGE))) return rc;
@@ -240,7 +240,7 @@ int set_attrs(DevCtx &c) {
     if ((rc = set_smem(k_fwd_chw<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_chw<double, 512, 2>, TAB_BYTES))) return rc;
 
-    c.attr_set = true;
+    c.attr_set.store(true, std::memory_order_release);
     return NPHUSL_OK;
 }
 

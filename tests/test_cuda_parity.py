@@ -1313,3 +1313,59 @@ def test_nv12_size_fuzz(cu):
             ey, euv = cu.nv12_edit_nv12(yd, ud, matrix=matrix, full_range=full, **ed)
             oy, ouv = orc.rgb_to_nv12(np.asarray(cu.edit_rgb(want, **ed)), matrix, full)
             assert np.array_equal(np.asarray(ey), oy) and np.array_equal(np.asarray(euv), ouv), (trial, w, h, "loop")
+
+
+def test_concurrent_host_threads_on_one_device(cu):
+    """SURVEY 8b threading: the shim is re-entrant per (device, stream).  Eight host threads hammer one
+    GPU at once -- device arrays on their own streams, pageable host arrays (which share the per-device
+    staging pipeline), pinned non-blocking calls, fused edits, LUT mode, new-array results from the
+    recycling pools -- and every result is what the single-threaded call gives."""
+    import threading
+    import torch
+    rng = np.random.default_rng(99)
+    imgs = [rng.integers(0, 256, (97 + 13 * i, 211, 3), dtype=np.uint8) for i in range(8)]
+    want_hsl = [np.asarray(cu._rgb_to_husl(a)) for a in imgs]
+    want_edit = [np.asarray(cu.edit_rgb(a, lightness=(0, 50), l=(1, 20))) for a in imgs]
+    cu.lut_generate()
+    want_lut = [np.asarray(cu._rgb_to_husl(a, mode="lut")) for a in imgs]
+    errors = []
+
+    def worker(i):
+        try:
+            a = imgs[i]
+            s = cu.Stream()
+            d = torch.from_numpy(a).cuda()
+            for rep in range(12):
+                kind = (i + rep) % 5
+                if kind == 0:                                   # device in, new device result, own stream
+                    h = cu._rgb_to_husl(d, stream=s)
+                    back = cu._husl_to_rgb(h, stream=s)
+                    s.synchronize()
+                    assert np.array_equal(np.asarray(h), want_hsl[i]) and np.array_equal(np.asarray(back), a)
+                elif kind == 1:                                 # pageable host arrays through the staging pipeline
+                    h = cu._rgb_to_husl(a)
+                    assert np.array_equal(h, want_hsl[i]) and np.array_equal(cu._husl_to_rgb(h), a)
+                elif kind == 2:                                 # pinned, non-blocking
+                    pin, out = cu.pinned_empty(a.shape, np.uint8), cu.pinned_empty(a.shape, np.float64)
+                    pin[...] = a
+                    cu._rgb_to_husl(pin, out=out, stream=s, blocking=False)
+                    s.synchronize()
+                    assert np.array_equal(out, want_hsl[i])
+                elif kind == 3:                                 # fused edit, host and device
+                    assert np.array_equal(cu.edit_rgb(a, lightness=(0, 50), l=(1, 20)), want_edit[i])
+                    e = cu.edit_rgb(d, stream=s, lightness=(0, 50), l=(1, 20))
+                    s.synchronize()
+                    assert np.array_equal(np.asarray(e), want_edit[i])
+                else:                                           # LUT mode shares the per-device tables
+                    assert np.array_equal(cu._rgb_to_husl(a, mode="lut"), want_lut[i])
+            s.close()
+        except BaseException as ex:                             # noqa: BLE001 -- reported by the main thread
+            errors.append((i, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not any(t.is_alive() for t in threads), "a worker hung"
+    assert not errors, errors
