@@ -12,6 +12,10 @@
 #include "husl_kernels.cuh"
 #include "../../include/nphusl_cuda.h"
 
+#ifndef HUSL_EDIT_UNROLL
+#define HUSL_EDIT_UNROLL 1     // tile loop of k_edit unrolled by this factor (A/B knob)
+#endif
+
 namespace husl {
 
 __device__ __forceinline__ void ldg_f64x4(const double *p, double &a, double &b, double &c, double &d) {
@@ -212,6 +216,8 @@ k_edit(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n_
         const uint32_t *p = in + tile * 96 + lane * 3;
         w0 = ldg_u32(p); w1 = ldg_u32(p + 1); w2 = ldg_u32(p + 2);
     }
+    constexpr int UNROLL = HUSL_EDIT_UNROLL;
+#pragma unroll UNROLL
     for (; tile < n_tiles; tile += nw) {
         uint32_t n0 = 0, n1 = 0, n2 = 0;
         if (tile + nw < n_tiles) {

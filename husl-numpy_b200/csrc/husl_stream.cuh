@@ -60,6 +60,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 // L2 eviction-priority policies for the bulk copies (A/B knobs, see nphusl_cuda_api.cu)
+#ifndef HUSL_INVCP_UNROLL
+#define HUSL_INVCP_UNROLL 1    // tile loop of k_inv_cp unrolled by this factor (A/B knob)
+#endif
 #ifndef HUSL_FWD_ST_HINT
 #define HUSL_FWD_ST_HINT 0      // 0 none | 1 evict_first | 2 evict_last | 3 no_allocate-like (evict_first, fraction 1)
 #endif
@@ -343,6 +346,8 @@ k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_t
         cp_async_commit();
     }
     int st = 0;
+    constexpr int UNROLL = HUSL_INVCP_UNROLL;
+#pragma unroll UNROLL
     for (long long tile = first; tile < n_tiles; tile += nw) {
         cp_async_wait<IST - 1>();
         __syncwarp();
