@@ -16,6 +16,10 @@
 #include "husl_strided.cuh"
 #include "husl_nv12.cuh"
 
+#ifndef HUSL_ROWS_UNROLL
+#define HUSL_ROWS_UNROLL 1     // row loop of k_rows_fwd (HUSL output) unrolled by this factor (A/B knob)
+#endif
+
 namespace husl {
 
 // The walk: slot -> (segment column, first row); rows are numbered through all frames.  Only the
@@ -92,6 +96,8 @@ k_rows_fwd(const View2 in, const View2 out) {
             }
         };
         fetch(pos, w0, w1, w2, w3);
+        constexpr int UNROLL = HUE ? 1 : HUSL_ROWS_UNROLL;
+#pragma unroll UNROLL
         for (; pos.in(w);) {
             const RowPos nxt = pos.next(w);
             uint32_t n0, n1, n2, n3;

@@ -11,7 +11,7 @@ from nphusl import _cuda
 
 case, paths = sys.argv[1], sys.argv[2:]
 NAMES = ("nphusl_cuda_rgb_edit_rgb", "nphusl_cuda_rgb_planes_edit", "nphusl_cuda_rgb_to_hue", "nphusl_cuda_rgb_to_husl",
-         "nphusl_cuda_husl_to_rgb")
+         "nphusl_cuda_husl_to_rgb", "nphusl_cuda_nv12_to_husl", "nphusl_cuda_rgb_to_husl_strided")
 
 
 def load(path):
@@ -33,6 +33,12 @@ hue32 = torch.empty(shape[:-1], dtype=torch.float32, device="cuda")
 e_arc = _cuda.Edit(hue=(250, 290), invert=True, l=(0.5, 0))
 e_l = _cuda.Edit(l=(0.5, 0))
 libs[0].nphusl_cuda_rgb_to_husl(rgb.data_ptr(), 0, 1, 3, h32.data_ptr(), 1, 1, n, 0, 0, None)
+ysurf = torch.randint(0, 256, (8 * 2160, 3840), dtype=torch.uint8, device="cuda", generator=g)
+uvsurf = torch.randint(0, 256, (8 * 1080, 3840), dtype=torch.uint8, device="cuda", generator=g)
+nv = _cuda.Nv12(ysurf.data_ptr(), uvsurf.data_ptr(), 3840, 3840, 3840, 8 * 2160, 1, 0)
+# crop [:, 100:2060, 200:3640] of the batch -> contiguous float32 HUSL
+crop_in = _cuda.View(rgb.data_ptr() + (100 * 3840 + 200) * 3, 0, 8, 1960, 3440, 2160 * 3840 * 3, 3840 * 3, 3, 1)
+crop_out = _cuda.View(h32.data_ptr(), 1, 8, 1960, 3440, 1960 * 3440 * 12, 3440 * 12, 12, 4)
 
 
 def call(lib):
@@ -49,6 +55,10 @@ def call(lib):
         rc = lib.nphusl_cuda_rgb_to_husl(rgb.data_ptr(), 0, 1, 3, h32.data_ptr(), 1, 1, n, 0, 0, None)
     elif case == "inv32":
         rc = lib.nphusl_cuda_husl_to_rgb(h32.data_ptr(), 1, 1, back.data_ptr(), 0, 1, n, 0, None)
+    elif case == "nv12_f32":
+        rc = lib.nphusl_cuda_nv12_to_husl(ctypes.byref(nv), h32.data_ptr(), 1, 0, 0, None)
+    elif case == "crop_fwd32":
+        rc = lib.nphusl_cuda_rgb_to_husl_strided(ctypes.byref(crop_in), ctypes.byref(crop_out), 0, 0, None)
     else:
         raise SystemExit("unknown case")
     assert rc == 0
