@@ -11,7 +11,8 @@ from nphusl import _cuda
 
 case, paths = sys.argv[1], sys.argv[2:]
 NAMES = ("nphusl_cuda_rgb_edit_rgb", "nphusl_cuda_rgb_planes_edit", "nphusl_cuda_rgb_to_hue", "nphusl_cuda_rgb_to_husl",
-         "nphusl_cuda_husl_to_rgb", "nphusl_cuda_nv12_to_husl", "nphusl_cuda_rgb_to_husl_strided")
+         "nphusl_cuda_husl_to_rgb", "nphusl_cuda_nv12_to_husl", "nphusl_cuda_rgb_to_husl_strided",
+         "nphusl_cuda_rgb_to_husl_planar", "nphusl_cuda_rgb_planes_to_husl_planes", "nphusl_cuda_nv12_edit_rgb")
 
 
 def load(path):
@@ -55,6 +56,14 @@ def call(lib):
         rc = lib.nphusl_cuda_rgb_to_husl(rgb.data_ptr(), 0, 1, 3, h32.data_ptr(), 1, 1, n, 0, 0, None)
     elif case == "inv32":
         rc = lib.nphusl_cuda_husl_to_rgb(h32.data_ptr(), 1, 1, back.data_ptr(), 0, 1, n, 0, None)
+    elif case == "planar_fwd32":
+        p = h32.data_ptr()
+        rc = lib.nphusl_cuda_rgb_to_husl_planar(rgb.data_ptr(), p, p + 4 * n, p + 8 * n, 1, n, 0, None)
+    elif case == "chw_fwd32":
+        p, q = h32.data_ptr(), rgb.data_ptr()
+        rc = lib.nphusl_cuda_rgb_planes_to_husl_planes(q, q + n, q + 2 * n, p, p + 4 * n, p + 8 * n, 1, n, 0, None)
+    elif case == "nv12_edit":
+        rc = lib.nphusl_cuda_nv12_edit_rgb(ctypes.byref(nv), ctypes.byref(e_arc), back.data_ptr(), 0, None)
     elif case == "nv12_f32":
         rc = lib.nphusl_cuda_nv12_to_husl(ctypes.byref(nv), h32.data_ptr(), 1, 0, 0, None)
     elif case == "crop_fwd32":
