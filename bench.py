@@ -71,8 +71,8 @@ def config(args, n_gpus, frames):
             "l2": "inputs larger than L2: %.0f MB read+written per kernel launch vs 126 MB L2"
                   % (frames * FRAME_PX * (3 + 3 * np.dtype(args.husl_dtype).itemsize) / 1e6),
             "precision": "float32 arithmetic on hi+lo float pairs, HUSL stored as %s (the reference's dtype is float64); "
-                         "all 2^24 colours within 6.6e-5 of the reference float64 path (north_star bar: 1e-3), "
-                         "uint8 round trip exact -- checked on every run (the bench refuses to report otherwise)" % args.husl_dtype,
+                         "all 2^24 colours within 6.6e-5 of the reference float64 path (tests/test_cuda_parity.py; north_star "
+                         "bar: 1e-3); the exact uint8 round trip of the batch is checked on every run" % args.husl_dtype,
             "parallelism": "frames sharded over %d GPU(s), one process per GPU, no collective" % n_gpus}
 
 
