@@ -12,8 +12,12 @@ from contextlib import contextmanager
 
 from . import nphusl as _api
 
-# preference order of enable_best_optimized(): first backend that has the function wins
+# every switchable backend, in the reference's preference order with CUDA in front
 ORDER = ("cuda", "simd", "cython", "numexpr", "numpy")
+# enable_best_optimized(): first backend that has the function wins.  NumPy is NOT in this list: the
+# reference falls back to it silently (__init__.py:45-50); here a missing GPU must be loud, so the
+# slow CPU path only ever runs when the caller asked for it by name.
+BEST_ORDER = ("cuda", "simd", "cython", "numexpr")
 TABLES = {"cuda": _api.CUDA, "simd": _api.SIMD, "cython": _api.CYTHON,
           "numexpr": _api.NUMEXPR, "numpy": _api.NUMPY}
 
@@ -30,7 +34,7 @@ class Switchboard:
 
     def best(self):
         for name in _api.BACKEND_NAMES:
-            fn = next((TABLES[b][name] for b in ORDER if TABLES[b].get(name)), None)
+            fn = next((TABLES[b][name] for b in BEST_ORDER if TABLES[b].get(name)), None)
             bind(name, fn or _api._unbound(name), self.mirror)
 
     def enable(self, backend):

@@ -9,14 +9,24 @@ names ``_rgb_to_husl`` / ``_husl_to_rgb`` / ``_rgb_to_hue`` -- so
 (``nphusl/__init__.py:45-88``).
 
 What differs: the registry has a fifth dictionary,
-``CUDA``, filled from ``nphusl/_cuda.py`` and preferred over everything else;
-this repository ships NO CPU implementation of the path (the reference's
-NumPy / NumExpr / Cython / SIMD modules are not part of it), so the other four
-dictionaries are only filled when such a module is registered from outside
-(``register_backend``).  With no backend bound the public functions raise
-``RuntimeError`` -- they never compute on the CPU behind the caller's back.
+``CUDA``, filled from ``nphusl/_cuda.py`` and preferred over everything else.
+``NUMPY`` is filled from ``nphusl/_numpy.py`` (a from-scratch float64 NumPy
+backend, the one ``enable_numpy()`` / ``back_to_std=True`` select, and whose
+step functions -- ``_to_light``, ``_max_lh_chroma``, ``_rgb_to_lch`` ... -- are
+importable from this module like in the reference); the NumExpr / Cython /
+SIMD dictionaries are only filled when such a module is registered from outside
+(``register_backend``).  The NumPy backend is never chosen implicitly for the
+public conversions: ``enable_best_optimized()`` binds CUDA or nothing, and with
+nothing bound the public functions raise ``RuntimeError`` -- they never compute
+on the CPU behind the caller's back.
 """
 from . import transform
+from . import _numpy
+# step functions of the NumPy chain, under the reference's names (nphusl.py:104-392)
+from ._numpy import (_lch_to_husl, _max_lh_chroma, _bounds, _ray_length, _luv_to_lch, _xyz_to_luv,   # noqa: F401
+                     _to_light, _to_linear, _dot_product, _rgb_to_lch, _rgb_to_xyz, _lch_to_rgb,
+                     _xyz_to_rgb, _lch_to_luv, _from_linear, _husl_to_lch, _luv_to_xyz, _from_light,
+                     _channel, L_MAX, L_MIN)
 
 __all__ = ["to_husl", "to_rgb", "to_hue", "edit", "CUDA", "SIMD", "CYTHON", "NUMEXPR", "NUMPY",
            "register_backend", "BACKEND_NAMES"]
@@ -28,14 +38,15 @@ CUDA = {}      # nphusl/_cuda.py -> libnphusl_cuda.so (sm_100a kernels)
 SIMD = {}      # reference: nphusl/_simd_opt.pyx (not shipped here)
 CYTHON = {}    # reference: nphusl/_cython_opt.pyx (not shipped here)
 NUMEXPR = {}   # reference: nphusl/_numexpr_opt.py (not shipped here)
-NUMPY = {}     # reference: nphusl/nphusl.py:104-392 (not shipped here)
+NUMPY = {name: getattr(_numpy, name) for name in _numpy.REGISTERED}   # nphusl/_numpy.py (reference: nphusl.py:104-392)
 
 
 def _unbound(name):
     def missing(*args, **kwargs):
         raise RuntimeError(
-            "nphusl: no backend is bound for {}: libnphusl_cuda.so is not built or no GPU is "
-            "visible, and this package has no CPU implementation (see nphusl._cuda.load())".format(name))
+            "nphusl: no backend is bound for {}: libnphusl_cuda.so is not built or no GPU is visible "
+            "(see nphusl._cuda.load()).  The CUDA backend has no CPU fallback; the NumPy backend is only "
+            "used when selected explicitly with nphusl.enable_numpy() / nphusl.numpy_enabled()".format(name))
     missing.__name__ = name
     missing.unbound = True
     return missing

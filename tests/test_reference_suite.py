@@ -1,5 +1,7 @@
 """The reference's API-level tests (tests/test.py) replayed against the CUDA
-backend, with the reference's OWN acceptance criteria (`_diff`, `_diff_husl`:
+backend (``[cuda]``, needs the GPU) and the NumPy backend (``[numpy]``, runs on CPU) --
+the counterpart of the reference's ``__with_cuda`` / ``__with_numpy`` test clones
+(tests/test.py:33-67) -- with the reference's OWN acceptance criteria (`_diff`, `_diff_husl`:
 both HUSL arrays converted back with to_rgb must agree within 2 levels, else
 |dH| <= 0.3, |dS| <= 2.0, |dL| <= 0.1; tests/test.py:697-727) and the float64
 oracle standing in for the third-party `husl` package those tests import.
@@ -11,15 +13,17 @@ import pytest
 
 import oracle as orc
 
-pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def nph():
+@pytest.fixture(scope="module", params=[pytest.param("cuda", marks=pytest.mark.gpu), "numpy"])
+def nph(request):
     import nphusl
-    from nphusl import _cuda
-    assert _cuda.available()
-    nphusl.enable_cuda()
+    if request.param == "cuda":
+        from nphusl import _cuda
+        assert _cuda.available()
+        nphusl.enable_cuda()
+    else:
+        nphusl.enable_numpy()
     yield nphusl
     nphusl.enable_best_optimized()
 
