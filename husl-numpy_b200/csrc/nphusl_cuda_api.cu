@@ -89,6 +89,7 @@ size_t lut_esize(int type) { return type == NPHUSL_LUT_U16 ? 2 : type == NPHUSL_
 // download-type call (device -> host result) and a host -> host call never
 // queue behind one another: H2D of one call overlaps D2H of another.
 struct Staging {
+    std::mutex mu;                       // one host-streamed call at a time per set (NOT DevCtx::mu: device-pointer calls never wait here)
     cudaStream_t st[NSLOT] = {};
     cudaEvent_t done[NSLOT] = {};
     void *din[NSLOT] = {}, *dout[NSLOT] = {};
@@ -566,7 +567,6 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
     if (n <= 0) return NPHUSL_OK;
     if (src_loc == NPHUSL_DEVICE && dst_loc == NPHUSL_DEVICE) return kernel(src, dst, n, user);
 
-    std::lock_guard<std::mutex> lk(c.mu);   // staging buffers are per device
     size_t chunk = g_chunk_px.load();
     if (!chunk) {
         // default: about 8 chunks per call so copies and kernels of neighbouring
@@ -581,6 +581,7 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
     const bool src_pin = src_host && is_pinned(src), dst_pin = dst_host && is_pinned(dst);
     const bool all_pinned = (!src_host || src_pin) && (!dst_host || dst_pin);
     Staging &g = c.set[src_host && dst_host ? SET_BOTH : (src_host ? SET_UP : SET_DOWN)];
+    std::lock_guard<std::mutex> lk(g.mu);   // the set's staging buffers and slot streams
     int rc;
     if (src_host && (rc = ensure(g.din, &g.din_cap, chunk * in_px, false, NSLOT))) return rc;
     if (dst_host && (rc = ensure(g.dout, &g.dout_cap, chunk * out_px, false, NSLOT))) return rc;
@@ -593,9 +594,10 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
 
     struct Pending { char *dst; size_t bytes; bool live; } pend[NSLOT] = {};
     long long off = 0, nchunks = 0;
-    for (long long ci = 0; off < n; ++ci, off += chunk, ++nchunks) {
-        const int s = (int)(ci % NSLOT);
-        const long long npx = (n - off < (long long)chunk) ? n - off : (long long)chunk;
+    // one chunk: refill slot s, convert, start the download.  Any failure leaves the loop; the copies
+    // already enqueued from / into the caller's buffers are drained below before the error is returned
+    // (the caller may drop those buffers as soon as it sees the status).
+    auto submit = [&](long long ci, int s, long long npx) -> int {
         // slot reuse: device-side buffers are protected by the slot stream's own
         // order; the pinned bounce buffers are touched by the HOST, so a pageable
         // call must wait for the slot's previous chunk before refilling it
@@ -613,7 +615,8 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
             in_dev = (const char *)src + off * in_px;
         }
         void *out_dev = dst_host ? g.dout[s] : (void *)((char *)dst + off * out_px);
-        if ((rc = kernel(in_dev, out_dev, npx, g.st[s]))) return rc;
+        int krc = kernel(in_dev, out_dev, npx, g.st[s]);
+        if (krc) return krc;
         if (dst_host) {
             char *hp = (char *)dst + off * out_px;
             if (dst_pin) {
@@ -624,6 +627,16 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
             }
         }
         CU(cudaEventRecord(g.done[s], g.st[s]));
+        return NPHUSL_OK;
+    };
+    for (long long ci = 0; off < n; ++ci, off += chunk, ++nchunks) {
+        const long long npx = (n - off < (long long)chunk) ? n - off : (long long)chunk;
+        if ((rc = submit(ci, (int)(ci % NSLOT), npx))) {
+            const std::string why = t_err;
+            for (int s = 0; s < NSLOT; ++s) cudaStreamSynchronize(g.st[s]);
+            cudaGetLastError();
+            return fail(rc, why);
+        }
     }
     const int used = nchunks < NSLOT ? (int)nchunks : NSLOT;
     if (all_pinned && t_host_async) {
@@ -1582,6 +1595,43 @@ int nphusl_cuda_stream_synchronize(void *stream, int device) {
     DeviceGuard guard;
     CU(cudaSetDevice(device));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_event_record(void **event, void *stream, int device) {
+    DeviceGuard guard;
+    if (!event) return fail(NPHUSL_ERR_ARG, "event_record: null out pointer");
+    CU(cudaSetDevice(device));
+    if (!*event) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        *event = (void *)e;
+    }
+    CU(cudaEventRecord((cudaEvent_t)*event, (cudaStream_t)stream));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_event_query(void *event, int *done) {
+    if (!event || !done) return fail(NPHUSL_ERR_ARG, "event_query: null argument");
+    const cudaError_t e = cudaEventQuery((cudaEvent_t)event);
+    if (e == cudaSuccess) { *done = 1; return NPHUSL_OK; }
+    if (e == cudaErrorNotReady) { cudaGetLastError(); *done = 0; return NPHUSL_OK; }
+    return fail(NPHUSL_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+}
+
+int nphusl_cuda_stream_wait_event(void *stream, void *event, int device) {
+    DeviceGuard guard;
+    if (!event) return fail(NPHUSL_ERR_ARG, "stream_wait_event: null event");
+    CU(cudaSetDevice(device));
+    CU(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_event_destroy(void *event, int device) {
+    DeviceGuard guard;
+    if (!event) return NPHUSL_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaEventDestroy((cudaEvent_t)event));
     return NPHUSL_OK;
 }
 

@@ -103,6 +103,10 @@ SIGNATURES = {
     "nphusl_cuda_stream_destroy": (_i, [_vp, _i]),
     "nphusl_cuda_stream_synchronize": (_i, [_vp, _i]),
     "nphusl_cuda_device_synchronize": (_i, [_i]),
+    "nphusl_cuda_event_record": (_i, [ctypes.POINTER(_vp), _vp, _i]),
+    "nphusl_cuda_event_query": (_i, [_vp, _ip]),
+    "nphusl_cuda_stream_wait_event": (_i, [_vp, _vp, _i]),
+    "nphusl_cuda_event_destroy": (_i, [_vp, _i]),
     "nphusl_cuda_pointer_info": (_i, [_vp, _ip, _ip, _ip]),
     "nphusl_cuda_device_info": (_i, [_i, ctypes.c_char_p, _sz, _ip, ctypes.POINTER(_sz)]),
 }
@@ -202,6 +206,17 @@ def _stream_ptr(stream):
     return ctypes.c_void_p(int(stream))
 
 
+def _stream_key(stream) -> int:
+    """The stream's handle as an int (0 = the NULL / legacy default stream)."""
+    if stream is None:
+        return 0
+    if hasattr(stream, "cuda_stream"):
+        return int(stream.cuda_stream)
+    if hasattr(stream, "ptr"):
+        return int(stream.ptr or 0)
+    return int(stream)
+
+
 class Stream:
     """A non-blocking CUDA stream owned through the C ABI."""
 
@@ -230,16 +245,27 @@ class _DevicePool:
     """Recycles device blocks of dropped ``DeviceArray``s.  cudaMalloc + cudaFree cost 0.6 ms per
     result (cudaFree also synchronises the device), sixty times the conversion of a 1080p frame;
     with the pool a call that returns a new DeviceArray costs what a call with ``out=`` costs.
-    A block is handed out again in stream order of the NEXT call that needs one: code that drops
-    a result while a kernel on a *different* non-blocking stream still reads it must keep the
-    reference until that stream is synchronised (the contract of torch's caching allocator)."""
+
+    Reuse is ordered by streams, not by luck.  Every ``DeviceArray`` remembers the streams the
+    library used it on.  A block released after use on ONE stream goes to that stream's free list
+    and is handed out again only to a call on the same stream (stream order makes that safe), or to
+    a call on another stream after that stream has been made to wait on an event recorded behind
+    the block's last use.  A block that was used on SEVERAL streams is parked with one event per
+    stream and becomes reusable (by any stream) when all of them have completed.  Work the library
+    cannot see -- a block exported through ``__cuda_array_interface__`` and used by other code on
+    its own stream -- must be announced with ``DeviceArray.record_stream(stream)`` before the
+    array is dropped."""
+
+    ANY = -1                             # free-list key of blocks that are idle on every stream
 
     def __init__(self):
         self.max_cached = int(os.environ.get("NPHUSL_DEVICE_CACHE_MB", "16384")) << 20
-        self.free = {}                   # (device, cap) -> [ptr, ...]
+        self.free = {}                   # (device, cap) -> {stream_key: [ptr, ...]}
+        self.parked = []                 # [ptr, cap, device, [event, ...]]: in use on several streams when dropped
+        self.events = {}                 # device -> [event, ...] spare events
         self.cached = 0
-        self.lock = threading.Lock()
-        self.hits = self.misses = 0
+        self.lock = threading.RLock()    # re-entrant: a GC pass inside alloc() may finalise a DeviceArray -> release()
+        self.hits = self.misses = self.waits = 0
 
     @staticmethod
     def size_class(nbytes):
@@ -249,14 +275,59 @@ class _DevicePool:
             return 1 << (nbytes - 1).bit_length()
         return (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20)
 
-    def alloc(self, nbytes, device):
+    def _event(self, device, stream_key):
+        """-> an event recorded now on `stream_key` (0 when that stream no longer takes work)"""
+        spare = self.events.get(device)
+        ev = ctypes.c_void_p(spare.pop() if spare else None)
+        if load().nphusl_cuda_event_record(ctypes.byref(ev), ctypes.c_void_p(stream_key or None), device):
+            if ev.value:
+                self.events.setdefault(device, []).append(ev.value)
+            return 0
+        return ev.value
+
+    def _reap(self):
+        """parked blocks whose events have all completed become reusable by any stream"""
+        if not self.parked:
+            return
+        lib, done, still = load(), ctypes.c_int(), []
+        for ent in self.parked:
+            ptr, cap, device, evs = ent
+            while evs:
+                if lib.nphusl_cuda_event_query(ctypes.c_void_p(evs[-1]), ctypes.byref(done)) or not done.value:
+                    break
+                self.events.setdefault(device, []).append(evs.pop())
+            if evs:
+                still.append(ent)
+            else:
+                self.free.setdefault((device, cap), {}).setdefault(self.ANY, []).append(ptr)
+        self.parked = still
+
+    def alloc(self, nbytes, device, stream_key=0):
         cap = self.size_class(nbytes)
         with self.lock:
-            lst = self.free.get((device, cap))
-            if lst:
-                self.cached -= cap
-                self.hits += 1
-                return lst.pop(), cap
+            self._reap()
+            by_stream = self.free.get((device, cap))
+            if by_stream:
+                for key in (stream_key, self.ANY):
+                    lst = by_stream.get(key)
+                    if lst:
+                        self.cached -= cap
+                        self.hits += 1
+                        return lst.pop(), cap
+                # a block last used on ANOTHER stream: this stream waits for that stream's tail
+                for key, lst in by_stream.items():
+                    if not lst:
+                        continue
+                    ev = self._event(device, key)
+                    if not ev:
+                        continue                 # that stream is gone; its blocks are reclaimed by trim()
+                    ok = load().nphusl_cuda_stream_wait_event(ctypes.c_void_p(stream_key or None), ctypes.c_void_p(ev), device) == 0
+                    self.events.setdefault(device, []).append(ev)
+                    if ok:
+                        self.cached -= cap
+                        self.hits += 1
+                        self.waits += 1
+                        return lst.pop(), cap
             self.misses += 1
         p = ctypes.c_void_p()
         rc = load().nphusl_cuda_malloc(ctypes.byref(p), cap, device)
@@ -265,23 +336,41 @@ class _DevicePool:
             _check(load().nphusl_cuda_malloc(ctypes.byref(p), cap, device), "malloc")
         return p.value or 0, cap
 
-    def release(self, ptr, cap, device):
+    def release(self, ptr, cap, device, streams=()):
+        """`streams`: keys of the streams the block was used on"""
         with self.lock:
-            if self.cached + cap <= self.max_cached:
-                self.free.setdefault((device, cap), []).append(ptr)
-                self.cached += cap
-                return
+            if self.cached + cap <= self.max_cached and _lib is not None:
+                keys = list(streams)
+                if len(keys) <= 1:
+                    key = keys[0] if keys else self.ANY
+                    self.free.setdefault((device, cap), {}).setdefault(key, []).append(ptr)
+                    self.cached += cap
+                    return
+                evs = [self._event(device, k) for k in keys]
+                if all(evs):
+                    self.parked.append([ptr, cap, device, evs])
+                    self.cached += cap
+                    return
+                self.events.setdefault(device, []).extend(e for e in evs if e)
         if _lib is not None:
-            _lib.nphusl_cuda_free(ctypes.c_void_p(ptr), device)
+            _lib.nphusl_cuda_free(ctypes.c_void_p(ptr), device)      # cudaFree waits for the device: always safe
 
     def trim(self):
         with self.lock:
-            blocks = [(p, dev) for (dev, _), lst in self.free.items() for p in lst]
+            blocks = [(p, dev) for (dev, _), by in self.free.items() for lst in by.values() for p in lst]
+            blocks += [(ent[0], ent[2]) for ent in self.parked]
+            events = [(e, ent[2]) for ent in self.parked for e in ent[3]]
+            events += [(e, dev) for dev, lst in self.events.items() for e in lst]
             self.free.clear()
+            self.parked = []
+            self.events.clear()
             self.cached = 0
         for p, dev in blocks:
             if _lib is not None:
                 _lib.nphusl_cuda_free(ctypes.c_void_p(p), dev)
+        for e, dev in events:
+            if _lib is not None:
+                _lib.nphusl_cuda_event_destroy(ctypes.c_void_p(e), dev)
 
 
 _device_pool = _DevicePool()
@@ -294,7 +383,8 @@ def empty_cache():
 
 
 def device_pool_stats():
-    return {"cached_bytes": _device_pool.cached, "hits": _device_pool.hits, "misses": _device_pool.misses}
+    return {"cached_bytes": _device_pool.cached, "hits": _device_pool.hits, "misses": _device_pool.misses,
+            "cross_stream_waits": _device_pool.waits, "parked": len(_device_pool.parked)}
 
 
 class DeviceArray:
@@ -302,14 +392,27 @@ class DeviceArray:
     pool).  Speaks ``__cuda_array_interface__`` v3, so ``torch.as_tensor(a, device="cuda")``
     wraps it without a copy."""
 
-    def __init__(self, shape, dtype, device=None):
+    def __init__(self, shape, dtype, device=None, stream=None):
+        """``stream``: the stream the array will first be used on (its block may have been last
+        used there, or is made to wait for its previous user, see ``_DevicePool``)."""
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
         self.device = _default_device if device is None else device
         self.size = _prod(self.shape) if self.shape else 1
         self.nbytes = self.size * self.dtype.itemsize
-        self.ptr, self._cap = _device_pool.alloc(self.nbytes, self.device)
+        key = _stream_key(stream)
+        self.ptr, self._cap = _device_pool.alloc(self.nbytes, self.device, key)
+        self._streams = {key}
         self._owner = True
+
+    def record_stream(self, stream):
+        """Tell the pool the array is (also) in use on ``stream`` -- for work enqueued by OTHER code
+        (a torch kernel on ``torch.as_tensor(a, device="cuda")``, say); the library's own calls
+        record their stream themselves.  The block is not reused before that work has finished."""
+        root = self
+        while getattr(root, "_base", None) is not None:
+            root = root._base
+        root._streams.add(_stream_key(stream))
 
     @property
     def ndim(self):
@@ -323,7 +426,7 @@ class DeviceArray:
     @classmethod
     def from_host(cls, arr, device=None, stream=None):
         arr = np.ascontiguousarray(arr)
-        d = cls(arr.shape, arr.dtype, device)
+        d = cls(arr.shape, arr.dtype, device, stream)
         _check(load().nphusl_cuda_memcpy(d.ptr, arr.ctypes.data, d.nbytes, 1, d.device, _stream_ptr(stream)), "memcpy h2d")
         return d
 
@@ -331,6 +434,7 @@ class DeviceArray:
         if out is None:
             out = np.empty(self.shape, self.dtype)
         assert out.nbytes == self.nbytes and out.flags.c_contiguous
+        self.record_stream(stream)
         _check(load().nphusl_cuda_memcpy(out.ctypes.data, self.ptr, self.nbytes, 2, self.device, _stream_ptr(stream)), "memcpy d2h")
         return out
 
@@ -343,6 +447,7 @@ class DeviceArray:
         v.ptr = self.ptr + byte_offset
         v._owner = False
         v._base = self                      # keeps the allocation alive
+        v._streams = None                   # stream use is recorded on the owning array
         return v
 
     def reshape(self, *shape):
@@ -381,7 +486,7 @@ class DeviceArray:
 
     def free(self):
         if getattr(self, "_owner", False) and self.ptr:
-            _device_pool.release(self.ptr, self._cap, self.device)
+            _device_pool.release(self.ptr, self._cap, self.device, self._streams)
             self._owner = False
         self.ptr = 0
 
@@ -392,27 +497,40 @@ class DeviceArray:
             pass
 
 
-class PinnedArray(np.ndarray):
-    """numpy view over page-locked host memory (``pinned_empty``)."""
-    _pin_ptr = None
+class _PinnedOwner:
+    """Owner of one ``cudaHostAlloc`` block.  Arrays made by ``pinned_empty`` are plain
+    ``numpy.ndarray``s whose ``.base`` chain ends here, so EVERY view derived from them --
+    ``np.asarray(p)``, ``p.view(...)``, slices, ``torch.from_numpy(p)`` -- keeps the block
+    page-locked and allocated (an ndarray subclass with ``__del__`` does not: numpy collapses
+    ``.base`` past the subclass instance)."""
+    __slots__ = ("ptr", "shape", "typestr")
+
+    def __init__(self, ptr, shape, dtype):
+        self.ptr, self.shape, self.typestr = ptr, tuple(shape), np.dtype(dtype).str
+
+    @property
+    def __array_interface__(self):
+        return {"shape": self.shape, "typestr": self.typestr, "data": (self.ptr, False), "version": 3}
 
     def __del__(self):
-        p = getattr(self, "_pin_ptr", None)
-        if p and _lib is not None:
-            _lib.nphusl_cuda_host_free(ctypes.c_void_p(p))
+        if self.ptr and _lib is not None:
+            try:
+                _lib.nphusl_cuda_host_free(ctypes.c_void_p(self.ptr))
+            except Exception:
+                pass
+            self.ptr = 0
 
 
 def pinned_empty(shape, dtype):
-    """Page-locked host array: host-pointer calls then DMA straight from/into
-    it instead of staging through the library's own pinned slots."""
+    """Page-locked host array (a plain ``numpy.ndarray``): host-pointer calls then DMA straight
+    from / into it instead of staging through the library's own pinned slots.  The block is freed
+    when the last array or view referring to it is gone."""
     dtype = np.dtype(dtype)
+    shape = tuple(int(x) for x in shape) if hasattr(shape, "__iter__") else (int(shape),)
     n = _prod(shape) * dtype.itemsize
     p = ctypes.c_void_p()
     _check(load().nphusl_cuda_host_alloc(ctypes.byref(p), n), "host_alloc")
-    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=_prod(shape)).reshape(shape).view(PinnedArray)
-    arr._pin_ptr = p.value
-    return arr
+    return np.asarray(_PinnedOwner(p.value, shape, dtype))
 
 
 # ---------------------------------------------------------------------------
@@ -458,7 +576,7 @@ class _PinnedPool:
         self.free = {}                   # cap -> [ptr, ...]
         self.cached = 0
         self.outstanding = 0
-        self.lock = threading.Lock()
+        self.lock = threading.RLock()    # re-entrant: see _DevicePool.lock
         self.hits = self.misses = 0
 
     def empty(self, shape, dtype):
@@ -665,8 +783,9 @@ def _describe_out(out, shape, dtype, allowed, what, strided_ok=False):
             raise ValueError("{} must be C-contiguous and writeable".format(what))
         b = _Buf()
         b.ptr, b.shape, b.dtype, b.loc, b.device, b.keep, b.channels = out.ctypes.data, out.shape, out.dtype, HOST, None, out, 3
-    if _prod(b.shape) != _prod(shape):
-        raise ValueError("{} has {} elements, expected shape {}".format(what, _prod(b.shape), tuple(shape)))
+    if tuple(b.shape) != tuple(shape) and [n for n in b.shape if n != 1] != [n for n in shape if n != 1]:
+        # only unit axes may differ (the squeezed single pixel, a batch of one frame)
+        raise ValueError("{} has shape {}, expected {}".format(what, tuple(b.shape), tuple(shape)))
     if b.dtype not in allowed:
         raise ValueError("{} dtype {} unsupported here (allowed: {})".format(what, b.dtype, ", ".join(str(np.dtype(d)) for d in allowed)))
     return b
@@ -681,13 +800,32 @@ def _pick_device(device, *bufs):
     return _default_device
 
 
-def _make_out(src, out, shape, dtype, allowed, device, what, strided_ok=False):
+def _touch(stream, *objs):
+    """Record that the library uses these arrays on ``stream`` (block reuse is ordered by it,
+    see ``_DevicePool``).  Only our own ``DeviceArray``s -- bare, or wrapped by
+    ``transform.GrayDevice`` / ``RgbaDevice`` -- are tracked; torch owns its tensors."""
+    key = None
+    for o in objs:
+        if type(o) is not DeviceArray:
+            o = getattr(o, "base", None)
+            if type(o) is not DeviceArray:
+                continue
+        while o._streams is None:
+            o = o._base
+        if key is None:
+            key = _stream_key(stream)
+        o._streams.add(key)
+
+
+def _make_out(src, out, shape, dtype, allowed, device, what, strided_ok=False, stream=None):
     """-> (_Buf, object to return)"""
     if out is not None:
         b = _describe_out(out, shape, dtype, allowed, what, strided_ok)
+        _touch(stream, out, src.keep)
         return b, out
+    _touch(stream, src.keep)
     if src.loc == DEVICE:
-        d = DeviceArray(shape, dtype, device)
+        d = DeviceArray(shape, dtype, device, stream)
         b = _Buf()
         b.ptr, b.shape, b.dtype, b.loc, b.device, b.keep, b.channels = d.ptr, d.shape, d.dtype, DEVICE, d.device, d, 3
         return b, d
@@ -795,7 +933,7 @@ def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, dev
     if not src.shape or src.shape[-1] != 3:
         raise ValueError("expected (..., 3) RGB, got shape {}".format(src.shape))
     dev = _pick_device(device, src)
-    dst, ret = _make_out(src, out, src.shape, dtype, _FLOATS, dev, "out", True)
+    dst, ret = _make_out(src, out, src.shape, dtype, _FLOATS, dev, "out", True, stream)
     dev = _pick_device(device, src, dst)                  # host input, `out` on another GPU: go where `out` lives
     n = _prod(src.shape[:-1])
     if src.strides is not None or dst.strides is not None:
@@ -820,7 +958,7 @@ def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None, block
         raise ValueError("expected (..., 3) RGB, got shape {}".format(src.shape))
     dev = _pick_device(device, src)
     shape = src.shape[:-1]
-    dst, ret = _make_out(src, out, shape, dtype, _FLOATS, dev, "out", True)
+    dst, ret = _make_out(src, out, shape, dtype, _FLOATS, dev, "out", True, stream)
     dev = _pick_device(device, src, dst)
     n = _prod(shape)
     if src.strides is not None or dst.strides is not None:
@@ -853,7 +991,7 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
     if not src.shape or src.shape[-1] != 3:
         raise ValueError("expected (..., 3) HUSL, got shape {}".format(src.shape))
     dev = _pick_device(device, src)
-    dst, ret = _make_out(src, out, src.shape, dtype, _ANY, dev, "out", True)
+    dst, ret = _make_out(src, out, src.shape, dtype, _ANY, dev, "out", True, stream)
     dev = _pick_device(device, src, dst)
     n = _prod(src.shape[:-1])
     if src.strides is not None or dst.strides is not None:
@@ -909,9 +1047,10 @@ def rgb_to_husl_planar(rgb, out=None, dtype=np.float32, stream=None, device=None
         dst = _describe_out(out, shape, dtype, _FLOATS, "out")
         ret = out
     else:
-        d = DeviceArray(shape, np.dtype(dtype if out is None else out.dtype), dev)
+        d = DeviceArray(shape, np.dtype(dtype if out is None else out.dtype), dev, stream)
         dst = _describe_device(d, "out")
         ret = d
+    _touch(stream, src.keep, ret)
     plane = n * dst.dtype.itemsize
     if channels_first:
         _check(lib.nphusl_cuda_rgb_planes_to_husl_planes(src.ptr, src.ptr + n, src.ptr + 2 * n,
@@ -947,9 +1086,10 @@ def husl_planar_to_rgb(hsl, out=None, stream=None, device=None, channels_first=F
         dst = _describe_out(out, shape, np.uint8, (np.dtype(np.uint8),), "out")
         ret = out
     else:
-        d = DeviceArray(shape, np.uint8, dev)
+        d = DeviceArray(shape, np.uint8, dev, stream)
         dst = _describe_device(d, "out")
         ret = d
+    _touch(stream, src.keep, ret)
     plane = n * src.dtype.itemsize
     if channels_first:
         _check(lib.nphusl_cuda_husl_planes_to_rgb_planes(src.ptr, src.ptr + plane, src.ptr + 2 * plane, _DT[src.dtype],
@@ -1004,7 +1144,7 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
         if src.dtype != np.uint8 or not src.shape or src.shape[0] != 3:
             raise ValueError("channels_first edit takes uint8 (3, ...) planes, got {} {}".format(src.dtype, src.shape))
         dev = _pick_device(device, src)
-        dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out")
+        dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out", False, stream)
         if dst.loc != DEVICE:
             raise ValueError("channels_first edit writes device arrays")
         n = _prod(src.shape[1:])
@@ -1015,7 +1155,7 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
     if src.dtype != np.uint8 or src.channels != 3 or not src.shape or src.shape[-1] != 3:
         raise ValueError("edit_rgb takes uint8 RGB (..., 3), got {} {}".format(src.dtype, src.shape))
     dev = _pick_device(device, src)
-    dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out", True)
+    dst, ret = _make_out(src, out, src.shape, np.uint8, (np.dtype(np.uint8),), dev, "out", True, stream)
     dev = _pick_device(device, src, dst)
     n = _prod(src.shape[:-1])
     if src.strides is not None or dst.strides is not None:
@@ -1087,13 +1227,15 @@ def _nv12_surface(y, uv, matrix, full_range):
     return Nv12(yp, up, ypitch, upitch, w, h, MATRICES[matrix], int(bool(full_range))), (h, w), dev, (keep, keep2)
 
 
-def _nv12_out(out, shape, dtype, allowed, dev):
+def _nv12_out(out, shape, dtype, allowed, dev, stream, keep):
+    _touch(stream, *keep)
     if out is None:
-        d = DeviceArray(shape, dtype, dev)
+        d = DeviceArray(shape, dtype, dev, stream)
         return d.ptr, d.dtype, d
     b = _describe_out(out, shape, dtype, allowed, "out")
     if b.loc != DEVICE:
         raise ValueError("out: NV12 conversions write device arrays")
+    _touch(stream, out)
     return b.ptr, b.dtype, out
 
 
@@ -1101,7 +1243,7 @@ def nv12_to_rgb(y, uv=None, out=None, matrix="bt709", full_range=False, stream=N
     """NV12 decoder surface -> uint8 RGB ``(H, W, 3)`` on the device (integer BT.601 / BT.709
     conversion documented in include/nphusl_cuda.h)."""
     src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
-    ptr, _, ret = _nv12_out(out, (h, w, 3), np.uint8, (np.dtype(np.uint8),), dev)
+    ptr, _, ret = _nv12_out(out, (h, w, 3), np.uint8, (np.dtype(np.uint8),), dev, stream, keep)
     _check(load().nphusl_cuda_nv12_to_rgb(ctypes.byref(src), ptr, dev, _stream_ptr(stream)), "nv12_to_rgb")
     return ret
 
@@ -1112,7 +1254,7 @@ def nv12_to_husl(y, uv=None, out=None, dtype=np.float32, matrix="bt709", full_ra
     ``to_husl(nv12_to_rgb(...))`` bit for bit."""
     src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
     shape = (h, w) if hue_only else (h, w, 3)
-    ptr, dt, ret = _nv12_out(out, shape, dtype, _FLOATS, dev)
+    ptr, dt, ret = _nv12_out(out, shape, dtype, _FLOATS, dev, stream, keep)
     _check(load().nphusl_cuda_nv12_to_husl(ctypes.byref(src), ptr, _DT[dt], int(bool(hue_only)), dev, _stream_ptr(stream)),
            "nv12_to_husl")
     return ret
@@ -1129,19 +1271,20 @@ def nv12_edit_rgb(y, uv=None, edit=None, out=None, matrix="bt709", full_range=Fa
     elif edit_args:
         raise TypeError("pass either an Edit or its fields as keywords, not both")
     src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
-    ptr, _, ret = _nv12_out(out, (h, w, 3), np.uint8, (np.dtype(np.uint8),), dev)
+    ptr, _, ret = _nv12_out(out, (h, w, 3), np.uint8, (np.dtype(np.uint8),), dev, stream, keep)
     _check(load().nphusl_cuda_nv12_edit_rgb(ctypes.byref(src), ctypes.byref(edit), ptr, dev, _stream_ptr(stream)), "nv12_edit_rgb")
     return ret
 
 
-def _nv12_dest(h, w, out_y, out_uv, matrix, full_range, dev):
+def _nv12_dest(h, w, out_y, out_uv, matrix, full_range, dev, stream=None):
     """-> (Nv12 descriptor of the destination, (y, uv) arrays to return)"""
     if h % 2 or w % 2:
         raise ValueError("an NV12 destination needs even width and height, got {}x{}".format(w, h))
     if (out_y is None) != (out_uv is None):
         raise ValueError("pass both out_y and out_uv, or neither")
     if out_y is None:
-        out_y, out_uv = DeviceArray((h, w), np.uint8, dev), DeviceArray((h // 2, w), np.uint8, dev)
+        out_y, out_uv = DeviceArray((h, w), np.uint8, dev, stream), DeviceArray((h // 2, w), np.uint8, dev, stream)
+    _touch(stream, out_y, out_uv)
     yp, ys, ypitch, ydev, _ = _plane(out_y, "out_y")
     up, us, upitch, udev, _ = _plane(out_uv, "out_uv")
     if tuple(ys) != (h, w) or us[0] != h // 2 or _prod(us[1:]) != w or ydev != dev or udev != dev:
@@ -1160,7 +1303,8 @@ def rgb_to_nv12(rgb, out_y=None, out_uv=None, matrix="bt709", full_range=False, 
     if src.dtype != np.uint8 or len(src.shape) != 3 or src.shape[-1] != 3:
         raise ValueError("rgb_to_nv12 takes uint8 (H, W, 3), got {} {}".format(src.dtype, src.shape))
     dev = _pick_device(None, src)
-    dst, ret = _nv12_dest(src.shape[0], src.shape[1], out_y, out_uv, matrix, full_range, dev)
+    dst, ret = _nv12_dest(src.shape[0], src.shape[1], out_y, out_uv, matrix, full_range, dev, stream)
+    _touch(stream, src.keep)
     _check(load().nphusl_cuda_rgb_to_nv12(src.ptr, ctypes.byref(dst), dev, _stream_ptr(stream)), "rgb_to_nv12")
     return ret
 
@@ -1175,7 +1319,8 @@ def nv12_edit_nv12(y, uv=None, edit=None, out_y=None, out_uv=None, matrix="bt709
     elif edit_args:
         raise TypeError("pass either an Edit or its fields as keywords, not both")
     src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
-    dst, ret = _nv12_dest(h, w, out_y, out_uv, out_matrix or matrix, full_range if out_full_range is None else out_full_range, dev)
+    dst, ret = _nv12_dest(h, w, out_y, out_uv, out_matrix or matrix, full_range if out_full_range is None else out_full_range, dev, stream)
+    _touch(stream, *keep)
     _check(load().nphusl_cuda_nv12_edit_nv12(ctypes.byref(src), ctypes.byref(edit), ctypes.byref(dst), dev, _stream_ptr(stream)),
            "nv12_edit_nv12")
     return ret

@@ -315,20 +315,22 @@ def reshape_husl_input(fn):
 
 def reshape_rgba_input(fn):
     """4-channel input is premultiplied by its alpha (i.e. composited over
-    black, reference ``transform.py:221-230``) and handed on as float RGB.
-    Integer RGBA keeps the reference's quirk of yielding *float64 values in
-    0..255* (App. D-5); only float RGBA is meaningful end to end."""
+    black, reference ``transform.py:221-230``) and handed on as float RGB in
+    [0, 1].  Integer RGBA becomes ``c/255 * a/255`` -- the value the CUDA
+    kernels compute for a uint8 RGBA device array -- NOT the reference's
+    accidental *float64 values in 0..255* (App. D-5: its ``astype(arr.dtype)``
+    runs after ``arr`` was rebound to the float product, so every backend then
+    reads 0..255 as if it were [0, 1]; only float RGBA is tested there)."""
     @wraps(fn)
     def wrapped(arr, *args, **kwargs):
         if len(arr.shape) in (2, 3) and arr.shape[-1] == 4:
             _alert_rgba("Assumed RGBA with white background")
             if is_device_array(arr):
                 return fn(RgbaDevice(arr), *args, **kwargs)
-            is_int = np.issubdtype(arr.dtype, np.integer)
-            alpha = arr[..., 3] / 255.0 if is_int else arr[..., 3]
-            arr = arr[..., :3] * alpha[..., None]
-            if is_int:
-                arr = np.round(arr).astype(arr.dtype)
+            if np.issubdtype(arr.dtype, np.integer):
+                arr = (arr[..., :3] / 255.0) * (arr[..., 3] / 255.0)[..., None]
+            else:
+                arr = arr[..., :3] * arr[..., 3][..., None]
         return fn(arr, *args, **kwargs)
     return wrapped
 

@@ -288,6 +288,14 @@ int nphusl_cuda_memcpy(void *dst, const void *src, size_t bytes, int kind, int d
 int nphusl_cuda_stream_create(void **stream, int device);
 int nphusl_cuda_stream_destroy(void *stream, int device);
 int nphusl_cuda_stream_synchronize(void *stream, int device);
+/* Events (timing disabled): the host side orders the reuse of device blocks across streams with them.
+ * event_record creates the event when *event == NULL and records it on `stream`; event_query returns
+ * NPHUSL_OK with *done = 1 when everything recorded before it has finished, 0 when not yet;
+ * stream_wait_event makes later work on `stream` wait for the event. */
+int nphusl_cuda_event_record(void **event, void *stream, int device);
+int nphusl_cuda_event_query(void *event, int *done);
+int nphusl_cuda_stream_wait_event(void *stream, void *event, int device);
+int nphusl_cuda_event_destroy(void *event, int device);
 int nphusl_cuda_device_synchronize(int device);
 /* loc_out: NPHUSL_HOST (pageable or pinned; *pinned_out says which) or NPHUSL_DEVICE */
 int nphusl_cuda_pointer_info(const void *ptr, int *loc_out, int *device_out, int *pinned_out);

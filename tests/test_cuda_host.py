@@ -252,3 +252,168 @@ def test_nv12_struct_matches_header_and_surface_description():
         _cuda._nv12_surface(np.zeros((4, 4), np.uint8), None, "bt709", False)             # host planes are refused
     with pytest.raises(ValueError):
         _cuda._nv12_surface(FakeDev((1621, 1920), "|u1", device=0), None, "bt709", False)  # not 3/2 * height rows
+
+
+def _fake_runtime(monkeypatch):
+    """malloc/free standing in for the CUDA allocation calls of the C ABI, plus scriptable events."""
+    import ctypes
+    from nphusl import _cuda
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes = ctypes.c_void_p, [ctypes.c_size_t]
+    libc.free.argtypes = [ctypes.c_void_p]
+
+    class FakeLib:
+        live, host_live = set(), set()
+        events, done, waits, next_event, destroyed = {}, set(), [], [1000], []
+
+        @classmethod
+        def nphusl_cuda_malloc(cls, pp, n, dev):
+            p = libc.malloc(max(n, 64))
+            pp._obj.value = p
+            cls.live.add(p)
+            return 0
+
+        @classmethod
+        def nphusl_cuda_free(cls, p, dev):
+            cls.live.discard(p.value)
+            libc.free(p)
+            return 0
+
+        @classmethod
+        def nphusl_cuda_host_alloc(cls, pp, n):
+            p = libc.malloc(max(n, 64))
+            pp._obj.value = p
+            cls.host_live.add(p)
+            return 0
+
+        @classmethod
+        def nphusl_cuda_host_free(cls, p):
+            cls.host_live.discard(p.value)
+            libc.free(p)
+            return 0
+
+        @classmethod
+        def nphusl_cuda_event_record(cls, pev, stream, dev):
+            if not pev._obj.value:
+                cls.next_event[0] += 1
+                pev._obj.value = cls.next_event[0]
+            cls.events[pev._obj.value] = stream.value or 0
+            cls.done.discard(pev._obj.value)
+            return 0
+
+        @classmethod
+        def nphusl_cuda_event_query(cls, ev, pdone):
+            pdone._obj.value = 1 if ev.value in cls.done else 0
+            return 0
+
+        @classmethod
+        def nphusl_cuda_stream_wait_event(cls, stream, ev, dev):
+            cls.waits.append((stream.value or 0, cls.events[ev.value]))
+            return 0
+
+        @classmethod
+        def nphusl_cuda_event_destroy(cls, ev, dev):
+            cls.destroyed.append(ev.value)
+            return 0
+
+    monkeypatch.setattr(_cuda, "load", lambda: FakeLib)
+    monkeypatch.setattr(_cuda, "_lib", FakeLib)
+    return FakeLib
+
+
+def test_device_pool_orders_block_reuse_by_stream(monkeypatch):
+    """_DevicePool: a dropped block is reused on its own stream by stream order, on another stream only
+    behind an event wait, and a block dropped while in use on several streams only after all of their
+    events completed (free lists keyed by (device, size) alone let stream s2 overwrite a block
+    a kernel on s1 was still reading)."""
+    from nphusl import _cuda
+    fake = _fake_runtime(monkeypatch)
+    pool = _cuda._DevicePool()
+    n = 3 << 20
+    p1, cap = pool.alloc(n, 0, 11)
+    assert pool.misses == 1 and cap == 4 << 20
+    pool.release(p1, cap, 0, {11})
+    p2, _ = pool.alloc(n, 0, 11)                         # same stream: plain reuse, no event traffic
+    assert p2 == p1 and pool.hits == 1 and not fake.waits and not fake.events
+    pool.release(p2, cap, 0, {11})
+    p3, _ = pool.alloc(n, 0, 22)                         # other stream: 22 waits for the tail of 11
+    assert p3 == p1 and fake.waits == [(22, 11)] and pool.waits == 1
+    pool.release(p3, cap, 0, {22, 33})                   # in use on two streams when dropped: parked
+    assert len(pool.parked) == 1 and sorted(fake.events.values())[-2:] == [22, 33]
+    p4, _ = pool.alloc(n, 0, 22)                         # events pending: NOT handed out, not even to 22
+    assert p4 != p1 and pool.misses == 2
+    fake.done.update(fake.events)                        # both streams passed their events
+    p5, _ = pool.alloc(n, 0, 44)
+    assert p5 == p1 and not pool.parked and len(fake.waits) == 1      # idle on every stream: no wait needed
+    pool.release(p4, cap, 0, ())                         # never used by a kernel
+    pool.release(p5, cap, 0, {44})
+    assert pool.cached == 2 * cap
+    # a second device never sees device 0's blocks
+    p6, _ = pool.alloc(n, 1, 44)
+    assert p6 not in (p1, p4) and pool.misses == 3
+    pool.release(p6, cap, 1, {44})
+    pool.trim()
+    assert not fake.live and pool.cached == 0 and sorted(fake.destroyed) == sorted(set(fake.events))
+    # over budget: released straight to the driver
+    pool.max_cached = 0
+    p7, _ = pool.alloc(n, 0, 0)
+    pool.release(p7, cap, 0, {0})
+    assert not fake.live
+
+
+def test_device_array_records_the_streams_it_is_used_on(monkeypatch):
+    from nphusl import _cuda
+    _fake_runtime(monkeypatch)
+    monkeypatch.setattr(_cuda, "_device_pool", _cuda._DevicePool())
+
+    class S:
+        def __init__(self, h):
+            self.cuda_stream = h
+    a = _cuda.DeviceArray((4, 6, 3), np.float32, 0, S(7))
+    assert a._streams == {7}
+    v = a[1:3].reshape(-1, 3)
+    _cuda._touch(S(9), v, np.zeros(3), None)             # views record on the owner; host arrays are ignored
+    assert a._streams == {7, 9}
+    a.record_stream(None)
+    assert a._streams == {0, 7, 9}
+
+    class Wrapper:                                        # transform.GrayDevice / RgbaDevice keep the array in .base
+        base = a
+    _cuda._touch(5, Wrapper())
+    assert a._streams == {0, 5, 7, 9}
+    ptr = a.ptr
+    del v
+    a.free()
+    assert len(_cuda._device_pool.parked) == 1 and _cuda._device_pool.parked[0][0] == ptr
+
+
+def test_pinned_empty_block_outlives_every_view(monkeypatch):
+    """pinned_empty returns a plain ndarray whose .base chain owns the page-locked block: base-class views
+    (np.asarray, .view(np.ndarray), slices) keep it alive (an ndarray subclass with __del__ freed
+    the block while such views -- and in-flight DMA -- still used it)."""
+    import gc
+    from nphusl import _cuda
+    fake = _fake_runtime(monkeypatch)
+    a = _cuda.pinned_empty((64, 5), np.float64)
+    assert type(a) is np.ndarray and a.shape == (64, 5) and a.flags.writeable and a.flags.c_contiguous
+    assert len(fake.host_live) == 1
+    a[...] = 2.5
+    views = [np.asarray(a), a.view(np.ndarray), np.ascontiguousarray(a), a[3:9, 1], a.reshape(-1).view(np.uint8)]
+    del a
+    gc.collect()
+    assert len(fake.host_live) == 1 and all(v.flat[0] in (2.5, 0) for v in views[:4]) and views[0][5, 2] == 2.5
+    while views:
+        views.pop()
+        gc.collect()
+        assert len(fake.host_live) == (1 if views else 0)
+    assert _cuda.pinned_empty(7, np.uint8).shape == (7,)
+
+
+def test_out_must_have_the_result_shape():
+    from nphusl import _cuda
+    ok = _cuda._describe_out(np.empty((1, 4, 5, 3)), (4, 5, 3), np.float64, _cuda._FLOATS, "out")     # unit axes may differ
+    assert ok.shape == (1, 4, 5, 3)
+    _cuda._describe_out(np.empty(3), (1, 3), np.float64, _cuda._FLOATS, "out")                          # the squeezed single pixel
+    for bad in ((3, 20), (60,), (5, 4, 3)):
+        with pytest.raises(ValueError, match="shape"):
+            _cuda._describe_out(np.empty(bad), (4, 5, 3), np.float64, _cuda._FLOATS, "out")

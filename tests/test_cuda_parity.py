@@ -701,10 +701,13 @@ def test_rgba_device_arrays_are_premultiplied_on_load(cu):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         got8 = nphusl.to_husl(torch.from_numpy(u8).cuda()).copy_to_host()
+        host8 = nphusl.to_husl(u8)                                    # host uint8 RGBA: the same values
     ref8 = orc.rgb_to_husl((u8[:, :3] / 255.0) * (u8[:, 3:] / 255.0))
     sat = ref8[:, 1] > 0.1
     assert hue_diff(got8[sat, 0], ref8[sat, 0]).max() < TOL
     assert np.abs(got8[:, 1:] - ref8[:, 1:]).max() < TOL
+    assert hue_diff(host8[sat, 0], got8[sat, 0]).max() < 2e-4
+    assert np.abs(host8[:, 1:] - got8[:, 1:]).max() < 2e-4
 
 
 def test_lut_mode_with_other_table_sizes(cu):
