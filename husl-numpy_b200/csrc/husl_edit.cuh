@@ -1,0 +1,85 @@
+// husl_edit.cuh -- the HUSL-space select + affine edit shared by the fused uint8 kernels
+// (husl_fused.cuh, husl_nv12*.cuh, husl_rows.cuh), by the edit-on-load variants of the inverse
+// kernels (husl_stream.cuh: to_rgb(hsl, edit=...)) and by the in-place HUSL edit kernel below.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "../../include/nphusl_cuda.h"
+
+namespace husl {
+
+// Selection: a pixel is selected when H lies on the arc [h_lo, h_hi] (h_lo > h_hi
+// means the arc through 360/0) AND S in [s_lo, s_hi] AND L in [l_lo, l_hi];
+// `invert` selects the complement.  Selected pixels get H' = H*h_mul + h_add
+// (wrapped to [0, 360)), S' = clamp(S*s_mul + s_add, 0, 100), L' likewise; a
+// channel whose (mul, add) is (1, 0) is left exactly as it is, like the channels a
+// caller's `hsl[..., 2][mask] *= 0.5` never touches.  Every pixel -- selected or
+// not -- goes through the float32 HUSL round trip, exactly as
+// to_rgb(edit(to_husl(rgb, dtype=float32))) does.
+// EH / ES / RSL are compile-time promises of the dispatcher ("the hue / saturation
+// channel may be edited", "a saturation or lightness range may be bounded"): the
+// streaming kernels are instantiated per combination so that an edit which only
+// scales L inside a hue arc (README.md:77-81) carries no hue-wrap, saturation or
+// range arithmetic at all.  <true, true, true> is valid for every descriptor.
+template <bool EH = true, bool ES = true, bool RSL = true>
+__device__ __forceinline__ void apply_edit(const nphusl_edit &e, float &h, float &s, float &l) {
+    bool sel = (e.h_lo <= e.h_hi) ? (h >= e.h_lo && h <= e.h_hi) : (h >= e.h_lo || h <= e.h_hi);
+    if (RSL) sel = sel && s >= e.s_lo && s <= e.s_hi && l >= e.l_lo && l <= e.l_hi;
+    sel = e.invert ? !sel : sel;
+    if (EH) {
+        float hn = __fadd_rn(__fmul_rn(h, e.h_mul), e.h_add);
+        hn = hn - 360.0f * floorf(hn * (1.0f / 360.0f));
+        hn = (hn >= 360.0f || hn < 0.0f) ? 0.0f : hn;
+        h = (sel && (e.h_mul != 1.0f || e.h_add != 0.0f)) ? hn : h;
+    }
+    if (ES) {
+        const float sn = fminf(fmaxf(__fadd_rn(__fmul_rn(s, e.s_mul), e.s_add), 0.0f), 100.0f);
+        s = (sel && (e.s_mul != 1.0f || e.s_add != 0.0f)) ? sn : s;
+    }
+    const float ln = fminf(fmaxf(__fadd_rn(__fmul_rn(l, e.l_mul), e.l_add), 0.0f), 100.0f);
+    l = (sel && (e.l_mul != 1.0f || e.l_add != 0.0f)) ? ln : l;
+}
+
+// what the dispatcher may promise for a descriptor (host side)
+struct EditShape {
+    bool eh, es, rsl;
+    __host__ explicit EditShape(const nphusl_edit &e)
+        : eh(e.h_mul != 1.0f || e.h_add != 0.0f), es(e.s_mul != 1.0f || e.s_add != 0.0f),
+          rsl(!(e.s_lo == -INFINITY && e.s_hi == INFINITY && e.l_lo == -INFINITY && e.l_hi == INFINITY)) {}
+};
+
+// kernel argument that costs nothing when a kernel is instantiated without the edit stage
+template <bool EDIT> struct EditArg {};
+template <> struct EditArg<true> { nphusl_edit e; };
+template <bool EDIT>
+__device__ __forceinline__ void edit_on_load(const EditArg<EDIT> &, float &, float &, float &) {}
+template <>
+__device__ __forceinline__ void edit_on_load<true>(const EditArg<true> &a, float &h, float &s, float &l) {
+    apply_edit<true, true, true>(a.e, h, s, l);
+}
+
+// ---------------------------------------------------------------------------------
+// in-place (or out-of-place) edit of an interleaved HUSL array: what a caller's
+// `hsl[..., 2][mask] *= 0.5` (README.md:77-81) does, as one pass over the array
+// ---------------------------------------------------------------------------------
+// One thread per pixel, three scalar accesses each: neighbouring threads cover neighbouring
+// triplets, so every 32-byte sector is fully used; the array is read once and written once
+// (24 / 48 B per pixel).  The arithmetic is float32 on the float32 value of each channel,
+// exactly what the fused kernels apply in registers; unselected pixels and untouched
+// channels are written back bit for bit.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_husl_edit(const T *in, T *out, long long n, const nphusl_edit e) {   // out may be in
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T h0 = in[3 * i], s0 = in[3 * i + 1], l0 = in[3 * i + 2];
+        float h = (float)h0, s = (float)s0, l = (float)l0;
+        const float hf = h, sf = s, lf = l;
+        apply_edit<true, true, true>(e, h, s, l);
+        out[3 * i] = (h == hf) ? h0 : (T)h;
+        out[3 * i + 1] = (s == sf) ? s0 : (T)s;
+        out[3 * i + 2] = (l == lf) ? l0 : (T)l;
+    }
+}
+
+}  // namespace husl

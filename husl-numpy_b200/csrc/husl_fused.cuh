@@ -10,7 +10,7 @@
 //       of 15 + 24 + 15 for three calls with a float32 intermediate).
 #pragma once
 #include "husl_kernels.cuh"
-#include "../../include/nphusl_cuda.h"
+#include "husl_edit.cuh"
 
 #ifndef HUSL_PLANAR_UNROLL
 #define HUSL_PLANAR_UNROLL 1   // tile loops of k_fwd_planar / k_fwd_chw (float32 planes) unrolled by this factor (A/B knob)
@@ -170,46 +170,7 @@ k_inv_planar_any(const T *__restrict__ H, const T *__restrict__ S, const T *__re
 // ---------------------------------------------------------------------------------
 // fused edit: uint8 RGB -> HUSL (registers) -> select + affine edit -> uint8 RGB
 // ---------------------------------------------------------------------------------
-// Selection: a pixel is selected when H lies on the arc [h_lo, h_hi] (h_lo > h_hi
-// means the arc through 360/0) AND S in [s_lo, s_hi] AND L in [l_lo, l_hi];
-// `invert` selects the complement.  Selected pixels get H' = H*h_mul + h_add
-// (wrapped to [0, 360)), S' = clamp(S*s_mul + s_add, 0, 100), L' likewise; a
-// channel whose (mul, add) is (1, 0) is left exactly as it is, like the channels a
-// caller's `hsl[..., 2][mask] *= 0.5` never touches.  Every pixel -- selected or
-// not -- goes through the float32 HUSL round trip, exactly as
-// to_rgb(edit(to_husl(rgb, dtype=float32))) does.
-// EH / ES / RSL are compile-time promises of the dispatcher ("the hue / saturation
-// channel may be edited", "a saturation or lightness range may be bounded"): the
-// streaming kernels are instantiated per combination so that an edit which only
-// scales L inside a hue arc (README.md:77-81) carries no hue-wrap, saturation or
-// range arithmetic at all.  <true, true, true> is valid for every descriptor.
-template <bool EH = true, bool ES = true, bool RSL = true>
-__device__ __forceinline__ void apply_edit(const nphusl_edit &e, float &h, float &s, float &l) {
-    bool sel = (e.h_lo <= e.h_hi) ? (h >= e.h_lo && h <= e.h_hi) : (h >= e.h_lo || h <= e.h_hi);
-    if (RSL) sel = sel && s >= e.s_lo && s <= e.s_hi && l >= e.l_lo && l <= e.l_hi;
-    sel = e.invert ? !sel : sel;
-    if (EH) {
-        float hn = __fadd_rn(__fmul_rn(h, e.h_mul), e.h_add);
-        hn = hn - 360.0f * floorf(hn * (1.0f / 360.0f));
-        hn = (hn >= 360.0f || hn < 0.0f) ? 0.0f : hn;
-        h = (sel && (e.h_mul != 1.0f || e.h_add != 0.0f)) ? hn : h;
-    }
-    if (ES) {
-        const float sn = fminf(fmaxf(__fadd_rn(__fmul_rn(s, e.s_mul), e.s_add), 0.0f), 100.0f);
-        s = (sel && (e.s_mul != 1.0f || e.s_add != 0.0f)) ? sn : s;
-    }
-    const float ln = fminf(fmaxf(__fadd_rn(__fmul_rn(l, e.l_mul), e.l_add), 0.0f), 100.0f);
-    l = (sel && (e.l_mul != 1.0f || e.l_add != 0.0f)) ? ln : l;
-}
-
-// what the dispatcher may promise for a descriptor (host side)
-struct EditShape {
-    bool eh, es, rsl;
-    __host__ explicit EditShape(const nphusl_edit &e)
-        : eh(e.h_mul != 1.0f || e.h_add != 0.0f), es(e.s_mul != 1.0f || e.s_add != 0.0f),
-          rsl(!(e.s_lo == -INFINITY && e.s_hi == INFINITY && e.l_lo == -INFINITY && e.l_hi == INFINITY)) {}
-};
-
+// (selection / edit rule, apply_edit and EditShape: husl_edit.cuh)
 template <int BLOCK, int MINB, bool EH, bool ES, bool RSL>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_edit(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const nphusl_edit e) {

@@ -26,6 +26,7 @@
 //     arithmetic is float32 (+ hi/lo pairs where it matters).
 #pragma once
 #include "husl_math.cuh"
+#include "husl_edit.cuh"
 
 #ifndef HUSL_FWD_UNROLL
 #define HUSL_FWD_UNROLL 2   // tile loop of k_fwd_u8<.., HUE = false> unrolled by this factor
@@ -307,13 +308,15 @@ k_fwd_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, int c
     }
 }
 
-template <typename TIn, typename TOut>
+template <typename TIn, typename TOut, bool EDIT = false>
 __global__ void __launch_bounds__(256)
-k_inv_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
+k_inv_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, const EditArg<EDIT> ea = EditArg<EDIT>()) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float R, G, B;
-        rgb255_from_husl<sizeof(TOut) != 1, sizeof(TIn) == 8>((float)in[3 * i], (float)in[3 * i + 1], (float)in[3 * i + 2], R, G, B);
+        float h = (float)in[3 * i], s = (float)in[3 * i + 1], l = (float)in[3 * i + 2];
+        edit_on_load<EDIT>(ea, h, s, l);
+        rgb255_from_husl<sizeof(TOut) != 1, sizeof(TIn) == 8>(h, s, l, R, G, B);
         if (sizeof(TOut) == 1) {
             out[3 * i] = (TOut)(round_u8_bits(R) & 0xFF);
             out[3 * i + 1] = (TOut)(round_u8_bits(G) & 0xFF);

@@ -206,9 +206,12 @@ struct InvSmem {
     static constexpr int PER_WARP = IST * Tile<TIn>::BYTES + 2 * U8_TILE + 64;
 };
 
-template <typename TIn, int BLOCK, int MINB, int IST>
+// EDIT: the caller's HUSL-space select + edit (husl_edit.cuh) is applied to the loaded values before
+// the inverse -- to_rgb(hsl, edit=...) -- so a to_husl -> edit -> to_rgb pipeline needs no pass of its own
+// over the 24 B/px HUSL array for the edit.
+template <typename TIn, int BLOCK, int MINB, int IST, bool EDIT = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles) {
+k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const EditArg<EDIT> ea = EditArg<EDIT>()) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TB = Tile<TIn>::BYTES;
@@ -274,6 +277,7 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
+            edit_on_load<EDIT>(ea, hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2]);
             rgb255_from_husl<false, sizeof(TIn) == 8>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }
@@ -320,9 +324,9 @@ struct InvCpSmem {
     static constexpr int PER_WARP = IST * Tile<float>::BYTES + U8_TILE;
 };
 
-template <int BLOCK, int MINB, int IST>
+template <int BLOCK, int MINB, int IST, bool EDIT = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles) {
+k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const EditArg<EDIT> ea = EditArg<EDIT>()) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TB = Tile<float>::BYTES;
@@ -372,6 +376,7 @@ k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_t
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
+            edit_on_load<EDIT>(ea, hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2]);
             rgb255_from_husl(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }

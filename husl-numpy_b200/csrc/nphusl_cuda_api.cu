@@ -279,10 +279,11 @@ int launch_fwd_any(DevCtx &c, const void *in, void *out, long long n, int channe
 }
 
 template <typename TIn, typename TOut>
-int launch_inv_any(DevCtx &c, const void *in, void *out, long long n, cudaStream_t s) {
+int launch_inv_any(DevCtx &c, const void *in, void *out, long long n, cudaStream_t s, const nphusl_edit *edit = nullptr) {
     if (n <= 0) return NPHUSL_OK;
     const int grid = grid_for(n, 256, c.sms * 8);
-    k_inv_any<TIn, TOut><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n);
+    if (edit) k_inv_any<TIn, TOut, true><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n, EditArg<true>{*edit});
+    else k_inv_any<TIn, TOut><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n);
     g_launches++;
     return check_launch("k_inv_any");
 }
@@ -372,10 +373,32 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
 #undef FWD_ANY
 }
 
-int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, long long n, cudaStream_t s) {
+// `edit` != NULL: the HUSL-space edit is applied to every loaded pixel first (to_rgb(hsl, edit=...));
+// the ring kernels have an EDIT instantiation, every other layout takes the generic kernel
+int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, long long n, cudaStream_t s,
+                const nphusl_edit *edit = nullptr) {
     int rc;
     long long done = 0;
-    if (out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 4) && n >= TILE_PX) {
+    if (edit && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
+        const long long tiles = n / TILE_PX;
+        static std::atomic<bool> attr32[MAX_DEV], attr64[MAX_DEV];
+        const EditArg<true> ea{*edit};
+        if (in_dt == NPHUSL_F32) {
+            constexpr int sm = (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP;
+            if ((rc = flt_attr(attr32, c, k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, true>, sm))) return rc;
+            k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, true><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK, sm, s>>>(
+                (const float *)in, (uint32_t *)out, tiles, ea);
+        } else {
+            constexpr int sm = (INV64_BLOCK / 32) * InvSmem<double, INV64_IST>::PER_WARP;
+            if ((rc = flt_attr(attr64, c, k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST, true>, sm))) return rc;
+            k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST, true><<<grid_for(tiles, INV64_BLOCK / 32, c.sms * INV64_MINB), INV64_BLOCK, sm, s>>>(
+                (const double *)in, (uint32_t *)out, tiles, ea);
+        }
+        g_launches++;
+        if ((rc = check_launch("k_inv (edit on load)"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    if (!edit && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 4) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
         constexpr int W = INV_BLOCK / 32;
         if (use_tma() && aligned(out, 16)) {
@@ -402,7 +425,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
         if ((rc = check_launch("k_inv_u8"))) return rc;
         done = tiles * TILE_PX;
     }
-    if (out_dt != NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
+    if (!edit && out_dt != NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
         // float RGB in [0,1] out (what the reference's _husl_to_rgb returns, _cython_opt.pyx:177-192)
         const long long tiles = n / TILE_PX;
         const int grid = grid_for(tiles, FLT_BLOCK / 32, c.sms * FLT_MINB);
@@ -422,7 +445,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
     if (rest <= 0) return NPHUSL_OK;
     const char *ip = (const char *)in + done * 3 * dsize(in_dt);
     char *op = (char *)out + done * 3 * dsize(out_dt);
-#define INV_ANY(TI, TO) return launch_inv_any<TI, TO>(c, ip, op, rest, s)
+#define INV_ANY(TI, TO) return launch_inv_any<TI, TO>(c, ip, op, rest, s, edit)
     if (in_dt == NPHUSL_F32) {
         if (out_dt == NPHUSL_U8) INV_ANY(float, uint8_t);
         if (out_dt == NPHUSL_F32) INV_ANY(float, float);
@@ -860,6 +883,43 @@ int nphusl_cuda_husl_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc,
         return run_inv_dev(*c, i, hsl_dtype, o, rgb_dtype, n, s);
     };
     return run_streamed(*c, hsl, hsl_loc, in_px, rgb, rgb_loc, out_px, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+int nphusl_cuda_husl_edit_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc, const nphusl_edit *edit,
+                                 void *rgb, int rgb_dtype, int rgb_loc,
+                                 size_t n_pixels, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!hsl || !rgb || !edit) return fail(NPHUSL_ERR_ARG, "husl_edit_to_rgb: null argument");
+    if ((hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) || !dsize(rgb_dtype))
+        return fail(NPHUSL_ERR_ARG, "husl_edit_to_rgb: hsl must be f32/f64 and rgb u8/f32/f64");
+    if (!ok_loc(hsl_loc) || !ok_loc(rgb_loc)) return fail(NPHUSL_ERR_ARG, "husl_edit_to_rgb: bad buffer location");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    const nphusl_edit e = *edit;
+    const size_t in_px = 3 * dsize(hsl_dtype), out_px = 3 * dsize(rgb_dtype);
+    auto kern = [=](const void *i, void *o, long long n, cudaStream_t s) -> int {
+        return run_inv_dev(*c, i, hsl_dtype, o, rgb_dtype, n, s, &e);
+    };
+    return run_streamed(*c, hsl, hsl_loc, in_px, rgb, rgb_loc, out_px, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+int nphusl_cuda_husl_edit(const void *hsl_in, void *hsl_out, int hsl_dtype, size_t n_pixels,
+                          const nphusl_edit *edit, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!hsl_in || !hsl_out || !edit) return fail(NPHUSL_ERR_ARG, "husl_edit: null argument");
+    if (hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) return fail(NPHUSL_ERR_ARG, "husl_edit: hsl must be f32/f64");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    const long long n = (long long)n_pixels;
+    const int grid = grid_for(n, 256, c->sms * 8);
+    if (hsl_dtype == NPHUSL_F32) k_husl_edit<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)hsl_in, (float *)hsl_out, n, *edit);
+    else k_husl_edit<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)hsl_in, (double *)hsl_out, n, *edit);
+    g_launches++;
+    return check_launch("k_husl_edit");
 }
 
 // ---- planar HUSL and the fused edit --------------------------------------------------------

@@ -34,7 +34,7 @@ import threading
 import numpy as np
 
 __all__ = ["_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue", "rgb_to_husl_planar", "husl_planar_to_rgb",
-           "edit_rgb", "Edit", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "rgb_to_nv12", "nv12_edit_nv12", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
+           "edit_rgb", "edit_husl", "Edit", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "rgb_to_nv12", "nv12_edit_nv12", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
 
 def _prod(shape):
     """Number of elements of a shape (np.prod on a tuple costs 3 us and runs several times per call)."""
@@ -77,6 +77,8 @@ SIGNATURES = {
     "nphusl_cuda_rgb_planes_to_husl_planes": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _sz, _i, _vp]),
     "nphusl_cuda_husl_planes_to_rgb_planes": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "nphusl_cuda_rgb_edit_rgb": (_i, [_vp, _i, _vp, _i, _sz, _vp, _i, _vp]),
+    "nphusl_cuda_husl_edit_to_rgb": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _sz, _i, _vp]),
+    "nphusl_cuda_husl_edit": (_i, [_vp, _vp, _i, _sz, _vp, _i, _vp]),
     "nphusl_cuda_rgb_planes_edit": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "nphusl_cuda_rgb_to_husl_strided": (_i, [_vp, _vp, _i, _i, _vp]),
     "nphusl_cuda_husl_to_rgb_strided": (_i, [_vp, _vp, _i, _vp]),
@@ -971,11 +973,26 @@ def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None, block
     return ret
 
 
-def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocking=True):
+def _as_edit(edit):
+    """``Edit`` | dict of its keywords -> ``Edit``"""
+    if isinstance(edit, Edit):
+        return edit
+    if isinstance(edit, dict):
+        return Edit(**edit)
+    raise TypeError("edit must be an nphusl._cuda.Edit or a dict of its keywords, got {!r}".format(type(edit)))
+
+
+def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocking=True, edit=None):
     """HUSL -> RGB on the GPU (kernel (b) rgb_from_husl).  Replaces
     ``_cython_opt._husl_to_rgb`` (_cython_opt.pyx:177-192); with the default
     ``dtype=uint8`` the round/abs/cast tail of ``to_rgb`` is fused in, float
-    dtypes return RGB in [0, 1] like the reference callable."""
+    dtypes return RGB in [0, 1] like the reference callable.
+
+    ``edit`` (an ``Edit`` or a dict of its keywords): the callers' HUSL-space edit of
+    README.md:77-98 -- ``hsl[..., 2][mask] *= 0.5`` between ``to_husl`` and ``to_rgb`` --
+    applied to every pixel as it is loaded, so the pipeline needs no pass of its own over
+    the HUSL array: ``to_rgb(hsl, edit=dict(hue=(250, 290), invert=True, l=(0.5, 0)))``
+    equals ``to_rgb(edit_husl(hsl, ...))``; ``hsl`` itself is left untouched."""
     lib = load()
     if _is_device(hsl):
         src = _describe_device(hsl, "hsl", strided_ok=True)
@@ -995,11 +1012,17 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
     dev = _pick_device(device, src, dst)
     n = _prod(src.shape[:-1])
     if src.strides is not None or dst.strides is not None:
+        if edit is not None:
+            raise ValueError("to_rgb(edit=...) takes C-contiguous arrays")
         _strided_call("nphusl_cuda_husl_to_rgb_strided", src, dst, len(src.shape) - 1, [], dev, stream)
         return ret
     with _host_async(lib, blocking):
-        rc = lib.nphusl_cuda_husl_to_rgb(src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
-                                         n, dev, _stream_ptr(stream))
+        if edit is not None:
+            rc = lib.nphusl_cuda_husl_edit_to_rgb(src.ptr, _DT[src.dtype], src.loc, ctypes.byref(_as_edit(edit)),
+                                                  dst.ptr, _DT[dst.dtype], dst.loc, n, dev, _stream_ptr(stream))
+        else:
+            rc = lib.nphusl_cuda_husl_to_rgb(src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
+                                             n, dev, _stream_ptr(stream))
     _check(rc, "husl_to_rgb")
     return ret
 
@@ -1167,6 +1190,35 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
     return ret
 
 
+def edit_husl(hsl, edit=None, out=None, stream=None, **edit_args):
+    """Apply a select + affine edit to a HUSL DEVICE array (``(..., 3)`` float32 / float64) in one
+    pass: what ``hue, lightness = hsl[..., 0], hsl[..., 2]; lightness[~bluish] *= 0.5`` does
+    (README.md:77-81).  In place by default (``out=None`` returns ``hsl``); ``out`` may be another
+    device array of the same shape and dtype.  ``to_rgb(hsl, edit=...)`` applies the same edit
+    without touching the array at all."""
+    if edit is None:
+        edit = Edit(**edit_args)
+    elif edit_args:
+        raise TypeError("pass either an Edit or its fields as keywords, not both")
+    if not _is_device(hsl):
+        raise ValueError("edit_husl takes device arrays (edit a host array with numpy, or use to_rgb(hsl, edit=...))")
+    src = _describe_device(hsl, "hsl")
+    if src.dtype not in _FLOATS or not src.shape or src.shape[-1] != 3:
+        raise ValueError("edit_husl takes float32/float64 (..., 3) HUSL, got {} {}".format(src.dtype, src.shape))
+    dev = _pick_device(None, src)
+    if out is None:
+        dst, ret = src, hsl
+    else:
+        dst = _describe_out(out, src.shape, src.dtype, (src.dtype,), "out")
+        if dst.loc != DEVICE:
+            raise ValueError("out: edit_husl writes device arrays")
+        ret = out
+    _touch(stream, hsl, ret)
+    _check(load().nphusl_cuda_husl_edit(src.ptr, dst.ptr, _DT[src.dtype], _prod(src.shape[:-1]), ctypes.byref(_as_edit(edit)),
+                                        dev, _stream_ptr(stream)), "husl_edit")
+    return ret
+
+
 # ---------------------------------------------------------------------------
 # video-decoder surfaces (NV12) as the load stage
 # ---------------------------------------------------------------------------
@@ -1309,15 +1361,55 @@ def rgb_to_nv12(rgb, out_y=None, out_uv=None, matrix="bt709", full_range=False, 
     return ret
 
 
+def _nv12_edit_nv12_host(y, uv, edit, out_y, out_uv, matrix, full_range, out_matrix, out_full_range, stream, device, blocking):
+    """HOST planes (frames as a capture card or a software decoder leaves them): 1.5 bytes per pixel
+    over the link each way instead of the 3 of packed RGB.  Pinned arrays (``pinned_empty``) are
+    DMA'd directly and with ``blocking=False`` the call only enqueues on ``stream``."""
+    lib = load()
+    y = np.ascontiguousarray(y, dtype=np.uint8)
+    if uv is None or y.ndim != 2:
+        raise ValueError("host NV12 input: pass the luma plane (H, W) and the interleaved chroma plane (H/2, W)")
+    uv = np.ascontiguousarray(uv, dtype=np.uint8)
+    h, w = y.shape
+    if h % 2 or w % 2 or uv.shape[0] != h // 2 or uv.size != (h // 2) * w:
+        raise ValueError("host NV12 input: even width and height, chroma plane of {} x {} bytes; got {} and {}".format(
+            h // 2, w, y.shape, uv.shape))
+    dev = _default_device if device is None else int(device)
+    if out_y is None:
+        out_y = _pinned_pool.empty((h, w), np.uint8)
+        out_y = np.empty((h, w), np.uint8) if out_y is None else out_y
+    if out_uv is None:
+        out_uv = _pinned_pool.empty(uv.shape, np.uint8)
+        out_uv = np.empty(uv.shape, np.uint8) if out_uv is None else out_uv
+    for name, o, like in (("out_y", out_y, y), ("out_uv", out_uv, uv)):
+        if not isinstance(o, np.ndarray) or o.dtype != np.uint8 or o.shape != like.shape or not o.flags.c_contiguous:
+            raise ValueError("{}: expected a C-contiguous uint8 host array of shape {}".format(name, like.shape))
+    sp = _stream_ptr(stream)
+    dy, duv = DeviceArray((h, w), np.uint8, dev, stream), DeviceArray((h // 2, w), np.uint8, dev, stream)
+    _check(lib.nphusl_cuda_memcpy(dy.ptr, y.ctypes.data, y.nbytes, 1, dev, sp), "memcpy h2d")
+    _check(lib.nphusl_cuda_memcpy(duv.ptr, uv.ctypes.data, uv.nbytes, 1, dev, sp), "memcpy h2d")
+    nv12_edit_nv12(dy, duv, edit, out_y=dy, out_uv=duv, matrix=matrix, full_range=full_range,      # in place on the device
+                   out_matrix=out_matrix, out_full_range=out_full_range, stream=stream)
+    _check(lib.nphusl_cuda_memcpy(out_y.ctypes.data, dy.ptr, y.nbytes, 2, dev, sp), "memcpy d2h")
+    _check(lib.nphusl_cuda_memcpy(out_uv.ctypes.data, duv.ptr, uv.nbytes, 2, dev, sp), "memcpy d2h")
+    if blocking:
+        synchronize(dev, stream)
+    return out_y, out_uv
+
+
 def nv12_edit_nv12(y, uv=None, edit=None, out_y=None, out_uv=None, matrix="bt709", full_range=False,
-                   out_matrix=None, out_full_range=None, stream=None, **edit_args):
+                   out_matrix=None, out_full_range=None, stream=None, device=None, blocking=True, **edit_args):
     """The whole video loop in one pass: NV12 -> HUSL -> select + edit -> NV12 (3 bytes of memory
     traffic per pixel).  Equals ``rgb_to_nv12(nv12_edit_rgb(...))`` bit for bit; ``out_y`` / ``out_uv``
-    may be the source planes themselves.  Returns ``(y, uv)``."""
+    may be the source planes themselves.  Returns ``(y, uv)``.  Host planes (numpy arrays) are uploaded,
+    edited and downloaded (``device`` / ``blocking`` apply to that form only)."""
     if edit is None:
         edit = Edit(**edit_args)
     elif edit_args:
         raise TypeError("pass either an Edit or its fields as keywords, not both")
+    if isinstance(y, np.ndarray):
+        return _nv12_edit_nv12_host(y, uv, edit, out_y, out_uv, matrix, full_range, out_matrix, out_full_range,
+                                    stream, device, blocking)
     src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
     dst, ret = _nv12_dest(h, w, out_y, out_uv, out_matrix or matrix, full_range if out_full_range is None else out_full_range, dev, stream)
     _touch(stream, *keep)

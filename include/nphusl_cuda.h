@@ -150,6 +150,20 @@ typedef struct nphusl_edit {
 int nphusl_cuda_rgb_edit_rgb(const void *rgb_in, int in_loc, void *rgb_out, int out_loc,
                              size_t n_pixels, const nphusl_edit *edit, int device, void *stream);
 
+/* The three-call form of the same pipeline, for callers that keep the HUSL array (README.md:77-98:
+ * hsl = to_husl(img); <edit hsl>; out = to_rgb(hsl)):
+ *  - husl_edit_to_rgb: husl_to_rgb with the edit applied to every pixel as it is loaded -- the HUSL
+ *    array is read once, nothing is written back to it; equals husl_to_rgb(husl_edit(hsl)).  Same
+ *    buffer rules as nphusl_cuda_husl_to_rgb (host or device on either side).
+ *  - husl_edit: the edit written into a HUSL array (hsl_out may be hsl_in); DEVICE pointers.
+ * The edit arithmetic is float32 on the float32 value of each channel (what the fused kernel applies
+ * in registers); unselected pixels and channels whose (mul, add) is (1, 0) are passed on bit for bit. */
+int nphusl_cuda_husl_edit_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc, const nphusl_edit *edit,
+                                 void *rgb, int rgb_dtype, int rgb_loc,
+                                 size_t n_pixels, int device, void *stream);
+int nphusl_cuda_husl_edit(const void *hsl_in, void *hsl_out, int hsl_dtype, size_t n_pixels,
+                          const nphusl_edit *edit, int device, void *stream);
+
 /* The same fused edit on channels-first uint8 planes (what nvJPEG and video
  * decoders hand out); DEVICE pointers only; outputs may alias the inputs. */
 int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,

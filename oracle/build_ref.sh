@@ -16,10 +16,9 @@
 #   * nphusl/_simd.c (+ _linear_lookup.c, _scale_const.c) is compiled four ways
 #     (setup.py:99-128 flag sets) into plain shared objects exporting
 #     rgb_to_husl_nd (_simd.h:4-5).
-#   * nphusl/_cython_opt.pyx is cythonized to a scratch dir and compiled as
-#     the extension module `refhost._cython_opt`; the two modules it imports from
-#     its package (`constants`, `transform`, _cython_opt.pyx:5-6) are provided by
-#     a generated package that re-exports THIS repo's own host-side mirrors.
+#   * the reference package itself (its Python modules byte-compiled, its two
+#     .pyx modules cythonized and compiled) becomes oracle/_ref/refpkg/nphusl_ref:
+#     see step 3.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${REF:-/root/reference}"
@@ -31,7 +30,7 @@ fi
 PY="${PYTHON:-python}"
 # NB: the image exports CC=/opt/gcc/bin/gcc, which lacks libgomp.spec (SURVEY App. B fix 2)
 CC="${REF_CC:-/usr/bin/gcc}"
-mkdir -p "$OUT/gen" "$OUT/shim" "$OUT/refhost" "$OUT/scratch"
+mkdir -p "$OUT/gen" "$OUT/shim" "$OUT/scratch"
 printf 'import numpy as np\nnp.float = float\nnp.int = int\n' > "$OUT/shim/sitecustomize.py"
 
 # 1. generated lookup tables (outputs only under oracle/_ref/gen)
@@ -71,25 +70,38 @@ LUTF="$OUT/gen_float/_light_lookup.c $OUT/gen_float/_chroma_lookup.c -DUSE_LIGHT
 $CC -O2             $BASE $INCF $SRC $LUTF                      -o "$OUT/libsimd_lutf_strict.so" -lm
 $CC -O2             $BASE $INCF $SRC $LUTF -DINTERPOLATE_CHROMA -o "$OUT/libsimd_lutf_interp_strict.so" -lm
 
-# 3. _cython_opt (Cython + OpenMP float64 kernels: the only compiled HUSL->RGB)
-cat > "$OUT/refhost/__init__.py" <<'PYEOF'
-# generated by oracle/build_ref.sh - host package for the reference's _cython_opt
-PYEOF
-cat > "$OUT/refhost/constants.py" <<'PYEOF'
-# generated by oracle/build_ref.sh: re-export of this repo's own constants mirror
-from nphusl.constants import *  # noqa: F401,F403
-PYEOF
-cat > "$OUT/refhost/transform.py" <<'PYEOF'
-# generated by oracle/build_ref.sh: re-export of this repo's own transform mirror
-from nphusl.transform import *  # noqa: F401,F403
-from nphusl.transform import rgb_float_input, float_input  # noqa: F401
+# 3. the reference PACKAGE itself, compiled: oracle/_ref/refpkg/nphusl_ref/
+#    * its four Python modules (__init__, nphusl, transform, constants) are byte-compiled WHERE THEY LIE into
+#      sourceless .pyc files (a build output like the .so files: no reference source enters the repository);
+#    * _cython_opt.pyx and _simd_opt.pyx are cythonized into a scratch dir and compiled with the flags of
+#      the reference's setup.py:99-128 (default build: light LUT + chroma LUT + atan2 approximation).
+#    Every import inside the package is relative, so it loads under the name `nphusl_ref` next to this
+#    repository's own `nphusl`.  bench.py --impl reference and the cpu_baseline leg drive the reference through
+#    ITS public API (nphusl_ref.to_husl / to_rgb / to_hue) and ITS stock dispatch (SIMD, then Cython); none of
+#    this repository's host code is on that path.  The only patches are the two from SURVEY App. B that a
+#    current toolchain forces: np.float / np.int aliases (set by oracle.ref_package() before the import) and
+#    Cython language level 2 for _simd_opt.pyx's integer division (a command-line flag, not an edit).
+PKG="$OUT/refpkg/nphusl_ref"
+rm -rf "$OUT/refhost" "$OUT/refpkg"
+mkdir -p "$PKG"
+"$PY" - "$REF/nphusl" "$PKG" <<'PYEOF'
+import py_compile, sys, os
+src, dst = sys.argv[1:3]
+for name in ("__init__", "nphusl", "transform", "constants"):
+    py_compile.compile(os.path.join(src, name + ".py"), cfile=os.path.join(dst, name + ".pyc"), doraise=True,
+                       dfile="<reference>/nphusl/%s.py" % name,
+                       invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
 PYEOF
 NPINC="$($PY -c 'import numpy; print(numpy.get_include())')"
 PYINC="$($PY -c 'import sysconfig; print(sysconfig.get_paths()["include"])')"
 EXT="$($PY -c 'import sysconfig; print(sysconfig.get_config_var("EXT_SUFFIX"))')"
-"$PY" -m cython -3 --module-name refhost._cython_opt \
+CYFLAGS="-fopenmp -O3 -ffast-math -ftree-vectorize -mtune=native -shared -fPIC -w -DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION"
+"$PY" -m cython -3 --module-name nphusl_ref._cython_opt \
     "$REF/nphusl/_cython_opt.pyx" -o "$OUT/scratch/_cython_opt.c" >/dev/null 2>&1
-$CC -O3 -ffast-math -fopenmp -shared -fPIC -w -DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION \
-    -I"$NPINC" -I"$PYINC" "$OUT/scratch/_cython_opt.c" -o "$OUT/refhost/_cython_opt$EXT" -lm
+$CC $CYFLAGS -I"$NPINC" -I"$PYINC" "$OUT/scratch/_cython_opt.c" -o "$PKG/_cython_opt$EXT" -lm
+"$PY" -m cython -2 --module-name nphusl_ref._simd_opt -I "$REF/nphusl" \
+    "$REF/nphusl/_simd_opt.pyx" -o "$OUT/scratch/_simd_opt.c" >/dev/null 2>&1
+$CC $CYFLAGS -fcommon -std=c99 -I"$NPINC" -I"$PYINC" $INC "$OUT/scratch/_simd_opt.c" $SRC $LUTS \
+    -o "$PKG/_simd_opt$EXT" -lm
 rm -rf "$OUT/scratch"
-echo "build_ref: built $(ls "$OUT"/*.so | wc -l) _simd variants + refhost/_cython_opt$EXT"
+echo "build_ref: built $(ls "$OUT"/*.so | wc -l) _simd variants + refpkg/nphusl_ref ($(ls "$PKG" | tr '\n' ' '))"

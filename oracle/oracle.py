@@ -14,7 +14,7 @@ package never imports this module and has no CPU fallback.
   include/nphusl_cuda.h specifies for decoder surfaces (not reference code: the
   reference's callers decode with imageio / moviepy, examples.py:117-134), plus
   ``nv12_to_rgb_float`` (the textbook float matrix, to bound the integer one), ``rgb_to_nv12`` (the encode side);
-* ``ref_simd(...)``, ``ref_tables()``, ``ref_cython()`` -- the reference's own
+* ``ref_simd(...)``, ``ref_tables()``, ``ref_cython()``, ``ref_package()`` -- the reference's own
   compiled code (``oracle/_ref``, built by ``oracle/build_ref.sh`` from the
   sources under /root/reference; present on the GPU box as prebuilt files).
 """
@@ -298,15 +298,34 @@ def ref_linear_table():
     return np.frombuffer((ctypes.c_double * 256).in_dll(l, "linear_table"), dtype=np.float64).copy()
 
 
+def ref_package():
+    """The reference package itself (nphusl 1.5.0), as compiled by build_ref.sh into
+    ``oracle/_ref/refpkg/nphusl_ref``: byte-compiled ``__init__`` / ``nphusl`` / ``transform`` /
+    ``constants`` plus its ``_cython_opt`` and ``_simd_opt`` extension modules.  Imported under the
+    name ``nphusl_ref`` (all of its imports are relative), so it can sit beside this repository's
+    ``nphusl`` in one process; nothing of this repository is on its code path.  The removed
+    ``np.float`` / ``np.int`` aliases it still uses are restored first (SURVEY App. B fix 1)."""
+    import warnings
+    if not hasattr(np, "float"):
+        np.float = float
+    if not hasattr(np, "int"):
+        np.int = int
+    p = os.path.join(REF_DIR, "refpkg")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # "No numexpr" etc.
+        import nphusl_ref
+    return nphusl_ref
+
+
+def have_ref_package():
+    return os.path.isdir(os.path.join(REF_DIR, "refpkg", "nphusl_ref"))
+
+
 def ref_cython():
-    """The reference's Cython+OpenMP module (nphusl/_cython_opt.pyx), compiled
-    by build_ref.sh as ``refhost._cython_opt``: the only compiled HUSL->RGB /
-    hue-only code the reference has.  Needs this repo's host package on
-    sys.path (it supplies the `constants` / `transform` modules the .pyx
-    imports from its parent package)."""
-    pkg = os.path.join(HERE, "..", "husl-numpy_b200")
-    for p in (os.path.abspath(pkg), REF_DIR):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    import refhost._cython_opt as m
+    """The reference's Cython+OpenMP module (nphusl/_cython_opt.pyx): the only compiled
+    HUSL->RGB / hue-only code the reference has."""
+    ref_package()
+    import nphusl_ref._cython_opt as m
     return m

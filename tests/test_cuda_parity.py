@@ -1372,3 +1372,153 @@ def test_concurrent_host_threads_on_one_device(cu):
         t.join(120)
     assert not any(t.is_alive() for t in threads), "a worker hung"
     assert not errors, errors
+
+
+# ---- round 2: the edit inside the three-call pipeline, NV12 host planes, frame streams, pool ordering ----
+
+README_EDIT = dict(hue=(250, 290), invert=True, l=(0.5, 0))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_to_rgb_applies_the_edit_on_load(cu, dtype):
+    """to_rgb(hsl, edit=...) == to_rgb(edit_husl(hsl)) == the fused nphusl.edit(rgb) bit for bit, for host and
+    device HUSL arrays, whole tiles, ragged tails and unaligned bases; `hsl` itself is not modified; and the
+    result is within +-1 LSB of the float64 oracle doing the README edit (configs[3])."""
+    torch = pytest.importorskip("torch")
+    import nphusl
+    rng = np.random.default_rng(31)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    for shape in ((5, 3), (131, 3), (4741, 3), (3, 360, 640, 3)):
+        rgb = rng.integers(0, 256, shape, dtype=np.uint8)
+        want = nphusl.edit(rgb, **README_EDIT)
+        hsl = cu._rgb_to_husl(rgb, dtype=dtype)
+        keep = hsl.copy()
+        with nphusl.cuda_enabled():
+            got = nphusl.to_rgb(hsl, edit=README_EDIT)                       # host array, dict form
+        assert got.dtype == np.uint8 and np.array_equal(got, want) and np.array_equal(hsl, keep)
+        d = torch.from_numpy(hsl).cuda()
+        out = torch.empty(shape, dtype=torch.uint8, device="cuda")
+        with nphusl.cuda_enabled():
+            r = nphusl.to_rgb(d, out=out, edit=cu.Edit(**README_EDIT))       # device array, Edit form
+        assert r is out and np.array_equal(out.cpu().numpy(), want) and np.array_equal(d.cpu().numpy(), keep)
+        # an unaligned view of the same data goes through the generic kernel
+        flat = torch.empty(hsl.size + 1, dtype=tdt, device="cuda")
+        flat[1:].copy_(d.reshape(-1))
+        un = cu._husl_to_rgb(flat[1:].view(*shape), edit=README_EDIT)
+        assert np.array_equal(un.copy_to_host(), want)
+        # the explicit pass over the array, in place and into another array
+        e = cu.edit_husl(d.clone(), **README_EDIT)
+        assert np.array_equal(cu._husl_to_rgb(e).copy_to_host(), want)
+        o2 = torch.empty_like(d)
+        assert cu.edit_husl(d, cu.Edit(**README_EDIT), out=o2) is o2 and torch.equal(o2, e) and np.array_equal(d.cpu().numpy(), keep)
+        ed = e.cpu().numpy()
+        sel = ~((keep[..., 0] >= 250) & (keep[..., 0] <= 290))
+        assert np.array_equal(ed[..., :2], keep[..., :2])                    # H and S pass through bit for bit
+        assert np.array_equal(ed[..., 2][~sel], keep[..., 2][~sel]) and np.array_equal(ed[..., 2][sel], keep[..., 2][sel] * dtype(0.5))
+        # float RGB output takes the edit as well
+        f = cu._husl_to_rgb(d, dtype=np.float32, edit=README_EDIT).copy_to_host()
+        assert np.abs(np.round(f * 255.0) - want).max() <= 1
+    o = orc.rgb_to_husl(rgb)
+    ob = (o[..., 0] > 250) & (o[..., 0] < 290)                               # README.md:77-81 verbatim
+    o[..., 2][~ob] *= 0.5
+    od = np.abs(orc.husl_to_rgb(o).astype(int) - want.astype(int))
+    edge = np.minimum(np.abs(o[..., 0] - 250), np.abs(o[..., 0] - 290)) < 1e-3
+    assert od[~edge].max() <= 1 and (od[~edge] != 0).mean() < 2e-3
+    with pytest.raises(TypeError):
+        cu._husl_to_rgb(hsl, edit="darken")
+    with pytest.raises(ValueError):
+        cu.edit_husl(hsl, **README_EDIT)                                     # host arrays: use numpy, or to_rgb(edit=)
+
+
+def test_nv12_edit_nv12_with_host_planes(cu):
+    """NV12 planes in HOST memory (1.5 B/px over the link each way): equal to the device-resident call;
+    pinned planes with blocking=False only enqueue."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(32)
+    h, w = 360, 640
+    y = rng.integers(16, 236, (h, w), dtype=np.uint8)
+    uv = rng.integers(16, 241, (h // 2, w), dtype=np.uint8)
+    wy, wuv = cu.nv12_edit_nv12(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda(), **README_EDIT)
+    wy, wuv = wy.copy_to_host(), wuv.copy_to_host()
+    gy, guv = cu.nv12_edit_nv12(y, uv, **README_EDIT)                        # pageable in, pooled results out
+    assert gy.shape == (h, w) and guv.shape == (h // 2, w) and np.array_equal(gy, wy) and np.array_equal(guv, wuv)
+    py, puv = cu.pinned_empty((h, w), np.uint8), cu.pinned_empty((h // 2, w), np.uint8)
+    oy, ouv = cu.pinned_empty((h, w), np.uint8), cu.pinned_empty((h // 2, w), np.uint8)
+    py[...], puv[...] = y, uv
+    oy[...], ouv[...] = 0, 0
+    s = cu.Stream()
+    ry, ruv = cu.nv12_edit_nv12(py, puv, cu.Edit(**README_EDIT), out_y=oy, out_uv=ouv, stream=s, blocking=False)
+    s.synchronize()
+    assert ry is oy and ruv is ouv and np.array_equal(oy, wy) and np.array_equal(ouv, wuv)
+    with pytest.raises(ValueError):
+        cu.nv12_edit_nv12(y, uv[:, :-2], **README_EDIT)
+    with pytest.raises(ValueError):
+        cu.nv12_edit_nv12(y, uv, out_y=np.empty((h, w + 2), np.uint8), out_uv=ouv, **README_EDIT)
+
+
+def test_stream_frames_converts_a_cyclic_video_exactly(cu):
+    """_shard.stream_frames (BASELINE configs[4] at toy size): frame i of the stream is pool[i % P]; every
+    frame's round trip arrives in the host ring bit for bit, in order, whatever the batch / pool / shard
+    arithmetic; with an edit the frames equal the fused edit of the source frame."""
+    import nphusl
+    from nphusl import _shard
+    rng = np.random.default_rng(33)
+    P, H, W = 5, 96, 256
+    pool = cu.pinned_empty((P, H, W, 3), np.uint8)
+    pool[...] = rng.integers(0, 256, pool.shape, dtype=np.uint8)
+    ndev = min(2, cu.device_count())
+    for n, batch, first, edit in ((23, 4, 0, None), (7, 3, 9, None), (11, 8, 2, cu.Edit(**README_EDIT))):
+        seen = {}
+
+        def sink(dev, i, frames):
+            for j, f in enumerate(frames):
+                seen[i + j] = f.copy()
+        called = []
+        res = _shard.stream_frames(pool, n, devices=list(range(ndev)), first_frame=first, batch=batch, dtype=np.float32,
+                                   edit=edit, ready=lambda: called.append(1), on_batch=sink)
+        assert called == [1] and res["frames"] == n and sorted(seen) == list(range(first, first + n))
+        assert sum(v["frames"] for v in res["per_device"].values()) == n and res["seconds"] > 0
+        for i, f in seen.items():
+            want = pool[i % P] if edit is None else nphusl.edit(pool[i % P], **README_EDIT)
+            assert np.array_equal(f, want), i
+        for dev, (i, p, m, view) in res["last"].items():
+            assert p == i % P and np.array_equal(view[0], seen[i])
+    # a pageable pool works too (staged through the library's pinned slots), without a sink
+    res = _shard.stream_frames(np.array(pool), 6, devices=[0], batch=4)
+    i, p, m, view = res["last"][0]
+    assert (i, p, m) == (5, 0, 1) and np.array_equal(view[0], pool[0])
+    with pytest.raises(ValueError):
+        _shard.stream_frames(pool[..., 0], 4)
+
+
+def test_dropped_device_results_are_not_reused_under_a_running_kernel(cu):
+    """`x = to_husl(a, stream=s1); y = to_rgb(x, stream=s1); del x; to_husl(b, stream=s2)` must not let
+    the s2 call overwrite x's block while the s1 kernel still reads it.  The s1 stream is kept busy so the race
+    window is wide; with the stream-ordered pool y is always the round trip of a."""
+    torch = pytest.importorskip("torch")
+    import gc
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randint(0, 256, (4, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g)
+    b = torch.randint(0, 256, (4, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g)
+    busy = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    cu.empty_cache()
+    w0 = cu.device_pool_stats()["cross_stream_waits"]
+    for _ in range(8):
+        with torch.cuda.stream(s1):
+            for _ in range(6):
+                busy.add_(1)                                          # ~0.1 ms each: s1 runs well behind the host
+        x = cu._rgb_to_husl(a, dtype=np.float32, stream=s1)
+        y = cu._husl_to_rgb(x, stream=s1)
+        ptr = x.ptr
+        del x
+        gc.collect()
+        z = cu._rgb_to_husl(b, dtype=np.float32, stream=s2)          # same size class: takes x's block ...
+        assert z.ptr == ptr                                           # ... but only behind an event wait on s1's tail
+        r = cu._husl_to_rgb(z, stream=s2)
+        torch.cuda.synchronize()
+        assert np.array_equal(y.copy_to_host(), a.cpu().numpy())
+        assert np.array_equal(r.copy_to_host(), b.cpu().numpy())
+        del y, z, r
+        gc.collect()
+    assert cu.device_pool_stats()["cross_stream_waits"] > w0
