@@ -316,7 +316,7 @@ k_inv_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, const
         float R, G, B;
         float h = (float)in[3 * i], s = (float)in[3 * i + 1], l = (float)in[3 * i + 2];
         edit_on_load<EDIT>(ea, h, s, l);
-        rgb255_from_husl<sizeof(TOut) != 1, sizeof(TIn) == 8>(h, s, l, R, G, B);
+        rgb255_from_husl<sizeof(TOut) != 1, sizeof(TIn) == 8 && !EDIT>(h, s, l, R, G, B);
         if (sizeof(TOut) == 1) {
             out[3 * i] = (TOut)(round_u8_bits(R) & 0xFF);
             out[3 * i + 1] = (TOut)(round_u8_bits(G) & 0xFF);

@@ -278,7 +278,9 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
             edit_on_load<EDIT>(ea, hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2]);
-            rgb255_from_husl<false, sizeof(TIn) == 8>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
+            // the edit-on-load instantiation uses the fused kernels' formulation (k_edit), so that
+            // to_rgb(to_husl(x), edit=e) == nphusl.edit(x, e) bit for bit for float64 HUSL as well
+            rgb255_from_husl<false, sizeof(TIn) == 8 && !EDIT>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }
         const uint32_t o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);

@@ -66,8 +66,10 @@ int fail(int code, const std::string &msg) {
 #define CU(call)                                                                         \
     do {                                                                                 \
         cudaError_t e_ = (call);                                                         \
-        if (e_ != cudaSuccess)                                                           \
+        if (e_ != cudaSuccess) {                                                         \
+            cudaGetLastError(); /* reported here: must not surface again at the next launch check */ \
             return fail(NPHUSL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+        }                                                                                \
     } while (0)
 
 size_t dsize(int dt) { return dt == NPHUSL_U8 ? 1 : dt == NPHUSL_F32 ? 4 : dt == NPHUSL_F64 ? 8 : 0; }

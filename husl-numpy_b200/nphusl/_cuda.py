@@ -227,13 +227,20 @@ class Stream:
         p = ctypes.c_void_p()
         _check(load().nphusl_cuda_stream_create(ctypes.byref(p), self.device), "stream_create")
         self.ptr = p.value or 0
+        _device_pool.revive(self.ptr)
 
     def synchronize(self):
         _check(load().nphusl_cuda_stream_synchronize(ctypes.c_void_p(self.ptr), self.device), "stream_synchronize")
 
     def close(self):
+        """Wait for the stream's work, then destroy it.  The wait is what lets the block pool forget the
+        stream: nothing that ran on it can still be using a device block, and its handle is never
+        handed to the driver again (a destroyed handle is a dangling pointer)."""
         if self.ptr:
-            load().nphusl_cuda_stream_destroy(ctypes.c_void_p(self.ptr), self.device)
+            lib = load()
+            lib.nphusl_cuda_stream_synchronize(ctypes.c_void_p(self.ptr), self.device)
+            _device_pool.retire(self.ptr)
+            lib.nphusl_cuda_stream_destroy(ctypes.c_void_p(self.ptr), self.device)
             self.ptr = 0
 
     def __del__(self):
@@ -256,7 +263,10 @@ class _DevicePool:
     stream and becomes reusable (by any stream) when all of them have completed.  Work the library
     cannot see -- a block exported through ``__cuda_array_interface__`` and used by other code on
     its own stream -- must be announced with ``DeviceArray.record_stream(stream)`` before the
-    array is dropped."""
+    array is dropped.  Streams are named by their handle: a handle the pool still remembers must stay
+    valid.  The library's own ``Stream.close()`` drains the stream and tells the pool to forget it;
+    torch's streams live in a per-device pool that is never destroyed; whoever passes raw handles of
+    their own keeps them alive (or calls ``empty_cache()`` before destroying them)."""
 
     ANY = -1                             # free-list key of blocks that are idle on every stream
 
@@ -266,8 +276,23 @@ class _DevicePool:
         self.parked = []                 # [ptr, cap, device, [event, ...]]: in use on several streams when dropped
         self.events = {}                 # device -> [event, ...] spare events
         self.cached = 0
+        self.retired = set()             # handles of streams that were drained and destroyed (Stream.close)
         self.lock = threading.RLock()    # re-entrant: a GC pass inside alloc() may finalise a DeviceArray -> release()
         self.hits = self.misses = self.waits = 0
+
+    def retire(self, stream_key):
+        """The stream was synchronised and is about to be destroyed: its blocks are idle everywhere."""
+        with self.lock:
+            self.retired.add(stream_key)
+            for by in self.free.values():
+                lst = by.pop(stream_key, None)
+                if lst:
+                    by.setdefault(self.ANY, []).extend(lst)
+
+    def revive(self, stream_key):
+        """A new stream got a handle value an old one had."""
+        with self.lock:
+            self.retired.discard(stream_key)
 
     @staticmethod
     def size_class(nbytes):
@@ -342,7 +367,7 @@ class _DevicePool:
         """`streams`: keys of the streams the block was used on"""
         with self.lock:
             if self.cached + cap <= self.max_cached and _lib is not None:
-                keys = list(streams)
+                keys = [k for k in streams if k not in self.retired]
                 if len(keys) <= 1:
                     key = keys[0] if keys else self.ANY
                     self.free.setdefault((device, cap), {}).setdefault(key, []).append(ptr)

@@ -72,7 +72,8 @@ $CC -O2             $BASE $INCF $SRC $LUTF -DINTERPOLATE_CHROMA -o "$OUT/libsimd
 
 # 3. the reference PACKAGE itself, compiled: oracle/_ref/refpkg/nphusl_ref/
 #    * its four Python modules (__init__, nphusl, transform, constants) are byte-compiled WHERE THEY LIE into
-#      sourceless .pyc files (a build output like the .so files: no reference source enters the repository);
+#      marshalled code objects (<name>.code, a build output like the .so files: no reference source enters
+#      the repository) with a generated three-line loader each;
 #    * _cython_opt.pyx and _simd_opt.pyx are cythonized into a scratch dir and compiled with the flags of
 #      the reference's setup.py:99-128 (default build: light LUT + chroma LUT + atan2 approximation).
 #    Every import inside the package is relative, so it loads under the name `nphusl_ref` next to this
@@ -85,12 +86,21 @@ PKG="$OUT/refpkg/nphusl_ref"
 rm -rf "$OUT/refhost" "$OUT/refpkg"
 mkdir -p "$PKG"
 "$PY" - "$REF/nphusl" "$PKG" <<'PYEOF'
-import py_compile, sys, os
+# Byte-compile the reference's Python modules where they lie.  The code objects are stored as
+# <name>.code (marshal; *.pyc files do not travel to the GPU box) next to a generated three-line
+# loader <name>.py that executes them in the module's namespace.
+import marshal, os, sys
 src, dst = sys.argv[1:3]
+LOADER = ("# generated by oracle/build_ref.sh: runs the byte-compiled reference module nphusl/%s.py (see %s.code)\n"
+          "import marshal as _m, os as _o\n"
+          "exec(_m.load(open(_o.path.join(_o.path.dirname(__file__), %r), 'rb')), globals())\n")
 for name in ("__init__", "nphusl", "transform", "constants"):
-    py_compile.compile(os.path.join(src, name + ".py"), cfile=os.path.join(dst, name + ".pyc"), doraise=True,
-                       dfile="<reference>/nphusl/%s.py" % name,
-                       invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    with open(os.path.join(src, name + ".py")) as f:
+        code = compile(f.read(), "<reference>/nphusl/%s.py" % name, "exec", dont_inherit=True)
+    with open(os.path.join(dst, name + ".code"), "wb") as f:
+        marshal.dump(code, f)
+    with open(os.path.join(dst, name + ".py"), "w") as f:
+        f.write(LOADER % (name, name, name + ".code"))
 PYEOF
 NPINC="$($PY -c 'import numpy; print(numpy.get_include())')"
 PYINC="$($PY -c 'import sysconfig; print(sysconfig.get_paths()["include"])')"

@@ -301,7 +301,8 @@ def ref_linear_table():
 def ref_package():
     """The reference package itself (nphusl 1.5.0), as compiled by build_ref.sh into
     ``oracle/_ref/refpkg/nphusl_ref``: byte-compiled ``__init__`` / ``nphusl`` / ``transform`` /
-    ``constants`` plus its ``_cython_opt`` and ``_simd_opt`` extension modules.  Imported under the
+    ``constants`` (marshalled code objects behind generated loaders) plus its ``_cython_opt`` and
+    ``_simd_opt`` extension modules.  Imported under the
     name ``nphusl_ref`` (all of its imports are relative), so it can sit beside this repository's
     ``nphusl`` in one process; nothing of this repository is on its code path.  The removed
     ``np.float`` / ``np.int`` aliases it still uses are restored first (SURVEY App. B fix 1)."""
@@ -320,7 +321,7 @@ def ref_package():
 
 
 def have_ref_package():
-    return os.path.isdir(os.path.join(REF_DIR, "refpkg", "nphusl_ref"))
+    return os.path.exists(os.path.join(REF_DIR, "refpkg", "nphusl_ref", "nphusl.code"))
 
 
 def ref_cython():

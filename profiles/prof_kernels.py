@@ -30,7 +30,24 @@ ysurf = torch.randint(0, 256, (frames * 2160, 3840), dtype=torch.uint8, device="
 uvsurf = torch.randint(0, 256, (frames * 1080, 3840), dtype=torch.uint8, device="cuda", generator=g)
 f64in = (rgb[:2].to(torch.float64) / 255.0).contiguous()
 f64out = torch.empty_like(f64in)
+f32in, f32out = f64in.to(torch.float32), torch.empty(f64in.shape, dtype=torch.float32, device="cuda")
+grey = torch.rand((2 * 2160, 3840), dtype=torch.float64, device="cuda", generator=g)
+grey_hue = torch.empty_like(grey)
+edit = _cuda.Edit(hue=(250, 290), invert=True, l=(0.5, 0))
+_cuda.lut_generate()
+import nphusl  # noqa: E402
+import warnings  # noqa: E402
+warnings.simplefilter("ignore")
 for _ in range(reps):
+    _cuda._rgb_to_husl(rgb, out=h64, mode="lut")  # the reference's default build, bit-exact LUT mode
+    _cuda._rgb_to_husl(rgb, out=h64, mode="lut_interp")
+    _cuda._rgb_to_husl(f32in, out=f32out, dtype=np.float32)   # float32 RGB -> float32 HUSL
+    nphusl.to_hue(grey, out=grey_hue)             # grayscale float64 -> hue (config 3)
+    _cuda._rgb_to_husl(rgb, out=h64)
+    _cuda._husl_to_rgb(h64, out=back, edit=edit)  # to_rgb with the edit applied on load (bench headline step)
+    _cuda._rgb_to_husl(rgb, out=h32)
+    _cuda._husl_to_rgb(h32, out=back, edit=edit)
+    _cuda.edit_husl(h64, edit)
     _cuda._rgb_to_husl(rgb, out=h64)
     _cuda._husl_to_rgb(h64, out=back)
     _cuda._rgb_to_husl(rgb, out=h32)

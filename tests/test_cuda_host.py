@@ -348,6 +348,18 @@ def test_device_pool_orders_block_reuse_by_stream(monkeypatch):
     pool.release(p4, cap, 0, ())                         # never used by a kernel
     pool.release(p5, cap, 0, {44})
     assert pool.cached == 2 * cap
+    # a stream that was drained and destroyed (Stream.close) is forgotten: its blocks are idle everywhere and
+    # its handle is never given to the driver again
+    p8, _ = pool.alloc(n, 0, 55)
+    assert p8 in (p1, p4)
+    pool.release(p8, cap, 0, {55})
+    n_events = len(fake.events)
+    pool.retire(55)
+    p9, _ = pool.alloc(n, 0, 66)
+    assert p9 == p8 and len(fake.events) == n_events and len(fake.waits) == 1
+    pool.release(p9, cap, 0, {55, 66})                   # 55 is retired: one live stream left -> plain free list
+    assert not pool.parked
+    pool.revive(55)
     # a second device never sees device 0's blocks
     p6, _ = pool.alloc(n, 1, 44)
     assert p6 not in (p1, p4) and pool.misses == 3
