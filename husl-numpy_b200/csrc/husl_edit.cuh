@@ -46,17 +46,21 @@ struct EditShape {
     __host__ explicit EditShape(const nphusl_edit &e)
         : eh(e.h_mul != 1.0f || e.h_add != 0.0f), es(e.s_mul != 1.0f || e.s_add != 0.0f),
           rsl(!(e.s_lo == -INFINITY && e.s_hi == INFINITY && e.l_lo == -INFINITY && e.l_hi == INFINITY)) {}
+    __host__ int code() const { return (eh ? 1 : 0) | (es ? 2 : 0) | (rsl ? 4 : 0); }
 };
 
-// kernel argument that costs nothing when a kernel is instantiated without the edit stage
-template <bool EDIT> struct EditArg {};
-template <> struct EditArg<true> { nphusl_edit e; };
-template <bool EDIT>
-__device__ __forceinline__ void edit_on_load(const EditArg<EDIT> &, float &, float &, float &) {}
-template <>
-__device__ __forceinline__ void edit_on_load<true>(const EditArg<true> &a, float &h, float &s, float &l) {
-    apply_edit<true, true, true>(a.e, h, s, l);
+// Edit stage of kernels that can run with or without one.  ED = -1: no edit (the argument is an empty
+// struct and the stage compiles to nothing); ED = 0..7: EditShape bits (1 = hue may be edited, 2 = saturation
+// may be edited, 4 = a saturation / lightness range may be bounded), so an edit that only scales L inside a
+// hue arc (README.md:77-81) adds a handful of instructions; 7 is valid for every descriptor.
+template <int ED> struct EditArg { nphusl_edit e; };
+template <> struct EditArg<-1> {};
+template <int ED>
+__device__ __forceinline__ void edit_on_load(const EditArg<ED> &a, float &h, float &s, float &l) {
+    apply_edit<(ED & 1) != 0, (ED & 2) != 0, (ED & 4) != 0>(a.e, h, s, l);
 }
+template <>
+__device__ __forceinline__ void edit_on_load<-1>(const EditArg<-1> &, float &, float &, float &) {}
 
 // ---------------------------------------------------------------------------------
 // in-place (or out-of-place) edit of an interleaved HUSL array: what a caller's

@@ -187,7 +187,7 @@ k_inv_flt(const TIn *__restrict__ in, TOut *__restrict__ out, long long n_tiles)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
-            rgb255_from_husl<true, sizeof(TIn) == 8>(v[3 * j], v[3 * j + 1], v[3 * j + 2], R, G, B);
+            rgb255_from_husl<true, wide_in<TIn>()>(v[3 * j], v[3 * j + 1], v[3 * j + 2], R, G, B);
             r[3 * j] = R * (1.0f / 255.0f); r[3 * j + 1] = G * (1.0f / 255.0f); r[3 * j + 2] = B * (1.0f / 255.0f);
         }
         store12<TOut>(stage, lane, r, out + tile * (TILE_PX * 3));

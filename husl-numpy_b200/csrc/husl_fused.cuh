@@ -130,7 +130,7 @@ k_inv_planar(const TIn *__restrict__ H, const TIn *__restrict__ S, const TIn *__
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
-            rgb255_from_husl<false, sizeof(TIn) == 8>(h[j], s[j], l[j], R, G, B);
+            rgb255_from_husl<false, wide_in<TIn>()>(h[j], s[j], l[j], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }
         uint32_t o0, o1, o2;
@@ -160,7 +160,7 @@ k_inv_planar_any(const T *__restrict__ H, const T *__restrict__ S, const T *__re
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float R, G, B;
-        rgb255_from_husl<false, sizeof(T) == 8>((float)H[i], (float)S[i], (float)L[i], R, G, B);
+        rgb255_from_husl<false, wide_in<T>()>((float)H[i], (float)S[i], (float)L[i], R, G, B);
         out[3 * i] = (uint8_t)(round_u8_bits(R) & 0xFF);
         out[3 * i + 1] = (uint8_t)(round_u8_bits(G) & 0xFF);
         out[3 * i + 2] = (uint8_t)(round_u8_bits(B) & 0xFF);
@@ -303,7 +303,7 @@ k_inv_chw(const TIn *__restrict__ H, const TIn *__restrict__ S, const TIn *__res
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float r, g, b;
-            rgb255_from_husl<false, sizeof(TIn) == 8>(h[j], s[j], l[j], r, g, b);
+            rgb255_from_husl<false, wide_in<TIn>()>(h[j], s[j], l[j], r, g, b);
             q[3 * j] = round_u8_bits(r); q[3 * j + 1] = round_u8_bits(g); q[3 * j + 2] = round_u8_bits(b);
         }
         // plane words: byte j of a word = pixel j of this lane
@@ -336,7 +336,7 @@ k_inv_chw_any(const T *__restrict__ H, const T *__restrict__ S, const T *__restr
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float r, g, b;
-        rgb255_from_husl<false, sizeof(T) == 8>((float)H[i], (float)S[i], (float)L[i], r, g, b);
+        rgb255_from_husl<false, wide_in<T>()>((float)H[i], (float)S[i], (float)L[i], r, g, b);
         R[i] = (uint8_t)(round_u8_bits(r) & 0xFF);
         G[i] = (uint8_t)(round_u8_bits(g) & 0xFF);
         B[i] = (uint8_t)(round_u8_bits(b) & 0xFF);

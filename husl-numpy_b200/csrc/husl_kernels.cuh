@@ -229,7 +229,7 @@ k_inv_u8(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_til
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
-            rgb255_from_husl<false, sizeof(TIn) == 8>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
+            rgb255_from_husl<false, wide_in<TIn>()>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }
         // pack 12 low bytes into 3 words (PRMT), lane-contiguous 12 B -> staging -> coalesced
@@ -308,15 +308,38 @@ k_fwd_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, int c
     }
 }
 
-template <typename TIn, typename TOut, bool EDIT = false>
+// Grayscale -> hue (reshape_image_input's grayscale route into to_hue, transform.py:168-173, 210-215).
+// R = G = B makes both hue forms equal their grey offsets (husl_math.cuh: hue_forms), so every non-black grey
+// has ONE hue -- hue_deg(GREY_V, GREY_U), the hue of white -- and black has 0: no linearisation, no arctangent
+// per pixel, the kernel is a pure 16 B/px (float64 -> float64) stream.  Bit-identical to k_fwd_any<.., HUE>
+// on a grey image, including what that kernel answers for negative, NaN and overflowing inputs.
+template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
-k_inv_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, const EditArg<EDIT> ea = EditArg<EDIT>()) {
+k_gray_hue(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
+    const float grey_hue = hue_deg(GREY_V, GREY_U);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool lit;
+        if (sizeof(TIn) == 1) {
+            lit = in[i] != 0;
+        } else {
+            const double c = (double)in[i];
+            // the linear value the general kernel would form is positive and finite (lin_f64: x^2.4 through float x)
+            lit = (c > 0.04045) ? ((float)fma(c, 1.0 / 1.055, 0.055 / 1.055) < INFINITY) : ((float)(c * (1.0 / 12.92)) > 0.0f);
+        }
+        out[i] = (TOut)(lit ? grey_hue : 0.0f);
+    }
+}
+
+template <typename TIn, typename TOut, int ED = -1>
+__global__ void __launch_bounds__(256)
+k_inv_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, const EditArg<ED> ea = EditArg<ED>()) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float R, G, B;
         float h = (float)in[3 * i], s = (float)in[3 * i + 1], l = (float)in[3 * i + 2];
-        edit_on_load<EDIT>(ea, h, s, l);
-        rgb255_from_husl<sizeof(TOut) != 1, sizeof(TIn) == 8 && !EDIT>(h, s, l, R, G, B);
+        edit_on_load<ED>(ea, h, s, l);
+        rgb255_from_husl<sizeof(TOut) != 1, wide_in<TIn>() && ED < 0>(h, s, l, R, G, B);
         if (sizeof(TOut) == 1) {
             out[3 * i] = (TOut)(round_u8_bits(R) & 0xFF);
             out[3 * i + 1] = (TOut)(round_u8_bits(G) & 0xFF);

@@ -20,12 +20,20 @@ namespace husl {
 // times the int scale (the default, LIGHT_SCALE = CHROMA_SCALE = 100), or float /
 // double holding the 4- / 3-decimal literal itself (scales 1).  The kernels are
 // templated on the element type; the arithmetic on the promoted double is the same.
+//
+// Derived tables (k_lut_prepare, built once when tables are installed) take IEEE operations
+// whose operands come from a table out of the per-pixel path without changing a bit:
+//   prod[k][c]  = coef_k * linear[c]            the nine products of the XYZ matrix (_simd.c:171-173)
+//   light_q[i]  = light_table_big[i] / LIGHT_SCALE                                  (_simd.c:495)
 struct LutParams {
     const double *linear;     // 256, 6-decimal values (_linear_lookup.c:9-42)
     const void *light;        // 3*seg entries (light_table_big)
     const void *chroma;       // nh*nl entries (chroma_table)
+    const double *prod;       // 9 * 256 (derived)
+    const double *light_q;    // 3*seg (derived)
     int seg, nh, nl;
     double ystep[3], ythresh[2], hstep, lstep;
+    double r_ystep[3], r_hstep, r_lstep;   // RN(1 / step), for the exactly rounded divisions below
     double light_scale;       // LIGHT_SCALE
     double sat_scale;         // 100 * CHROMA_SCALE (_simd.c:334)
 };
@@ -35,15 +43,27 @@ __device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b
 __device__ __forceinline__ double ds(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dd(double a, double b) { return __ddiv_rn(a, b); }
 
+// a / b given rb = RN(1/b): q0 = RN(a*rb) is within an ulp of the quotient, the residual
+// r = a - q0*b is exact in one FMA, and RN(q0 + r*rb) is the correctly rounded quotient
+// (Markstein's division step).  3 DP instructions instead of the ~13 of a general
+// __ddiv_rn (reciprocal seed, Newton iterations, range fix-ups).  Used where the divisor is a
+// run-time constant of the tables (index steps) or shared by two quotients (u', v'); every
+// input this kernel can see is one of the 2^24 colours, and the sha256 of the whole cube
+// against the reference's own C output (tests/test_cuda_parity.py) pins the result bit for bit.
+__device__ __forceinline__ double cdiv(double a, double b, double rb) {
+    const double q0 = __dmul_rn(a, rb);
+    const double r = __fma_rn(-q0, b, a);
+    return __fma_rn(r, rb, q0);
+}
+
 // _simd.c:485-496
-template <typename TT>
 __device__ __forceinline__ double lut_light(const LutParams &t, double y) {
     double idx;
-    if (y < t.ythresh[0]) idx = dd(y, t.ystep[0]);
-    else if (y < t.ythresh[1]) idx = da(dd(ds(y, t.ythresh[0]), t.ystep[1]), (double)t.seg);
-    else idx = da(dd(ds(y, t.ythresh[1]), t.ystep[2]), (double)(t.seg * 2));
+    if (y < t.ythresh[0]) idx = cdiv(y, t.ystep[0], t.r_ystep[0]);
+    else if (y < t.ythresh[1]) idx = da(cdiv(ds(y, t.ythresh[0]), t.ystep[1], t.r_ystep[1]), (double)t.seg);
+    else idx = da(cdiv(ds(y, t.ythresh[1]), t.ystep[2], t.r_ystep[2]), (double)(t.seg * 2));
     const double r = fmax(0.0, fmin((double)(3 * t.seg - 1), (double)roundf(__double2float_rn(idx))));
-    return dd((double)static_cast<const TT *>(t.light)[(unsigned short)r], t.light_scale);
+    return __ldg(t.light_q + (unsigned short)r);
 }
 
 // _simd.c:279-281
@@ -52,29 +72,12 @@ __device__ __forceinline__ double lut_atan(double z) {
     return ds(dm(0.78539816339744830962, z), dm(dm(z, ds(az, 1.0)), da(0.2447, dm(0.0663, az))));
 }
 
-// _simd.c:288-315
-__device__ __forceinline__ double lut_atan2(double y, double x) {
-    const double PI_ = 3.141592653589793, PIBY2 = 1.5707963267948966;
-    if (x == 0.0) {
-        if (y > 0.0) return PIBY2;
-        if (y == 0.0) return 0.0;
-        return -PIBY2;
-    }
-    const double z = dd(y, x);
-    double at;
-    if (fabs(z) < 1.0) {
-        at = dd(z, da(1.0, dm(dm(0.28, z), z)));
-        if (x < 0.0) return (y < 0.0) ? ds(at, PI_) : da(at, PI_);
-    } else {
-        at = ds(PIBY2, dd(z, da(dm(z, z), 0.28)));
-        if (y < 0.0) return ds(at, PI_);
-    }
-    return at;
-}
-
-// _simd.c:246-266
+// _simd.c:246-266 with :288-315 inlined.  to_hue calls the atan2 approximation only when
+// |v/u| >= 1, and that function divides the same two numbers again: its z is this z, its
+// "|z| < 1" branch cannot be taken, and what is left is the u == 0 guard and one division.
 __device__ __forceinline__ double lut_hue(double u, double v) {
     const double DEG_PER_RAD = 180.0 / 3.14159265358979323846;
+    const double PI_ = 3.141592653589793, PIBY2 = 1.5707963267948966;
     const double z = dd(v, u);
     double hue;
     if (fabs(z) < 1.0) {
@@ -82,7 +85,14 @@ __device__ __forceinline__ double lut_hue(double u, double v) {
         if (u < 0) hue = da(hue, 180.0);
         else if (v < 0) hue = da(hue, 360.0);
     } else {
-        hue = dm(lut_atan2(v, u), DEG_PER_RAD);
+        double at;
+        if (u == 0.0) {
+            at = (v > 0.0) ? PIBY2 : ((v == 0.0) ? 0.0 : -PIBY2);
+        } else {
+            at = ds(PIBY2, dd(z, da(dm(z, z), 0.28)));
+            if (v < 0.0) at = ds(at, PI_);
+        }
+        hue = dm(at, DEG_PER_RAD);
         if (hue < 0.0) hue = da(hue, 360.0);
     }
     return hue;
@@ -92,51 +102,70 @@ __device__ __forceinline__ double lut_hue(double u, double v) {
 template <bool INTERP, typename TT>
 __device__ __forceinline__ double lut_chroma(const LutParams &t, double l, double h) {
     const TT *chroma = static_cast<const TT *>(t.chroma);
-    const double hs = dd(h, t.hstep), ls = dd(l, t.lstep);
+    const double hs = cdiv(h, t.hstep, t.r_hstep), ls = cdiv(l, t.lstep, t.r_lstep);
     if (!INTERP) {
         const unsigned short hi = (unsigned short)fmax(0.0, fmin((double)(t.nh - 1), (double)roundf(__double2float_rn(hs))));
         const unsigned short li = (unsigned short)fmax(0.0, fmin((double)(t.nl - 1), (double)roundf(__double2float_rn(ls))));
-        return fmax(1e-10, (double)chroma[(size_t)hi * t.nl + li]);
+        return fmax(1e-10, (double)__ldg(chroma + (size_t)hi * t.nl + li));
     }
     const unsigned short hf = (unsigned short)fmax(0.0, fmin((double)(t.nh - 2), (double)floorf(__double2float_rn(hs))));
     const unsigned short lf = (unsigned short)fmax(0.0, fmin((double)(t.nl - 2), (double)floorf(__double2float_rn(ls))));
-    const double c00 = chroma[(size_t)hf * t.nl + lf];
-    const double c10 = chroma[(size_t)(hf + 1) * t.nl + lf];
-    const double c01 = chroma[(size_t)hf * t.nl + lf + 1];
-    const double c11 = chroma[(size_t)(hf + 1) * t.nl + lf + 1];
+    const double c00 = __ldg(chroma + (size_t)hf * t.nl + lf);
+    const double c10 = __ldg(chroma + (size_t)(hf + 1) * t.nl + lf);
+    const double c01 = __ldg(chroma + (size_t)hf * t.nl + lf + 1);
+    const double c11 = __ldg(chroma + (size_t)(hf + 1) * t.nl + lf + 1);
     const double hn = ds(hs, (double)hf), ln = ds(ls, (double)lf);
     const double hv = ds(1.0, hn), lv = ds(1.0, ln);
     const double c = da(da(da(dm(dm(c00, hv), lv), dm(dm(c10, hn), lv)), dm(dm(c01, hv), ln)), dm(dm(c11, hn), ln));
     return fmax((double)1e-10f, c);
 }
 
-// rgb_to_husl_nd, default build: _simd.c:87-225
+// One pixel of rgb_to_husl_nd, default build (_simd.c:128-225).  `prod` is the 9 x 256 product table
+// (shared memory in the tile kernel, global / L1 in the one-pixel-per-thread kernel).
+template <bool INTERP, typename TT>
+__device__ __forceinline__ void lut_pixel(const LutParams &t, const double *prod, uint32_t r, uint32_t g, uint32_t b,
+                                          double &H, double &S, double &L) {
+    const double REF_U = 0.19783000664283, REF_V = 0.46831999493879;
+    const double x = da(da(prod[r], prod[256 + g]), prod[512 + b]);
+    const double y = da(da(prod[768 + r], prod[1024 + g]), prod[1280 + b]);
+    const double z = da(da(prod[1536 + r], prod[1792 + g]), prod[2048 + b]);
+    const double vs = da(da(x, dm(15.0, y)), dm(3.0, z));
+    const double rvs = __drcp_rn(vs);
+    const double var_u = cdiv(dm(4.0, x), vs, rvs), var_v = cdiv(dm(9.0, y), vs, rvs);
+    const double l = lut_light(t, y);
+    const double l13 = dm(l, 13.0);
+    const double u = dm(l13, ds(var_u, REF_U)), v = dm(l13, ds(var_v, REF_V));
+    const double h = lut_hue(u, v);
+    const double mc = lut_chroma<INTERP, TT>(t, l, h);
+    const double sat = dd(dm(t.sat_scale, __dsqrt_rn(da(dm(u, u), dm(v, v)))), mc);
+    // _simd.c:205-212: pure white and pure black are answered with constants
+    const bool white = (r & g & b) == 255u, black = (r | g | b) == 0u;
+    H = white ? 19.916405993809086 : (black ? 0.0 : h);
+    S = (white || black) ? 0.0 : fmin(sat, 100.0);
+    L = white ? 100.0 : (black ? 0.0 : l);
+}
+
+// rgb_to_husl_nd, one pixel per thread: tails (< 128 pixels) and unaligned buffers
 template <bool INTERP, typename TT>
 __global__ void __launch_bounds__(256)
 k_fwd_lut(const uint8_t *__restrict__ rgb, double *__restrict__ hsl, long long n, LutParams t) {
-    const double REF_U = 0.19783000664283, REF_V = 0.46831999493879;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint8_t r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+        double H, S, L;
+        lut_pixel<INTERP, TT>(t, t.prod, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], H, S, L);
         double *o = hsl + 3 * i;
-        if (r == 255 && g == 255 && b == 255) { o[0] = 19.916405993809086; o[1] = 0.0; o[2] = 100.0; continue; }
-        if (!r && !g && !b) { o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; continue; }
-        const double rl = t.linear[r], gl = t.linear[g], bl = t.linear[b];
-        const double x = da(da(dm(0.412391, rl), dm(0.357584, gl)), dm(0.180481, bl));
-        const double y = da(da(dm(0.212639, rl), dm(0.715169, gl)), dm(0.072192, bl));
-        const double z = da(da(dm(0.019331, rl), dm(0.119195, gl)), dm(0.950532, bl));
-        const double vs = da(da(x, dm(15.0, y)), dm(3.0, z));
-        const double var_u = dd(dm(4.0, x), vs), var_v = dd(dm(9.0, y), vs);
-        const double l = lut_light<TT>(t, y);
-        const double l13 = dm(l, 13.0);
-        const double u = dm(l13, ds(var_u, REF_U)), v = dm(l13, ds(var_v, REF_V));
-        const double h = lut_hue(u, v);
-        const double mc = lut_chroma<INTERP, TT>(t, l, h);
-        const double sat = dd(dm(t.sat_scale, __dsqrt_rn(da(dm(u, u), dm(v, v)))), mc);
-        o[0] = h;
-        o[1] = fmin(sat, 100.0);
-        o[2] = l;
+        o[0] = H; o[1] = S; o[2] = L;
     }
+}
+
+// derived tables, see LutParams
+template <typename TT>
+__global__ void k_lut_prepare(const double *linear, const TT *light, int n_light, double light_scale,
+                              double *prod, double *light_q) {
+    const double coef[9] = {0.412391, 0.357584, 0.180481, 0.212639, 0.715169, 0.072192, 0.019331, 0.119195, 0.950532};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 9 * 256) prod[i] = __dmul_rn(coef[i >> 8], linear[i & 255]);
+    if (i < n_light) light_q[i] = __ddiv_rn((double)light[i], light_scale);
 }
 
 // ---- device-side table generation (make_lookup_tables:8-9) -------------------------------

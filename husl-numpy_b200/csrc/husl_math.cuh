@@ -218,6 +218,15 @@ __device__ __forceinline__ float from_linear_255(float v) {
 // shorter form tried, although the short forms are faster stand-alone (0.280 vs
 // 0.284 ms).  The float32 kernels (48 warps/SM, issue-bound) gain 7 % from the
 // short form (profiles/r01_ab_variants.txt, runs 22-27).
+// Round 2: ONE formulation for every HUSL input type (HUSL_WIDE_F64 = 0): to_rgb of a float64 array, of the
+// same values as float32, with or without an edit applied on load, and the fused uint8 kernels all produce
+// the same bits.  The long-hand form stays selectable as an A/B knob (it was worth 1 % of the float64
+// to_husl -> to_rgb pipeline and cost the bit-for-bit equality of those paths).
+#ifndef HUSL_WIDE_F64
+#define HUSL_WIDE_F64 0
+#endif
+template <typename T> __host__ __device__ constexpr bool wide_in() { return HUSL_WIDE_F64 && sizeof(T) == 8; }
+
 template <bool EXACT_EXT = false, bool WIDE = false>
 __device__ __forceinline__ void rgb255_from_husl(float H, float S, float L,
                                                  float &R, float &G, float &B) {

@@ -188,7 +188,7 @@ k_rows_inv(const View2 in, const View2 out) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float Rr, G, B;
-                rgb255_from_husl<false, sizeof(TIn) == 8>(v[3 * j], v[3 * j + 1], v[3 * j + 2], Rr, G, B);
+                rgb255_from_husl<false, wide_in<TIn>()>(v[3 * j], v[3 * j + 1], v[3 * j + 2], Rr, G, B);
                 q[3 * j] = round_u8_bits(Rr); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
             }
             uint32_t o0, o1, o2;

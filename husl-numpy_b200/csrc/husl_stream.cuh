@@ -209,9 +209,9 @@ struct InvSmem {
 // EDIT: the caller's HUSL-space select + edit (husl_edit.cuh) is applied to the loaded values before
 // the inverse -- to_rgb(hsl, edit=...) -- so a to_husl -> edit -> to_rgb pipeline needs no pass of its own
 // over the 24 B/px HUSL array for the edit.
-template <typename TIn, int BLOCK, int MINB, int IST, bool EDIT = false>
+template <typename TIn, int BLOCK, int MINB, int IST, int ED = -1>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const EditArg<EDIT> ea = EditArg<EDIT>()) {
+k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const EditArg<ED> ea = EditArg<ED>()) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TB = Tile<TIn>::BYTES;
@@ -277,10 +277,10 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
-            edit_on_load<EDIT>(ea, hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2]);
+            edit_on_load<ED>(ea, hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2]);
             // the edit-on-load instantiation uses the fused kernels' formulation (k_edit), so that
             // to_rgb(to_husl(x), edit=e) == nphusl.edit(x, e) bit for bit for float64 HUSL as well
-            rgb255_from_husl<false, sizeof(TIn) == 8 && !EDIT>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
+            rgb255_from_husl<false, wide_in<TIn>() && ED < 0>(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }
         const uint32_t o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
@@ -326,9 +326,9 @@ struct InvCpSmem {
     static constexpr int PER_WARP = IST * Tile<float>::BYTES + U8_TILE;
 };
 
-template <int BLOCK, int MINB, int IST, bool EDIT = false>
+template <int BLOCK, int MINB, int IST, int ED = -1>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const EditArg<EDIT> ea = EditArg<EDIT>()) {
+k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const EditArg<ED> ea = EditArg<ED>()) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TB = Tile<float>::BYTES;
@@ -378,7 +378,7 @@ k_inv_cp(const float *__restrict__ in, uint32_t *__restrict__ out, long long n_t
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float R, G, B;
-            edit_on_load<EDIT>(ea, hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2]);
+            edit_on_load<ED>(ea, hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2]);
             rgb255_from_husl(hsl[3 * j], hsl[3 * j + 1], hsl[3 * j + 2], R, G, B);
             q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
         }

@@ -81,7 +81,7 @@ k_inv_strided(const View2 in, const View2 out) {
         for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < in.cols; x += xstep) {
             const char *p = irow + x * in.cs;
             float R, G, B;
-            rgb255_from_husl<sizeof(TOut) != 1, sizeof(TIn) == 8>((float)*reinterpret_cast<const TIn *>(p), (float)*reinterpret_cast<const TIn *>(p + in.es),
+            rgb255_from_husl<sizeof(TOut) != 1, wide_in<TIn>()>((float)*reinterpret_cast<const TIn *>(p), (float)*reinterpret_cast<const TIn *>(p + in.es),
                                                 (float)*reinterpret_cast<const TIn *>(p + 2 * in.es), R, G, B);
             char *o = orow + x * out.cs;
             if (sizeof(TOut) == 1) {

@@ -20,6 +20,7 @@
 #include "husl_kernels.cuh"
 #include "husl_stream.cuh"
 #include "husl_lut.cuh"
+#include "husl_lut_tile.cuh"
 #include "husl_nv12.cuh"
 #include "husl_nv12_out.cuh"
 #include "husl_float.cuh"
@@ -79,7 +80,7 @@ struct Lut {
     int seg = 0, nh = 0, nl = 0;
     int type = NPHUSL_LUT_U16;           // element type of light / chroma
     void *light = nullptr, *chroma = nullptr;
-    double *linear = nullptr;
+    double *linear = nullptr, *prod = nullptr, *light_q = nullptr;   // prod / light_q: derived tables (husl_lut.cuh)
     double light_scale = 100, chroma_scale = 100;
     LutParams p{};
 };
@@ -284,7 +285,7 @@ template <typename TIn, typename TOut>
 int launch_inv_any(DevCtx &c, const void *in, void *out, long long n, cudaStream_t s, const nphusl_edit *edit = nullptr) {
     if (n <= 0) return NPHUSL_OK;
     const int grid = grid_for(n, 256, c.sms * 8);
-    if (edit) k_inv_any<TIn, TOut, true><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n, EditArg<true>{*edit});
+    if (edit) k_inv_any<TIn, TOut, 7><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n, EditArg<7>{*edit});
     else k_inv_any<TIn, TOut><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n);
     g_launches++;
     return check_launch("k_inv_any");
@@ -311,6 +312,18 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
     int rc;
     const size_t out_px = (HUE ? 1 : 3) * dsize(out_dt);
     long long done = 0;
+    if (HUE && channels == 1) {
+        // grayscale -> hue is a constant per lit pixel: one streaming kernel, no per-pixel colour math
+        if (n <= 0) return NPHUSL_OK;
+        const int grid = grid_for(n, 256, c.sms * 8);
+#define GRAY_GO(TI, TO) k_gray_hue<TI, TO><<<grid, 256, 0, s>>>((const TI *)in, (TO *)out, n)
+        if (in_dt == NPHUSL_U8) { if (out_dt == NPHUSL_F32) GRAY_GO(uint8_t, float); else GRAY_GO(uint8_t, double); }
+        else if (in_dt == NPHUSL_F32) { if (out_dt == NPHUSL_F32) GRAY_GO(float, float); else GRAY_GO(float, double); }
+        else { if (out_dt == NPHUSL_F32) GRAY_GO(double, float); else GRAY_GO(double, double); }
+#undef GRAY_GO
+        g_launches++;
+        return check_launch("k_gray_hue");
+    }
     if (in_dt == NPHUSL_U8 && channels == 3 && aligned(in, 4) && aligned(out, HUE ? 32 : 16) && n >= TILE_PX) {
         if ((rc = set_attrs(c))) return rc;
         const long long tiles = n / TILE_PX;
@@ -383,19 +396,35 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
     long long done = 0;
     if (edit && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
-        static std::atomic<bool> attr32[MAX_DEV], attr64[MAX_DEV];
-        const EditArg<true> ea{*edit};
-        if (in_dt == NPHUSL_F32) {
-            constexpr int sm = (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP;
-            if ((rc = flt_attr(attr32, c, k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, true>, sm))) return rc;
-            k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, true><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK, sm, s>>>(
-                (const float *)in, (uint32_t *)out, tiles, ea);
-        } else {
-            constexpr int sm = (INV64_BLOCK / 32) * InvSmem<double, INV64_IST>::PER_WARP;
-            if ((rc = flt_attr(attr64, c, k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST, true>, sm))) return rc;
-            k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST, true><<<grid_for(tiles, INV64_BLOCK / 32, c.sms * INV64_MINB), INV64_BLOCK, sm, s>>>(
-                (const double *)in, (uint32_t *)out, tiles, ea);
+        const int code = EditShape(*edit).code();
+        // instantiated per edit shape like k_edit: README-style edits (L scaled inside / outside a hue arc) carry no
+        // hue-wrap, saturation or range arithmetic
+#define INV_EDIT(ED) do { \
+        const EditArg<ED> ea{*edit}; \
+        if (in_dt == NPHUSL_F32) { \
+            constexpr int sm = (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP; \
+            static std::atomic<bool> attr32[MAX_DEV]; \
+            if ((rc = flt_attr(attr32, c, k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, ED>, sm))) return rc; \
+            k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, ED><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK, sm, s>>>( \
+                (const float *)in, (uint32_t *)out, tiles, ea); \
+        } else { \
+            constexpr int sm = (INV64_BLOCK / 32) * InvSmem<double, INV64_IST>::PER_WARP; \
+            static std::atomic<bool> attr64[MAX_DEV]; \
+            if ((rc = flt_attr(attr64, c, k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST, ED>, sm))) return rc; \
+            k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST, ED><<<grid_for(tiles, INV64_BLOCK / 32, c.sms * INV64_MINB), INV64_BLOCK, sm, s>>>( \
+                (const double *)in, (uint32_t *)out, tiles, ea); \
+        } } while (0)
+        switch (code) {
+            case 0: INV_EDIT(0); break;
+            case 1: INV_EDIT(1); break;
+            case 2: INV_EDIT(2); break;
+            case 3: INV_EDIT(3); break;
+            case 4: INV_EDIT(4); break;
+            case 5: INV_EDIT(5); break;
+            case 6: INV_EDIT(6); break;
+            default: INV_EDIT(7); break;
         }
+#undef INV_EDIT
         g_launches++;
         if ((rc = check_launch("k_inv (edit on load)"))) return rc;
         done = tiles * TILE_PX;
@@ -459,12 +488,43 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
 #undef INV_ANY
 }
 
+#ifndef NPHUSL_LUT_BLOCK
+#define NPHUSL_LUT_BLOCK 256
+#define NPHUSL_LUT_MINB 3
+#endif
+constexpr int LUT_BLOCK = NPHUSL_LUT_BLOCK, LUT_MINB = NPHUSL_LUT_MINB, LUT_OST = 2;
+
 int run_lut_dev(DevCtx &c, const void *in, void *out, long long n, int mode, cudaStream_t s) {
     if (!c.lut.ready) return fail(NPHUSL_ERR_NO_LUT, "LUT mode: call nphusl_cuda_lut_generate or nphusl_cuda_lut_upload first");
     if (n <= 0) return NPHUSL_OK;
-    const int grid = grid_for(n, 256, c.sms * 8);
-#define LUT_GO(TT) do { if (mode == NPHUSL_LUT) k_fwd_lut<false, TT><<<grid, 256, 0, s>>>((const uint8_t *)in, (double *)out, n, c.lut.p); \
-                        else k_fwd_lut<true, TT><<<grid, 256, 0, s>>>((const uint8_t *)in, (double *)out, n, c.lut.p); } while (0)
+    int rc;
+    long long done = 0;
+    if (aligned(in, 4) && aligned(out, 16) && n >= TILE_PX) {
+        // whole 128-pixel tiles: the streaming skeleton (husl_lut_tile.cuh)
+        const long long tiles = n / TILE_PX;
+        constexpr int sm = LUT_PROD_BYTES + (LUT_BLOCK / 32) * LUT_OST * Tile<double>::BYTES;
+        const int grid = grid_for(tiles, LUT_BLOCK / 32, c.sms * LUT_MINB);
+#define LUT_TILE(INTERP, TT) do { \
+        static std::atomic<bool> attr_done[MAX_DEV]; \
+        if ((rc = flt_attr(attr_done, c, k_fwd_lut_tile<INTERP, TT, LUT_BLOCK, LUT_MINB, LUT_OST>, sm))) return rc; \
+        k_fwd_lut_tile<INTERP, TT, LUT_BLOCK, LUT_MINB, LUT_OST><<<grid, LUT_BLOCK, sm, s>>>((const uint32_t *)in, (double *)out, tiles, c.lut.p); } while (0)
+#define LUT_TILE_T(TT) do { if (mode == NPHUSL_LUT) LUT_TILE(false, TT); else LUT_TILE(true, TT); } while (0)
+        if (c.lut.type == NPHUSL_LUT_U16) LUT_TILE_T(uint16_t);
+        else if (c.lut.type == NPHUSL_LUT_F32) LUT_TILE_T(float);
+        else LUT_TILE_T(double);
+#undef LUT_TILE_T
+#undef LUT_TILE
+        g_launches++;
+        if ((rc = check_launch("k_fwd_lut_tile"))) return rc;
+        done = tiles * TILE_PX;
+    }
+    const long long rest = n - done;
+    if (rest <= 0) return NPHUSL_OK;
+    const uint8_t *ip = (const uint8_t *)in + 3 * done;
+    double *op = (double *)out + 3 * done;
+    const int grid = grid_for(rest, 256, c.sms * 8);
+#define LUT_GO(TT) do { if (mode == NPHUSL_LUT) k_fwd_lut<false, TT><<<grid, 256, 0, s>>>(ip, op, rest, c.lut.p); \
+                        else k_fwd_lut<true, TT><<<grid, 256, 0, s>>>(ip, op, rest, c.lut.p); } while (0)
     if (c.lut.type == NPHUSL_LUT_U16) LUT_GO(uint16_t);
     else if (c.lut.type == NPHUSL_LUT_F32) LUT_GO(float);
     else LUT_GO(double);
@@ -1431,18 +1491,41 @@ int nphusl_cuda_rgb_edit_rgb_strided(const nphusl_view *rgb_in, const nphusl_vie
 }
 
 // ---- lookup tables ---------------------------------------------------------------------
+// derived tables and reciprocal steps (husl_lut.cuh), once the tables and steps are installed
+static int lut_finish(DevCtx &c) {
+    Lut &l = c.lut;
+    for (int i = 0; i < 3; ++i) l.p.r_ystep[i] = 1.0 / l.p.ystep[i];
+    l.p.r_hstep = 1.0 / l.p.hstep;
+    l.p.r_lstep = 1.0 / l.p.lstep;
+    const int n_light = 3 * l.seg, n = n_light > 9 * 256 ? n_light : 9 * 256;
+    if (l.type == NPHUSL_LUT_U16) k_lut_prepare<uint16_t><<<(n + 255) / 256, 256>>>(l.linear, (const uint16_t *)l.light, n_light, l.light_scale, l.prod, l.light_q);
+    else if (l.type == NPHUSL_LUT_F32) k_lut_prepare<float><<<(n + 255) / 256, 256>>>(l.linear, (const float *)l.light, n_light, l.light_scale, l.prod, l.light_q);
+    else k_lut_prepare<double><<<(n + 255) / 256, 256>>>(l.linear, (const double *)l.light, n_light, l.light_scale, l.prod, l.light_q);
+    g_launches++;
+    int rc = check_launch("k_lut_prepare");
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    l.ready = true;
+    return NPHUSL_OK;
+}
+
 static int lut_alloc(DevCtx &c, int seg, int nh, int nl, int type, double light_scale, double chroma_scale) {
     Lut &l = c.lut;
     if (l.light) cudaFree(l.light);
     if (l.chroma) cudaFree(l.chroma);
     if (!l.linear) CU(cudaMalloc(&l.linear, 256 * sizeof(double)));
+    if (!l.prod) CU(cudaMalloc(&l.prod, 9 * 256 * sizeof(double)));
+    if (l.light_q) cudaFree(l.light_q);
     l.light = l.chroma = nullptr;
+    l.light_q = nullptr;
     l.ready = false;
+    CU(cudaMalloc(&l.light_q, sizeof(double) * 3 * seg));
     CU(cudaMalloc(&l.light, lut_esize(type) * 3 * seg));
     CU(cudaMalloc(&l.chroma, lut_esize(type) * (size_t)nh * nl));
     l.seg = seg; l.nh = nh; l.nl = nl; l.type = type;
     l.light_scale = light_scale; l.chroma_scale = chroma_scale;
     l.p.linear = l.linear; l.p.light = l.light; l.p.chroma = l.chroma;
+    l.p.prod = l.prod; l.p.light_q = l.light_q;
     l.p.seg = seg; l.p.nh = nh; l.p.nl = nl;
     l.p.light_scale = light_scale;
     l.p.sat_scale = 100 * chroma_scale;
@@ -1511,9 +1594,7 @@ int nphusl_cuda_lut_generate_typed(int device, int light_seg, int nh, int nl, in
 #undef GEN_GO
     g_launches += 2;
     if ((rc = check_launch("k_gen_light / k_gen_chroma"))) return rc;
-    CU(cudaDeviceSynchronize());
-    l.ready = true;
-    return NPHUSL_OK;
+    return lut_finish(*c);
 }
 
 int nphusl_cuda_lut_generate(int device, int light_seg, int nh, int nl) {
@@ -1544,8 +1625,7 @@ int nphusl_cuda_lut_upload_typed(int device, int table_type, double light_scale,
     for (int i = 0; i < 2; ++i) l.p.ythresh[i] = y_thresh2[i];
     l.p.hstep = h_idx_step;
     l.p.lstep = l_idx_step;
-    l.ready = true;
-    return NPHUSL_OK;
+    return lut_finish(*c);
 }
 
 int nphusl_cuda_lut_upload(int device, const uint16_t *light, int light_seg,
