@@ -43,59 +43,110 @@ __device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b
 __device__ __forceinline__ double ds(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dd(double a, double b) { return __ddiv_rn(a, b); }
 
-// a / b given rb = RN(1/b): q0 = RN(a*rb) is within an ulp of the quotient, the residual
-// r = a - q0*b is exact in one FMA, and RN(q0 + r*rb) is the correctly rounded quotient
-// (Markstein's division step).  3 DP instructions instead of the ~13 of a general
-// __ddiv_rn (reciprocal seed, Newton iterations, range fix-ups).  Used where the divisor is a
-// run-time constant of the tables (index steps) or shared by two quotients (u', v'); every
-// input this kernel can see is one of the 2^24 colours, and the sha256 of the whole cube
-// against the reference's own C output (tests/test_cuda_parity.py) pins the result bit for bit.
+// ---- straight-line IEEE division / reciprocal / square root -----------------------------------------
+// __ddiv_rn, __drcp_rn and __dsqrt_rn each carry a range check and a CALL to a slow path (denormals,
+// overflow); five of them per pixel cut the pixel's instruction stream into branch regions the compiler
+// cannot interleave, and this kernel lives on instruction-level parallelism: one pixel is a chain of
+// ~100 dependent FP64 operations plus a table gather that is answered by L2.  Every operand below is a
+// normal number well inside the double range (linear light, Luv coordinates, table steps), so the fast
+// paths alone are written out: a hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20), Newton / Goldschmidt
+// refinement in FMAs, and a final residual correction (Markstein) that makes the last rounding the
+// correctly rounded one.  What the kernel computes is pinned bit for bit by the sha256 of all 2^24 colours
+// against the reference's own C output (tests/test_cuda_parity.py::test_lut_mode_bit_exact_on_cube).
+__device__ __forceinline__ double rcp_seed(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    return r;
+}
+__device__ __forceinline__ double rsqrt_seed(double a) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return r;
+}
+// 1/b to within an ulp: r0 (1 + e + e^2), e = 1 - b r0
+__device__ __forceinline__ double rcp_near(double b) {
+    const double r0 = rcp_seed(b);
+    const double e = __fma_rn(-b, r0, 1.0);
+    return __fma_rn(r0, __fma_rn(e, e, e), r0);
+}
+// a / b given rb ~ 1/b (within an ulp): q0 = RN(a*rb) is within an ulp of the quotient, the residual
+// r = a - q0*b is exact in one FMA, and RN(q0 + r*rb) is the correctly rounded quotient (Markstein's
+// division step).  3 DP instructions; used directly where the divisor is a run-time constant of the
+// tables (index steps) or shared by two quotients (u', v').
 __device__ __forceinline__ double cdiv(double a, double b, double rb) {
     const double q0 = __dmul_rn(a, rb);
     const double r = __fma_rn(-q0, b, a);
     return __fma_rn(r, rb, q0);
 }
+__device__ __forceinline__ double div_rn(double a, double b) { return cdiv(a, b, rcp_near(b)); }
+// sqrt(a), a > 0: Goldschmidt on g ~ sqrt(a), h ~ 1/(2 sqrt(a)), then g + (a - g*g) * h
+__device__ __forceinline__ double sqrt_rn(double a) {
+    const double y = rsqrt_seed(a);
+    double g = __dmul_rn(a, y), h = __dmul_rn(0.5, y);
+    double r = __fma_rn(-g, h, 0.5);
+    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+    r = __fma_rn(-g, h, 0.5);
+    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+    const double d = __fma_rn(-g, g, a);
+    const double res = __fma_rn(d, h, g);
+    return (a == 0.0) ? 0.0 : res;
+}
 
-// _simd.c:485-496
-__device__ __forceinline__ double lut_light(const LutParams &t, double y) {
-    double idx;
-    if (y < t.ythresh[0]) idx = cdiv(y, t.ystep[0], t.r_ystep[0]);
-    else if (y < t.ythresh[1]) idx = da(cdiv(ds(y, t.ythresh[0]), t.ystep[1], t.r_ystep[1]), (double)t.seg);
-    else idx = da(cdiv(ds(y, t.ythresh[1]), t.ystep[2], t.r_ystep[2]), (double)(t.seg * 2));
-    const double r = fmax(0.0, fmin((double)(3 * t.seg - 1), (double)roundf(__double2float_rn(idx))));
-    return __ldg(t.light_q + (unsigned short)r);
+// (unsigned short)fmax(0, fmin(hi, (double)roundf((float)x))) of _simd.c:403-404,494 in integer registers:
+// roundf is trunc(x + copysign(0.5, x)) with the sum rounded toward zero (so 0.49999997f stays below 1),
+// exact for |x| < 2^23; the clamp to [0, hi] then runs on the integer.  x is an index of a few thousand at
+// most, never NaN for a pixel whose result is used (black and white are answered with constants).
+__device__ __forceinline__ int round_clamp(double x, int hi) {
+    const float f = __double2float_rn(x);
+    const int i = __float2int_rz(__fadd_rz(f, copysignf(0.5f, f)));
+    return min(max(i, 0), hi);
+}
+// ... and with floorf (:364-365)
+__device__ __forceinline__ int floor_clamp(double x, int hi) {
+    const int i = __float2int_rd(__double2float_rn(x));
+    return min(max(i, 0), hi);
+}
+
+// constants whose low word is not zero live in constant memory: FP64 instructions take them as operands
+// straight from the bank instead of re-materialising two 32-bit halves per use
+__constant__ double LUT_K[12] = {0.78539816339744830962, 0.2447, 0.0663, 180.0 / 3.14159265358979323846,
+                                 3.141592653589793, 1.5707963267948966, 0.28, 0.19783000664283, 0.46831999493879,
+                                 19.916405993809086, 1e-10, (double)1e-10f};
+enum { K_PI4 = 0, K_A, K_B, K_DEG, K_PI, K_PIBY2, K_028, K_REFU, K_REFV, K_WHITE_HUE, K_TINY, K_TINYF };
+
+// _simd.c:485-496.  The three segments differ only in (origin, step, index base): selected first, divided
+// once.  Segment 0 is y / step exactly as written there (y - 0.0 and + 0.0 change nothing).
+__device__ __forceinline__ double lut_light(const LutParams &t, const double *light_q, double y) {
+    const bool s0 = y < t.ythresh[0], s1 = y < t.ythresh[1];
+    const double org = s0 ? 0.0 : (s1 ? t.ythresh[0] : t.ythresh[1]);
+    const double step = s0 ? t.ystep[0] : (s1 ? t.ystep[1] : t.ystep[2]);
+    const double rstep = s0 ? t.r_ystep[0] : (s1 ? t.r_ystep[1] : t.r_ystep[2]);
+    const double base = s0 ? 0.0 : (s1 ? (double)t.seg : (double)(t.seg * 2));
+    const double idx = da(cdiv(ds(y, org), step, rstep), base);
+    return light_q[round_clamp(idx, 3 * t.seg - 1)];
 }
 
 // _simd.c:279-281
 __device__ __forceinline__ double lut_atan(double z) {
     const double az = fabs(z);
-    return ds(dm(0.78539816339744830962, z), dm(dm(z, ds(az, 1.0)), da(0.2447, dm(0.0663, az))));
+    return ds(dm(LUT_K[K_PI4], z), dm(dm(z, ds(az, 1.0)), da(LUT_K[K_A], dm(LUT_K[K_B], az))));
 }
 
-// _simd.c:246-266 with :288-315 inlined.  to_hue calls the atan2 approximation only when
-// |v/u| >= 1, and that function divides the same two numbers again: its z is this z, its
-// "|z| < 1" branch cannot be taken, and what is left is the u == 0 guard and one division.
+// _simd.c:246-266 with :288-315 inlined, branch-free.  to_hue calls the atan2 approximation only when
+// |v/u| >= 1, and that function divides the same two numbers again: its z is this z, its "|z| < 1" branch
+// cannot be taken, and what is left is the u == 0 guard and one division.  Both sides are evaluated and
+// one is selected (a warp of a natural image needs both anyway).
 __device__ __forceinline__ double lut_hue(double u, double v) {
-    const double DEG_PER_RAD = 180.0 / 3.14159265358979323846;
-    const double PI_ = 3.141592653589793, PIBY2 = 1.5707963267948966;
-    const double z = dd(v, u);
-    double hue;
-    if (fabs(z) < 1.0) {
-        hue = dm(lut_atan(z), DEG_PER_RAD);
-        if (u < 0) hue = da(hue, 180.0);
-        else if (v < 0) hue = da(hue, 360.0);
-    } else {
-        double at;
-        if (u == 0.0) {
-            at = (v > 0.0) ? PIBY2 : ((v == 0.0) ? 0.0 : -PIBY2);
-        } else {
-            at = ds(PIBY2, dd(z, da(dm(z, z), 0.28)));
-            if (v < 0.0) at = ds(at, PI_);
-        }
-        hue = dm(at, DEG_PER_RAD);
-        if (hue < 0.0) hue = da(hue, 360.0);
-    }
-    return hue;
+    const double DEG_PER_RAD = LUT_K[K_DEG], PI_ = LUT_K[K_PI], PIBY2 = LUT_K[K_PIBY2];
+    const double z = div_rn(v, u);
+    double ha = dm(lut_atan(z), DEG_PER_RAD);
+    ha = (u < 0) ? da(ha, 180.0) : ((v < 0) ? da(ha, 360.0) : ha);
+    double at = ds(PIBY2, div_rn(z, da(dm(z, z), LUT_K[K_028])));
+    at = (v < 0.0) ? ds(at, PI_) : at;
+    at = (u == 0.0) ? ((v > 0.0) ? PIBY2 : ((v == 0.0) ? 0.0 : -PIBY2)) : at;
+    double hb = dm(at, DEG_PER_RAD);
+    hb = (hb < 0.0) ? da(hb, 360.0) : hb;
+    return (fabs(z) < 1.0) ? ha : hb;
 }
 
 // _simd.c:399-406 / :360-387
@@ -104,45 +155,65 @@ __device__ __forceinline__ double lut_chroma(const LutParams &t, double l, doubl
     const TT *chroma = static_cast<const TT *>(t.chroma);
     const double hs = cdiv(h, t.hstep, t.r_hstep), ls = cdiv(l, t.lstep, t.r_lstep);
     if (!INTERP) {
-        const unsigned short hi = (unsigned short)fmax(0.0, fmin((double)(t.nh - 1), (double)roundf(__double2float_rn(hs))));
-        const unsigned short li = (unsigned short)fmax(0.0, fmin((double)(t.nl - 1), (double)roundf(__double2float_rn(ls))));
-        return fmax(1e-10, (double)__ldg(chroma + (size_t)hi * t.nl + li));
+        const int hi = round_clamp(hs, t.nh - 1), li = round_clamp(ls, t.nl - 1);
+        return fmax(LUT_K[K_TINY], (double)__ldg(chroma + (unsigned)(hi * t.nl + li)));
     }
-    const unsigned short hf = (unsigned short)fmax(0.0, fmin((double)(t.nh - 2), (double)floorf(__double2float_rn(hs))));
-    const unsigned short lf = (unsigned short)fmax(0.0, fmin((double)(t.nl - 2), (double)floorf(__double2float_rn(ls))));
-    const double c00 = __ldg(chroma + (size_t)hf * t.nl + lf);
-    const double c10 = __ldg(chroma + (size_t)(hf + 1) * t.nl + lf);
-    const double c01 = __ldg(chroma + (size_t)hf * t.nl + lf + 1);
-    const double c11 = __ldg(chroma + (size_t)(hf + 1) * t.nl + lf + 1);
+    const int hf = floor_clamp(hs, t.nh - 2), lf = floor_clamp(ls, t.nl - 2);
+    const TT *c0 = chroma + (unsigned)(hf * t.nl + lf);
+    const double c00 = __ldg(c0), c10 = __ldg(c0 + t.nl), c01 = __ldg(c0 + 1), c11 = __ldg(c0 + t.nl + 1);
     const double hn = ds(hs, (double)hf), ln = ds(ls, (double)lf);
     const double hv = ds(1.0, hn), lv = ds(1.0, ln);
     const double c = da(da(da(dm(dm(c00, hv), lv), dm(dm(c10, hn), lv)), dm(dm(c01, hv), ln)), dm(dm(c11, hn), ln));
-    return fmax((double)1e-10f, c);
+    return fmax(LUT_K[K_TINYF], c);
 }
 
-// One pixel of rgb_to_husl_nd, default build (_simd.c:128-225).  `prod` is the 9 x 256 product table
-// (shared memory in the tile kernel, global / L1 in the one-pixel-per-thread kernel).
-template <bool INTERP, typename TT>
-__device__ __forceinline__ void lut_pixel(const LutParams &t, const double *prod, uint32_t r, uint32_t g, uint32_t b,
-                                          double &H, double &S, double &L) {
-    const double REF_U = 0.19783000664283, REF_V = 0.46831999493879;
-    const double x = da(da(prod[r], prod[256 + g]), prod[512 + b]);
-    const double y = da(da(prod[768 + r], prod[1024 + g]), prod[1280 + b]);
-    const double z = da(da(prod[1536 + r], prod[1792 + g]), prod[2048 + b]);
-    const double vs = da(da(x, dm(15.0, y)), dm(3.0, z));
-    const double rvs = __drcp_rn(vs);
-    const double var_u = cdiv(dm(4.0, x), vs, rvs), var_v = cdiv(dm(9.0, y), vs, rvs);
-    const double l = lut_light(t, y);
-    const double l13 = dm(l, 13.0);
-    const double u = dm(l13, ds(var_u, REF_U)), v = dm(l13, ds(var_v, REF_V));
-    const double h = lut_hue(u, v);
-    const double mc = lut_chroma<INTERP, TT>(t, l, h);
-    const double sat = dd(dm(t.sat_scale, __dsqrt_rn(da(dm(u, u), dm(v, v)))), mc);
-    // _simd.c:205-212: pure white and pure black are answered with constants
-    const bool white = (r & g & b) == 255u, black = (r | g | b) == 0u;
-    H = white ? 19.916405993809086 : (black ? 0.0 : h);
-    S = (white || black) ? 0.0 : fmin(sat, 100.0);
-    L = white ? 100.0 : (black ? 0.0 : l);
+// NP pixels of rgb_to_husl_nd, default build (_simd.c:128-225), stage by stage.  `prod` is the 9 x 256
+// product table and `light_q` the pre-divided light table (shared memory in the tile kernel, global / L1 in
+// the one-pixel-per-thread kernel).  c[3p .. 3p+2] = R, G, B bytes of pixel p; o[3p .. 3p+2] = H, S, L.
+// Walking the NP pixels through each stage together gives the scheduler NP independent dependency chains
+// (the kernel is bound by FP64 / table latency, not by a pipe) and loads each stage's constants once.
+template <bool INTERP, typename TT, int NP>
+__device__ __forceinline__ void lut_pixels(const LutParams &t, const double *prod, const double *light_q,
+                                           const uint32_t (&c)[3 * NP], double (&o)[3 * NP]) {
+    double y[NP], vu[NP], vv[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const uint32_t r = c[3 * p], g = c[3 * p + 1], b = c[3 * p + 2];
+        const double x = da(da(prod[r], prod[256 + g]), prod[512 + b]);
+        y[p] = da(da(prod[768 + r], prod[1024 + g]), prod[1280 + b]);
+        const double z = da(da(prod[1536 + r], prod[1792 + g]), prod[2048 + b]);
+        const double vs = da(da(x, dm(15.0, y[p])), dm(3.0, z));
+        const double rvs = rcp_near(vs);
+        vu[p] = cdiv(dm(4.0, x), vs, rvs);
+        vv[p] = cdiv(dm(9.0, y[p]), vs, rvs);
+    }
+    double l[NP], u[NP], v[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) l[p] = lut_light(t, light_q, y[p]);
+    {
+        const double REF_U = LUT_K[K_REFU], REF_V = LUT_K[K_REFV];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const double l13 = dm(l[p], 13.0);
+            u[p] = dm(l13, ds(vu[p], REF_U));
+            v[p] = dm(l13, ds(vv[p], REF_V));
+        }
+    }
+    double h[NP], mc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) h[p] = lut_hue(u[p], v[p]);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) mc[p] = lut_chroma<INTERP, TT>(t, l[p], h[p]);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const double sat = div_rn(dm(t.sat_scale, sqrt_rn(da(dm(u[p], u[p]), dm(v[p], v[p])))), mc[p]);
+        // _simd.c:205-212: pure white and pure black are answered with constants
+        const uint32_t r = c[3 * p], g = c[3 * p + 1], b = c[3 * p + 2];
+        const bool white = (r & g & b) == 255u, black = (r | g | b) == 0u;
+        o[3 * p] = white ? LUT_K[K_WHITE_HUE] : (black ? 0.0 : h[p]);
+        o[3 * p + 1] = (white || black) ? 0.0 : fmin(sat, 100.0);
+        o[3 * p + 2] = white ? 100.0 : (black ? 0.0 : l[p]);
+    }
 }
 
 // rgb_to_husl_nd, one pixel per thread: tails (< 128 pixels) and unaligned buffers
@@ -151,10 +222,11 @@ __global__ void __launch_bounds__(256)
 k_fwd_lut(const uint8_t *__restrict__ rgb, double *__restrict__ hsl, long long n, LutParams t) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        double H, S, L;
-        lut_pixel<INTERP, TT>(t, t.prod, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], H, S, L);
+        const uint32_t c[3] = {rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+        double r[3];
+        lut_pixels<INTERP, TT, 1>(t, t.prod, t.light_q, c, r);
         double *o = hsl + 3 * i;
-        o[0] = H; o[1] = S; o[2] = L;
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
     }
 }
 

@@ -489,10 +489,13 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
 }
 
 #ifndef NPHUSL_LUT_BLOCK
-#define NPHUSL_LUT_BLOCK 256
-#define NPHUSL_LUT_MINB 3
+#define NPHUSL_LUT_BLOCK 512       // A/B on B200 (profiles/r02_ab_lut.txt): 512 x 1 with 4 pixels per lane in flight
+#define NPHUSL_LUT_MINB 1         // (114 registers) 0.756 ms; 512 x 2 / 2 pixels 0.796; 384 x 2 / 4 0.776; 256 x 2 / 4 0.770
 #endif
-constexpr int LUT_BLOCK = NPHUSL_LUT_BLOCK, LUT_MINB = NPHUSL_LUT_MINB, LUT_OST = 2;
+#ifndef NPHUSL_LUT_NP
+#define NPHUSL_LUT_NP 4             // pixels of a lane walked through the stages together (1, 2 or 4)
+#endif
+constexpr int LUT_BLOCK = NPHUSL_LUT_BLOCK, LUT_MINB = NPHUSL_LUT_MINB, LUT_NP = NPHUSL_LUT_NP;
 
 int run_lut_dev(DevCtx &c, const void *in, void *out, long long n, int mode, cudaStream_t s) {
     if (!c.lut.ready) return fail(NPHUSL_ERR_NO_LUT, "LUT mode: call nphusl_cuda_lut_generate or nphusl_cuda_lut_upload first");
@@ -500,19 +503,22 @@ int run_lut_dev(DevCtx &c, const void *in, void *out, long long n, int mode, cud
     int rc;
     long long done = 0;
     if (aligned(in, 4) && aligned(out, 16) && n >= TILE_PX) {
-        // whole 128-pixel tiles: the streaming skeleton (husl_lut_tile.cuh)
+        // whole 128-pixel tiles: the streaming kernel (husl_lut_tile.cuh)
         const long long tiles = n / TILE_PX;
-        constexpr int sm = LUT_PROD_BYTES + (LUT_BLOCK / 32) * LUT_OST * Tile<double>::BYTES;
         const int grid = grid_for(tiles, LUT_BLOCK / 32, c.sms * LUT_MINB);
-#define LUT_TILE(INTERP, TT) do { \
+        const bool light_smem = 3 * c.lut.seg * 8 <= LUT_LIGHT_SMEM_MAX;
+#define LUT_TILE(INTERP, TT, LS) do { \
+        constexpr int sm = LUT_PROD_BYTES + (LS ? LUT_LIGHT_SMEM_MAX : 0) + (LUT_BLOCK / 32) * Tile<double>::BYTES; \
         static std::atomic<bool> attr_done[MAX_DEV]; \
-        if ((rc = flt_attr(attr_done, c, k_fwd_lut_tile<INTERP, TT, LUT_BLOCK, LUT_MINB, LUT_OST>, sm))) return rc; \
-        k_fwd_lut_tile<INTERP, TT, LUT_BLOCK, LUT_MINB, LUT_OST><<<grid, LUT_BLOCK, sm, s>>>((const uint32_t *)in, (double *)out, tiles, c.lut.p); } while (0)
-#define LUT_TILE_T(TT) do { if (mode == NPHUSL_LUT) LUT_TILE(false, TT); else LUT_TILE(true, TT); } while (0)
+        if ((rc = flt_attr(attr_done, c, k_fwd_lut_tile<INTERP, TT, LUT_BLOCK, LUT_MINB, LS, LUT_NP>, sm))) return rc; \
+        k_fwd_lut_tile<INTERP, TT, LUT_BLOCK, LUT_MINB, LS, LUT_NP><<<grid, LUT_BLOCK, sm, s>>>((const uint32_t *)in, (double *)out, tiles, c.lut.p); } while (0)
+#define LUT_TILE_L(INTERP, TT) do { if (light_smem) LUT_TILE(INTERP, TT, true); else LUT_TILE(INTERP, TT, false); } while (0)
+#define LUT_TILE_T(TT) do { if (mode == NPHUSL_LUT) LUT_TILE_L(false, TT); else LUT_TILE_L(true, TT); } while (0)
         if (c.lut.type == NPHUSL_LUT_U16) LUT_TILE_T(uint16_t);
         else if (c.lut.type == NPHUSL_LUT_F32) LUT_TILE_T(float);
         else LUT_TILE_T(double);
 #undef LUT_TILE_T
+#undef LUT_TILE_L
 #undef LUT_TILE
         g_launches++;
         if ((rc = check_launch("k_fwd_lut_tile"))) return rc;

@@ -15,6 +15,18 @@ for p in (os.path.join(ROOT, "husl-numpy_b200"), os.path.join(ROOT, "oracle"), R
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# options of tests/performance_test.py, the reference's own (conftest.py:5-13) with "cuda" in front
+DEFAULT_IMPLS = "cuda numpy".split()
+
+
+def pytest_addoption(parser):
+    parser.addoption("--impls", action="store", nargs="*", default=DEFAULT_IMPLS,
+                     help="backends to time: cuda numpy reference (reference = the reference package's own best backends on the CPU)")
+    parser.addoption("--iters", action="store", type=int, default=3, help="best of this many timeit runs")
+    parser.addoption("--img", action="store", default="small",
+                     help="small (270x480) | 1080p | 4m (2000x2000) | 4k | cube (4096x4096, all 2^24 colours) | path to a .npy uint8 image")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

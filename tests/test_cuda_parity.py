@@ -1526,23 +1526,32 @@ def test_dropped_device_results_are_not_reused_under_a_running_kernel(cu):
 
 def test_grayscale_hue_stream_kernel_equals_the_general_kernel(cu):
     """to_hue of a grayscale image (config 3) runs k_gray_hue: one constant per lit pixel.  It must answer exactly
-    what the general kernel answers for the same image materialised as R = G = B, for uint8 / float32 / float64
-    greys, the values around the linear / power switch, 0, denormals, negatives, NaN and overflowing inputs."""
+    what the general kernels answer for the same image materialised as R = G = B: uint8 / float32 / float64 greys
+    incl. 0, -0, negatives, NaN and the values around the linear / power switch (tiled float kernel + tail), and
+    -- against the one-pixel-per-thread kernel, whose code it abbreviates -- float-denormal and overflowing inputs."""
     import warnings
     import nphusl
     rng = np.random.default_rng(34)
-    special = np.array([0.0, -0.0, 1e-320, 1e-45, 1e-39, 5e-38, 1e-30, 0.04045, np.nextafter(0.04045, 1), 0.5, 1.0, 2.0,
-                        -0.25, np.nan, np.inf, -np.inf, 1e30, 3.5e38, 3.7e38, 1e39, 1e300])
+    ordinary = np.array([0.0, -0.0, 1e-30, 0.04045, np.nextafter(0.04045, 1), 0.5, 1.0, 2.0, -0.25, np.nan, 1e30])
+    exotic = np.array([1e-320, 1e-45, 1e-39, 5e-38, np.inf, -np.inf, 3.5e38, 3.7e38, 1e39, 1e300])
     for dt in (np.float64, np.float32, np.uint8):
         with np.errstate(over="ignore", invalid="ignore"):
             grey = (rng.integers(0, 256, (37, 129)) if dt == np.uint8 else rng.random((37, 129))).astype(dt)
             if dt != np.uint8:
-                grey.reshape(-1)[:special.size] = special.astype(dt)
+                grey.reshape(-1)[:ordinary.size] = ordinary.astype(dt)
         g3 = np.ascontiguousarray(np.repeat(grey[..., None], 3, -1))
         for odt in (np.float64, np.float32):
-            want = cu._rgb_to_hue(g3, dtype=odt)                                       # 3 stored channels: general kernel
+            want = cu._rgb_to_hue(g3, dtype=odt)                                       # 3 stored channels: general kernels
             got = cu._rgb_to_hue(np.broadcast_to(grey[..., None], grey.shape + (3,)), dtype=odt)   # 0-stride view: 1 channel
-            assert got.shape == grey.shape and got.dtype == odt and np.array_equal(got, want)
+            assert got.shape == grey.shape and got.dtype == odt
+            bad = np.flatnonzero(got.reshape(-1) != want.reshape(-1))
+            assert bad.size == 0, (dt, odt, grey.reshape(-1)[bad][:8], got.reshape(-1)[bad][:8], want.reshape(-1)[bad][:8])
+            if dt != np.uint8:
+                with np.errstate(over="ignore"):
+                    ex = exotic.astype(dt)                                             # 10 pixels: the one-pixel-per-thread kernel
+                w = cu._rgb_to_hue(np.ascontiguousarray(np.repeat(ex[:, None], 3, -1)), dtype=odt)
+                g = cu._rgb_to_hue(np.broadcast_to(ex[:, None], ex.shape + (3,)), dtype=odt)
+                assert np.array_equal(g, w), (dt, odt, ex, g, w)
         if dt != np.uint8:
             with warnings.catch_warnings(), nphusl.cuda_enabled():
                 warnings.simplefilter("ignore")
