@@ -319,15 +319,24 @@ k_gray_hue(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
     const float grey_hue = hue_deg(GREY_V, GREY_U);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        bool lit;
+        float h;
         if (sizeof(TIn) == 1) {
-            lit = in[i] != 0;
+            h = in[i] != 0 ? grey_hue : 0.0f;
         } else {
             const double c = (double)in[i];
-            // the linear value the general kernel would form is positive and finite (lin_f64: x^2.4 through float x)
-            lit = (c > 0.04045) ? ((float)fma(c, 1.0 / 1.055, 0.055 / 1.055) < INFINITY) : ((float)(c * (1.0 / 12.92)) > 0.0f);
+            if (c <= 1e15) {
+                // lit <=> the linear value the general kernel forms is a positive float (lin_f64)
+                const bool lit = (c > 0.04045) ? true : ((float)(c * (1.0 / 12.92)) > 0.0f);
+                h = lit ? grey_hue : 0.0f;
+            } else {
+                // NaN, or so large that the float linear value overflows: whatever the general code answers
+                LinPx p;
+                lin_f64(c, p.hg, p.lg);
+                p.hr = p.hb = p.hg; p.lr = p.lb = p.lg;
+                h = hue_from_diff(make_diff(p));
+            }
         }
-        out[i] = (TOut)(lit ? grey_hue : 0.0f);
+        out[i] = (TOut)h;
     }
 }
 

@@ -198,11 +198,11 @@ constexpr int FLT_BLOCK = NPHUSL_FLT_BLOCK, FLT_MINB = NPHUSL_FLT_MINB, FLT_IST 
 #define NPHUSL_FWD64_OST 2
 #endif
 #ifndef NPHUSL_INV64_BLOCK
-#define NPHUSL_INV64_BLOCK 256
-#define NPHUSL_INV64_MINB 2
+#define NPHUSL_INV64_BLOCK 384      // round 2 (profiles/r02_ab_inv.txt): 384 x 2 with a 2-stage ring beats 256 x 2 / 3 stages inside the
+#define NPHUSL_INV64_MINB 2        // to_husl -> to_rgb(edit) step (0.6141 -> 0.5975 ms) and without the edit (0.6104 -> 0.6039)
 #endif
 #ifndef NPHUSL_INV64_IST
-#define NPHUSL_INV64_IST 3
+#define NPHUSL_INV64_IST 2
 #endif
 constexpr int FWD64_BLOCK = NPHUSL_FWD64_BLOCK, FWD64_OST = NPHUSL_FWD64_OST;
 constexpr int INV64_BLOCK = NPHUSL_INV64_BLOCK, INV64_MINB = NPHUSL_INV64_MINB, INV64_IST = NPHUSL_INV64_IST;

@@ -1532,8 +1532,8 @@ def test_grayscale_hue_stream_kernel_equals_the_general_kernel(cu):
     import warnings
     import nphusl
     rng = np.random.default_rng(34)
-    ordinary = np.array([0.0, -0.0, 1e-30, 0.04045, np.nextafter(0.04045, 1), 0.5, 1.0, 2.0, -0.25, np.nan, 1e30])
-    exotic = np.array([1e-320, 1e-45, 1e-39, 5e-38, np.inf, -np.inf, 3.5e38, 3.7e38, 1e39, 1e300])
+    ordinary = np.array([0.0, -0.0, 1e-30, 0.04045, np.nextafter(0.04045, 1), 0.5, 1.0, 2.0, 1e6, -0.25, np.nan])
+    exotic = np.array([1e-320, 1e-45, 1e-39, 5e-38, np.inf, -np.inf, 1e14, 1e16, 1e30, 3.5e38, 3.7e38, 1e39, 1e300])
     for dt in (np.float64, np.float32, np.uint8):
         with np.errstate(over="ignore", invalid="ignore"):
             grey = (rng.integers(0, 256, (37, 129)) if dt == np.uint8 else rng.random((37, 129))).astype(dt)
@@ -1548,14 +1548,14 @@ def test_grayscale_hue_stream_kernel_equals_the_general_kernel(cu):
             assert bad.size == 0, (dt, odt, grey.reshape(-1)[bad][:8], got.reshape(-1)[bad][:8], want.reshape(-1)[bad][:8])
             if dt != np.uint8:
                 with np.errstate(over="ignore"):
-                    ex = exotic.astype(dt)                                             # 10 pixels: the one-pixel-per-thread kernel
+                    ex = exotic.astype(dt)                                             # 13 pixels: the one-pixel-per-thread kernel
                 w = cu._rgb_to_hue(np.ascontiguousarray(np.repeat(ex[:, None], 3, -1)), dtype=odt)
                 g = cu._rgb_to_hue(np.broadcast_to(ex[:, None], ex.shape + (3,)), dtype=odt)
-                assert np.array_equal(g, w), (dt, odt, ex, g, w)
+                assert np.array_equal(g, w, equal_nan=True), (dt, odt, ex, g, w)
         if dt != np.uint8:
             with warnings.catch_warnings(), nphusl.cuda_enabled():
                 warnings.simplefilter("ignore")
                 hue = nphusl.to_hue(grey)                                                # public grayscale route
             assert np.array_equal(hue, cu._rgb_to_hue(g3))
-            lit = hue[np.isfinite(grey) & (grey > 1e-30) & (grey < 1e30)]
+            lit = hue[np.isfinite(grey) & (grey > 1e-30) & (grey < 1e7)]
             assert np.all(np.abs(lit - 19.916405993809086) < 1e-3)
