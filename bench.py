@@ -353,10 +353,10 @@ class Ranks:
         elif store is not None:
             while True:
                 try:
-                    store.wait([key], __import__("datetime").timedelta(seconds=5))
+                    store.wait([key], __import__("datetime").timedelta(seconds=600))
                     break
                 except Exception:
-                    time.sleep(0.05)
+                    time.sleep(0.5)
         self.barrier()
         return res
 
@@ -395,15 +395,22 @@ def run_video(args, rk, nphusl, _cuda, hdt):
     # ---- ONE process (rank 0) drives every GPU of the job through the same function
     def in_process():
         devs = list(range(rk.world)) if rk.world > 1 else [rk.local]
-        ps = []
-        for _ in range(2):
-            res = _shard.stream_frames(pool, n, devices=devs, batch=B, dtype=hdt)
-            check(res)
-            ps.append(res["seconds"])
-        t = min(ps)
-        return {"gpus": len(devs), "seconds": round(t, 4), "fps_4k": round(n / t, 1), "mpix_s": round(n * FRAME_PX / t / 1e6, 1),
-                "all_passes_fps_4k": [round(n / x, 1) for x in ps],
-                "per_device_seconds": {str(d): round(v["seconds"], 4) for d, v in res["per_device"].items()}}
+        rec = {"gpus": len(devs)}
+        for schedule in ("static", "dynamic"):
+            ps = []
+            for _ in range(2):
+                res = _shard.stream_frames(pool, n, devices=devs, batch=B, dtype=hdt, schedule=schedule)
+                check(res)
+                ps.append(res["seconds"])
+            t = min(ps)
+            one = {"seconds": round(t, 4), "fps_4k": round(n / t, 1), "mpix_s": round(n * FRAME_PX / t / 1e6, 1),
+                   "all_passes_fps_4k": [round(n / x, 1) for x in ps],
+                   "per_device": {str(d): [v["frames"], round(v["seconds"], 4)] for d, v in sorted(res["per_device"].items())}}
+            if schedule == "static":
+                rec.update(one)                      # same partition as process_per_gpu: contiguous blocks of the stream
+            else:
+                rec["dynamic"] = one                 # batches first come, first served (only one process can do this)
+        return rec
     try:
         out["in_process"] = rk.park_until("nphusl_bench_inproc", in_process)
     except Exception as e:                                   # e.g. another rank's context leaves too little memory
@@ -451,7 +458,7 @@ def jpeg_leg(args, rk, torch, _cuda, B):
         out_bytes = sum(int(e.numel()) for e in outs)
         px = B * FRAME_PX
         return {"value": px * rk.world * reps / dt / 1e6, "unit": UNIT, "steps": reps,
-                "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "h2d_bytes_per_step": in_bytes * rk.world, "d2h_bytes_per_step": out_bytes * rk.world,
                 "compressed_bytes_per_pixel": {"in": round(in_bytes / px, 4), "out": round(out_bytes / px, 4)},
                 "path": "torchvision.io.decode_jpeg(device='cuda') -> nphusl._cuda.edit_rgb(channels_first=True, in place) -> "
                         "torchvision.io.encode_jpeg (nvJPEG) -> .cpu(); quality 90; decode + encode are library code, "
@@ -660,7 +667,7 @@ def run_cuda(args):
                 nphusl.to_rgb(host_hsl, out=host_out, edit=edit)
             t = timed_e2e(step_host_husl, 3, warm=1)
             e2e_extra["host_husl"] = {"value": px * world * 3 / t / 1e6, "unit": UNIT, "steps": 3,
-                                      "h2d_bytes_per_step": px * (3 + 3 * hdt.itemsize), "d2h_bytes_per_step": px * (3 + 3 * hdt.itemsize),
+                                      "h2d_bytes_per_step": px * (3 + 3 * hdt.itemsize) * world, "d2h_bytes_per_step": px * (3 + 3 * hdt.itemsize) * world,
                                       "path": "nphusl.to_husl(host u8 -> HOST %s HUSL), nphusl.to_rgb(HOST HUSL -> host u8, edit on load): the "
                                               "reference's data flow, pinned buffers, blocking calls" % hdt}
             if not np.array_equal(host_out, expect.cpu().numpy()):
@@ -690,7 +697,7 @@ def run_cuda(args):
             if not (np.array_equal(y_out, want_y) and np.array_equal(uv_out, want_uv)):
                 raise SystemExit("bench.py: NV12 e2e result differs from the device-resident result")
             e2e_extra["nv12"] = {"value": px * world * Ke / t / 1e6, "unit": UNIT, "steps": Ke,
-                                 "h2d_bytes_per_step": px * 3 // 2, "d2h_bytes_per_step": px * 3 // 2,
+                                 "h2d_bytes_per_step": px * 3 // 2 * world, "d2h_bytes_per_step": px * 3 // 2 * world,
                                  "path": "nphusl._cuda.nv12_edit_nv12(pinned host Y + UV planes in, pinned host planes out, blocking=False on two "
                                          "alternating streams): H2D, ONE fused kernel NV12 -> HUSL -> edit -> NV12, D2H; BT.709 video range"}
             del y_in, uv_in, y_out, uv_out
@@ -823,7 +830,8 @@ def run_cuda(args):
                else ("to_rgb", "k_inv_tma<double,edit>" if f64 else "k_inv_cp<float,edit>", t_inv))
         achieved = px * bpp / (dom[2] * 1e-3) / 1e9
         kname = dom[1]
-        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": px * 3, "d2h_bytes_per_step": px * 3,
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": px * 3 * world, "d2h_bytes_per_step": px * 3 * world,
+               "bytes_scope": "whole job (all %d ranks), like `value`" % world,
                "steps": Ke, "link_gbs": link, "blocking_calls_mpix_s": e2e_blocking,
                "path": "nphusl.to_husl(pinned host u8 -> device HUSL) + nphusl.to_rgb(device HUSL -> pinned host u8, edit=...), "
                        "blocking=False on two alternating streams; wall clock incl. final synchronize, max over ranks"}

@@ -1783,6 +1783,50 @@ int nphusl_cuda_event_destroy(void *event, int device) {
     return NPHUSL_OK;
 }
 
+int nphusl_cuda_graph_begin(void *stream, int device) {
+    DeviceGuard guard;
+    if (!stream) return fail(NPHUSL_ERR_ARG, "graph_begin: capture needs a stream of its own (not the NULL stream)");
+    DevCtx *c;
+    int rc = ctx_get(device, &c);
+    if (rc) return rc;
+    if ((rc = set_attrs(*c))) return rc;       // one-time kernel attributes are not stream work: do them before capturing
+    CU(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_graph_end(void *stream, int device, void **graph_exec) {
+    DeviceGuard guard;
+    if (!stream || !graph_exec) return fail(NPHUSL_ERR_ARG, "graph_end: null argument");
+    CU(cudaSetDevice(device));
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamEndCapture((cudaStream_t)stream, &g));
+    cudaGraphExec_t e = nullptr;
+    const cudaError_t err = cudaGraphInstantiate(&e, g, 0);
+    cudaGraphDestroy(g);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(NPHUSL_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+    }
+    *graph_exec = (void *)e;
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_graph_launch(void *graph_exec, void *stream, int device) {
+    DeviceGuard guard;
+    if (!graph_exec) return fail(NPHUSL_ERR_ARG, "graph_launch: null graph");
+    CU(cudaSetDevice(device));
+    CU(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_graph_destroy(void *graph_exec, int device) {
+    DeviceGuard guard;
+    if (!graph_exec) return NPHUSL_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return NPHUSL_OK;
+}
+
 int nphusl_cuda_device_synchronize(int device) {
     DeviceGuard guard;
     CU(cudaSetDevice(device));

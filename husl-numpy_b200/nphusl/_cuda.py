@@ -34,7 +34,7 @@ import threading
 import numpy as np
 
 __all__ = ["_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue", "rgb_to_husl_planar", "husl_planar_to_rgb",
-           "edit_rgb", "edit_husl", "Edit", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "rgb_to_nv12", "nv12_edit_nv12", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
+           "edit_rgb", "edit_husl", "Edit", "Graph", "graph", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "rgb_to_nv12", "nv12_edit_nv12", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
 
 def _prod(shape):
     """Number of elements of a shape (np.prod on a tuple costs 3 us and runs several times per call)."""
@@ -109,6 +109,10 @@ SIGNATURES = {
     "nphusl_cuda_event_query": (_i, [_vp, _ip]),
     "nphusl_cuda_stream_wait_event": (_i, [_vp, _vp, _i]),
     "nphusl_cuda_event_destroy": (_i, [_vp, _i]),
+    "nphusl_cuda_graph_begin": (_i, [_vp, _i]),
+    "nphusl_cuda_graph_end": (_i, [_vp, _i, ctypes.POINTER(_vp)]),
+    "nphusl_cuda_graph_launch": (_i, [_vp, _vp, _i]),
+    "nphusl_cuda_graph_destroy": (_i, [_vp, _i]),
     "nphusl_cuda_pointer_info": (_i, [_vp, _ip, _ip, _ip]),
     "nphusl_cuda_device_info": (_i, [_i, ctypes.c_char_p, _sz, _ip, ctypes.POINTER(_sz)]),
 }
@@ -248,6 +252,90 @@ class Stream:
             self.close()
         except Exception:
             pass
+
+
+class Graph:
+    """A recorded sequence of device-array calls, replayed with ONE call (a CUDA graph).
+
+    Per-frame loops are bound by the host side of a call -- a 1080p frame is 10 us of kernel time and
+    a call costs about as much -- so the loop body is recorded once and replayed::
+
+        g = nphusl._cuda.Graph()
+        with g.capture() as s:                       # s: the stream to pass to the recorded calls
+            nphusl.to_husl(frame, out=hsl, stream=s)
+            nphusl.to_rgb(hsl, out=back, stream=s, edit=e)
+        for f in frames:
+            frame.copy_(f)                           # the recorded calls read / write the SAME buffers
+            g.replay()                               # on g.stream (or replay(stream=...))
+        g.synchronize()
+
+    Only calls whose arrays all live on the device can be recorded, every array they use must be passed
+    in (``out=``: results of a recorded call cannot be allocated while recording) and must stay alive as
+    long as the graph is replayed.  ``graph(fn)`` records ``fn(stream)`` in one line."""
+
+    def __init__(self, device=None, stream=None):
+        self.device = _default_device if device is None else device
+        self.stream = Stream(self.device) if stream is None else stream
+        self._exec = 0
+        self._keep = []
+
+    def capture(self):
+        return _GraphCapture(self)
+
+    def replay(self, stream=None):
+        if not self._exec:
+            raise CudaError("Graph.replay before capture")
+        _check(load().nphusl_cuda_graph_launch(ctypes.c_void_p(self._exec), _stream_ptr(self.stream if stream is None else stream),
+                                               self.device), "graph_launch")
+
+    __call__ = replay
+
+    def synchronize(self):
+        synchronize(self.device, self.stream)
+
+    def close(self):
+        if self._exec and _lib is not None:
+            _lib.nphusl_cuda_graph_destroy(ctypes.c_void_p(self._exec), self.device)
+        self._exec = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _GraphCapture:
+    def __init__(self, g):
+        self.g = g
+
+    def __enter__(self):
+        g = self.g
+        g.close()
+        if not _stream_key(g.stream):
+            raise ValueError("Graph: capture needs a stream of its own, not the NULL stream")
+        _check(load().nphusl_cuda_graph_begin(_stream_ptr(g.stream), g.device), "graph_begin")
+        return g.stream
+
+    def __exit__(self, exc_type, exc, tb):
+        g = self.g
+        e = ctypes.c_void_p()
+        rc = load().nphusl_cuda_graph_end(_stream_ptr(g.stream), g.device, ctypes.byref(e))
+        if exc_type is None:
+            _check(rc, "graph_end")
+            g._exec = e.value or 0
+        elif e.value:
+            load().nphusl_cuda_graph_destroy(e, g.device)
+        return False
+
+
+def graph(fn, device=None, stream=None):
+    """Record ``fn(stream)`` -- a function issuing device-array calls on the stream it is given -- and
+    return the ``Graph``; ``g.replay()`` (or ``g()``) re-runs it."""
+    g = Graph(device, stream)
+    with g.capture() as s:
+        fn(s)
+    return g
 
 
 class _DevicePool:

@@ -130,7 +130,7 @@ def frame_batches(start: int, stop: int, pool_len: int, batch: int):
 
 
 def stream_frames(pool, n_frames, devices=None, first_frame=0, batch=8, dtype=np.float64, edit=None,
-                  ready=None, on_batch=None):
+                  ready=None, on_batch=None, schedule="static"):
     """Run ``to_husl`` -> (``edit``) -> ``to_rgb`` over ``n_frames`` frames of a stream whose frame
     ``i`` is ``pool[i % len(pool)]`` (``pool``: ``(P, H, W, 3)`` uint8 host array, page-locked for
     direct DMA).  The stream is cut into contiguous blocks, one per device; each device is driven
@@ -138,6 +138,11 @@ def stream_frames(pool, n_frames, devices=None, first_frame=0, batch=8, dtype=np
     page-locked result batches, so the upload of batch k+1 overlaps the download of batch k.
     Every frame's uint8 result lands in host memory (the ring slot is then free for ``on_batch``
     -- a sink such as an encoder -- or simply overwritten two batches later).
+
+    ``schedule``: ``"static"`` gives every device one contiguous block of the stream
+    (``shard_bounds``); ``"dynamic"`` hands the batches out first come, first served, in stream order,
+    each device keeping at most two in flight -- the GPUs of one box do not all see the same host link
+    (PCIe switch / NUMA placement), and the faster ones then convert more of the stream.
 
     ``ready``: called once from the calling thread when every device has allocated its buffers and
     run one untimed batch, right before the timed region starts (a cross-process barrier, when
@@ -152,8 +157,16 @@ def stream_frames(pool, n_frames, devices=None, first_frame=0, batch=8, dtype=np
     if pool.ndim != 4 or pool.shape[-1] != 3 or pool.dtype != np.uint8:
         raise ValueError("pool: expected (P, H, W, 3) uint8 frames, got {} {}".format(pool.dtype, pool.shape))
     devices = _devices(devices)
-    blocks = [(d, first_frame + a, first_frame + b)
-              for d, (a, b) in zip(devices, shard_bounds(n_frames, len(devices))) if b > a]
+    if schedule not in ("static", "dynamic"):
+        raise ValueError("schedule must be 'static' or 'dynamic'")
+    dynamic = schedule == "dynamic"
+    if dynamic:
+        blocks = [(d, first_frame, first_frame + n_frames) for d in devices] if n_frames > 0 else []
+        shared = frame_batches(first_frame, first_frame + n_frames, len(pool), batch)
+        shared_lock = threading.Lock()
+    else:
+        blocks = [(d, first_frame + a, first_frame + b)
+                  for d, (a, b) in zip(devices, shard_bounds(n_frames, len(devices))) if b > a]
     frame_shape = tuple(pool.shape[1:])
     setup_done = threading.Barrier(len(blocks) + 1)
     go = threading.Barrier(len(blocks) + 1)
@@ -184,17 +197,29 @@ def stream_frames(pool, n_frames, devices=None, first_frame=0, batch=8, dtype=np
             return
         try:
             t0 = time.perf_counter()
-            k, rec = 0, None
-            for i, p, n in frame_batches(a, b, len(pool), batch):
+            k, rec, frames = 0, None, 0
+            own = None if dynamic else frame_batches(a, b, len(pool), batch)
+            while True:
+                if dynamic:
+                    if k >= 2:
+                        streams[k & 1].synchronize()         # at most two batches in flight: the ring slot is free again
+                    with shared_lock:
+                        item = next(shared, None)
+                else:
+                    item = next(own, None)
+                if item is None:
+                    break
+                i, p, n = item
                 s = submit(k, p, n)
                 rec = (i, p, n, k & 1)
+                frames += n
                 if on_batch is not None:
                     s.synchronize()
                     on_batch(dev, i, ring[k & 1][:n])
                 k += 1
             for s in streams:
                 s.synchronize()
-            stats[dev] = {"frames": b - a, "seconds": time.perf_counter() - t0, "batches": k}
+            stats[dev] = {"frames": frames, "seconds": time.perf_counter() - t0, "batches": k}
             if rec is not None:
                 last[dev] = (rec[0], rec[1], rec[2], ring[rec[3]][:rec[2]])
         except BaseException as e:                           # noqa: BLE001

@@ -310,6 +310,14 @@ int nphusl_cuda_event_record(void **event, void *stream, int device);
 int nphusl_cuda_event_query(void *event, int *done);
 int nphusl_cuda_stream_wait_event(void *stream, void *event, int device);
 int nphusl_cuda_event_destroy(void *event, int device);
+/* CUDA graphs: per-frame loops are bound by launch / call overhead (a 1080p frame is 10 us of kernel time), so
+ * a sequence of DEVICE-pointer calls issued on `stream` between graph_begin and graph_end is recorded instead of
+ * executed, and graph_launch replays the whole sequence with one call.  The buffers the recorded calls named
+ * must stay allocated; their CONTENTS are read at replay time.  Host-pointer calls cannot be recorded. */
+int nphusl_cuda_graph_begin(void *stream, int device);
+int nphusl_cuda_graph_end(void *stream, int device, void **graph_exec);
+int nphusl_cuda_graph_launch(void *graph_exec, void *stream, int device);
+int nphusl_cuda_graph_destroy(void *graph_exec, int device);
 int nphusl_cuda_device_synchronize(int device);
 /* loc_out: NPHUSL_HOST (pageable or pinned; *pinned_out says which) or NPHUSL_DEVICE */
 int nphusl_cuda_pointer_info(const void *ptr, int *loc_out, int *device_out, int *pinned_out);

@@ -1467,7 +1467,8 @@ def test_stream_frames_converts_a_cyclic_video_exactly(cu):
     pool = cu.pinned_empty((P, H, W, 3), np.uint8)
     pool[...] = rng.integers(0, 256, pool.shape, dtype=np.uint8)
     ndev = min(2, cu.device_count())
-    for n, batch, first, edit in ((23, 4, 0, None), (7, 3, 9, None), (11, 8, 2, cu.Edit(**README_EDIT))):
+    for n, batch, first, edit, schedule in ((23, 4, 0, None, "static"), (7, 3, 9, None, "static"), (11, 8, 2, cu.Edit(**README_EDIT), "static"),
+                                            (29, 4, 3, None, "dynamic"), (9, 2, 0, cu.Edit(**README_EDIT), "dynamic")):
         seen = {}
 
         def sink(dev, i, frames):
@@ -1475,7 +1476,7 @@ def test_stream_frames_converts_a_cyclic_video_exactly(cu):
                 seen[i + j] = f.copy()
         called = []
         res = _shard.stream_frames(pool, n, devices=list(range(ndev)), first_frame=first, batch=batch, dtype=np.float32,
-                                   edit=edit, ready=lambda: called.append(1), on_batch=sink)
+                                   edit=edit, ready=lambda: called.append(1), on_batch=sink, schedule=schedule)
         assert called == [1] and res["frames"] == n and sorted(seen) == list(range(first, first + n))
         assert sum(v["frames"] for v in res["per_device"].values()) == n and res["seconds"] > 0
         for i, f in seen.items():
@@ -1559,3 +1560,36 @@ def test_grayscale_hue_stream_kernel_equals_the_general_kernel(cu):
             assert np.array_equal(hue, cu._rgb_to_hue(g3))
             lit = hue[np.isfinite(grey) & (grey > 1e-30) & (grey < 1e7)]
             assert np.all(np.abs(lit - 19.916405993809086) < 1e-3)
+
+
+def test_graph_api_records_and_replays_a_frame_loop(cu):
+    """nphusl._cuda.Graph / graph(): the per-frame loop to_husl -> to_rgb(edit) recorded once through the C ABI
+    (no torch involved) and replayed with one call per frame; results equal the direct calls."""
+    import nphusl
+    rng = np.random.default_rng(35)
+    frames = rng.integers(0, 256, (5, 270, 480, 3), dtype=np.uint8)
+    cur = cu.DeviceArray(frames.shape[1:], np.uint8)
+    hsl = cu.DeviceArray(frames.shape[1:], np.float32)
+    out = cu.DeviceArray(frames.shape[1:], np.uint8)
+    edit = cu.Edit(**README_EDIT)
+    g = cu.Graph()
+    n0 = cu.launch_count()
+    with g.capture() as s, nphusl.cuda_enabled():
+        nphusl.to_husl(cur, out=hsl, stream=s)
+        nphusl.to_rgb(hsl, out=out, stream=s, edit=edit)
+    assert cu.launch_count() - n0 == 2                          # recorded, and counted once
+    lib = cu.load()
+    for f in frames:
+        cu._check(lib.nphusl_cuda_memcpy(cur.ptr, f.ctypes.data, f.nbytes, 1, cur.device, cu._stream_ptr(g.stream)), "h2d")
+        g.replay()
+        g.synchronize()
+        assert np.array_equal(out.copy_to_host(), nphusl.edit(f, **README_EDIT))
+    hue = cu.DeviceArray(frames.shape[1:3], np.float32)
+    g2 = cu.graph(lambda s: cu._rgb_to_hue(cur, out=hue, stream=s))
+    g2()
+    g2.synchronize()
+    assert np.array_equal(hue.copy_to_host(), cu._rgb_to_hue(frames[-1], dtype=np.float32))
+    with pytest.raises(cu.CudaError):
+        cu.Graph().replay()
+    g.close()
+    g2.close()

@@ -83,3 +83,65 @@ def test_two_rank_gloo_sharding():
         assert sum(c[1] for c in allcs) == 5 and [c[1] for c in allcs] == [3, 2]
         assert all(c[2] == 0 for c in allcs)                       # exact round trip on every shard
         assert abs(sum(c[0] for c in allcs) - whole) < 1e-6        # shards tile the batch
+
+
+def test_frame_batches_cover_a_cyclic_stream():
+    """frame i of a video stream is pool[i % P]: batches never straddle the pool's end"""
+    for start, stop, P, B in ((0, 1000, 32, 8), (125, 250, 32, 8), (3, 40, 5, 4), (0, 7, 16, 8), (9, 9, 4, 2), (0, 10, 3, 8)):
+        got = list(_shard.frame_batches(start, stop, P, B))
+        frames = [i + j for i, p, n in got for j in range(n)]
+        assert frames == list(range(start, stop))
+        assert all(1 <= n <= B and p == i % P and p + n <= P for i, p, n in got)
+    assert [n for _, _, n in _shard.frame_batches(0, 1000, 32, 8)] == [8] * 125
+    with pytest.raises(ValueError):
+        list(_shard.frame_batches(0, 4, 0, 2))
+
+
+def test_stream_frames_schedules_with_fake_backend(monkeypatch):
+    """stream_frames' host logic (block partition, dynamic hand-out, ring slots, `last` bookkeeping) with the
+    CUDA calls replaced by numpy stand-ins -- the two world-size-2 style partitions of the video on CPU."""
+    import threading
+
+    class FakeStream:
+        def __init__(self, dev):
+            self.dev = dev
+
+        def synchronize(self):
+            pass
+
+    class FakeDev:
+        def __init__(self, shape, dtype, dev, stream=None):
+            self.a = np.zeros(shape, dtype)
+
+        def __getitem__(self, k):
+            v = FakeDev.__new__(FakeDev)
+            v.a = self.a[k]
+            return v
+    lock, log = threading.Lock(), []
+
+    def fwd(src, out=None, stream=None, device=None, blocking=True):
+        out.a[...] = src.astype(out.a.dtype) + 1000 * (device + 1)
+        with lock:
+            log.append((device, src.shape[0]))
+
+    def inv(h, out=None, stream=None, device=None, blocking=True, edit=None):
+        out[...] = (h.a - 1000 * (device + 1)).astype(np.uint8)
+    for name, obj in (("Stream", FakeStream), ("DeviceArray", FakeDev), ("pinned_empty", lambda s, d: np.zeros(s, d)),
+                      ("_rgb_to_husl", fwd), ("_husl_to_rgb", inv)):
+        monkeypatch.setattr(_shard._cuda, name, obj)
+    pool = np.random.default_rng(1).integers(0, 256, (6, 4, 5, 3), dtype=np.uint8)
+    for schedule in ("static", "dynamic"):
+        seen = {}
+        log.clear()
+        res = _shard.stream_frames(pool, 17, devices=[0, 1], first_frame=2, batch=4, dtype=np.float64, schedule=schedule,
+                                   on_batch=lambda dev, i, fr: seen.update({i + j: (dev, f.copy()) for j, f in enumerate(fr)}))
+        assert sorted(seen) == list(range(2, 19)) and res["frames"] == 17
+        assert all(np.array_equal(f, pool[i % 6]) for i, (d, f) in seen.items())
+        assert sum(v["frames"] for v in res["per_device"].values()) == 17
+        if schedule == "static":                               # contiguous blocks: frames 2..10 on device 0, 11..18 on device 1
+            assert {d for i, (d, f) in seen.items() if i <= 10} == {0} and {d for i, (d, f) in seen.items() if i > 10} == {1}
+            assert res["per_device"][0]["frames"] == 9 and res["per_device"][1]["frames"] == 8
+        for dev, (i, p, n, view) in res["last"].items():
+            assert p == i % 6 and np.array_equal(view, pool[p:p + n])
+    with pytest.raises(ValueError):
+        _shard.stream_frames(pool, 4, devices=[0], schedule="round-robin")
