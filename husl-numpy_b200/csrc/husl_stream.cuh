@@ -180,9 +180,18 @@ k_fwd_tma(const uint32_t *__restrict__ in, TOut *__restrict__ out, long long n_t
                 *reinterpret_cast<float4 *>(wr + 16 * k) =
                     make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
         } else {
+            // Lanes are 96 bytes (24 banks) apart, so lanes l and l + 4 of a quarter-warp would hit the same four
+            // banks with their k-th 16-byte chunk (2-way conflict on every STS.128: 17.4 M conflicts per launch in
+            // the round-1 ncu capture).  Lanes whose bit 2 is set write their chunks one position ahead
+            // (k + 1 mod 6): the eight lanes of a quarter-warp then cover all 32 banks.
+            const bool rot = (lane & 4) != 0;
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
-                *reinterpret_cast<double2 *>(wr + 16 * k) = make_double2((double)r[2 * k], (double)r[2 * k + 1]);
+            for (int k = 0; k < 6; ++k) {
+                constexpr int K6 = 6;
+                const int k1 = (k + 1) % K6;
+                const float a = rot ? r[2 * k1] : r[2 * k], b = rot ? r[2 * k1 + 1] : r[2 * k + 1];
+                *reinterpret_cast<double2 *>(wr + (rot ? 16 * k1 : 16 * k)) = make_double2((double)a, (double)b);
+            }
         }
         fence_async_smem();
         __syncwarp();

@@ -107,6 +107,7 @@ struct DevCtx {
     int dev = -1, sms = 0;
     Staging set[NSETS];
     cudaEvent_t gate = nullptr;
+    std::atomic<bool> ready{false};      // init done: ctx_get's lock-free fast path
     std::atomic<bool> attr_set{false};   // device-pointer calls reach set_attrs() from any thread without c.mu
     Lut lut;
 };
@@ -115,6 +116,12 @@ DevCtx g_ctx[MAX_DEV];
 
 // ---- per-device initialisation -------------------------------------------------
 int ctx_get(int device, DevCtx **out) {
+    // fast path of every call after the first on a device: no device-count query, no mutex
+    if (device >= 0 && device < MAX_DEV && g_ctx[device].ready.load(std::memory_order_acquire)) {
+        CU(cudaSetDevice(device));
+        *out = &g_ctx[device];
+        return NPHUSL_OK;
+    }
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
         cudaGetLastError();
@@ -149,6 +156,7 @@ int ctx_get(int device, DevCtx **out) {
             }
         CU(cudaEventCreateWithFlags(&c.gate, cudaEventDisableTiming));
         c.init = true;
+        c.ready.store(true, std::memory_order_release);
     }
     *out = &c;
     return NPHUSL_OK;

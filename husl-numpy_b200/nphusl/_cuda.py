@@ -1012,21 +1012,17 @@ def _views(bufs, pixel_ndim):
 # the three backend callables
 # ---------------------------------------------------------------------------
 
-class _host_async:
-    """``blocking=False``: for this one call, on this thread, pinned-host
-    buffers are only enqueued (nphusl_cuda_set_host_async); pageable memory
-    still completes before the call returns."""
-
-    def __init__(self, lib, blocking):
-        self.lib, self.on = lib, not blocking
-
-    def __enter__(self):
-        if self.on:
-            self.lib.nphusl_cuda_set_host_async(1)
-
-    def __exit__(self, *exc):
-        if self.on:
-            self.lib.nphusl_cuda_set_host_async(0)
+def _call(lib, blocking, fn, *args):
+    """Invoke a C ABI conversion.  ``blocking=False``: for this one call, on this thread, pinned-host
+    buffers are only enqueued (nphusl_cuda_set_host_async); pageable memory still completes before
+    the call returns.  The default (blocking) path is the bare foreign call."""
+    if blocking:
+        return fn(*args)
+    lib.nphusl_cuda_set_host_async(1)
+    try:
+        return fn(*args)
+    finally:
+        lib.nphusl_cuda_set_host_async(0)
 
 
 
@@ -1056,11 +1052,10 @@ def _rgb_to_husl(rgb, out=None, dtype=np.float64, mode="exact", stream=None, dev
             raise ValueError("LUT modes take C-contiguous arrays")
         _strided_call("nphusl_cuda_rgb_to_husl_strided", src, dst, len(src.shape) - 1, [0], dev, stream)
         return ret
-    with _host_async(lib, blocking):
-        rc = lib.nphusl_cuda_rgb_to_husl(src.ptr, _DT[src.dtype], src.loc, src.channels,
-                                         dst.ptr, _DT[dst.dtype], dst.loc, n, MODES[mode], dev,
-                                         _stream_ptr(stream))
-    _check(rc, "rgb_to_husl")
+    rc = _call(lib, blocking, lib.nphusl_cuda_rgb_to_husl, src.ptr, _DT[src.dtype], src.loc, src.channels,
+               dst.ptr, _DT[dst.dtype], dst.loc, n, MODES[mode], dev, _stream_ptr(stream))
+    if rc:
+        _check(rc, "rgb_to_husl")
     return ret
 
 
@@ -1079,10 +1074,10 @@ def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None, block
     if src.strides is not None or dst.strides is not None:
         _strided_call("nphusl_cuda_rgb_to_husl_strided", src, dst, len(shape), [1], dev, stream)
         return ret
-    with _host_async(lib, blocking):
-        rc = lib.nphusl_cuda_rgb_to_hue(src.ptr, _DT[src.dtype], src.loc, src.channels,
-                                        dst.ptr, _DT[dst.dtype], dst.loc, n, dev, _stream_ptr(stream))
-    _check(rc, "rgb_to_hue")
+    rc = _call(lib, blocking, lib.nphusl_cuda_rgb_to_hue, src.ptr, _DT[src.dtype], src.loc, src.channels,
+               dst.ptr, _DT[dst.dtype], dst.loc, n, dev, _stream_ptr(stream))
+    if rc:
+        _check(rc, "rgb_to_hue")
     return ret
 
 
@@ -1129,14 +1124,14 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
             raise ValueError("to_rgb(edit=...) takes C-contiguous arrays")
         _strided_call("nphusl_cuda_husl_to_rgb_strided", src, dst, len(src.shape) - 1, [], dev, stream)
         return ret
-    with _host_async(lib, blocking):
-        if edit is not None:
-            rc = lib.nphusl_cuda_husl_edit_to_rgb(src.ptr, _DT[src.dtype], src.loc, ctypes.byref(_as_edit(edit)),
-                                                  dst.ptr, _DT[dst.dtype], dst.loc, n, dev, _stream_ptr(stream))
-        else:
-            rc = lib.nphusl_cuda_husl_to_rgb(src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
-                                             n, dev, _stream_ptr(stream))
-    _check(rc, "husl_to_rgb")
+    if edit is not None:
+        rc = _call(lib, blocking, lib.nphusl_cuda_husl_edit_to_rgb, src.ptr, _DT[src.dtype], src.loc, ctypes.byref(_as_edit(edit)),
+                   dst.ptr, _DT[dst.dtype], dst.loc, n, dev, _stream_ptr(stream))
+    else:
+        rc = _call(lib, blocking, lib.nphusl_cuda_husl_to_rgb, src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
+                   n, dev, _stream_ptr(stream))
+    if rc:
+        _check(rc, "husl_to_rgb")
     return ret
 
 
@@ -1297,9 +1292,9 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
     if src.strides is not None or dst.strides is not None:
         _strided_call("nphusl_cuda_rgb_edit_rgb_strided", src, dst, len(src.shape) - 1, [ctypes.byref(edit)], dev, stream)
         return ret
-    with _host_async(lib, blocking):
-        rc = lib.nphusl_cuda_rgb_edit_rgb(src.ptr, src.loc, dst.ptr, dst.loc, n, ctypes.byref(edit), dev, _stream_ptr(stream))
-    _check(rc, "rgb_edit_rgb")
+    rc = _call(lib, blocking, lib.nphusl_cuda_rgb_edit_rgb, src.ptr, src.loc, dst.ptr, dst.loc, n, ctypes.byref(edit), dev, _stream_ptr(stream))
+    if rc:
+        _check(rc, "rgb_edit_rgb")
     return ret
 
 

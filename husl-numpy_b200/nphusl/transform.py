@@ -260,8 +260,11 @@ def reshape_image_input(fn):
     @wraps(fn)
     def wrapped(arr, *args, **kwargs):
         arr = _as_array(arr)
-        shape = tuple(arr.shape)
+        shape = arr.shape
         ndim = len(shape)
+        if ndim >= 2 and shape[-1] == 3:                 # an RGB image or a batch of them: nothing to fix
+            return fn(arr, *args, **kwargs)
+        shape = tuple(shape)
         size = math.prod(shape) if shape else 1
         channels = shape[-1] if shape else 0
         bad = ValueError("Unrecognized image shape: {}".format(shape))
@@ -296,7 +299,10 @@ def reshape_husl_input(fn):
     @wraps(fn)
     def wrapped(arr, *args, **kwargs):
         arr = _as_array(arr)
-        shape = tuple(arr.shape)
+        shape = arr.shape
+        if len(shape) >= 2 and shape[-1] == 3:
+            return fn(arr, *args, **kwargs)
+        shape = tuple(shape)
         size = math.prod(shape) if shape else 1
         bad = ValueError("Unrecognized HSL shape: {}".format(shape))
         if len(shape) == 1:
@@ -323,7 +329,7 @@ def reshape_rgba_input(fn):
     reads 0..255 as if it were [0, 1]; only float RGBA is tested there)."""
     @wraps(fn)
     def wrapped(arr, *args, **kwargs):
-        if len(arr.shape) in (2, 3) and arr.shape[-1] == 4:
+        if arr.shape[-1] == 4 and len(arr.shape) in (2, 3):
             _alert_rgba("Assumed RGBA with white background")
             if is_device_array(arr):
                 return fn(RgbaDevice(arr), *args, **kwargs)

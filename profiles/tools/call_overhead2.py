@@ -19,16 +19,20 @@ res = {}
 edit = _cuda.Edit(hue=(250, 290), invert=True, l=(0.5, 0))
 
 
+ts = torch.cuda.Stream()                 # everything runs and is timed on this stream (graphs are replayed onto it)
+torch.cuda.set_stream(ts)
+
+
 def rate(fn, px, reps=400):
     for _ in range(20):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    a.record()
+    a.record(ts)
     for _ in range(reps):
         fn()
-    b.record()
+    b.record(ts)
     host = (time.perf_counter() - t0) / reps
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
@@ -42,31 +46,31 @@ for name, shape in (("1080p", (1080, 1920, 3)), ("4k", (2160, 3840, 3))):
     for dt, tdt in (("f64", torch.float64), ("f32", torch.float32)):
         hsl = torch.empty(shape, dtype=tdt, device="cuda")
         s = torch.cuda.current_stream()
-        res["%s_to_husl_%s_public_api" % (name, dt)] = rate(lambda: nphusl.to_husl(frame, out=hsl), px)
-        res["%s_to_husl_%s_backend_callable" % (name, dt)] = rate(lambda: _cuda._rgb_to_husl(frame, out=hsl), px)
+        res["%s_to_husl_%s_public_api" % (name, dt)] = rate(lambda: nphusl.to_husl(frame, out=hsl, stream=ts), px)
+        res["%s_to_husl_%s_backend_callable" % (name, dt)] = rate(lambda: _cuda._rgb_to_husl(frame, out=hsl, stream=ts), px)
         g = _cuda.graph(lambda st: _cuda._rgb_to_husl(frame, out=hsl, stream=st))
-        res["%s_to_husl_%s_graph" % (name, dt)] = rate(g.replay, px)
+        res["%s_to_husl_%s_graph" % (name, dt)] = rate(lambda: g.replay(ts), px)
 
         def rt():
-            nphusl.to_husl(frame, out=hsl)
-            nphusl.to_rgb(hsl, out=back)
+            nphusl.to_husl(frame, out=hsl, stream=ts)
+            nphusl.to_rgb(hsl, out=back, stream=ts)
         res["%s_round_trip_%s_public_api" % (name, dt)] = rate(rt, px)
 
         def rec(st):
             nphusl.to_husl(frame, out=hsl, stream=st)
             nphusl.to_rgb(hsl, out=back, stream=st)
         g2 = _cuda.graph(rec)
-        res["%s_round_trip_%s_graph" % (name, dt)] = rate(g2.replay, px)
-        g2.synchronize()
+        res["%s_round_trip_%s_graph" % (name, dt)] = rate(lambda: g2.replay(ts), px)
+        torch.cuda.synchronize()
         assert torch.equal(back, frame)
 
         def rec_e(st):
             nphusl.to_husl(frame, out=hsl, stream=st)
             nphusl.to_rgb(hsl, out=back, stream=st, edit=edit)
         g3 = _cuda.graph(rec_e)
-        res["%s_edit_pipeline_%s_graph" % (name, dt)] = rate(g3.replay, px)
+        res["%s_edit_pipeline_%s_graph" % (name, dt)] = rate(lambda: g3.replay(ts), px)
         # 8 frames per replay: the loop body of a batch of small frames as ONE graph
         g8 = _cuda.graph(lambda st: [rec(st) for _ in range(8)])
-        r8 = rate(g8.replay, 8 * px, reps=100)
+        r8 = rate(lambda: g8.replay(ts), 8 * px, reps=100)
         res["%s_round_trip_%s_graph_of_8" % (name, dt)] = r8
 print(json.dumps(res, indent=1))
