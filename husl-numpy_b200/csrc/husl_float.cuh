@@ -52,6 +52,19 @@ __device__ __forceinline__ void read12(const unsigned char *rd, double (&v)[12])
     }
 }
 
+// the lane's 12 values in their own type (float channels reach lin_f64's float overload unconverted)
+template <typename T>
+__device__ __forceinline__ void read12n(const unsigned char *rd, T (&v)[12]) {
+    constexpr int PER = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int k = 0; k < 12 / PER; ++k) {
+        const float4 raw = *reinterpret_cast<const float4 *>(rd + 16 * k);
+        const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) v[PER * k + q] = e[q];
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void read12f(const unsigned char *rd, float (&v)[12]) {
     if (sizeof(T) == 4) {
@@ -117,8 +130,8 @@ k_fwd_flt(const TIn *__restrict__ in, TOut *__restrict__ out, long long n_tiles)
     for (long long tile = first; tile < n_tiles; tile += nw) {
         cp_async_wait<IST - 1>();
         __syncwarp();
-        double v[12];
-        read12<TIn>(ibuf + st * TB + lane * Tile<TIn>::LANE, v);
+        TIn v[12];
+        read12n<TIn>(ibuf + st * TB + lane * Tile<TIn>::LANE, v);
         __syncwarp();
         {
             const long long t = tile + (long long)IST * nw;

@@ -276,16 +276,16 @@ template <typename TIn>
 __device__ __forceinline__ LinPx load_px(const TIn *in, long long i, int channels) {
     LinPx p;
     if (channels == 3) {
-        lin_f64((double)in[3 * i], p.hr, p.lr);
-        lin_f64((double)in[3 * i + 1], p.hg, p.lg);
-        lin_f64((double)in[3 * i + 2], p.hb, p.lb);
+        lin_f64(in[3 * i], p.hr, p.lr);
+        lin_f64(in[3 * i + 1], p.hg, p.lg);
+        lin_f64(in[3 * i + 2], p.hb, p.lb);
     } else if (channels == 4) {      // float RGBA in [0,1]: rgb * alpha (transform.py:221-230)
         const double a = (double)in[4 * i + 3];
         lin_f64((double)in[4 * i] * a, p.hr, p.lr);
         lin_f64((double)in[4 * i + 1] * a, p.hg, p.lg);
         lin_f64((double)in[4 * i + 2] * a, p.hb, p.lb);
     } else {
-        lin_f64((double)in[i], p.hg, p.lg);
+        lin_f64(in[i], p.hg, p.lg);
         p.hr = p.hb = p.hg; p.lr = p.lb = p.lg;
     }
     return p;
@@ -331,7 +331,8 @@ k_gray_hue(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
             } else {
                 // NaN, or so large that the float linear value overflows: whatever the general code answers
                 LinPx p;
-                lin_f64(c, p.hg, p.lg);
+                if (sizeof(TIn) == 4) lin_f64((float)in[i], p.hg, p.lg);
+                else lin_f64(c, p.hg, p.lg);
                 p.hr = p.hb = p.hg; p.lr = p.lb = p.lg;
                 h = hue_from_diff(make_diff(p));
             }

@@ -94,9 +94,21 @@ __device__ __forceinline__ float hue_deg(float nv, float nu) {
 // r is seeded by MUFU lg2/ex2 (1e-6 relative) and polished by ONE division-free
 // Newton step in float64, r <- r*(6 - x*r^5)/5 (error ~3e-12); 11 DP operations
 // instead of the ~120 instructions of a general pow().
-__device__ __forceinline__ void lin_f64(double c, float &hi, float &lo) {
+// The XU pipe (MUFU and every float <-> double conversion, 16 lanes per SM) is what bounds the float-input
+// kernels -- ncu: 81 % busy in k_fwd_flt<float, float> with 8 XU operations per channel -- so conversions are
+// spent sparingly: the MUFU seed takes a float argument the caller already has (`xf`), and the result is split
+// into hi + lo by Veltkamp's trick in FP64 (t = v (2^29 + 1); h = t - (t - v) is v rounded to 24 bits) so that
+// only the two final narrowings convert: 4 conversions + 2 MUFU per channel.
+__device__ __forceinline__ void split_f64(double v, float &hi, float &lo) {
+    const double t = v * 536870913.0;
+    const double h = t - (t - v);
+    hi = (float)h;
+    lo = (float)(v - h);
+}
+
+// xf: (c + 0.055) / 1.055 to float accuracy (only seeds the Newton step)
+__device__ __forceinline__ void lin_f64_seeded(double c, float xf, float &hi, float &lo) {
     const double x = fma(c, 1.0 / 1.055, 0.055 / 1.055);
-    const float xf = (float)x;
     double r = (double)mufu_ex2(mufu_lg2(xf) * -0.2f);
     const double r2 = r * r;
     const double r5 = r2 * r2 * r;
@@ -104,9 +116,15 @@ __device__ __forceinline__ void lin_f64(double c, float &hi, float &lo) {
     double t = x * (r * r);
     t = t * t;
     t = t * t;
-    const double v = (c > 0.04045) ? t : c * (1.0 / 12.92);
-    hi = (float)v;
-    lo = (float)(v - (double)hi);
+    split_f64((c > 0.04045) ? t : c * (1.0 / 12.92), hi, lo);
+}
+
+__device__ __forceinline__ void lin_f64(double c, float &hi, float &lo) {
+    lin_f64_seeded(c, (float)fma(c, 1.0 / 1.055, 0.055 / 1.055), hi, lo);
+}
+// a float32 channel: the seed argument is formed in float, no narrowing conversion at all
+__device__ __forceinline__ void lin_f64(float c, float &hi, float &lo) {
+    lin_f64_seeded((double)c, fmaf(c, 1.0f / 1.055f, 0.055f / 1.055f), hi, lo);
 }
 
 // ---- forward core --------------------------------------------------------------

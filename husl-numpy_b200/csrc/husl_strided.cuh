@@ -37,9 +37,9 @@ __device__ __forceinline__ LinPx load_px_strided<uint8_t>(const char *p, long lo
 template <typename T>
 __device__ __forceinline__ LinPx load_px_strided(const char *p, long long es) {
     LinPx px;
-    lin_f64((double)*reinterpret_cast<const T *>(p), px.hr, px.lr);
-    lin_f64((double)*reinterpret_cast<const T *>(p + es), px.hg, px.lg);
-    lin_f64((double)*reinterpret_cast<const T *>(p + 2 * es), px.hb, px.lb);
+    lin_f64(*reinterpret_cast<const T *>(p), px.hr, px.lr);
+    lin_f64(*reinterpret_cast<const T *>(p + es), px.hg, px.lg);
+    lin_f64(*reinterpret_cast<const T *>(p + 2 * es), px.hb, px.lb);
     return px;
 }
 
