@@ -783,6 +783,7 @@ def run_cuda(args):
                 ("to_husl_u8_f64_lut", "k_fwd_lut", lambda: _cuda._rgb_to_husl(dev_in, out=dev_hsl, stream=stream, mode="lut"), 27),
                 ("to_husl_u8_f32", "k_fwd_u8<float>", lambda: _cuda._rgb_to_husl(dev_in, out=h32, stream=stream), 15),
                 ("to_rgb_f32_u8", "k_inv_cp<float>", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream), 15),
+                ("to_rgb_f32_u8_edit", "k_inv_cp<float,edit>", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream, edit=edit), 15),
                 ("to_hue_u8_f64", "k_fwd_u8<double,hue>", lambda: _cuda._rgb_to_hue(dev_in, out=hue64, stream=stream), 11),
                 ("to_hue_u8_f32", "k_fwd_u8<float,hue>", lambda: _cuda._rgb_to_hue(dev_in, out=hue32, stream=stream), 7),
                 ("fused_edit_u8_u8", "k_edit", lambda: _cuda.edit_rgb(dev_in, edit, out=dev_out, stream=stream), 6)):
@@ -805,6 +806,7 @@ def run_cuda(args):
         if hv64 is not None:
             record("nv12_to_husl_f64", "k_nv12<husl,double>", lambda: _cuda.nv12_to_husl(ysurf, uvsurf, out=hv64, stream=stream), 25.5, px)
         record("nv12_to_husl_f32", "k_nv12<husl,float>", lambda: _cuda.nv12_to_husl(ysurf, uvsurf, out=hv32, stream=stream), 13.5, px)
+        record("edit_husl_f64_in_place", "k_husl_edit<double>", lambda: _cuda.edit_husl(dev_hsl, edit, stream=stream), 48, px)
         record("nv12_edit_nv12", "k_to_nv12<nv12>", lambda: _cuda.nv12_edit_nv12(ysurf, uvsurf, edit, out_y=ysurf, out_uv=uvsurf, stream=stream), 3, px)
         record("frgb_f64_to_husl_f64", "k_fwd_flt<double,double>", lambda: _cuda._rgb_to_husl(f64in, out=f64out, stream=stream), 48, px2)
         record("husl_f64_to_frgb_f64", "k_inv_flt<double,double>",
@@ -812,7 +814,7 @@ def run_cuda(args):
         record("frgb_f32_to_husl_f32", "k_fwd_flt<float,float>", lambda: _cuda._rgb_to_husl(f32in, out=f32out, dtype=np.float32, stream=stream), 24, px2)
         with __import__("warnings").catch_warnings():
             __import__("warnings").simplefilter("ignore")
-            record("gray_f64_to_hue_f64", "k_fwd_any<gray>", lambda: nphusl.to_hue(g64, out=gh64, stream=stream), 16, px2)
+            record("gray_f64_to_hue_f64", "k_gray_hue", lambda: nphusl.to_hue(g64, out=gh64, stream=stream), 16, px2)
         del h32, hue64, hue32, ysurf, uvsurf, f64in, f64out, f32in, f32out, g64, gh64
 
     # ---- cpu baseline (rank 0, N=1 only) ---------------------------------------------

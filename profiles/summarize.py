@@ -14,7 +14,8 @@ import sys
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum",
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread",
@@ -61,5 +62,23 @@ def full(path):
                 print("   %-85s %s %s" % (m, r[idx[m]], units[idx[m]]))
 
 
+def traffic(path):
+    """-> JSON fragment for profiles/traffic.json: DRAM bytes and warp instructions per profiled launch, keyed by kernel name"""
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = collections.OrderedDict()
+    for r in rows[2:]:
+        def val(m):
+            return float(r[idx[m]].replace(",", "")) * scale.get(units[idx[m]], 1)
+        out.setdefault(r[idx["Kernel Name"]], {"dram_bytes": int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum")),
+                                              "warp_inst": int(val("smsp__inst_executed.sum")),
+                                              "us": round(float(r[idx["gpu__time_duration.sum"]]) * {"us": 1, "ms": 1e3, "ns": 1e-3}[units[idx["gpu__time_duration.sum"]]], 1)})
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
