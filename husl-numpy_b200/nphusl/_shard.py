@@ -231,7 +231,11 @@ def stream_frames(pool, n_frames, devices=None, first_frame=0, batch=8, dtype=np
     try:
         setup_done.wait()
         if ready is not None:
-            ready()
+            try:
+                ready()
+            except BaseException as e:                       # noqa: BLE001 - workers must not wait for a start that never comes
+                errors.append(e)
+                go.abort()
         go.wait()
     except threading.BrokenBarrierError:
         pass

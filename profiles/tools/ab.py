@@ -74,8 +74,8 @@ for name, fn, b in (("pipeline_f64", pipe64, 54), ("pipeline_f32", pipe32, 30),
                     ("planar_inv_f32", lambda: _cuda.husl_planar_to_rgb(pl32, out=back), 15),
                     ("planar_fwd_f64", lambda: _cuda.rgb_to_husl_planar(rgb, out=pl64), 27),
                     ("planar_inv_f64", lambda: _cuda.husl_planar_to_rgb(pl64, out=back), 27),
-                    ("chw_fwd_f32", lambda: _cuda.rgb_to_husl_planar(rgb.view(3, -1), out=pl32, channels_first=True), 15),
-                    ("chw_inv_f32", lambda: _cuda.husl_planar_to_rgb(pl32, out=back.view(3, -1), channels_first=True), 15),
+                    ("chw_fwd_f32", lambda: _cuda.rgb_to_husl_planar(rgb.view(3, -1), out=pl32.view(3, -1), channels_first=True), 15),
+                    ("chw_inv_f32", lambda: _cuda.husl_planar_to_rgb(pl32.view(3, -1), out=back.view(3, -1), channels_first=True), 15),
                     ("fused_edit_u8", lambda: _cuda.edit_rgb(rgb, out=back, hue=(250, 290), invert=True, l=(0.5, 0)), 6),
                     ("fused_edit_chw_u8", lambda: _cuda.edit_rgb(rgb.view(3, -1), out=back.view(3, -1), channels_first=True,
                                                                 hue=(250, 290), invert=True, l=(0.5, 0)), 6)):

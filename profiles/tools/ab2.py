@@ -62,6 +62,16 @@ if "edit" in want or "pipe" in want:
     res["inv32_ms"] = timed(lambda: _cuda._husl_to_rgb(h32, out=back))
     res["inv32_edit_ms"] = timed(lambda: _cuda._husl_to_rgb(h32, out=back, edit=edit))
     del h32
+if "hue" in want:
+    hue32 = torch.empty(rgb.shape[:-1], dtype=torch.float32, device="cuda")
+    hue64 = torch.empty(rgb.shape[:-1], dtype=torch.float64, device="cuda")
+    h32 = torch.empty(rgb.shape, dtype=torch.float32, device="cuda")
+    res["hue32_ms"] = timed(lambda: _cuda._rgb_to_hue(rgb, out=hue32))
+    res["hue64_ms"] = timed(lambda: _cuda._rgb_to_hue(rgb, out=hue64))
+    res["fwd32_ms"] = timed(lambda: _cuda._rgb_to_husl(rgb, out=h32))
+    res["fwd64_ms"] = timed(lambda: _cuda._rgb_to_husl(rgb, out=h64))
+    res["fused_edit_ms"] = timed(lambda: _cuda.edit_rgb(rgb, edit, out=back))
+    del hue32, hue64, h32
 if "flt" in want:
     f64in = (rgb[:2].to(torch.float64) / 255.0).contiguous()
     f32in = f64in.to(torch.float32)
