@@ -21,19 +21,18 @@ namespace husl {
 // double holding the 4- / 3-decimal literal itself (scales 1).  The kernels are
 // templated on the element type; the arithmetic on the promoted double is the same.
 //
-// Derived tables (k_lut_prepare, built once when tables are installed) take IEEE operations
+// A derived table (k_lut_prepare, built once when tables are installed) takes an IEEE operation
 // whose operands come from a table out of the per-pixel path without changing a bit:
-//   prod[k][c]  = coef_k * linear[c]            the nine products of the XYZ matrix (_simd.c:171-173)
 //   light_q[i]  = light_table_big[i] / LIGHT_SCALE                                  (_simd.c:495)
 struct LutParams {
     const double *linear;     // 256, 6-decimal values (_linear_lookup.c:9-42)
     const void *light;        // 3*seg entries (light_table_big)
     const void *chroma;       // nh*nl entries (chroma_table)
-    const double *prod;       // 9 * 256 (derived)
     const double *light_q;    // 3*seg (derived)
     int seg, nh, nl;
     double ystep[3], ythresh[2], hstep, lstep;
     double r_ystep[3], r_hstep, r_lstep;   // RN(1 / step), for the exactly rounded divisions below
+    double yorg[3], ybase[3];              // per light segment: origin (0, ythresh[0], ythresh[1]) and index base (0, seg, 2 seg)
     double light_scale;       // LIGHT_SCALE
     double sat_scale;         // 100 * CHROMA_SCALE (_simd.c:334)
 };
@@ -80,16 +79,17 @@ __device__ __forceinline__ double cdiv(double a, double b, double rb) {
 }
 __device__ __forceinline__ double div_rn(double a, double b) { return cdiv(a, b, rcp_near(b)); }
 // sqrt(a), a > 0: Goldschmidt on g ~ sqrt(a), h ~ 1/(2 sqrt(a)), then g + (a - g*g) * h
-__device__ __forceinline__ double sqrt_rn(double a) {
+template <bool GUARD = true> __device__ __forceinline__ double sqrt_rn(double a) {
     const double y = rsqrt_seed(a);
     double g = __dmul_rn(a, y), h = __dmul_rn(0.5, y);
     double r = __fma_rn(-g, h, 0.5);
     g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
     r = __fma_rn(-g, h, 0.5);
-    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+    g = __fma_rn(g, r, g);
+    if (GUARD) h = __fma_rn(h, r, h);   // the correction below is ~2^-53 g: h good to 2^-40 after one refinement serves it
     const double d = __fma_rn(-g, g, a);
     const double res = __fma_rn(d, h, g);
-    return (a == 0.0) ? 0.0 : res;
+    return (GUARD && a == 0.0) ? 0.0 : res;
 }
 
 // (unsigned short)fmax(0, fmin(hi, (double)roundf((float)x))) of _simd.c:403-404,494 in integer registers:
@@ -106,13 +106,32 @@ __device__ __forceinline__ int floor_clamp(double x, int hi) {
     const int i = __float2int_rd(__double2float_rn(x));
     return min(max(i, 0), hi);
 }
+// The same two for the tile kernel's straight-line path (FAST): every index it rounds is >= 0 for a pixel whose
+// result is used (y - origin >= 0 by the choice of the segment, H in [0, 360], L >= 0), so copysign and the
+// lower clamp go; an unsigned minimum keeps whatever a NaN / infinity of a pixel that is answered elsewhere
+// (black, white, u == 0: see lut_pixels) converts to inside the table.
+__device__ __forceinline__ int round_clamp_pos(double x, int hi) {
+    const float f = __double2float_rn(x);
+    return (int)min((unsigned)__float2int_rz(__fadd_rz(f, 0.5f)), (unsigned)hi);
+}
+__device__ __forceinline__ int floor_clamp_pos(double x, int hi) {
+    return (int)min((unsigned)__float2int_rd(__double2float_rn(x)), (unsigned)hi);
+}
+template <bool FAST> __device__ __forceinline__ int round_idx(double x, int hi) {
+    return FAST ? round_clamp_pos(x, hi) : round_clamp(x, hi);
+}
+template <bool FAST> __device__ __forceinline__ int floor_idx(double x, int hi) {
+    return FAST ? floor_clamp_pos(x, hi) : floor_clamp(x, hi);
+}
 
 // constants whose low word is not zero live in constant memory: FP64 instructions take them as operands
 // straight from the bank instead of re-materialising two 32-bit halves per use
-__constant__ double LUT_K[12] = {0.78539816339744830962, 0.2447, 0.0663, 180.0 / 3.14159265358979323846,
+__constant__ double LUT_K[21] = {0.78539816339744830962, 0.2447, 0.0663, 180.0 / 3.14159265358979323846,
                                  3.141592653589793, 1.5707963267948966, 0.28, 0.19783000664283, 0.46831999493879,
-                                 19.916405993809086, 1e-10, (double)1e-10f};
-enum { K_PI4 = 0, K_A, K_B, K_DEG, K_PI, K_PIBY2, K_028, K_REFU, K_REFV, K_WHITE_HUE, K_TINY, K_TINYF };
+                                 19.916405993809086, 1e-10, (double)1e-10f,
+                                 0.412391, 0.357584, 0.180481, 0.212639, 0.715169, 0.072192, 0.019331, 0.119195, 0.950532};
+enum { K_PI4 = 0, K_A, K_B, K_DEG, K_PI, K_PIBY2, K_028, K_REFU, K_REFV, K_WHITE_HUE, K_TINY, K_TINYF,
+       K_XR, K_XG, K_XB, K_YR, K_YG, K_YB, K_ZR, K_ZG, K_ZB };
 
 // _simd.c:485-496.  The three segments differ only in (origin, step, index base): selected first, divided
 // once.  Segment 0 is y / step exactly as written there (y - 0.0 and + 0.0 change nothing).
@@ -124,6 +143,16 @@ __device__ __forceinline__ double lut_light(const LutParams &t, const double *li
     const double base = s0 ? 0.0 : (s1 ? (double)t.seg : (double)(t.seg * 2));
     const double idx = da(cdiv(ds(y, org), step, rstep), base);
     return light_q[round_clamp(idx, 3 * t.seg - 1)];
+}
+
+// The same with the segment's four parameters read from the kernel parameters by segment number (the count of
+// thresholds at or below y): indexed constant loads (LDC, the otherwise idle ADU pipe) instead of eight
+// 64-bit selects; a shared-memory table costs four wavefronts per 16-byte load even when all lanes read one of
+// three addresses, and the L1 data pipe is one of this kernel's three near-limits.
+__device__ __forceinline__ double lut_light_seg(const LutParams &t, const double *light_q, double y) {
+    const int row = (y >= t.ythresh[0] ? 1 : 0) + (y >= t.ythresh[1] ? 1 : 0);
+    const double idx = da(cdiv(ds(y, t.yorg[row]), t.ystep[row], t.r_ystep[row]), t.ybase[row]);
+    return light_q[round_clamp_pos(idx, 3 * t.seg - 1)];
 }
 
 // _simd.c:279-281
@@ -149,16 +178,45 @@ __device__ __forceinline__ double lut_hue(double u, double v) {
     return (fabs(z) < 1.0) ? ha : hb;
 }
 
+// lut_hue for u != 0 (the tile kernel answers u == 0 elsewhere, see lut_pixels), with the sign tests and the
+// selections on the integer side: FP64 compares and selects of double pairs share the FP64 pipe / cost two
+// FSEL each, and nvcc turns the nested ?: above into divergent branches.  With u != 0 neither u nor v can be
+// -0.0 (v = 13 L (v' - REF_V) with L > 0; x - x is +0), so "< 0" is the sign bit; the additive constants
+// 180, 360 (low words zero) and 0 are selected as high words and added unconditionally: ha + 0, at - 0 and
+// hb + 0 return their operand bit for bit because none of them can be -0.0 here (ha = -0 needs z = -0, i.e.
+// v = +0 with u < 0, which takes + 180; at and hb are differences that round to +0 when they vanish).
+__device__ __forceinline__ double lut_hue_nz(double u, double v, bool &z_not_finite) {
+    const double DEG_PER_RAD = LUT_K[K_DEG], PI_ = LUT_K[K_PI], PIBY2 = LUT_K[K_PIBY2];
+    const int uh = __double2hiint(u), vh = __double2hiint(v);
+    const double z = div_rn(v, u);
+    double ha = dm(lut_atan(z), DEG_PER_RAD);
+    ha = da(ha, __hiloint2double((uh < 0) ? 0x40668000 : ((vh < 0) ? 0x40768000 : 0), 0));
+    double at = ds(PIBY2, div_rn(z, da(dm(z, z), LUT_K[K_028])));
+    at = ds(at, __hiloint2double((vh < 0) ? __double2hiint(PI_) : 0, (vh < 0) ? __double2loint(PI_) : 0));
+    double hb = dm(at, DEG_PER_RAD);
+    hb = da(hb, __hiloint2double((__double2hiint(hb) < 0) ? 0x40768000 : 0, 0));
+    const unsigned az = (unsigned)(__double2hiint(z) & 0x7fffffff);
+    const bool below_one = az < 0x3ff00000u;     // |z| < 1, false for NaN
+    z_not_finite = az >= 0x7ff00000u;            // u == 0 (v / 0 is an infinity or NaN), or a NaN u or v
+    return __hiloint2double(below_one ? __double2hiint(ha) : __double2hiint(hb),
+                            below_one ? __double2loint(ha) : __double2loint(hb));
+}
+
 // _simd.c:399-406 / :360-387
-template <bool INTERP, typename TT>
+template <bool INTERP, typename TT, bool FAST>
 __device__ __forceinline__ double lut_chroma(const LutParams &t, double l, double h) {
     const TT *chroma = static_cast<const TT *>(t.chroma);
     const double hs = cdiv(h, t.hstep, t.r_hstep), ls = cdiv(l, t.lstep, t.r_lstep);
     if (!INTERP) {
-        const int hi = round_clamp(hs, t.nh - 1), li = round_clamp(ls, t.nl - 1);
-        return fmax(LUT_K[K_TINY], (double)__ldg(chroma + (unsigned)(hi * t.nl + li)));
+        const int hi = round_idx<FAST>(hs, t.nh - 1), li = round_idx<FAST>(ls, t.nl - 1);
+        const TT raw = __ldg(chroma + (unsigned)(hi * t.nl + li));
+        if (FAST && sizeof(TT) == 2) {      // fmax(1e-10, entry) of an unsigned integer entry: 1e-10 where it is 0
+            const double cv = (double)raw, tiny = LUT_K[K_TINY];
+            return __hiloint2double(raw == 0 ? __double2hiint(tiny) : __double2hiint(cv), raw == 0 ? __double2loint(tiny) : __double2loint(cv));
+        }
+        return fmax(LUT_K[K_TINY], (double)raw);
     }
-    const int hf = floor_clamp(hs, t.nh - 2), lf = floor_clamp(ls, t.nl - 2);
+    const int hf = floor_idx<FAST>(hs, t.nh - 2), lf = floor_idx<FAST>(ls, t.nl - 2);
     const TT *c0 = chroma + (unsigned)(hf * t.nl + lf);
     const double c00 = __ldg(c0), c10 = __ldg(c0 + t.nl), c01 = __ldg(c0 + 1), c11 = __ldg(c0 + t.nl + 1);
     const double hn = ds(hs, (double)hf), ln = ds(ls, (double)lf);
@@ -167,29 +225,41 @@ __device__ __forceinline__ double lut_chroma(const LutParams &t, double l, doubl
     return fmax(LUT_K[K_TINYF], c);
 }
 
-// NP pixels of rgb_to_husl_nd, default build (_simd.c:128-225), stage by stage.  `prod` is the 9 x 256
-// product table and `light_q` the pre-divided light table (shared memory in the tile kernel, global / L1 in
-// the one-pixel-per-thread kernel).  c[3p .. 3p+2] = R, G, B bytes of pixel p; o[3p .. 3p+2] = H, S, L.
+// NP pixels of rgb_to_husl_nd, default build (_simd.c:128-225), stage by stage.  `xyz(p, x, y, z)` hands over
+// pixel p's X, Y, Z (_simd.c:171-173; the two callers below differ in where the table operands come from),
+// `light_q` is the pre-divided light table (shared memory in the tile kernel, global / L1 in the
+// one-pixel-per-thread kernel).  c[3p .. 3p+2] = R, G, B bytes of pixel p; o[3p .. 3p+2] = H, S, L.
 // Walking the NP pixels through each stage together gives the scheduler NP independent dependency chains
-// (the kernel is bound by FP64 / table latency, not by a pipe) and loads each stage's constants once.
-template <bool INTERP, typename TT, int NP>
-__device__ __forceinline__ void lut_pixels(const LutParams &t, const double *prod, const double *light_q,
+// and loads each stage's constants once.
+//
+// FAST = false is the complete function.  FAST = true (tile kernel) leaves out everything that only three
+// kinds of pixel need -- the constants for pure white and pure black (_simd.c:205-212), the u == 0 guard of
+// the arctangent (:288-315) and sqrt(0) (u = v = 0 is a special case of u == 0) -- and returns whether any
+// of the NP pixels was of those kinds (or had a v / u that is not finite for another reason); the caller then
+// redoes that lane's pixels with FAST = false.  On the 2^24 colours with the default tables those are black,
+// white and (0, 0, 1), whose L index rounds to 0.  FAST also trims three FP64 operations whose result
+// provably (4x: a power of two) or on every one of the 2^24 colours (sha256 of the cube) stays the same.
+template <bool INTERP, typename TT, int NP, bool FAST, typename XYZ>
+__device__ __forceinline__ bool lut_pixels(const LutParams &t, const XYZ &xyz, const double *light_q,
                                            const uint32_t (&c)[3 * NP], double (&o)[3 * NP]) {
     double y[NP], vu[NP], vv[NP];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        const uint32_t r = c[3 * p], g = c[3 * p + 1], b = c[3 * p + 2];
-        const double x = da(da(prod[r], prod[256 + g]), prod[512 + b]);
-        y[p] = da(da(prod[768 + r], prod[1024 + g]), prod[1280 + b]);
-        const double z = da(da(prod[1536 + r], prod[1792 + g]), prod[2048 + b]);
+        double x, z;
+        xyz(p, x, y[p], z);
         const double vs = da(da(x, dm(15.0, y[p])), dm(3.0, z));
         const double rvs = rcp_near(vs);
-        vu[p] = cdiv(dm(4.0, x), vs, rvs);
+        if (FAST) {     // RN(4x / vs) = 4 RN(x / vs): the factor is an exponent increment (x = 0 is black, answered elsewhere)
+            const double q = cdiv(x, vs, rvs);
+            vu[p] = __hiloint2double(__double2hiint(q) + 0x00200000, __double2loint(q));
+        } else {
+            vu[p] = cdiv(dm(4.0, x), vs, rvs);
+        }
         vv[p] = cdiv(dm(9.0, y[p]), vs, rvs);
     }
     double l[NP], u[NP], v[NP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) l[p] = lut_light(t, light_q, y[p]);
+    for (int p = 0; p < NP; ++p) l[p] = FAST ? lut_light_seg(t, light_q, y[p]) : lut_light(t, light_q, y[p]);
     {
         const double REF_U = LUT_K[K_REFU], REF_V = LUT_K[K_REFV];
 #pragma unroll
@@ -200,20 +270,49 @@ __device__ __forceinline__ void lut_pixels(const LutParams &t, const double *pro
         }
     }
     double h[NP], mc[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) h[p] = lut_hue(u[p], v[p]);
-#pragma unroll
-    for (int p = 0; p < NP; ++p) mc[p] = lut_chroma<INTERP, TT>(t, l[p], h[p]);
+    bool special = false;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        const double sat = div_rn(dm(t.sat_scale, sqrt_rn(da(dm(u[p], u[p]), dm(v[p], v[p])))), mc[p]);
-        // _simd.c:205-212: pure white and pure black are answered with constants
-        const uint32_t r = c[3 * p], g = c[3 * p + 1], b = c[3 * p + 2];
-        const bool white = (r & g & b) == 255u, black = (r | g | b) == 0u;
-        o[3 * p] = white ? LUT_K[K_WHITE_HUE] : (black ? 0.0 : h[p]);
-        o[3 * p + 1] = (white || black) ? 0.0 : fmin(sat, 100.0);
-        o[3 * p + 2] = white ? 100.0 : (black ? 0.0 : l[p]);
+        if (FAST) {
+            bool znf;
+            h[p] = lut_hue_nz(u[p], v[p], znf);
+            special = special || znf;
+        } else {
+            h[p] = lut_hue(u[p], v[p]);
+        }
     }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) mc[p] = lut_chroma<INTERP, TT, FAST>(t, l[p], h[p]);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const double sat = div_rn(dm(t.sat_scale, sqrt_rn<!FAST>(da(dm(u[p], u[p]), dm(v[p], v[p])))), mc[p]);
+        const uint32_t r = c[3 * p], g = c[3 * p + 1], b = c[3 * p + 2];
+        if (FAST) {
+            // black: r + g + b == 0, white: == 765 (u == 0 was seen by lut_hue_nz: v / u is not finite)
+            const uint32_t sum = r + g + b;
+            special = special || sum == 0u || sum == 765u;
+            // fmin(sat, 100): sat >= 0, so "sat >= 100" is a compare of the high words (100.0 = 0x40590000'00000000)
+            const bool cap = (unsigned)__double2hiint(sat) >= 0x40590000u;
+            o[3 * p] = h[p];
+            o[3 * p + 1] = __hiloint2double(cap ? 0x40590000 : __double2hiint(sat), cap ? 0 : __double2loint(sat));
+            o[3 * p + 2] = l[p];
+        } else {
+            // _simd.c:205-212: pure white and pure black are answered with constants
+            const bool white = (r & g & b) == 255u, black = (r | g | b) == 0u;
+            o[3 * p] = white ? LUT_K[K_WHITE_HUE] : (black ? 0.0 : h[p]);
+            o[3 * p + 1] = (white || black) ? 0.0 : fmin(sat, 100.0);
+            o[3 * p + 2] = white ? 100.0 : (black ? 0.0 : l[p]);
+        }
+    }
+    return special;
+}
+
+// X, Y, Z of one pixel from its three table values of linear light: the nine products and six sums of
+// _simd.c:171-173 in the order written there, (c0 r + c1 g) + c2 b per row
+__device__ __forceinline__ void lut_xyz(double lr, double lg, double lb, double &x, double &y, double &z) {
+    x = da(da(dm(LUT_K[K_XR], lr), dm(LUT_K[K_XG], lg)), dm(LUT_K[K_XB], lb));
+    y = da(da(dm(LUT_K[K_YR], lr), dm(LUT_K[K_YG], lg)), dm(LUT_K[K_YB], lb));
+    z = da(da(dm(LUT_K[K_ZR], lr), dm(LUT_K[K_ZG], lg)), dm(LUT_K[K_ZB], lb));
 }
 
 // rgb_to_husl_nd, one pixel per thread: tails (< 128 pixels) and unaligned buffers
@@ -224,19 +323,19 @@ k_fwd_lut(const uint8_t *__restrict__ rgb, double *__restrict__ hsl, long long n
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t c[3] = {rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
         double r[3];
-        lut_pixels<INTERP, TT, 1>(t, t.prod, t.light_q, c, r);
+        const auto xyz = [&](int, double &x, double &y, double &z) {
+            lut_xyz(__ldg(t.linear + c[0]), __ldg(t.linear + c[1]), __ldg(t.linear + c[2]), x, y, z);
+        };
+        lut_pixels<INTERP, TT, 1, false>(t, xyz, t.light_q, c, r);
         double *o = hsl + 3 * i;
         o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
     }
 }
 
-// derived tables, see LutParams
+// derived table, see LutParams
 template <typename TT>
-__global__ void k_lut_prepare(const double *linear, const TT *light, int n_light, double light_scale,
-                              double *prod, double *light_q) {
-    const double coef[9] = {0.412391, 0.357584, 0.180481, 0.212639, 0.715169, 0.072192, 0.019331, 0.119195, 0.950532};
+__global__ void k_lut_prepare(const TT *light, int n_light, double light_scale, double *light_q) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 9 * 256) prod[i] = __dmul_rn(coef[i >> 8], linear[i & 255]);
     if (i < n_light) light_q[i] = __ddiv_rn((double)light[i], light_scale);
 }
 

@@ -80,7 +80,7 @@ struct Lut {
     int seg = 0, nh = 0, nl = 0;
     int type = NPHUSL_LUT_U16;           // element type of light / chroma
     void *light = nullptr, *chroma = nullptr;
-    double *linear = nullptr, *prod = nullptr, *light_q = nullptr;   // prod / light_q: derived tables (husl_lut.cuh)
+    double *linear = nullptr, *light_q = nullptr;   // light_q: derived table (husl_lut.cuh)
     double light_scale = 100, chroma_scale = 100;
     LutParams p{};
 };
@@ -497,8 +497,8 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
 }
 
 #ifndef NPHUSL_LUT_BLOCK
-#define NPHUSL_LUT_BLOCK 512       // A/B on B200 (profiles/r02_ab_lut.txt): 512 x 1 with 4 pixels per lane in flight
-#define NPHUSL_LUT_MINB 1         // (114 registers) 0.756 ms; 512 x 2 / 2 pixels 0.796; 384 x 2 / 4 0.776; 256 x 2 / 4 0.770
+#define NPHUSL_LUT_BLOCK 640       // A/B on B200 (profiles/r02_ab_lut.txt): 640 x 1 with 4 pixels per lane in flight
+#define NPHUSL_LUT_MINB 1         // 0.523 ms; 512 x 1 0.547; 768 x 1 0.588; 384 x 2 0.585
 #endif
 #ifndef NPHUSL_LUT_NP
 #define NPHUSL_LUT_NP 4             // pixels of a lane walked through the stages together (1, 2 or 4)
@@ -516,7 +516,7 @@ int run_lut_dev(DevCtx &c, const void *in, void *out, long long n, int mode, cud
         const int grid = grid_for(tiles, LUT_BLOCK / 32, c.sms * LUT_MINB);
         const bool light_smem = 3 * c.lut.seg * 8 <= LUT_LIGHT_SMEM_MAX;
 #define LUT_TILE(INTERP, TT, LS) do { \
-        constexpr int sm = LUT_PROD_BYTES + (LS ? LUT_LIGHT_SMEM_MAX : 0) + (LUT_BLOCK / 32) * Tile<double>::BYTES; \
+        constexpr int sm = lut_tile_smem<LS, LUT_BLOCK>(); \
         static std::atomic<bool> attr_done[MAX_DEV]; \
         if ((rc = flt_attr(attr_done, c, k_fwd_lut_tile<INTERP, TT, LUT_BLOCK, LUT_MINB, LS, LUT_NP>, sm))) return rc; \
         k_fwd_lut_tile<INTERP, TT, LUT_BLOCK, LUT_MINB, LS, LUT_NP><<<grid, LUT_BLOCK, sm, s>>>((const uint32_t *)in, (double *)out, tiles, c.lut.p); } while (0)
@@ -1511,10 +1511,14 @@ static int lut_finish(DevCtx &c) {
     for (int i = 0; i < 3; ++i) l.p.r_ystep[i] = 1.0 / l.p.ystep[i];
     l.p.r_hstep = 1.0 / l.p.hstep;
     l.p.r_lstep = 1.0 / l.p.lstep;
-    const int n_light = 3 * l.seg, n = n_light > 9 * 256 ? n_light : 9 * 256;
-    if (l.type == NPHUSL_LUT_U16) k_lut_prepare<uint16_t><<<(n + 255) / 256, 256>>>(l.linear, (const uint16_t *)l.light, n_light, l.light_scale, l.prod, l.light_q);
-    else if (l.type == NPHUSL_LUT_F32) k_lut_prepare<float><<<(n + 255) / 256, 256>>>(l.linear, (const float *)l.light, n_light, l.light_scale, l.prod, l.light_q);
-    else k_lut_prepare<double><<<(n + 255) / 256, 256>>>(l.linear, (const double *)l.light, n_light, l.light_scale, l.prod, l.light_q);
+    for (int i = 0; i < 3; ++i) {
+        l.p.yorg[i] = i ? l.p.ythresh[i - 1] : 0.0;
+        l.p.ybase[i] = (double)(l.seg * i);
+    }
+    const int n_light = 3 * l.seg;
+    if (l.type == NPHUSL_LUT_U16) k_lut_prepare<uint16_t><<<(n_light + 255) / 256, 256>>>((const uint16_t *)l.light, n_light, l.light_scale, l.light_q);
+    else if (l.type == NPHUSL_LUT_F32) k_lut_prepare<float><<<(n_light + 255) / 256, 256>>>((const float *)l.light, n_light, l.light_scale, l.light_q);
+    else k_lut_prepare<double><<<(n_light + 255) / 256, 256>>>((const double *)l.light, n_light, l.light_scale, l.light_q);
     g_launches++;
     int rc = check_launch("k_lut_prepare");
     if (rc) return rc;
@@ -1528,7 +1532,6 @@ static int lut_alloc(DevCtx &c, int seg, int nh, int nl, int type, double light_
     if (l.light) cudaFree(l.light);
     if (l.chroma) cudaFree(l.chroma);
     if (!l.linear) CU(cudaMalloc(&l.linear, 256 * sizeof(double)));
-    if (!l.prod) CU(cudaMalloc(&l.prod, 9 * 256 * sizeof(double)));
     if (l.light_q) cudaFree(l.light_q);
     l.light = l.chroma = nullptr;
     l.light_q = nullptr;
@@ -1539,7 +1542,7 @@ static int lut_alloc(DevCtx &c, int seg, int nh, int nl, int type, double light_
     l.seg = seg; l.nh = nh; l.nl = nl; l.type = type;
     l.light_scale = light_scale; l.chroma_scale = chroma_scale;
     l.p.linear = l.linear; l.p.light = l.light; l.p.chroma = l.chroma;
-    l.p.prod = l.prod; l.p.light_q = l.light_q;
+    l.p.light_q = l.light_q;
     l.p.seg = seg; l.p.nh = nh; l.p.nl = nl;
     l.p.light_scale = light_scale;
     l.p.sat_scale = 100 * chroma_scale;
