@@ -735,6 +735,44 @@ def test_lut_mode_with_other_table_sizes(cu):
         cu._rgb_to_husl(rgb.astype(np.float32) / 255, mode="lut")      # LUT modes take uint8, like _simd.c
 
 
+def test_lut_mode_pixels_the_streaming_pass_hands_back(cu):
+    """The LUT tile kernel's straight-line pass leaves black, white and u == 0 pixels (L index 0: u = v = 0)
+    to a second, complete pass over the lane that met one.  Whole tiles of them (letterbox bars, blown
+    highlights), single ones between ordinary pixels, and tables where more or fewer colours land in that
+    class (a light table whose first entries are 0, and one whose first entry is NOT 0: black must still be
+    answered with the constants of _simd.c:205-212) -- against the oracle, bit for bit, and against the
+    one-pixel-per-thread kernel (an odd base address keeps the data off the tile kernel)."""
+    rng = np.random.default_rng(41)
+    n = 128 * 300
+    rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    rgb[128 * 3:128 * 9] = 0                       # whole tiles of black
+    rgb[128 * 20:128 * 23] = 255                   # ... and of white
+    rgb[128 * 40:128 * 44] = (0, 0, 1)             # L index rounds to 0: u == v == 0 without being black
+    dark = rng.integers(0, 3, (128 * 30, 3), dtype=np.uint8)
+    rgb[128 * 60:128 * 90] = dark                  # every colour of {0, 1, 2}^3, mixed within lanes
+    rgb[128 * 100 + 5] = 0; rgb[128 * 101 + 77] = 255; rgb[128 * 102 + 127] = (0, 0, 1)
+    grey = rng.integers(0, 256, 128 * 20, dtype=np.uint8)
+    rgb[128 * 120:128 * 140] = grey[:, None]       # greys: u', v' at the white point
+    lt, st, th = orc.light_table()
+    ct, hs, ls = orc.chroma_table()
+    lt_zeros = lt.copy(); lt_zeros[:40] = 0        # many dark colours get L == 0
+    lt_lift = lt.copy(); lt_lift[0] = 7            # L(y = 0) != 0: black is no longer a fixed point of the chain
+    torch = pytest.importorskip("torch")
+    buf = np.zeros(rgb.size + 1, np.uint8)
+    buf[1:] = rgb.reshape(-1)
+    odd = torch.from_numpy(buf).cuda()[1:].view(n, 3)
+    for light in (lt, lt_zeros, lt_lift):
+        cu.lut_upload(light, st, th, ct, hs, ls, orc.linear_table6())
+        for mode in ("lut", "lut_interp"):
+            want = orc.simd_rgb_to_husl(rgb, mode, tables=(light, st, th, ct, hs, ls))
+            got = cu._rgb_to_husl(rgb, mode=mode)
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), mode
+            # the same pixels through the one-pixel-per-thread kernel
+            got1 = np.asarray(cu._rgb_to_husl(odd, mode=mode))
+            assert np.array_equal(got1.view(np.uint64), want.view(np.uint64)), mode
+    cu.lut_upload(lt, st, th, ct, hs, ls, orc.linear_table6())
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_channels_first_images(cu, dtype):
     """(3, H, W) uint8 planes (torch / vision layout) <-> (3, H, W) HUSL planes:
