@@ -170,6 +170,39 @@ def verify(c, n=2000, seed=0):
     return worst_s, worst_t
 
 
+POWG_TAU = 0.25       # |t| below which (1+t)^2.4 - 1 is taken from the polynomial
+POWG_DEG = 4
+
+
+def powg_coeffs():
+    """((1+t)^2.4 - 1) / t ~ polynomial of degree POWG_DEG on [-POWG_TAU, POWG_TAU] (Chebyshev-node fit, i.e.
+    near-minimax): the gain of the sRGB power segment between two NEARBY channel values, used by the float32
+    kernels to form differences of linear light without cancellation (husl_math.cuh: diff_from_f32).
+    Returns the coefficients and the maximum relative error of the fit."""
+    from numpy.polynomial import chebyshev as C, polynomial as P
+    k = np.arange(4000)
+    x = np.cos(np.pi * (k + 0.5) / 4000) * POWG_TAU
+    q = ((1 + x) ** 2.4 - 1) / x
+    coef = C.Chebyshev.fit(x, q, POWG_DEG, domain=[-POWG_TAU, POWG_TAU]).convert(kind=P.Polynomial).coef
+    coef = np.float32(coef).astype(np.float64)
+    xx = np.linspace(-POWG_TAU, POWG_TAU, 400001)
+    xx = xx[np.abs(xx) > 1e-7]
+    err = np.max(np.abs(P.polyval(xx, coef) / (((1 + xx) ** 2.4 - 1) / xx) - 1))
+    return coef, err
+
+
+def srgb_split():
+    """The float32 value at which a float32 channel switches from c/12.92 to the power segment exactly when the
+    float64 reference does (c > 0.04045 in double <=> c > SRGB_T in float, SRGB_T the largest float <= 0.04045),
+    the power segment's value there and the (tiny) jump between the two segments at that point."""
+    t = np.float32(0.04045)
+    if float(t) > 0.04045:
+        t = np.nextafter(t, np.float32(0))
+    assert float(t) <= 0.04045 < float(np.nextafter(t, np.float32(1)))
+    pt = ((float(t) + 0.055) / 1.055) ** 2.4
+    return float(t), pt, pt - float(t) / 12.92
+
+
 def emit(c, out):
     coef, err = atan_coeffs()
     p = lambda *a: print(*a, file=out)  # noqa: E731
@@ -191,6 +224,17 @@ def emit(c, out):
     p("constexpr int ATAN_TERMS = %d;" % ATAN_TERMS)
     for i, v in enumerate(coef):
         p("constexpr float ATAN_C%d = %.9ef;" % (i, v))
+    pg, perr = powg_coeffs()
+    p("// ((1+t)^2.4 - 1)/t ~ polynomial on |t| <= %.4g, max relative error %.2e (float32 channels, diff_from_f32)" % (POWG_TAU, perr))
+    p("constexpr float POWG_TAU = %.9ef;" % POWG_TAU)
+    p("constexpr int POWG_DEG = %d;" % POWG_DEG)
+    for i, v in enumerate(pg):
+        p("constexpr float POWG_C%d = %.9ef;" % (i, v))
+    t, pt, j = srgb_split()
+    p("// sRGB segment switch for float32 channels: largest float <= 0.04045, the power segment there, the jump")
+    p("constexpr float SRGB_T = %.9ef;" % t)
+    p("constexpr float SRGB_PT = %.9ef;" % pt)
+    p("constexpr float SRGB_J = %.9ef;" % j)
     p("}  // namespace husl")
 
 

@@ -106,6 +106,15 @@ __device__ __forceinline__ void store12(unsigned char *stage, int lane, const fl
     __syncwarp();
 }
 
+// one pixel's four quantities from its three channels: float64 channels are linearised in float64
+// (lin_f64), float32 channels go the float64-free way (diff_from_f32)
+__device__ __forceinline__ Diff diff_from_rgb(double r, double g, double b) {
+    LinPx p;
+    lin_f64(r, p.hr, p.lr); lin_f64(g, p.hg, p.lg); lin_f64(b, p.hb, p.lb);
+    return make_diff(p);
+}
+__device__ __forceinline__ Diff diff_from_rgb(float r, float g, float b) { return diff_from_f32(r, g, b); }
+
 template <typename TIn, typename TOut, bool HUE, int BLOCK, int MINB, int IST>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_fwd_flt(const TIn *__restrict__ in, TOut *__restrict__ out, long long n_tiles) {
@@ -141,11 +150,7 @@ k_fwd_flt(const TIn *__restrict__ in, TOut *__restrict__ out, long long n_tiles)
         if (HUE) {
             float h[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                LinPx p;
-                lin_f64(v[3 * j], p.hr, p.lr); lin_f64(v[3 * j + 1], p.hg, p.lg); lin_f64(v[3 * j + 2], p.hb, p.lb);
-                h[j] = hue_from_diff(make_diff(p));
-            }
+            for (int j = 0; j < 4; ++j) h[j] = hue_from_diff(diff_from_rgb(v[3 * j], v[3 * j + 1], v[3 * j + 2]));
             if (sizeof(TOut) == 4)
                 *(reinterpret_cast<float4 *>(out) + tile * 32 + lane) = make_float4(h[0], h[1], h[2], h[3]);
             else
@@ -153,11 +158,8 @@ k_fwd_flt(const TIn *__restrict__ in, TOut *__restrict__ out, long long n_tiles)
         } else {
             float r[12];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                LinPx p;
-                lin_f64(v[3 * j], p.hr, p.lr); lin_f64(v[3 * j + 1], p.hg, p.lg); lin_f64(v[3 * j + 2], p.hb, p.lb);
-                husl_from_diff<false>(make_diff(p), r[3 * j], r[3 * j + 1], r[3 * j + 2]);
-            }
+            for (int j = 0; j < 4; ++j)
+                husl_from_diff<false>(diff_from_rgb(v[3 * j], v[3 * j + 1], v[3 * j + 2]), r[3 * j], r[3 * j + 1], r[3 * j + 2]);
             store12<TOut>(stage, lane, r, out + tile * (TILE_PX * 3));
         }
         st = (st + 1 == IST) ? 0 : st + 1;

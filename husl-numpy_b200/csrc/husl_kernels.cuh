@@ -291,12 +291,23 @@ __device__ __forceinline__ LinPx load_px(const TIn *in, long long i, int channel
     return p;
 }
 
+// the pixel's four quantities (husl_math.cuh: Diff); three float32 channels take the float64-free route
+template <typename TIn>
+__device__ __forceinline__ Diff load_diff(const TIn *in, long long i, int channels) {
+    return make_diff(load_px<TIn>(in, i, channels));
+}
+template <>
+__device__ __forceinline__ Diff load_diff<float>(const float *in, long long i, int channels) {
+    if (channels == 3) return diff_from_f32(in[3 * i], in[3 * i + 1], in[3 * i + 2]);
+    return make_diff(load_px<float>(in, i, channels));
+}
+
 template <typename TIn, typename TOut, bool HUE>
 __global__ void __launch_bounds__(256)
 k_fwd_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, int channels) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const Diff d = make_diff(load_px<TIn>(in, i, channels));
+        const Diff d = load_diff<TIn>(in, i, channels);
         if (HUE) {
             out[i] = (TOut)hue_from_diff(d);
         } else {
@@ -322,6 +333,16 @@ k_gray_hue(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
         float h;
         if (sizeof(TIn) == 1) {
             h = in[i] != 0 ? grey_hue : 0.0f;
+        } else if (sizeof(TIn) == 4) {
+            // float32 channels: the general kernels form the pixel with diff_from_f32
+            const float c = (float)in[i];
+            if (c <= 1e15f) {
+                // lit <=> the linear value of G there is a positive float
+                const bool lit = (c > SRGB_T) ? true : (c * (1.0f / 12.92f) > 0.0f);
+                h = lit ? grey_hue : 0.0f;
+            } else {
+                h = hue_from_diff(diff_from_f32(c, c, c));      // NaN, +inf, or a power that overflows
+            }
         } else {
             const double c = (double)in[i];
             if (c <= 1e15) {
@@ -331,8 +352,7 @@ k_gray_hue(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
             } else {
                 // NaN, or so large that the float linear value overflows: whatever the general code answers
                 LinPx p;
-                if (sizeof(TIn) == 4) lin_f64((float)in[i], p.hg, p.lg);
-                else lin_f64(c, p.hg, p.lg);
+                lin_f64(c, p.hg, p.lg);
                 p.hr = p.hb = p.hg; p.lr = p.lb = p.lg;
                 h = hue_from_diff(make_diff(p));
             }

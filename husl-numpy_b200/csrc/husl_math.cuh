@@ -147,6 +147,54 @@ __device__ __forceinline__ Diff make_diff(const LinPx &p) {
     return d;
 }
 
+// ---- float32 channels: the same four quantities without float64 ------------------------------------
+// The float64 linearisation above exists because hue and saturation are built from DIFFERENCES of linear
+// channels: two float32-accurate powers of nearly equal channels cancel.  For FLOAT32 input the differences
+// can be formed without cancellation instead.  With T the segment switch, P(c) = ((c + 0.055)/1.055)^2.4 and
+// J = P(T) - T/12.92 (2.3e-9: the two sRGB segments do not quite meet),
+//     lin(c) = min(c, T)/12.92 + [P(max(c, T)) - P(T)] + J [c > T],
+// so lin(r) - lin(g) = (min(r,T) - min(g,T))/12.92 + [P(rb) - P(gb)] + J ([r > T] - [g > T]),  cb = max(c, T):
+// three terms of one sign.  The first is an exact float difference times a constant.  The middle one is
+// P(gb) ((1 + t)^2.4 - 1) with t = (rb - gb)/(gb + 0.055), again from an exact difference: a degree-4
+// polynomial in t for |t| < 1/4 (relative error 2e-7, gen_coeffs.powg_coeffs), and for larger |t| the plain
+// difference of the two MUFU powers, whose relative error 7e-7 (P_r + P_g)/|P_r - P_g| stays below 3e-6
+// there.  1 - lin(g) is the same difference with r = 1.  A relative error e of (dr, db) moves the hue by at
+// most cond(hue forms) e = 1.5 e rad = 86 e degrees: 3e-6 -> 2.6e-4 degrees against the bar of 1e-3
+// (tests/test_emul_math.py sweeps near-grey, near-switch, near-0 and near-1 pixels against the oracle).
+// 7 XU operations (6 MUFU lg2/ex2, one reciprocal) and no FP64 per pixel, against 18 XU + 45 FP64 for three
+// lin_f64 calls: the float32-input kernels leave the XU pipe (ncu: 81 % busy) for plain FP32 issue.
+// NaN channels propagate (the selects below, unlike fmaxf, keep a NaN); the reference returns NaN there too.
+__device__ __forceinline__ float srgb_pow(float cb) {           // P(cb), cb >= T
+    return mufu_ex2(mufu_lg2(fmaf(cb, 1.0f / 1.055f, 0.055f / 1.055f)) * 2.4f);
+}
+__device__ __forceinline__ float pow_gain(float t) {            // ((1 + t)^2.4 - 1) / t, |t| < POWG_TAU
+    static_assert(POWG_DEG == 4, "Horner chain below is written for degree 4");
+    float p = fmaf(POWG_C4, t, POWG_C3);
+    p = fmaf(p, t, POWG_C2);
+    p = fmaf(p, t, POWG_C1);
+    return fmaf(p, t, POWG_C0);
+}
+// lin(c) - lin(g) given c's and g's clamped parts; pc = P(cb), pg = P(gb), inv = 1/(gb + 0.055)
+__device__ __forceinline__ float lin_diff(float cb, float cl, float pc, float jc, float gb, float gl, float pg, float jg, float inv) {
+    const float t = (cb - gb) * inv;
+    const float pw = (fabsf(t) < POWG_TAU) ? (pg * t) * pow_gain(t) : pc - pg;
+    return fmaf(cl - gl, 1.0f / 12.92f, pw) + (jc - jg);
+}
+__device__ __forceinline__ Diff diff_from_f32(float r, float g, float b) {
+    const bool lr = r <= SRGB_T, lg = g <= SRGB_T, lb = b <= SRGB_T;      // false for NaN: the NaN stays in cb
+    const float rb = lr ? SRGB_T : r, gb = lg ? SRGB_T : g, bb = lb ? SRGB_T : b;
+    const float rl = fminf(r, SRGB_T), gl = fminf(g, SRGB_T), bl = fminf(b, SRGB_T);
+    const float jr = lr ? 0.0f : SRGB_J, jg = lg ? 0.0f : SRGB_J, jb = lb ? 0.0f : SRGB_J;
+    const float pr = srgb_pow(rb), pg = srgb_pow(gb), pb = srgb_pow(bb);
+    const float inv = mufu_rcp(gb + 0.055f);
+    Diff d;
+    d.dr = lin_diff(rb, rl, pr, jr, gb, gl, pg, jg, inv);
+    d.db = lin_diff(bb, bl, pb, jb, gb, gl, pg, jg, inv);
+    d.cg = lin_diff(1.0f, SRGB_T, 1.0f, SRGB_J, gb, gl, pg, jg, inv);
+    d.g = lg ? g * (1.0f / 12.92f) : pg;
+    return d;
+}
+
 // 4X - REF_U*D and 9Y - REF_V*D as linear forms of the differences.  Their
 // g-coefficients vanish (white point), so exact greys would give atan2(0, 0);
 // the float64 reference evaluates atan2 of its own rounding residue there and

@@ -43,6 +43,16 @@ __device__ __forceinline__ LinPx load_px_strided(const char *p, long long es) {
     return px;
 }
 
+template <typename T>
+__device__ __forceinline__ Diff load_diff_strided(const char *p, long long es) {
+    return make_diff(load_px_strided<T>(p, es));
+}
+template <>
+__device__ __forceinline__ Diff load_diff_strided<float>(const char *p, long long es) {
+    return diff_from_f32(*reinterpret_cast<const float *>(p), *reinterpret_cast<const float *>(p + es),
+                         *reinterpret_cast<const float *>(p + 2 * es));
+}
+
 // RGB view -> HUSL view (HUE: one value per pixel, out.es unused)
 template <typename TIn, typename TOut, bool HUE>
 __global__ void __launch_bounds__(256)
@@ -53,7 +63,7 @@ k_fwd_strided(const View2 in, const View2 out) {
         const char *irow = in.base + f * in.fs + y * in.rs;
         char *orow = out.base + f * out.fs + y * out.rs;
         for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < in.cols; x += xstep) {
-            const Diff d = make_diff(load_px_strided<TIn>(irow + x * in.cs, in.es));
+            const Diff d = load_diff_strided<TIn>(irow + x * in.cs, in.es);
             char *o = orow + x * out.cs;
             if (HUE) {
                 *reinterpret_cast<TOut *>(o) = (TOut)hue_from_diff(d);

@@ -199,6 +199,13 @@ constexpr int EDIT_BLOCK = NPHUSL_EDIT_BLOCK, EDIT_MINB = NPHUSL_EDIT_MINB, EDIT
 #define NPHUSL_FLT_IST 2
 #endif
 constexpr int FLT_BLOCK = NPHUSL_FLT_BLOCK, FLT_MINB = NPHUSL_FLT_MINB, FLT_IST = NPHUSL_FLT_IST;
+#ifndef NPHUSL_F32_BLOCK
+#define NPHUSL_F32_BLOCK 512        // k_fwd_flt<float, ...>: float32 channels, no FP64 (husl_math.cuh: diff_from_f32)
+#define NPHUSL_F32_MINB 2         // float32 out (issue-bound): 512 x 2 0.0792 ms, 1024 x 1 0.0792, 512 x 1 0.0813, 768 x 1 0.0812
+#define NPHUSL_F32_MINB64 1       // float64 out (HBM-bound):   512 x 1 0.1061 ms, 512 x 2 0.1092, 1024 x 1 0.1116
+#define NPHUSL_F32_IST 2
+#endif
+constexpr int F32_BLOCK = NPHUSL_F32_BLOCK, F32_MINB = NPHUSL_F32_MINB, F32_MINB64 = NPHUSL_F32_MINB64, F32_IST = NPHUSL_F32_IST;
 #ifndef NPHUSL_FWD64_BLOCK
 #define NPHUSL_FWD64_BLOCK 512
 #endif
@@ -372,14 +379,18 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
     if (in_dt != NPHUSL_U8 && channels == 3 && aligned(in, 16) && aligned(out, HUE ? 32 : 16) && n >= TILE_PX) {
         // float RGB in [0,1] (the Cython backend's own input type): cp.async input ring + staged stores
         const long long tiles = n / TILE_PX;
-        const int grid = grid_for(tiles, FLT_BLOCK / 32, c.sms * FLT_MINB);
-#define FLT_GO(TI, TO) do { \
-        constexpr int sm = (FLT_BLOCK / 32) * (HUE ? FltHueSmem<TI, FLT_IST>::PER_WARP : FltSmem<TI, TO, FLT_IST>::PER_WARP); \
+#define FLT_GO(TI, TO, BLK, MB, ST) do { \
+        constexpr int sm = (BLK / 32) * (HUE ? FltHueSmem<TI, ST>::PER_WARP : FltSmem<TI, TO, ST>::PER_WARP); \
         static std::atomic<bool> attr_done[MAX_DEV]; \
-        if ((rc = flt_attr(attr_done, c, k_fwd_flt<TI, TO, HUE, FLT_BLOCK, FLT_MINB, FLT_IST>, sm))) return rc; \
-        k_fwd_flt<TI, TO, HUE, FLT_BLOCK, FLT_MINB, FLT_IST><<<grid, FLT_BLOCK, sm, s>>>((const TI *)in, (TO *)out, tiles); } while (0)
-        if (in_dt == NPHUSL_F32) { if (out_dt == NPHUSL_F32) FLT_GO(float, float); else FLT_GO(float, double); }
-        else { if (out_dt == NPHUSL_F32) FLT_GO(double, float); else FLT_GO(double, double); }
+        if ((rc = flt_attr(attr_done, c, k_fwd_flt<TI, TO, HUE, BLK, MB, ST>, sm))) return rc; \
+        k_fwd_flt<TI, TO, HUE, BLK, MB, ST><<<grid_for(tiles, BLK / 32, c.sms * MB), BLK, sm, s>>>((const TI *)in, (TO *)out, tiles); } while (0)
+        if (in_dt == NPHUSL_F32) {
+            if (out_dt == NPHUSL_F32) FLT_GO(float, float, F32_BLOCK, F32_MINB, F32_IST);
+            else FLT_GO(float, double, F32_BLOCK, F32_MINB64, F32_IST);
+        } else {
+            if (out_dt == NPHUSL_F32) FLT_GO(double, float, FLT_BLOCK, FLT_MINB, FLT_IST);
+            else FLT_GO(double, double, FLT_BLOCK, FLT_MINB, FLT_IST);
+        }
 #undef FLT_GO
         g_launches++;
         if ((rc = check_launch("k_fwd_flt"))) return rc;

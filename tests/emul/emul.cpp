@@ -66,6 +66,28 @@ void emul_fwd_f64(const double *rgb, float *out, long long n) {
     }
 }
 
+// float32 channels through the float64-free formulation (diff_from_f32)
+void emul_fwd_f32(const float *rgb, float *out, long long n) {
+#pragma omp parallel for
+    for (long long i = 0; i < n; ++i)
+        husl_from_diff<false>(diff_from_f32(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]), out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+}
+// ... and its four intermediate quantities against float64: max relative error of dr, db, 1 - g, g
+void emul_diff_f32_err(const float *rgb, long long n, double *worst) {
+    double w[4] = {0, 0, 0, 0};
+    for (long long i = 0; i < n; ++i) {
+        const Diff d = diff_from_f32(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        const double lr = lin_d(rgb[3 * i]), lg = lin_d(rgb[3 * i + 1]), lb = lin_d(rgb[3 * i + 2]);
+        const double want[4] = {lr - lg, lb - lg, 1.0 - lg, lg};
+        const double got[4] = {d.dr, d.db, d.cg, d.g};
+        for (int k = 0; k < 4; ++k) {
+            const double e = want[k] != 0 ? fabs(got[k] - want[k]) / fabs(want[k]) : fabs(got[k]);
+            if (e > w[k]) w[k] = e;
+        }
+    }
+    for (int k = 0; k < 4; ++k) worst[k] = w[k];
+}
+
 // HUSL float32 -> companded RGB scaled to 0..255 (unrounded) and the uint8 bytes
 void emul_inv(const float *hsl, float *rgb255, uint8_t *u8, long long n) {
 #pragma omp parallel for
