@@ -735,6 +735,42 @@ def test_lut_mode_with_other_table_sizes(cu):
         cu._rgb_to_husl(rgb.astype(np.float32) / 255, mode="lut")      # LUT modes take uint8, like _simd.c
 
 
+def test_float32_channels_near_grey_near_the_switch_near_the_ends(cu):
+    """float32 RGB goes through the float64-free formulation (husl_math.cuh: diff_from_f32) in the tiled kernel,
+    the one-pixel-per-thread kernel (odd sizes) and the strided kernel.  The cases a float32-only chain could
+    lose -- channels a few ulps apart, both sides of the 0.04045 segment switch, near 0, near 1 -- against the
+    float64 oracle at the bar of 1e-3 (hue where S > 0.1), both output types; to_hue equals the H channel."""
+    rng = np.random.default_rng(43)
+    n = 128 * 400 + 77
+
+    def ulps(x, k):
+        return (x.view(np.int32) + k.astype(np.int32)).view(np.float32)
+    g = rng.random(n, dtype=np.float32) * np.float32(0.98) + np.float32(0.01)
+    sets = {"uniform": rng.random((n, 3), dtype=np.float32)}
+    for name, kmax in (("2ulp", 2), ("1e4ulp", 10 ** 4), ("1e6ulp", 10 ** 6)):
+        a = np.stack([ulps(g, rng.integers(-kmax, kmax + 1, n)), g, ulps(g, rng.integers(-kmax, kmax + 1, n))], 1)
+        sets[name] = np.clip(a, 0, 1).astype(np.float32)
+    t = np.float32(0.04045)
+    sets["switch"] = (t + (rng.random((n, 3), dtype=np.float32) - np.float32(0.5)) * np.float32(0.02)).astype(np.float32)
+    sets["switch_tight"] = ulps(np.full((n, 3), t, np.float32), rng.integers(-50, 51, (n, 3)))
+    sets["dark"] = rng.random((n, 3), dtype=np.float32) * np.float32(0.05)
+    sets["bright"] = np.float32(1) - rng.random((n, 3), dtype=np.float32) * np.float32(0.02)
+    for name, a in sets.items():
+        a = np.ascontiguousarray(a)
+        ref = orc.rgb_to_husl(a.astype(np.float64))
+        # away from the L > 99.99 / L < 0.01 clamps, where a float32 Y and a float64 Y may fall on different sides
+        mid = (ref[:, 2] > 0.02) & (ref[:, 2] < 99.98)
+        for odt in (np.float32, np.float64):
+            got = np.asarray(cu._rgb_to_husl(a, dtype=odt), np.float64)
+            assert got.dtype == np.float64 and got.shape == a.shape
+            check_husl(got[mid], ref[mid], ref[mid, 1] > 0.1)
+            hue = cu._rgb_to_hue(a, dtype=odt)
+            assert np.array_equal(np.asarray(hue, np.float64), got[:, 0]), name
+    # NaN channels stay NaN
+    bad = np.array([[np.nan, 0.5, 0.5], [0.5, np.nan, 0.5], [0.5, 0.5, np.nan]] * 50, np.float32)
+    assert np.isnan(cu._rgb_to_husl(bad, dtype=np.float32)).any(axis=1).all()
+
+
 def test_lut_mode_pixels_the_streaming_pass_hands_back(cu):
     """The LUT tile kernel's straight-line pass leaves black, white and u == 0 pixels (L index 0: u = v = 0)
     to a second, complete pass over the lane that met one.  Whole tiles of them (letterbox bars, blown
