@@ -672,6 +672,23 @@ def run_cuda(args):
                                               "reference's data flow, pinned buffers, blocking calls" % hdt}
             if not np.array_equal(host_out, expect.cpu().numpy()):
                 raise SystemExit("bench.py: host-HUSL e2e result is not the edited batch")
+            # the same data flow with the two directions of the link used at once: frame i on stream i % 2,
+            # to_husl (3 B/px up, 24 down) and to_rgb (24 up, 3 down) queued back to back, non-blocking --
+            # one stream's 24 B/px download runs beside the other's 24 B/px upload
+            host_out[...] = 0
+
+            def step_host_husl_overlapped(k):
+                for i in range(B):
+                    s = streams[i & 1]
+                    nphusl.to_husl(host_in[i], out=host_hsl[i], stream=s, blocking=False)
+                    nphusl.to_rgb(host_hsl[i], out=host_out[i], stream=s, blocking=False, edit=edit)
+            t = timed_e2e(step_host_husl_overlapped, 3, warm=1)
+            e2e_extra["host_husl"]["overlapped"] = {
+                "value": px * world * 3 / t / 1e6, "unit": UNIT, "steps": 3,
+                "path": "the same calls per FRAME, blocking=False on two alternating streams: the HUSL download of one frame "
+                        "beside the HUSL upload of the previous one (full-duplex link)"}
+            if not np.array_equal(host_out, expect.cpu().numpy()):
+                raise SystemExit("bench.py: overlapped host-HUSL e2e result is not the edited batch")
             del host_hsl
         except SystemExit:
             raise

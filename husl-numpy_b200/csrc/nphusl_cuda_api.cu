@@ -88,9 +88,15 @@ size_t lut_esize(int type) { return type == NPHUSL_LUT_U16 ? 2 : type == NPHUSL_
 
 // One staging set = NSLOT streams, each with a device-side chunk buffer per
 // direction and (for pageable callers) a pinned bounce buffer.  A device owns
-// three sets so that an upload-type call (host -> device result), a
+// several sets so that an upload-type call (host -> device result), a
 // download-type call (device -> host result) and a host -> host call never
 // queue behind one another: H2D of one call overlaps D2H of another.
+// Host -> host calls have TWO sets, one for calls that download more than they
+// upload and one for the rest: in the reference's data flow -- to_husl (3 B/px up,
+// 24 down) followed by to_rgb (24 up, 3 down) per frame -- non-blocking calls on two
+// user streams then run the HUSL download of one frame beside the HUSL upload of
+// another (full-duplex link) instead of queueing every chunk of every call on the
+// same three streams.
 struct Staging {
     std::mutex mu;                       // one host-streamed call at a time per set (NOT DevCtx::mu: device-pointer calls never wait here)
     cudaStream_t st[NSLOT] = {};
@@ -98,15 +104,15 @@ struct Staging {
     void *din[NSLOT] = {}, *dout[NSLOT] = {};
     void *pin[NSLOT] = {}, *pout[NSLOT] = {};
     size_t din_cap = 0, dout_cap = 0, pin_cap = 0, pout_cap = 0;
+    cudaEvent_t gate = nullptr;          // the caller's stream at the time of the call (recorded and waited on under mu)
 };
-enum { SET_UP = 0, SET_DOWN = 1, SET_BOTH = 2, NSETS = 3 };
+enum { SET_UP = 0, SET_DOWN = 1, SET_BOTH = 2, SET_BOTH_B = 3, NSETS = 4 };
 
 struct DevCtx {
     std::mutex mu;
     bool init = false;
     int dev = -1, sms = 0;
     Staging set[NSETS];
-    cudaEvent_t gate = nullptr;
     std::atomic<bool> ready{false};      // init done: ctx_get's lock-free fast path
     std::atomic<bool> attr_set{false};   // device-pointer calls reach set_attrs() from any thread without c.mu
     Lut lut;
@@ -149,12 +155,14 @@ int ctx_get(int device, DevCtx **out) {
             tab[i].y = (float)(v - (double)tab[i].x);
         }
         CU(cudaMemcpyToSymbol(g_lin_tab, tab, sizeof tab));
-        for (int k = 0; k < NSETS; ++k)
+        for (int k = 0; k < NSETS; ++k) {
             for (int s = 0; s < NSLOT; ++s) {
                 CU(cudaStreamCreateWithFlags(&c.set[k].st[s], cudaStreamNonBlocking));
                 CU(cudaEventCreateWithFlags(&c.set[k].done[s], cudaEventDisableTiming));
             }
-        CU(cudaEventCreateWithFlags(&c.gate, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c.set[k].gate, cudaEventDisableTiming));
+        }
+
         c.init = true;
         c.ready.store(true, std::memory_order_release);
     }
@@ -690,7 +698,10 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
     const bool src_host = src_loc == NPHUSL_HOST, dst_host = dst_loc == NPHUSL_HOST;
     const bool src_pin = src_host && is_pinned(src), dst_pin = dst_host && is_pinned(dst);
     const bool all_pinned = (!src_host || src_pin) && (!dst_host || dst_pin);
-    Staging &g = c.set[src_host && dst_host ? SET_BOTH : (src_host ? SET_UP : SET_DOWN)];
+    // host -> host calls: one set for calls that bring more bytes down than they send up (to_husl: 3 up, 24 down),
+    // the other for the rest (to_rgb: 24 up, 3 down), so that one kind runs beside the other
+    const int which = src_host && dst_host ? (out_px >= in_px ? SET_BOTH : SET_BOTH_B) : (src_host ? SET_UP : SET_DOWN);
+    Staging &g = c.set[which];
     std::lock_guard<std::mutex> lk(g.mu);   // the set's staging buffers and slot streams
     int rc;
     if (src_host && (rc = ensure(g.din, &g.din_cap, chunk * in_px, false, NSLOT))) return rc;
@@ -699,8 +710,8 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
     if (dst_host && !dst_pin && (rc = ensure(g.pout, &g.pout_cap, chunk * out_px, true, NSLOT))) return rc;
 
     // work submitted earlier on the caller's stream must be visible to ours
-    CU(cudaEventRecord(c.gate, user));
-    for (int s = 0; s < NSLOT; ++s) CU(cudaStreamWaitEvent(g.st[s], c.gate, 0));
+    CU(cudaEventRecord(g.gate, user));
+    for (int s = 0; s < NSLOT; ++s) CU(cudaStreamWaitEvent(g.st[s], g.gate, 0));
 
     struct Pending { char *dst; size_t bytes; bool live; } pend[NSLOT] = {};
     long long off = 0, nchunks = 0;
