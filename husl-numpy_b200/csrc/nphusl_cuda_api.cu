@@ -34,6 +34,14 @@ using namespace husl;
 
 thread_local std::string t_err;
 thread_local bool t_host_async = false;
+// host -> host calls: the small side in place (NPHUSL_ZERO_COPY=0 turns it off, an A/B knob)
+bool zero_copy_enabled() {
+    static const bool v = [] {
+        const char *e = std::getenv("NPHUSL_ZERO_COPY");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<size_t> g_chunk_px{0};
 
@@ -704,8 +712,21 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
     Staging &g = c.set[which];
     std::lock_guard<std::mutex> lk(g.mu);   // the set's staging buffers and slot streams
     int rc;
-    if (src_host && (rc = ensure(g.din, &g.din_cap, chunk * in_px, false, NSLOT))) return rc;
-    if (dst_host && (rc = ensure(g.dout, &g.dout_cap, chunk * out_px, false, NSLOT))) return rc;
+    // Host -> host calls on pinned buffers: the SMALL side (uint8, 3 B/px against 12 or 24 B/px of HUSL) is read or
+    // written by the kernel in place, through the device alias of the page-locked buffer, instead of through a copy.
+    // A copy of the small side shares the DMA queue of its direction with the 25 MB HUSL chunks of whatever call runs
+    // the other way (to_husl of one frame beside to_rgb of another: profiles/tools/host_husl_probe.py) and waits
+    // behind them chunk after chunk; loads and stores issued by the SMs interleave with that traffic packet by packet.
+    const char *src_alias = nullptr;
+    char *dst_alias = nullptr;
+    if (src_host && dst_host && all_pinned && zero_copy_enabled()) {
+        void *p = nullptr;
+        if (in_px * 4 <= out_px && cudaHostGetDevicePointer(&p, const_cast<void *>(src), 0) == cudaSuccess) src_alias = (const char *)p;
+        else if (out_px * 4 <= in_px && cudaHostGetDevicePointer(&p, dst, 0) == cudaSuccess) dst_alias = (char *)p;
+        cudaGetLastError();
+    }
+    if (src_host && !src_alias && (rc = ensure(g.din, &g.din_cap, chunk * in_px, false, NSLOT))) return rc;
+    if (dst_host && !dst_alias && (rc = ensure(g.dout, &g.dout_cap, chunk * out_px, false, NSLOT))) return rc;
     if (src_host && !src_pin && (rc = ensure(g.pin, &g.pin_cap, chunk * in_px, true, NSLOT))) return rc;
     if (dst_host && !dst_pin && (rc = ensure(g.pout, &g.pout_cap, chunk * out_px, true, NSLOT))) return rc;
 
@@ -727,7 +748,9 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
             if (pend[s].live) { par_memcpy(pend[s].dst, g.pout[s], pend[s].bytes); pend[s].live = false; }
         }
         const void *in_dev;
-        if (src_host) {
+        if (src_alias) {
+            in_dev = src_alias + off * in_px;
+        } else if (src_host) {
             const char *hp = (const char *)src + off * in_px;
             if (!src_pin) { par_memcpy(g.pin[s], hp, npx * in_px); hp = (const char *)g.pin[s]; }
             CU(cudaMemcpyAsync(g.din[s], hp, npx * in_px, cudaMemcpyHostToDevice, g.st[s]));
@@ -735,10 +758,10 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
         } else {
             in_dev = (const char *)src + off * in_px;
         }
-        void *out_dev = dst_host ? g.dout[s] : (void *)((char *)dst + off * out_px);
+        void *out_dev = dst_alias ? (void *)(dst_alias + off * out_px) : (dst_host ? g.dout[s] : (void *)((char *)dst + off * out_px));
         int krc = kernel(in_dev, out_dev, npx, g.st[s]);
         if (krc) return krc;
-        if (dst_host) {
+        if (dst_host && !dst_alias) {
             char *hp = (char *)dst + off * out_px;
             if (dst_pin) {
                 CU(cudaMemcpyAsync(hp, g.dout[s], npx * out_px, cudaMemcpyDeviceToHost, g.st[s]));
