@@ -63,6 +63,68 @@ template <>
 __device__ __forceinline__ void edit_on_load<-1>(const EditArg<-1> &, float &, float &, float &) {}
 
 // ---------------------------------------------------------------------------------
+// banded map (nphusl_bands, include/nphusl_cuda.h): the callers' hue_watermelon / melonize
+// (examples.py:56-103) -- bands of one channel painted alternately with two hues, optionally a
+// saturated stripe around every band centre
+// ---------------------------------------------------------------------------------
+struct BandsDev {
+    nphusl_bands b;
+    float last;          // index of the last band (host side, bands_dev())
+    float rwidth;        // 1 / width: only proposes a band, the edges decide
+};
+
+// SAT: the descriptor has s_half > 0.  x * (1 / width) proposes a band; the edges RN(k * width) themselves
+// decide, one band down or up if the product was rounded across an edge.  A value on an edge, outside
+// [0, total) or NaN fails the open-interval test of every band.  The stripe test looks at the centres of
+// the band and of its two neighbours: the centre nearest to x is always one of those three.
+template <bool SAT>
+__device__ __forceinline__ void apply_bands(const BandsDev &a, float &h, float &s, float l) {
+    const float x = a.b.src == NPHUSL_SRC_H ? h : (a.b.src == NPHUSL_SRC_S ? s : l);
+    const float w = a.b.width, total = a.b.total;
+    const float k0 = fminf(fmaxf(floorf(__fmul_rn(x, a.rwidth)), 0.0f), a.last);
+    const float e0 = __fmul_rn(k0, w), e1 = __fmul_rn(k0 + 1.0f, w);        // edges of band k0
+    const bool down = x <= e0 && k0 > 0.0f, up = x >= e1 && k0 < a.last;
+    const float k = down ? k0 - 1.0f : (up ? k0 + 1.0f : k0);
+    const float lo = down ? __fmul_rn(k, w) : (up ? e1 : e0);
+    const float hi = fminf(down ? e0 : (up ? __fmul_rn(k + 1.0f, w) : e1), total);
+    const bool in_band = x > lo && x < hi;
+    const bool odd = ((int)k & 1) != 0;
+    if (SAT) {
+        const float hw = a.b.s_half;
+        // centres of bands k - 1, k, k + 1 (edges lo_m = RN((k - 1) w), lo, hi, hi_p = min(RN((k + 2) w), total); hi = RN((k + 1) w) whenever band k + 1 exists)
+        const float lo_m = __fmul_rn(k - 1.0f, w), hi_p = fminf(__fmul_rn(k + 2.0f, w), total);
+        const float c0 = __fmul_rn(0.5f, __fadd_rn(lo, hi));
+        const float cm = __fmul_rn(0.5f, __fadd_rn(lo_m, lo));
+        const float cp = __fmul_rn(0.5f, __fadd_rn(hi, hi_p));
+        bool stripe = x > __fsub_rn(c0, hw) && x < __fadd_rn(c0, hw);
+        stripe = stripe || (k > 0.0f && x > __fsub_rn(cm, hw) && x < __fadd_rn(cm, hw));
+        stripe = stripe || (k < a.last && x > __fsub_rn(cp, hw) && x < __fadd_rn(cp, hw));
+        s = stripe ? a.b.s_value : s;
+    }
+    h = in_band ? (odd ? a.b.h_odd : a.b.h_even) : h;
+}
+
+__host__ inline BandsDev bands_dev(const nphusl_bands &b) {
+    BandsDev a;
+    a.b = b;
+    a.rwidth = 1.0f / b.width;
+    // the last band is the last k whose lower edge RN(k * width) lies below `total` (chunk(): it ends at `total`)
+    volatile float lo;
+    a.last = ceilf(b.total / b.width) - 1.0f;
+    for (lo = (a.last + 1.0f) * b.width; lo < b.total; lo = (a.last + 1.0f) * b.width) a.last += 1.0f;
+    for (lo = a.last * b.width; a.last > 0.0f && lo >= b.total; lo = a.last * b.width) a.last -= 1.0f;
+    return a;
+}
+
+// ED = 8 / 9: a banded map (without / with the saturation stripe) in the edit stage of the inverse kernels
+template <> struct EditArg<8> { BandsDev a; };
+template <> struct EditArg<9> { BandsDev a; };
+template <>
+__device__ __forceinline__ void edit_on_load<8>(const EditArg<8> &e, float &h, float &s, float &l) { apply_bands<false>(e.a, h, s, l); }
+template <>
+__device__ __forceinline__ void edit_on_load<9>(const EditArg<9> &e, float &h, float &s, float &l) { apply_bands<true>(e.a, h, s, l); }
+
+// ---------------------------------------------------------------------------------
 // in-place (or out-of-place) edit of an interleaved HUSL array: what a caller's
 // `hsl[..., 2][mask] *= 0.5` (README.md:77-81) does, as one pass over the array
 // ---------------------------------------------------------------------------------

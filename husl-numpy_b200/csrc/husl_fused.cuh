@@ -229,6 +229,63 @@ k_edit_any(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, long long 
 }
 
 // ---------------------------------------------------------------------------------
+// fused banded map: uint8 RGB -> HUSL (registers) -> bands (husl_edit.cuh: apply_bands) -> uint8 RGB,
+// the callers' hue_watermelon (examples.py:56-71) in one pass; k_edit's data movement
+// ---------------------------------------------------------------------------------
+template <int BLOCK, int MINB, bool SAT>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_bands(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n_tiles, const BandsDev a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    fill_table(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane8 = lane * 8;
+    const long long nw = (long long)gridDim.x * (BLOCK / 32);
+    long long tile = (long long)blockIdx.x * (BLOCK / 32) + warp;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    if (tile < n_tiles) {
+        const uint32_t *p = in + tile * 96 + lane * 3;
+        w0 = ldg_u32(p); w1 = ldg_u32(p + 1); w2 = ldg_u32(p + 2);
+    }
+    for (; tile < n_tiles; tile += nw) {
+        uint32_t n0 = 0, n1 = 0, n2 = 0;
+        if (tile + nw < n_tiles) {
+            const uint32_t *p = in + (tile + nw) * 96 + lane * 3;
+            n0 = ldg_u32(p); n1 = ldg_u32(p + 1); n2 = ldg_u32(p + 2);
+        }
+        LinPx px[4];
+        lookup4(smem, w0, w1, w2, lane8, px);
+        uint32_t q[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float h, s, l, R, G, B;
+            husl_from_diff<true>(make_diff(px[j]), h, s, l);
+            apply_bands<SAT>(a, h, s, l);
+            rgb255_from_husl(h, s, l, R, G, B);
+            q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
+        }
+        uint32_t o0, o1, o2;
+        pack12(q, o0, o1, o2);
+        uint32_t *dst = out + tile * 96 + lane * 3;
+        dst[0] = o0; dst[1] = o1; dst[2] = o2;
+        w0 = n0; w1 = n1; w2 = n2;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bands_any(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, long long n, const BandsDev a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float h, s, l, R, G, B;
+        husl_from_diff<true>(make_diff(load_px<uint8_t>(in, i, 3)), h, s, l);
+        apply_bands<true>(a, h, s, l);
+        rgb255_from_husl(h, s, l, R, G, B);
+        out[3 * i] = (uint8_t)(round_u8_bits(R) & 0xFF);
+        out[3 * i + 1] = (uint8_t)(round_u8_bits(G) & 0xFF);
+        out[3 * i + 2] = (uint8_t)(round_u8_bits(B) & 0xFF);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // channels-first images (torch / vision layout): R[], G[], B[] uint8 planes <-> H[], S[], L[] planes
 // ---------------------------------------------------------------------------------
 // Every access is one natural vector per lane per plane (a 32-bit word = 4 pixels

@@ -272,6 +272,8 @@ int set_attrs(DevCtx &c) {
     EDIT_ATTRS(false, false, false) EDIT_ATTRS(false, false, true) EDIT_ATTRS(false, true, false) EDIT_ATTRS(false, true, true)
     EDIT_ATTRS(true, false, false) EDIT_ATTRS(true, false, true) EDIT_ATTRS(true, true, false) EDIT_ATTRS(true, true, true)
 #undef EDIT_ATTRS
+    if ((rc = set_smem(k_bands<EDIT_BLOCK, EDIT_MINB, false>, TAB_BYTES))) return rc;
+    if ((rc = set_smem(k_bands<EDIT_BLOCK, EDIT_MINB, true>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_chw<float, 512, 2>, TAB_BYTES))) return rc;
     if ((rc = set_smem(k_fwd_chw<double, 512, 2>, TAB_BYTES))) return rc;
 
@@ -313,10 +315,12 @@ int launch_fwd_any(DevCtx &c, const void *in, void *out, long long n, int channe
 }
 
 template <typename TIn, typename TOut>
-int launch_inv_any(DevCtx &c, const void *in, void *out, long long n, cudaStream_t s, const nphusl_edit *edit = nullptr) {
+int launch_inv_any(DevCtx &c, const void *in, void *out, long long n, cudaStream_t s, const nphusl_edit *edit = nullptr,
+                   const BandsDev *bands = nullptr) {
     if (n <= 0) return NPHUSL_OK;
     const int grid = grid_for(n, 256, c.sms * 8);
-    if (edit) k_inv_any<TIn, TOut, 7><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n, EditArg<7>{*edit});
+    if (bands) k_inv_any<TIn, TOut, 9><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n, EditArg<9>{*bands});
+    else if (edit) k_inv_any<TIn, TOut, 7><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n, EditArg<7>{*edit});
     else k_inv_any<TIn, TOut><<<grid, 256, 0, s>>>((const TIn *)in, (TOut *)out, n);
     g_launches++;
     return check_launch("k_inv_any");
@@ -425,17 +429,24 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
 
 // `edit` != NULL: the HUSL-space edit is applied to every loaded pixel first (to_rgb(hsl, edit=...));
 // the ring kernels have an EDIT instantiation, every other layout takes the generic kernel
+template <int ED>
+EditArg<ED> edit_arg(const nphusl_edit *edit, const BandsDev *bands) {
+    if constexpr (ED >= 8) return EditArg<ED>{*bands};
+    else return EditArg<ED>{*edit};
+}
+
+// `bands` != NULL (instead of `edit`): a banded map in the same stage (husl_bands_to_rgb)
 int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, long long n, cudaStream_t s,
-                const nphusl_edit *edit = nullptr) {
+                const nphusl_edit *edit = nullptr, const BandsDev *bands = nullptr) {
     int rc;
     long long done = 0;
-    if (edit && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
+    if ((edit || bands) && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
-        const int code = EditShape(*edit).code();
+        const int code = bands ? (bands->b.s_half > 0.0f ? 9 : 8) : EditShape(*edit).code();
         // instantiated per edit shape like k_edit: README-style edits (L scaled inside / outside a hue arc) carry no
         // hue-wrap, saturation or range arithmetic
 #define INV_EDIT(ED) do { \
-        const EditArg<ED> ea{*edit}; \
+        const EditArg<ED> ea = edit_arg<ED>(edit, bands); \
         if (in_dt == NPHUSL_F32) { \
             constexpr int sm = (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP; \
             static std::atomic<bool> attr32[MAX_DEV]; \
@@ -457,6 +468,8 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
             case 4: INV_EDIT(4); break;
             case 5: INV_EDIT(5); break;
             case 6: INV_EDIT(6); break;
+            case 8: INV_EDIT(8); break;
+            case 9: INV_EDIT(9); break;
             default: INV_EDIT(7); break;
         }
 #undef INV_EDIT
@@ -464,7 +477,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
         if ((rc = check_launch("k_inv (edit on load)"))) return rc;
         done = tiles * TILE_PX;
     }
-    if (!edit && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 4) && n >= TILE_PX) {
+    if (!edit && !bands && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 4) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
         constexpr int W = INV_BLOCK / 32;
         if (use_tma() && aligned(out, 16)) {
@@ -491,7 +504,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
         if ((rc = check_launch("k_inv_u8"))) return rc;
         done = tiles * TILE_PX;
     }
-    if (!edit && out_dt != NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
+    if (!edit && !bands && out_dt != NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
         // float RGB in [0,1] out (what the reference's _husl_to_rgb returns, _cython_opt.pyx:177-192)
         const long long tiles = n / TILE_PX;
         const int grid = grid_for(tiles, FLT_BLOCK / 32, c.sms * FLT_MINB);
@@ -511,7 +524,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
     if (rest <= 0) return NPHUSL_OK;
     const char *ip = (const char *)in + done * 3 * dsize(in_dt);
     char *op = (char *)out + done * 3 * dsize(out_dt);
-#define INV_ANY(TI, TO) return launch_inv_any<TI, TO>(c, ip, op, rest, s, edit)
+#define INV_ANY(TI, TO) return launch_inv_any<TI, TO>(c, ip, op, rest, s, edit, bands)
     if (in_dt == NPHUSL_F32) {
         if (out_dt == NPHUSL_U8) INV_ANY(float, uint8_t);
         if (out_dt == NPHUSL_F32) INV_ANY(float, float);
@@ -1024,6 +1037,75 @@ int nphusl_cuda_husl_edit_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc, co
         return run_inv_dev(*c, i, hsl_dtype, o, rgb_dtype, n, s, &e);
     };
     return run_streamed(*c, hsl, hsl_loc, in_px, rgb, rgb_loc, out_px, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+// nphusl_bands as the kernels take it, or an error for a descriptor that describes no bands
+static int bands_check(const nphusl_bands *b, const char *what, BandsDev *out) {
+    if (!b) return fail(NPHUSL_ERR_ARG, std::string(what) + ": null argument");
+    if (b->src != NPHUSL_SRC_H && b->src != NPHUSL_SRC_S && b->src != NPHUSL_SRC_L)
+        return fail(NPHUSL_ERR_ARG, std::string(what) + ": bands.src must be NPHUSL_SRC_H, _S or _L");
+    if (!(b->width > 0.0f) || !(b->total > 0.0f) || !std::isfinite(b->width) || !std::isfinite(b->total))
+        return fail(NPHUSL_ERR_ARG, std::string(what) + ": bands.width and bands.total must be positive and finite");
+    if (!(b->total / b->width <= 1048576.0f))
+        return fail(NPHUSL_ERR_ARG, std::string(what) + ": more than 2^20 bands");
+    *out = bands_dev(*b);
+    return NPHUSL_OK;
+}
+
+int nphusl_cuda_husl_bands_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc, const nphusl_bands *bands,
+                                  void *rgb, int rgb_dtype, int rgb_loc,
+                                  size_t n_pixels, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!hsl || !rgb) return fail(NPHUSL_ERR_ARG, "husl_bands_to_rgb: null argument");
+    if ((hsl_dtype != NPHUSL_F32 && hsl_dtype != NPHUSL_F64) || rgb_dtype != NPHUSL_U8)
+        return fail(NPHUSL_ERR_ARG, "husl_bands_to_rgb: hsl must be f32/f64 and rgb u8");
+    if (!ok_loc(hsl_loc) || !ok_loc(rgb_loc)) return fail(NPHUSL_ERR_ARG, "husl_bands_to_rgb: bad buffer location");
+    BandsDev bd;
+    int rc = bands_check(bands, "husl_bands_to_rgb", &bd);
+    if (rc) return rc;
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    const size_t in_px = 3 * dsize(hsl_dtype), out_px = 3;
+    auto kern = [=](const void *i, void *o, long long n, cudaStream_t s) -> int {
+        return run_inv_dev(*c, i, hsl_dtype, o, rgb_dtype, n, s, nullptr, &bd);
+    };
+    return run_streamed(*c, hsl, hsl_loc, in_px, rgb, rgb_loc, out_px, (long long)n_pixels, (cudaStream_t)stream, kern);
+}
+
+int nphusl_cuda_rgb_bands_rgb(const void *rgb_in, int in_loc, void *rgb_out, int out_loc,
+                              size_t n_pixels, const nphusl_bands *bands, int device, void *stream) {
+    DeviceGuard guard;
+    if (n_pixels == 0) return NPHUSL_OK;
+    if (!rgb_in || !rgb_out) return fail(NPHUSL_ERR_ARG, "rgb_bands_rgb: null argument");
+    if (!ok_loc(in_loc) || !ok_loc(out_loc)) return fail(NPHUSL_ERR_ARG, "rgb_bands_rgb: bad buffer location");
+    BandsDev bd;
+    int rc = bands_check(bands, "rgb_bands_rgb", &bd);
+    if (rc) return rc;
+    DevCtx *c;
+    if ((rc = ctx_get(device, &c))) return rc;
+    const bool sat = bd.b.s_half > 0.0f;
+    auto kern = [=](const void *i, void *o, long long n, cudaStream_t st) -> int {
+        int r;
+        long long done = 0;
+        if (aligned(i, 4) && aligned(o, 4) && n >= TILE_PX) {
+            if ((r = set_attrs(*c))) return r;
+            const long long tiles = n / TILE_PX;
+            const int grid = grid_for(tiles, EDIT_W, c->sms * EDIT_MINB);
+            if (sat) k_bands<EDIT_BLOCK, EDIT_MINB, true><<<grid, EDIT_BLOCK, TAB_BYTES, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, bd);
+            else k_bands<EDIT_BLOCK, EDIT_MINB, false><<<grid, EDIT_BLOCK, TAB_BYTES, st>>>((const uint32_t *)i, (uint32_t *)o, tiles, bd);
+            g_launches++;
+            if ((r = check_launch("k_bands"))) return r;
+            done = tiles * TILE_PX;
+        }
+        if (n > done) {
+            k_bands_any<<<grid_for(n - done, 256, c->sms * 8), 256, 0, st>>>((const uint8_t *)i + 3 * done, (uint8_t *)o + 3 * done, n - done, bd);
+            g_launches++;
+            if ((r = check_launch("k_bands_any"))) return r;
+        }
+        return NPHUSL_OK;
+    };
+    return run_streamed(*c, rgb_in, in_loc, 3, rgb_out, out_loc, 3, (long long)n_pixels, (cudaStream_t)stream, kern);
 }
 
 int nphusl_cuda_husl_edit(const void *hsl_in, void *hsl_out, int hsl_dtype, size_t n_pixels,

@@ -34,7 +34,7 @@ import threading
 import numpy as np
 
 __all__ = ["_rgb_to_husl", "_husl_to_rgb", "_rgb_to_hue", "rgb_to_husl_planar", "husl_planar_to_rgb",
-           "edit_rgb", "edit_husl", "Edit", "Graph", "graph", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "rgb_to_nv12", "nv12_edit_nv12", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
+           "edit_rgb", "edit_husl", "Edit", "Bands", "Graph", "graph", "nv12_to_husl", "nv12_to_hue", "nv12_to_rgb", "nv12_edit_rgb", "rgb_to_nv12", "nv12_edit_nv12", "DeviceArray", "available", "CudaUnavailable", "CudaError"]
 
 def _prod(shape):
     """Number of elements of a shape (np.prod on a tuple costs 3 us and runs several times per call)."""
@@ -78,6 +78,8 @@ SIGNATURES = {
     "nphusl_cuda_husl_planes_to_rgb_planes": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "nphusl_cuda_rgb_edit_rgb": (_i, [_vp, _i, _vp, _i, _sz, _vp, _i, _vp]),
     "nphusl_cuda_husl_edit_to_rgb": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _sz, _i, _vp]),
+    "nphusl_cuda_husl_bands_to_rgb": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _sz, _i, _vp]),
+    "nphusl_cuda_rgb_bands_rgb": (_i, [_vp, _i, _vp, _i, _sz, _vp, _i, _vp]),
     "nphusl_cuda_husl_edit": (_i, [_vp, _vp, _i, _sz, _vp, _i, _vp]),
     "nphusl_cuda_rgb_planes_edit": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "nphusl_cuda_rgb_to_husl_strided": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -1082,12 +1084,20 @@ def _rgb_to_hue(rgb, out=None, dtype=np.float64, stream=None, device=None, block
 
 
 def _as_edit(edit):
-    """``Edit`` | dict of its keywords -> ``Edit``"""
-    if isinstance(edit, Edit):
+    """``Edit`` | ``Bands`` | dict of ``Edit``'s keywords -> the ctypes structure"""
+    if isinstance(edit, (Edit, Bands)):
         return edit
     if isinstance(edit, dict):
         return Edit(**edit)
-    raise TypeError("edit must be an nphusl._cuda.Edit or a dict of its keywords, got {!r}".format(type(edit)))
+    raise TypeError("edit must be an nphusl._cuda.Edit / Bands or a dict of Edit's keywords, got {!r}".format(type(edit)))
+
+
+def _need_edit(edit, who):
+    """entry points that take the select + affine ``Edit`` only"""
+    edit = _as_edit(edit)
+    if not isinstance(edit, Edit):
+        raise TypeError("{} takes an Edit; a Bands map goes to to_rgb(hsl, edit=...) or edit_rgb(rgb, edit=...)".format(who))
+    return edit
 
 
 def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocking=True, edit=None):
@@ -1100,7 +1110,8 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
     README.md:77-98 -- ``hsl[..., 2][mask] *= 0.5`` between ``to_husl`` and ``to_rgb`` --
     applied to every pixel as it is loaded, so the pipeline needs no pass of its own over
     the HUSL array: ``to_rgb(hsl, edit=dict(hue=(250, 290), invert=True, l=(0.5, 0)))``
-    equals ``to_rgb(edit_husl(hsl, ...))``; ``hsl`` itself is left untouched."""
+    equals ``to_rgb(edit_husl(hsl, ...))``; ``hsl`` itself is left untouched.  A ``Bands`` instead
+    (examples.py:56-103) paints bands of one channel with two alternating hues on load."""
     lib = load()
     if _is_device(hsl):
         src = _describe_device(hsl, "hsl", strided_ok=True)
@@ -1125,7 +1136,9 @@ def _husl_to_rgb(hsl, out=None, dtype=np.uint8, stream=None, device=None, blocki
         _strided_call("nphusl_cuda_husl_to_rgb_strided", src, dst, len(src.shape) - 1, [], dev, stream)
         return ret
     if edit is not None:
-        rc = _call(lib, blocking, lib.nphusl_cuda_husl_edit_to_rgb, src.ptr, _DT[src.dtype], src.loc, ctypes.byref(_as_edit(edit)),
+        edit = _as_edit(edit)
+        fn = lib.nphusl_cuda_husl_bands_to_rgb if isinstance(edit, Bands) else lib.nphusl_cuda_husl_edit_to_rgb
+        rc = _call(lib, blocking, fn, src.ptr, _DT[src.dtype], src.loc, ctypes.byref(edit),
                    dst.ptr, _DT[dst.dtype], dst.loc, n, dev, _stream_ptr(stream))
     else:
         rc = _call(lib, blocking, lib.nphusl_cuda_husl_to_rgb, src.ptr, _DT[src.dtype], src.loc, dst.ptr, _DT[dst.dtype], dst.loc,
@@ -1252,13 +1265,37 @@ class Edit(ctypes.Structure):
                          h[0], h[1], s[0], s[1], l[0], l[1])
 
 
+class Bands(ctypes.Structure):
+    """``nphusl_bands`` of include/nphusl_cuda.h: the banded map of the reference's callers
+    (examples.py:56-103).  The range ``[0, total)`` of channel ``src`` (``"h"``, ``"s"`` or ``"l"``) is cut
+    like ``chunk(total, width)``; a pixel strictly inside an even band gets hue ``h_even``, inside an odd
+    band ``h_odd``; with ``stripe=(half_width, saturation)`` pixels within ``half_width`` of a band centre
+    also get that saturation.  ``hue_watermelon``: ``Bands("h", 45, 360, 130, 360)``; one frame of
+    ``melonize``: ``Bands("l", chunksize, 100, 130, 360, stripe=(2, 100))``.  Pass it as ``edit=`` to
+    ``to_rgb`` (applied on load) or ``edit_rgb`` / ``nphusl.edit`` (fused uint8 -> uint8)."""
+    _fields_ = [("src", ctypes.c_int), ("width", ctypes.c_float), ("total", ctypes.c_float),
+                ("h_even", ctypes.c_float), ("h_odd", ctypes.c_float), ("s_half", ctypes.c_float), ("s_value", ctypes.c_float)]
+    SRC = {"h": 0, "hue": 0, "s": 1, "saturation": 1, "l": 2, "lightness": 2, 0: 0, 1: 1, 2: 2}
+
+    def __init__(self, src="h", width=45.0, total=None, h_even=130.0, h_odd=360.0, stripe=None):
+        if src not in self.SRC:
+            raise ValueError("Bands: src must be 'h', 's' or 'l', got {!r}".format(src))
+        code = self.SRC[src]
+        if total is None:
+            total = 360.0 if code == 0 else 100.0
+        if not (width > 0 and total > 0):
+            raise ValueError("Bands: width and total must be positive")
+        half, value = stripe if stripe is not None else (0.0, 0.0)
+        super().__init__(code, width, total, h_even, h_odd, half, value)
+
+
 def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, channels_first=False, **edit_args):
     """Fused ``to_rgb(edit(to_husl(rgb)))`` on uint8 pixels in one kernel pass.
 
     ``channels_first=True``: ``rgb`` (a device array) is ``(3, ...)`` planes, the
     layout nvJPEG / torchvision decoders produce; so is the result.
 
-    ``edit`` is an ``Edit`` (or pass its fields as keywords):
+    ``edit`` is an ``Edit`` (or pass its fields as keywords), or a ``Bands`` map (interleaved pixels only):
     ``edit_rgb(img, hue=(250, 290), invert=True, l=(0.5, 0))`` darkens every
     non-bluish pixel (README.md:77-81); ``edit_rgb(img, lightness=(0, 62),
     l=(0, 0))`` blacks out dim pixels (README.md:94-98).  Host or device arrays;
@@ -1268,6 +1305,10 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
         edit = Edit(**edit_args)
     elif edit_args:
         raise TypeError("pass either an Edit or its fields as keywords, not both")
+    edit = _as_edit(edit)
+    bands = isinstance(edit, Bands)
+    if bands and channels_first:
+        raise ValueError("a Bands map takes interleaved (..., 3) pixels")
     if channels_first:
         if not _is_device(rgb):
             raise ValueError("channels_first edit takes device arrays")
@@ -1290,9 +1331,12 @@ def edit_rgb(rgb, edit=None, out=None, stream=None, device=None, blocking=True, 
     dev = _pick_device(device, src, dst)
     n = _prod(src.shape[:-1])
     if src.strides is not None or dst.strides is not None:
+        if bands:
+            raise ValueError("a Bands map takes C-contiguous arrays")
         _strided_call("nphusl_cuda_rgb_edit_rgb_strided", src, dst, len(src.shape) - 1, [ctypes.byref(edit)], dev, stream)
         return ret
-    rc = _call(lib, blocking, lib.nphusl_cuda_rgb_edit_rgb, src.ptr, src.loc, dst.ptr, dst.loc, n, ctypes.byref(edit), dev, _stream_ptr(stream))
+    fn = lib.nphusl_cuda_rgb_bands_rgb if bands else lib.nphusl_cuda_rgb_edit_rgb
+    rc = _call(lib, blocking, fn, src.ptr, src.loc, dst.ptr, dst.loc, n, ctypes.byref(edit), dev, _stream_ptr(stream))
     if rc:
         _check(rc, "rgb_edit_rgb")
     return ret
@@ -1322,7 +1366,7 @@ def edit_husl(hsl, edit=None, out=None, stream=None, **edit_args):
             raise ValueError("out: edit_husl writes device arrays")
         ret = out
     _touch(stream, hsl, ret)
-    _check(load().nphusl_cuda_husl_edit(src.ptr, dst.ptr, _DT[src.dtype], _prod(src.shape[:-1]), ctypes.byref(_as_edit(edit)),
+    _check(load().nphusl_cuda_husl_edit(src.ptr, dst.ptr, _DT[src.dtype], _prod(src.shape[:-1]), ctypes.byref(_need_edit(edit, "edit_husl")),
                                         dev, _stream_ptr(stream)), "husl_edit")
     return ret
 
@@ -1430,6 +1474,7 @@ def nv12_edit_rgb(y, uv=None, edit=None, out=None, matrix="bt709", full_range=Fa
         edit = Edit(**edit_args)
     elif edit_args:
         raise TypeError("pass either an Edit or its fields as keywords, not both")
+    edit = _need_edit(edit, "nv12_edit_rgb")
     src, (h, w), dev, keep = _nv12_surface(y, uv, matrix, full_range)
     ptr, _, ret = _nv12_out(out, (h, w, 3), np.uint8, (np.dtype(np.uint8),), dev, stream, keep)
     _check(load().nphusl_cuda_nv12_edit_rgb(ctypes.byref(src), ctypes.byref(edit), ptr, dev, _stream_ptr(stream)), "nv12_edit_rgb")
@@ -1515,6 +1560,7 @@ def nv12_edit_nv12(y, uv=None, edit=None, out_y=None, out_uv=None, matrix="bt709
         edit = Edit(**edit_args)
     elif edit_args:
         raise TypeError("pass either an Edit or its fields as keywords, not both")
+    edit = _need_edit(edit, "nv12_edit_nv12")
     if isinstance(y, np.ndarray):
         return _nv12_edit_nv12_host(y, uv, edit, out_y, out_uv, matrix, full_range, out_matrix, out_full_range,
                                     stream, device, blocking)

@@ -164,6 +164,36 @@ int nphusl_cuda_husl_edit_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc, co
 int nphusl_cuda_husl_edit(const void *hsl_in, void *hsl_out, int hsl_dtype, size_t n_pixels,
                           const nphusl_edit *edit, int device, void *stream);
 
+/* A banded map, the other HUSL-space edit of the reference's callers (examples.py:56-103: hue_watermelon
+ * cuts the hue circle into bands of 45 degrees and paints them alternately green and pink, melonize does
+ * the same over lightness bands and saturates a stripe around every band centre).  The range [0, total)
+ * of channel `src` is cut the way chunk(total, width) cuts it (transform.py:300-308): band k covers the
+ * OPEN interval (k*width, min((k+1)*width, total)) -- a value exactly on a band edge, below 0 or at / above
+ * `total` belongs to no band and the pixel is passed on as it is, like the callers'
+ * np.logical_and(x > low, x < high).  A pixel in an even band gets H = h_even, in an odd band H = h_odd
+ * (examples.py:66-68: is_odd = low % (2*chunksize)).  If s_half > 0, a pixel whose `src` value lies strictly
+ * within s_half of a band centre (low + high)/2 additionally gets S = s_value (examples.py:97-99).  The
+ * selections use the pixel's ORIGINAL value of `src`; band edges and centres are formed in float32
+ * (k*width, 0.5*(low + high), centre -+ s_half), exact for the integer parameters the callers use.
+ * width > 0, total > 0, at most 2^20 bands. */
+enum { NPHUSL_SRC_H = 0, NPHUSL_SRC_S = 1, NPHUSL_SRC_L = 2 };
+typedef struct nphusl_bands {
+    int src;                         /* NPHUSL_SRC_H | _S | _L: the channel the bands are cut from */
+    float width, total;              /* chunk(total, width) */
+    float h_even, h_odd;             /* the hue painted into even / odd bands */
+    float s_half, s_value;           /* s_half > 0: S = s_value within s_half of a band centre */
+} nphusl_bands;
+/* husl_to_rgb with the banded map applied to every pixel as it is loaded (melonize renders ~200 frames
+ * from ONE HUSL array, examples.py:84-103: the array stays on the device untouched); same buffer rules as
+ * nphusl_cuda_husl_to_rgb, rgb_dtype U8. */
+int nphusl_cuda_husl_bands_to_rgb(const void *hsl, int hsl_dtype, int hsl_loc, const nphusl_bands *bands,
+                                  void *rgb, int rgb_dtype, int rgb_loc,
+                                  size_t n_pixels, int device, void *stream);
+/* fused to_husl -> banded map -> to_rgb on uint8 pixels (hue_watermelon in one pass); host or device,
+ * rgb_out may be rgb_in.  Equals husl_bands_to_rgb(rgb_to_husl(rgb -> F32)) bit for bit. */
+int nphusl_cuda_rgb_bands_rgb(const void *rgb_in, int in_loc, void *rgb_out, int out_loc,
+                              size_t n_pixels, const nphusl_bands *bands, int device, void *stream);
+
 /* The same fused edit on channels-first uint8 planes (what nvJPEG and video
  * decoders hand out); DEVICE pointers only; outputs may alias the inputs. */
 int nphusl_cuda_rgb_planes_edit(const void *r, const void *g, const void *b,

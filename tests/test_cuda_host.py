@@ -30,6 +30,30 @@ def test_edit_struct_matches_header():
     assert e.s_lo == -np.inf and e.l_hi == np.inf            # unspecified ranges are unbounded
 
 
+def test_bands_struct_matches_header():
+    text = open(os.path.join(ROOT, "include", "nphusl_cuda.h")).read()
+    body = re.search(r"typedef struct nphusl_bands \{(.*?)\} nphusl_bands;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            ctype, rest = decl.split(None, 1)
+            names += [(n.strip(), {"float": ctypes.c_float, "int": ctypes.c_int}[ctype]) for n in rest.split(",")]
+    assert names == list(_cuda.Bands._fields_) and ctypes.sizeof(_cuda.Bands) == 7 * 4
+    assert re.search(r"NPHUSL_SRC_H = 0, NPHUSL_SRC_S = 1, NPHUSL_SRC_L = 2", text)
+    b = _cuda.Bands("l", 7, h_even=130, h_odd=360, stripe=(2, 100))       # one frame of melonize, examples.py:84-103
+    assert (b.src, b.width, b.total, b.h_even, b.h_odd, b.s_half, b.s_value) == (2, 7.0, 100.0, 130.0, 360.0, 2.0, 100.0)
+    w = _cuda.Bands()                                                     # hue_watermelon, examples.py:56-71
+    assert (w.src, w.width, w.total, w.s_half) == (0, 45.0, 360.0, 0.0)
+    for bad in (dict(src="v"), dict(width=0), dict(width=-1), dict(total=0)):
+        with pytest.raises(ValueError):
+            _cuda.Bands(**bad)
+    with pytest.raises(TypeError):
+        _cuda._need_edit(w, "edit_husl")                                  # Edit-only entry points refuse a Bands
+    assert isinstance(_cuda._need_edit(dict(l=(0.5, 0)), "x"), _cuda.Edit)
+
+
 def test_rgb_input_description():
     d = _cuda._describe_rgb_in(np.zeros((4, 5, 3), np.uint8))
     assert (d.loc, d.channels, d.dtype, d.shape) == (_cuda.HOST, 3, np.uint8, (4, 5, 3))

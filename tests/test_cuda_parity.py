@@ -1697,3 +1697,108 @@ def test_device_generated_tables_vs_the_reference_tables_on_the_cube(cu, cube):
     assert ds.max() <= 0.5, ds.max()
     print("device-generated chroma table: %d entries differ by one count; %d of 16 777 216 colours change S, max |dS| = %.4f"
           % (n_entries, changed, ds.max()))
+
+
+# ---- the banded map of the reference's callers (examples.py:56-103) ----
+
+def bands_spec(hsl32, src, width, total, h_even, h_odd, stripe=None):
+    """hue_watermelon / one frame of melonize (examples.py:56-103) on a float32 HUSL array, written the
+    way the callers write it: for low, high in chunk(total, width): select = (x > low) & (x < high) ...
+    Band edges and centres in float32 (exact for the integer parameters the callers use)."""
+    f = np.float32
+    x = hsl32[..., src].copy()
+    out = hsl32.copy()
+    k = 0
+    while f(k) * f(width) < f(total):
+        lo, hi = f(k) * f(width), min(f(k + 1) * f(width), f(total))
+        out[..., 0][(x > lo) & (x < hi)] = f(h_odd if k & 1 else h_even)
+        if stripe:
+            c = f(0.5) * (lo + hi)
+            out[..., 1][(x > c - f(stripe[0])) & (x < c + f(stripe[0]))] = f(stripe[1])
+        k += 1
+    return out
+
+
+def test_banded_map_hue_watermelon_and_melonize(cu):
+    """nphusl._cuda.Bands: to_rgb(hsl, edit=Bands(...)) and the fused edit_rgb(rgb, edit=Bands(...)) equal
+    to_rgb of the callers' numpy loops over the float32 HUSL array, bit for bit -- whole tiles, tails,
+    host and device arrays, float32 and float64 HUSL; band edges, negative / out-of-range / NaN values
+    belong to no band; `hsl` is left untouched."""
+    torch = pytest.importorskip("torch")
+    import nphusl
+    from nphusl import chunk
+    rng = np.random.default_rng(77)
+    rgb = rng.integers(0, 256, (2, 270, 481, 3), dtype=np.uint8)
+    hsl = cu._rgb_to_husl(rgb, dtype=np.float32)
+
+    # hue_watermelon verbatim (examples.py:56-71), on the float32 HUSL array
+    hue = hsl[..., 0]
+    hue_out = hue.copy()
+    pink, green, chunksize = 360, 130, 45
+    for low, high in chunk(360, chunksize):
+        select = np.logical_and(hue > low, hue < high)
+        is_odd = low % (chunksize * 2)
+        hue_out[select] = pink if is_odd else green
+    melon = hsl.copy()
+    melon[..., 0] = hue_out
+    assert np.array_equal(melon, bands_spec(hsl, 0, 45, 360, 130, 360))
+    want = cu._husl_to_rgb(melon)
+    wm = cu.Bands("h", 45, 360, 130, 360)
+    keep = hsl.copy()
+    with nphusl.cuda_enabled():
+        assert np.array_equal(nphusl.to_rgb(hsl, edit=wm), want) and np.array_equal(hsl, keep)
+        assert np.array_equal(nphusl.edit(rgb, edit=wm), want)                    # fused, host arrays
+    d_rgb = torch.from_numpy(rgb).cuda()
+    out = torch.empty_like(d_rgb)
+    assert cu.edit_rgb(d_rgb, edit=wm, out=out) is out and np.array_equal(out.cpu().numpy(), want)
+    d64 = torch.from_numpy(hsl.astype(np.float64)).cuda()
+    assert np.array_equal(cu._husl_to_rgb(d64, edit=wm).copy_to_host(), want)      # float64 HUSL (TMA ring)
+    assert torch.equal(d64, torch.from_numpy(hsl.astype(np.float64)).cuda())
+
+    # melonize (examples.py:74-103): lightness bands of every chunksize it walks through, stripe of +-2 at S = 100
+    d32 = torch.from_numpy(hsl).cuda()
+    for cs in (1, 2, 3, 7, 10, 33, 45, 64, 99, 100, 250):
+        b = cu.Bands("l", cs, 100, 130, 360, stripe=(2, 100))
+        spec = bands_spec(hsl, 2, cs, 100, 130, 360, (2, 100))
+        if cs in (7, 100):      # the callers' loop verbatim
+            lit = hsl[..., 2]
+            o = hsl.copy()
+            for low, high in chunk(100, cs):
+                o[..., 0][np.logical_and(lit > low, lit < high)] = pink if low % (cs * 2) else green
+                ave = (low + high) / 2
+                o[..., 1][np.logical_and(lit > (ave - 2), lit < (ave + 2))] = 100
+            assert np.array_equal(o, spec)
+        w = cu._husl_to_rgb(spec)
+        assert np.array_equal(cu._husl_to_rgb(d32, edit=b).copy_to_host(), w), cs
+        assert np.array_equal(cu.edit_rgb(rgb, edit=b), w), cs
+    # ragged sizes and an unaligned base (generic kernels)
+    for n in (1, 5, 127, 129, 4741):
+        sub = np.ascontiguousarray(hsl.reshape(-1, 3)[:n])
+        b = cu.Bands("s", 12.5, 100, 10, 200, stripe=(1.5, 40))
+        w = cu._husl_to_rgb(bands_spec(sub, 1, 12.5, 100, 10, 200, (1.5, 40)))
+        assert np.array_equal(cu._husl_to_rgb(sub, edit=b), w)
+        assert np.array_equal(cu.edit_rgb(np.ascontiguousarray(rgb.reshape(-1, 3)[:n]), edit=b), w)
+        flat = torch.empty(3 * n + 1, dtype=torch.float32, device="cuda")
+        flat[1:].copy_(torch.from_numpy(sub).reshape(-1))
+        assert np.array_equal(cu._husl_to_rgb(flat[1:].view(n, 3), edit=b).copy_to_host(), w)
+    # values on band edges, outside [0, total), NaN: passed on as they are
+    edge = np.zeros((256, 3), np.float32)
+    edge[:, 0] = np.concatenate([np.arange(0, 405, 45), np.arange(0, 405, 45) + 1e-3, np.arange(0, 405, 45) - 1e-3,
+                                 [-10, -0.0, 359.99997, 360.00003, 720, np.nan, np.inf, -np.inf],
+                                 rng.uniform(-50, 410, 256 - 35)]).astype(np.float32)
+    edge[:, 1] = 80
+    edge[:, 2] = rng.uniform(20, 80, 256).astype(np.float32)
+    fin = np.isfinite(edge[:, 0])
+    got = cu._husl_to_rgb(edge, edit=wm)
+    assert np.array_equal(got[fin], cu._husl_to_rgb(bands_spec(edge, 0, 45, 360, 130, 360))[fin])
+    # bad descriptors and entry points that take an Edit only
+    with pytest.raises(ValueError):
+        cu.Bands("x", 45)
+    with pytest.raises(ValueError):
+        cu.Bands("h", 0)
+    with pytest.raises(cu.CudaError):
+        cu._husl_to_rgb(hsl, edit=cu.Bands("h", 1e-4, 360))                     # more than 2^20 bands
+    with pytest.raises(TypeError):
+        cu.edit_husl(d32, edit=wm)
+    with pytest.raises(cu.CudaError):
+        cu._husl_to_rgb(hsl, dtype=np.float32, edit=wm)                         # uint8 RGB only
