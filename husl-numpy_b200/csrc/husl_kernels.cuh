@@ -324,40 +324,52 @@ k_fwd_any(const TIn *__restrict__ in, TOut *__restrict__ out, long long n, int c
 // has ONE hue -- hue_deg(GREY_V, GREY_U), the hue of white -- and black has 0: no linearisation, no arctangent
 // per pixel, the kernel is a pure 16 B/px (float64 -> float64) stream.  Bit-identical to k_fwd_any<.., HUE>
 // on a grey image, including what that kernel answers for negative, NaN and overflowing inputs.
+template <typename TIn>
+__device__ __forceinline__ float gray_hue_px(TIn v, float grey_hue) {
+    if (sizeof(TIn) == 1) return v != 0 ? grey_hue : 0.0f;
+    if (sizeof(TIn) == 4) {
+        // float32 channels: the general kernels form the pixel with diff_from_f32
+        const float c = (float)v;
+        if (c <= 1e15f) {
+            // lit <=> the linear value of G there is a positive float
+            const bool lit = (c > SRGB_T) ? true : (c * (1.0f / 12.92f) > 0.0f);
+            return lit ? grey_hue : 0.0f;
+        }
+        return hue_from_diff(diff_from_f32(c, c, c));      // NaN, +inf, or a power that overflows
+    }
+    const double c = (double)v;
+    if (c <= 1e15) {
+        // lit <=> the linear value the general kernel forms is a positive float (lin_f64)
+        const bool lit = (c > 0.04045) ? true : ((float)(c * (1.0 / 12.92)) > 0.0f);
+        return lit ? grey_hue : 0.0f;
+    }
+    // NaN, or so large that the float linear value overflows: whatever the general code answers
+    LinPx p;
+    lin_f64(c, p.hg, p.lg);
+    p.hr = p.hb = p.hg; p.lr = p.lb = p.lg;
+    return hue_from_diff(make_diff(p));
+}
+
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 k_gray_hue(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
     const float grey_hue = hue_deg(GREY_V, GREY_U);
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float h;
-        if (sizeof(TIn) == 1) {
-            h = in[i] != 0 ? grey_hue : 0.0f;
-        } else if (sizeof(TIn) == 4) {
-            // float32 channels: the general kernels form the pixel with diff_from_f32
-            const float c = (float)in[i];
-            if (c <= 1e15f) {
-                // lit <=> the linear value of G there is a positive float
-                const bool lit = (c > SRGB_T) ? true : (c * (1.0f / 12.92f) > 0.0f);
-                h = lit ? grey_hue : 0.0f;
-            } else {
-                h = hue_from_diff(diff_from_f32(c, c, c));      // NaN, +inf, or a power that overflows
-            }
-        } else {
-            const double c = (double)in[i];
-            if (c <= 1e15) {
-                // lit <=> the linear value the general kernel forms is a positive float (lin_f64)
-                const bool lit = (c > 0.04045) ? true : ((float)(c * (1.0 / 12.92)) > 0.0f);
-                h = lit ? grey_hue : 0.0f;
-            } else {
-                // NaN, or so large that the float linear value overflows: whatever the general code answers
-                LinPx p;
-                lin_f64(c, p.hg, p.lg);
-                p.hr = p.hb = p.hg; p.lr = p.lb = p.lg;
-                h = hue_from_diff(make_diff(p));
-            }
-        }
-        out[i] = (TOut)h;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (TOut)gray_hue_px<TIn>(in[i], grey_hue);
+}
+
+// float64 -> float64 (config 3 of BASELINE.json: to_hue of a float64 grayscale image): four pixels per thread,
+// one 256-bit load and one 256-bit store each (whole DRAM sectors per request); 32-byte aligned bases, n_quads = n / 4
+__global__ void __launch_bounds__(256)
+k_gray_hue_wide(const double *__restrict__ in, double *__restrict__ out, long long n_quads) {
+    const float grey_hue = hue_deg(GREY_V, GREY_U);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += stride) {
+        double a, b, c, d;
+        asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(in + 4 * i));
+        stg_f64x4(out + 4 * i, (double)gray_hue_px<double>(a, grey_hue), (double)gray_hue_px<double>(b, grey_hue),
+                  (double)gray_hue_px<double>(c, grey_hue), (double)gray_hue_px<double>(d, grey_hue));
     }
 }
 

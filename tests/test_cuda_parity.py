@@ -1802,3 +1802,48 @@ def test_banded_map_hue_watermelon_and_melonize(cu):
         cu.edit_husl(d32, edit=wm)
     with pytest.raises(cu.CudaError):
         cu._husl_to_rgb(hsl, dtype=np.float32, edit=wm)                         # uint8 RGB only
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_edit_husl_pass_group_sizes_alignment_and_guard_bands(cu, dtype):
+    """The explicit edit pass (k_husl_edit_wide: 96-byte groups with 256-bit accesses + one-pixel-per-thread
+    rest) against numpy on the same float32 arithmetic: every size around the group size, bases at every
+    element offset (only 32-byte aligned ones take the wide kernel), in place and into another array, a
+    full edit (hue wrap, saturation clamp, ranges); nothing outside the array is written."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(5)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    ed = dict(hue=(300, 40), saturation=(10, 95), lightness=(5, 90), h=(1.0, 77.5), s=(1.5, -5), l=(0.8, 3))
+    f = np.float32
+
+    def spec(a):
+        h, s, l = (a[:, i].astype(f) for i in range(3))   # noqa: E741
+        sel = ((h >= 300) | (h <= 40)) & (s >= 10) & (s <= 95) & (l >= 5) & (l <= 90)
+        hn = h * f(1.0) + f(77.5)
+        hn = hn - f(360) * np.floor(hn * f(1.0 / 360.0))
+        hn = np.where((hn >= 360) | (hn < 0), f(0), hn)
+        sn = np.clip(s * f(1.5) + f(-5), 0, 100).astype(f)
+        ln = np.clip(l * f(0.8) + f(3), 0, 100).astype(f)
+        out = a.copy()
+        for i, (old, new) in enumerate(((h, hn), (s, sn), (l, ln))):
+            new = np.where(sel, new, old)
+            out[:, i] = np.where(new == old, a[:, i], new.astype(dtype))
+        return out
+
+    for n in (1, 3, 4, 7, 8, 9, 31, 32, 33, 257, 4099):
+        for off in range(0, 9):
+            a = np.stack([rng.uniform(0, 360, n), rng.uniform(0, 100, n), rng.uniform(0, 100, n)], axis=1).astype(dtype)
+            want = spec(a)
+            pad = 16
+            buf = torch.full((pad + off + 3 * n + pad,), -7.0, dtype=tdt, device="cuda")
+            view = buf[pad + off: pad + off + 3 * n].view(n, 3)
+            view.copy_(torch.from_numpy(a))
+            other = torch.full((pad + off + 3 * n + pad,), -9.0, dtype=tdt, device="cuda")
+            oview = other[pad + off: pad + off + 3 * n].view(n, 3)
+            assert cu.edit_husl(view, out=oview, **ed) is oview
+            assert np.array_equal(oview.cpu().numpy(), want) and np.array_equal(view.cpu().numpy(), a)
+            cu.edit_husl(view, **ed)                                        # in place
+            assert np.array_equal(view.cpu().numpy(), want), (n, off)
+            for b, fill in ((buf, -7.0), (other, -9.0)):
+                g = b.cpu().numpy()
+                assert np.all(g[:pad + off] == fill) and np.all(g[pad + off + 3 * n:] == fill), (n, off)
