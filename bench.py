@@ -823,10 +823,10 @@ def run_cuda(args):
         if hv64 is not None:
             record("nv12_to_husl_f64", "k_nv12<husl,double>", lambda: _cuda.nv12_to_husl(ysurf, uvsurf, out=hv64, stream=stream), 25.5, px)
         record("nv12_to_husl_f32", "k_nv12<husl,float>", lambda: _cuda.nv12_to_husl(ysurf, uvsurf, out=hv32, stream=stream), 13.5, px)
-        record("edit_husl_f64_in_place", "k_husl_edit<double>", lambda: _cuda.edit_husl(dev_hsl, edit, stream=stream), 48, px)
+        record("edit_husl_f64_in_place", "k_husl_edit_wide<double>", lambda: _cuda.edit_husl(dev_hsl, edit, stream=stream), 48, px)
         record("nv12_edit_nv12", "k_to_nv12<nv12>", lambda: _cuda.nv12_edit_nv12(ysurf, uvsurf, edit, out_y=ysurf, out_uv=uvsurf, stream=stream), 3, px)
         record("frgb_f64_to_husl_f64", "k_fwd_flt<double,double>", lambda: _cuda._rgb_to_husl(f64in, out=f64out, stream=stream), 48, px2)
-        record("husl_f64_to_frgb_f64", "k_inv_flt<double,double>",
+        record("husl_f64_to_frgb_f64", "k_inv_flt_wide",
                lambda: _cuda._husl_to_rgb(f64out, out=f64in, dtype=np.float64, stream=stream), 48, px2)
         record("frgb_f32_to_husl_f32", "k_fwd_flt<float,float>", lambda: _cuda._rgb_to_husl(f32in, out=f32out, dtype=np.float32, stream=stream), 24, px2)
         with __import__("warnings").catch_warnings():

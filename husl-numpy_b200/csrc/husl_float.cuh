@@ -211,4 +211,29 @@ k_inv_flt(const TIn *__restrict__ in, TOut *__restrict__ out, long long n_tiles)
     cp_async_wait<0>();
 }
 
+// float64 HUSL -> float64 RGB in [0,1] (what the reference's _husl_to_rgb returns, _cython_opt.pyx:177-246) with
+// 256-bit accesses: a thread owns 4 pixels = 96 bytes on either side, three LDG.256 in, three STG.256 out, no shared
+// memory at all -- the access pattern that took the explicit edit pass from 0.76 to 0.93 of the copy peak
+// (husl_edit.cuh: k_husl_edit_wide).  32-byte aligned bases; n_groups = n / 4, the rest goes to k_inv_any.
+__global__ void __launch_bounds__(256)
+k_inv_flt_wide(const double *__restrict__ in, double *__restrict__ out, long long n_groups) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        double v[12];
+        ldg_f64x4(in + 12 * g, v[0], v[1], v[2], v[3]);
+        ldg_f64x4(in + 12 * g + 4, v[4], v[5], v[6], v[7]);
+        ldg_f64x4(in + 12 * g + 8, v[8], v[9], v[10], v[11]);
+        double r[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float R, G, B;
+            rgb255_from_husl<true, wide_in<double>()>((float)v[3 * j], (float)v[3 * j + 1], (float)v[3 * j + 2], R, G, B);
+            r[3 * j] = (double)(R * (1.0f / 255.0f)); r[3 * j + 1] = (double)(G * (1.0f / 255.0f)); r[3 * j + 2] = (double)(B * (1.0f / 255.0f));
+        }
+        stg_f64x4(out + 12 * g, r[0], r[1], r[2], r[3]);
+        stg_f64x4(out + 12 * g + 4, r[4], r[5], r[6], r[7]);
+        stg_f64x4(out + 12 * g + 8, r[8], r[9], r[10], r[11]);
+    }
+}
+
 }  // namespace husl

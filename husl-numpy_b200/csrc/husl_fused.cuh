@@ -24,9 +24,6 @@
 
 namespace husl {
 
-__device__ __forceinline__ void ldg_f64x4(const double *p, double &a, double &b, double &c, double &d) {
-    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
 
 // lanes hold 4 consecutive pixels: unpack 3 words -> 4 x LinPx through the shared table
 __device__ __forceinline__ void lookup4(const unsigned char *tab, uint32_t w0, uint32_t w1, uint32_t w2,

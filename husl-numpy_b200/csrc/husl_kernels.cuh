@@ -47,6 +47,9 @@ constexpr int TAB_BYTES = 256 * 32 * 8; // replicated table: [value][lane] float
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t *p) { return __ldg(p); }
 
 // 256-bit global store (PTX 8.8+, sm_100+); p must be 32-byte aligned
+__device__ __forceinline__ void ldg_f64x4(const double *p, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 __device__ __forceinline__ void stg_f64x4(double *p, double a, double b, double c, double d) {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
@@ -357,20 +360,6 @@ k_gray_hue(const TIn *__restrict__ in, TOut *__restrict__ out, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = (TOut)gray_hue_px<TIn>(in[i], grey_hue);
-}
-
-// float64 -> float64 (config 3 of BASELINE.json: to_hue of a float64 grayscale image): four pixels per thread,
-// one 256-bit load and one 256-bit store each (whole DRAM sectors per request); 32-byte aligned bases, n_quads = n / 4
-__global__ void __launch_bounds__(256)
-k_gray_hue_wide(const double *__restrict__ in, double *__restrict__ out, long long n_quads) {
-    const float grey_hue = hue_deg(GREY_V, GREY_U);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += stride) {
-        double a, b, c, d;
-        asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(in + 4 * i));
-        stg_f64x4(out + 4 * i, (double)gray_hue_px<double>(a, grey_hue), (double)gray_hue_px<double>(b, grey_hue),
-                  (double)gray_hue_px<double>(c, grey_hue), (double)gray_hue_px<double>(d, grey_hue));
-    }
 }
 
 template <typename TIn, typename TOut, int ED = -1>

@@ -354,16 +354,6 @@ int run_fwd_dev(DevCtx &c, const void *in, int in_dt, int channels, void *out, i
     if (HUE && channels == 1) {
         // grayscale -> hue is a constant per lit pixel: one streaming kernel, no per-pixel colour math
         if (n <= 0) return NPHUSL_OK;
-        if (in_dt == NPHUSL_F64 && out_dt == NPHUSL_F64 && aligned(in, 32) && aligned(out, 32) && n >= 4) {
-            const long long quads = n / 4;
-            k_gray_hue_wide<<<grid_for(quads, 256, c.sms * 8), 256, 0, s>>>((const double *)in, (double *)out, quads);
-            g_launches++;
-            if ((rc = check_launch("k_gray_hue_wide"))) return rc;
-            in = (const double *)in + 4 * quads;
-            out = (double *)out + 4 * quads;
-            n -= 4 * quads;
-            if (n <= 0) return NPHUSL_OK;
-        }
         const int grid = grid_for(n, 256, c.sms * 8);
 #define GRAY_GO(TI, TO) k_gray_hue<TI, TO><<<grid, 256, 0, s>>>((const TI *)in, (TO *)out, n)
         if (in_dt == NPHUSL_U8) { if (out_dt == NPHUSL_F32) GRAY_GO(uint8_t, float); else GRAY_GO(uint8_t, double); }
@@ -520,6 +510,13 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
     }
     if (!edit && !bands && out_dt != NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
         // float RGB in [0,1] out (what the reference's _husl_to_rgb returns, _cython_opt.pyx:177-192)
+        if (in_dt == NPHUSL_F64 && out_dt == NPHUSL_F64 && aligned(in, 32) && aligned(out, 32)) {
+            const long long groups = n / 4;
+            k_inv_flt_wide<<<grid_for(groups, 256, c.sms * 8), 256, 0, s>>>((const double *)in, (double *)out, groups);
+            g_launches++;
+            if ((rc = check_launch("k_inv_flt_wide"))) return rc;
+            done = groups * 4;
+        } else {
         const long long tiles = n / TILE_PX;
         const int grid = grid_for(tiles, FLT_BLOCK / 32, c.sms * FLT_MINB);
 #define FLT_GO(TI, TO) do { \
@@ -533,6 +530,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
         g_launches++;
         if ((rc = check_launch("k_inv_flt"))) return rc;
         done = tiles * TILE_PX;
+        }
     }
     const long long rest = n - done;
     if (rest <= 0) return NPHUSL_OK;
