@@ -313,6 +313,40 @@ k_inv_tma(const TIn *__restrict__ in, uint32_t *__restrict__ out, long long n_ti
 }
 
 // ---------------------------------------------------------------------------------
+// (b) again, float64 HUSL with 32-byte aligned input: no ring at all
+// ---------------------------------------------------------------------------------
+// A thread reads its own 4 pixels (96 bytes) with three 256-bit loads (LDG.E.ENL2.256: every request is one whole DRAM
+// sector) and writes its 12 result bytes with three 32-bit stores; no shared memory, no mbarriers, no bulk copies.  Groups are
+// walked from the END of the image like k_inv_tma (the producer's last ~100 MB are still in L2).  Measured against the
+// TMA ring (profiles/r02_ab_inv.txt, session 3): to_rgb 0.294 -> 0.280 ms stand-alone, the to_husl -> to_rgb(edit) step
+// 0.598 -> 0.580 ms.  What matters is how many bytes an SM keeps in flight: one CTA of 1024 threads (32 warps x 3 KB) is the
+// optimum, 768 x 1 and 512 x 2 are within 1 %, 16 warps or 36 - 64 warps per SM lose 10 - 25 %.
+template <int BLOCK, int MINB, int ED = -1>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_inv_direct(const double *__restrict__ in, uint32_t *__restrict__ out, long long n_groups, const EditArg<ED> ea = EditArg<ED>()) {
+    const long long stride = (long long)gridDim.x * BLOCK;
+    for (long long g = (long long)blockIdx.x * BLOCK + threadIdx.x; g < n_groups; g += stride) {
+        const long long r = n_groups - 1 - g;
+        double v[12];
+        ldg_f64x4(in + 12 * r, v[0], v[1], v[2], v[3]);
+        ldg_f64x4(in + 12 * r + 4, v[4], v[5], v[6], v[7]);
+        ldg_f64x4(in + 12 * r + 8, v[8], v[9], v[10], v[11]);
+        uint32_t q[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float h = (float)v[3 * j], s = (float)v[3 * j + 1], l = (float)v[3 * j + 2], R, G, B;
+            edit_on_load<ED>(ea, h, s, l);
+            rgb255_from_husl<false, wide_in<double>() && ED < 0>(h, s, l, R, G, B);
+            q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
+        }
+        uint32_t *dst = out + 3 * r;
+        dst[0] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+        dst[1] = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+        dst[2] = __byte_perm(__byte_perm(q[8], q[9], 0x0040), __byte_perm(q[10], q[11], 0x0040), 0x5410);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // (b') rgb_from_husl, float32 HUSL: per-lane 16-byte async copies (LDGSTS) ring
 // ---------------------------------------------------------------------------------
 // The float32 inverse is bound by instruction issue (about 80 instructions per

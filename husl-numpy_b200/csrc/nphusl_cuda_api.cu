@@ -239,6 +239,10 @@ constexpr int HUSL_EDIT_CTAS = NPHUSL_HUSL_EDIT_CTAS;
 #ifndef NPHUSL_INV64_IST
 #define NPHUSL_INV64_IST 2
 #endif
+#ifndef NPHUSL_INVD_BLOCK
+#define NPHUSL_INVD_BLOCK 1024      // k_inv_direct: one CTA of 32 warps per SM (session 3 sweep: 1024 x 1 0.5798 ms per step, 768 x 1 0.5814,
+#endif                              // 512 x 2 0.5849, 384 x 2 0.5881, 256 x 4 0.5925; 16 warps 0.64, 36 - 64 warps 0.60 - 0.65; TMA ring 0.6008)
+constexpr int INVD_BLOCK = NPHUSL_INVD_BLOCK;
 constexpr int FWD64_BLOCK = NPHUSL_FWD64_BLOCK, FWD64_OST = NPHUSL_FWD64_OST;
 constexpr int INV64_BLOCK = NPHUSL_INV64_BLOCK, INV64_MINB = NPHUSL_INV64_MINB, INV64_IST = NPHUSL_INV64_IST;
 [[maybe_unused]] constexpr int FWD32_OST = NPHUSL_FWD32_OST;
@@ -447,6 +451,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
     if ((edit || bands) && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
         const int code = bands ? (bands->b.s_half > 0.0f ? 9 : 8) : EditShape(*edit).code();
+        long long tile_px = TILE_PX;            // pixels per unit of the kernel that ran (tiles of 128, or groups of 4)
         // instantiated per edit shape like k_edit: README-style edits (L scaled inside / outside a hue arc) carry no
         // hue-wrap, saturation or range arithmetic
 #define INV_EDIT(ED) do { \
@@ -457,6 +462,9 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
             if ((rc = flt_attr(attr32, c, k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, ED>, sm))) return rc; \
             k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, ED><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK, sm, s>>>( \
                 (const float *)in, (uint32_t *)out, tiles, ea); \
+        } else if (aligned(in, 32)) { \
+            k_inv_direct<INVD_BLOCK, 1, ED><<<grid_for(n / 4, INVD_BLOCK, c.sms), INVD_BLOCK, 0, s>>>((const double *)in, (uint32_t *)out, n / 4, ea); \
+            tile_px = 4; \
         } else { \
             constexpr int sm = (INV64_BLOCK / 32) * InvSmem<double, INV64_IST>::PER_WARP; \
             static std::atomic<bool> attr64[MAX_DEV]; \
@@ -479,10 +487,11 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
 #undef INV_EDIT
         g_launches++;
         if ((rc = check_launch("k_inv (edit on load)"))) return rc;
-        done = tiles * TILE_PX;
+        done = n / tile_px * tile_px;
     }
     if (!edit && !bands && out_dt == NPHUSL_U8 && aligned(in, 16) && aligned(out, 4) && n >= TILE_PX) {
         const long long tiles = n / TILE_PX;
+        long long tile_px = TILE_PX;
         constexpr int W = INV_BLOCK / 32;
         if (use_tma() && aligned(out, 16)) {
             if ((rc = set_attrs(c))) return rc;
@@ -493,7 +502,10 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
                 k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK,
                                                                (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP, s>>>(
                     (const float *)in, (uint32_t *)out, tiles);
-            else
+            else if (aligned(in, 32)) {
+                k_inv_direct<INVD_BLOCK, 1><<<grid_for(n / 4, INVD_BLOCK, c.sms), INVD_BLOCK, 0, s>>>((const double *)in, (uint32_t *)out, n / 4);
+                tile_px = 4;
+            } else
                 k_inv_tma<double, INV64_BLOCK, INV64_MINB, INV64_IST><<<grid_for(tiles, INV64_BLOCK / 32, c.sms * INV64_MINB), INV64_BLOCK,
                                                                         (INV64_BLOCK / 32) * InvSmem<double, INV64_IST>::PER_WARP, s>>>(
                     (const double *)in, (uint32_t *)out, tiles);
@@ -506,7 +518,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
         }
         g_launches++;
         if ((rc = check_launch("k_inv_u8"))) return rc;
-        done = tiles * TILE_PX;
+        done = n / tile_px * tile_px;
     }
     if (!edit && !bands && out_dt != NPHUSL_U8 && aligned(in, 16) && aligned(out, 16) && n >= TILE_PX) {
         // float RGB in [0,1] out (what the reference's _husl_to_rgb returns, _cython_opt.pyx:177-192)

@@ -1,5 +1,5 @@
-"""to_husl u8 -> f64 stand-alone and inside the to_husl -> to_rgb(edit) step, for the current
-NPHUSL_FWD64_DIRECT setting (A/B knob of nphusl_cuda_api.cu); grayscale f64 -> hue; 8 x 4K frames."""
+"""to_husl u8 -> f64 / to_rgb f64 -> u8 stand-alone and as the to_husl -> to_rgb(edit) step, for the current
+setting of an A/B environment knob of nphusl_cuda_api.cu; 8 x 4K frames, CUDA events around the Python calls."""
 import json
 import os
 import sys
@@ -28,8 +28,10 @@ def main():
     hsl = torch.empty(rgb.shape, dtype=torch.float64, device="cuda")
     out = torch.empty_like(rgb)
     ed = cu.Edit(hue=(250, 290), invert=True, l=(0.5, 0))
-    res = {"direct": os.environ.get("NPHUSL_FWD64_DIRECT", "0")}
+    res = {"lib": os.environ.get("NPHUSL_CUDA_LIB", "in-tree")}
     res["to_husl_f64_ms"] = round(timed(lambda: cu._rgb_to_husl(rgb, out=hsl)), 4)
+    res["to_rgb_f64_ms"] = round(timed(lambda: cu._husl_to_rgb(hsl, out=out)), 4)
+    res["to_rgb_f64_edit_ms"] = round(timed(lambda: cu._husl_to_rgb(hsl, out=out, edit=ed)), 4)
 
     def step():
         cu._rgb_to_husl(rgb, out=hsl)
@@ -46,12 +48,22 @@ def main():
         b.record(); torch.cuda.synchronize()
         t.append(a.elapsed_time(b) / 20)
     res["step_ms"] = round(float(np.median(t)), 4)
-    ref = cu._rgb_to_husl(rgb[:1].cpu().numpy())
-    assert np.array_equal(hsl[:1].cpu().numpy(), ref)
-    g = torch.rand(4000, 4000, dtype=torch.float64, device="cuda")
-    ho = torch.empty_like(g)
-    g3 = g[..., None].expand(-1, -1, 3)
-    res["gray_f64_hue_ms"] = round(timed(lambda: cu._rgb_to_hue(g3, out=ho)), 4)
+    def step0():
+        cu._rgb_to_husl(rgb, out=hsl)
+        cu._husl_to_rgb(hsl, out=out)
+    t = []
+    for _ in range(5):
+        for _ in range(3):
+            step0()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            step0()
+        b.record(); torch.cuda.synchronize()
+        t.append(a.elapsed_time(b) / 20)
+    res["step_no_edit_ms"] = round(float(np.median(t)), 4)
+    assert torch.equal(out, rgb)
     print(json.dumps(res))
 
 
