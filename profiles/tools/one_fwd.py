@@ -1,0 +1,9 @@
+import sys, os, numpy as np, torch
+sys.path.insert(0, "husl-numpy_b200")
+from nphusl import _cuda as cu
+rgb = torch.randint(0, 256, (8, 2160, 3840, 3), dtype=torch.uint8, device="cuda")
+hsl = torch.empty(rgb.shape, dtype=torch.float64, device="cuda")
+for _ in range(3):
+    cu._rgb_to_husl(rgb, out=hsl)
+torch.cuda.synchronize()
+print("ok")

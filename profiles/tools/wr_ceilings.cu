@@ -103,6 +103,17 @@ __global__ void k_fill_dynamic_warp(uint4 *__restrict__ b, size_t tiles, unsigne
     }
 }
 
+// fixed shares again, every CTA recording when it started and finished (globaltimer, ns) and on which SM it ran
+__global__ void k_fill16_timed(uint4 *__restrict__ b, size_t n, unsigned long long *t) {
+    unsigned long long t0, t1; unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = make_uint4(i, 1, 2, 3);
+    __syncthreads();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    if (threadIdx.x == 0) { t[3 * blockIdx.x] = t0; t[3 * blockIdx.x + 1] = t1; t[3 * blockIdx.x + 2] = sm; }
+}
+
 template <typename F>
 float best_ms(F launch, int reps = 15) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -144,6 +155,22 @@ int main() {
         rep("bulk 3 KB per warp, 4 in flight (warps, 1)", warps, 1, best_ms([&] { k_fill_bulk<3072, 4><<<sms, warps * 32, warps * 3072>>>((unsigned char *)hsl, bytes / 3072); }));
         rep("bulk 6 KB per warp, 2 in flight (warps, 1)", warps, 1, best_ms([&] { k_fill_bulk<6144, 2><<<sms, warps * 32, warps * 6144>>>((unsigned char *)hsl, bytes / 6144); }));
         if (warps <= 16) rep("bulk 12 KB per warp, 2 in flight (warps, 1)", warps, 1, best_ms([&] { k_fill_bulk<12288, 2><<<sms, warps * 32, warps * 12288>>>((unsigned char *)hsl, bytes / 12288); }));
+    }
+    {
+        unsigned long long *t, ht[3 * 148];
+        CK(cudaMalloc(&t, sizeof ht));
+        for (int rep_i = 0; rep_i < 2; ++rep_i) {
+            k_fill16_timed<<<sms, 1024>>>((uint4 *)hsl, n16, t);
+            CK(cudaMemcpy(ht, t, sizeof ht, cudaMemcpyDeviceToHost));
+        }
+        unsigned long long first = ~0ull;
+        for (int i = 0; i < sms; ++i) first = ht[3 * i] < first ? ht[3 * i] : first;
+        printf("fixed shares, 1024 x 1: per-CTA finish time (us after the first start), by SM id:\n");
+        std::vector<std::pair<unsigned, double>> v;
+        for (int i = 0; i < sms; ++i) v.push_back({(unsigned)ht[3 * i + 2], (ht[3 * i + 1] - first) / 1000.0});
+        std::sort(v.begin(), v.end());
+        for (int i = 0; i < sms; ++i) printf("%3u:%6.1f%s", v[i].first, v[i].second, (i % 12 == 11) ? "\n" : " ");
+        printf("\n");
     }
     unsigned *counter;
     CK(cudaMalloc(&counter, 4));
