@@ -795,8 +795,8 @@ def run_cuda(args):
             lut_ready = False
         for name, kern, fn, nbytes in (
                 ("to_husl_u8_f64", "k_fwd_tma<double>", lambda: _cuda._rgb_to_husl(dev_in, out=dev_hsl, stream=stream), 27),
-                ("to_rgb_f64_u8", "k_inv_tma<double>", lambda: _cuda._husl_to_rgb(dev_hsl, out=dev_out, stream=stream), 27),
-                ("to_rgb_f64_u8_edit", "k_inv_tma<double,edit>", lambda: _cuda._husl_to_rgb(dev_hsl, out=dev_out, stream=stream, edit=edit), 27),
+                ("to_rgb_f64_u8", "k_inv_direct", lambda: _cuda._husl_to_rgb(dev_hsl, out=dev_out, stream=stream), 27),
+                ("to_rgb_f64_u8_edit", "k_inv_direct<edit>", lambda: _cuda._husl_to_rgb(dev_hsl, out=dev_out, stream=stream, edit=edit), 27),
                 ("to_husl_u8_f64_lut", "k_fwd_lut", lambda: _cuda._rgb_to_husl(dev_in, out=dev_hsl, stream=stream, mode="lut"), 27),
                 ("to_husl_u8_f32", "k_fwd_u8<float>", lambda: _cuda._rgb_to_husl(dev_in, out=h32, stream=stream), 15),
                 ("to_rgb_f32_u8", "k_inv_cp<float>", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream), 15),
@@ -846,7 +846,7 @@ def run_cuda(args):
         hbm, which = peaks()
         f64 = hdt == np.float64
         dom = (("to_husl", "k_fwd_tma<double>" if f64 else "k_fwd_u8<float>", t_fwd) if t_fwd >= t_inv
-               else ("to_rgb", "k_inv_tma<double,edit>" if f64 else "k_inv_cp<float,edit>", t_inv))
+               else ("to_rgb", "k_inv_direct<edit>" if f64 else "k_inv_cp<float,edit>", t_inv))
         achieved = px * bpp / (dom[2] * 1e-3) / 1e9
         kname = dom[1]
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": px * 3 * world, "d2h_bytes_per_step": px * 3 * world,

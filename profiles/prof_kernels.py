@@ -3,7 +3,7 @@
 device-resident 4K frames) a few times -- the command ncu wraps:
 
   python profiles/prof_kernels.py > gpurun_out/plain.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'k_(fwd|inv|edit|nv12)' \
+  ncu --set full --clock-control none --import-source on -k regex:'k_(fwd|inv|edit|nv12|husl|gray|bands|to_nv12)' \
       -o gpurun_out/prof python profiles/prof_kernels.py
 """
 import os
@@ -61,6 +61,9 @@ for _ in range(reps):
     _cuda.nv12_edit_rgb(ysurf, uvsurf, out=back.view(-1, 3840, 3), l=(0.5, 0))
     _cuda._rgb_to_husl(f64in, out=f64out)         # float64 RGB in [0,1] (2 frames), tiled float kernels
     _cuda._husl_to_rgb(f64out, out=f64in, dtype=np.float64)
+    _cuda._husl_to_rgb(h64, out=back, edit=_cuda.Bands("h", 45, 360, 130, 360))                       # hue_watermelon on load
+    _cuda.edit_rgb(rgb, edit=_cuda.Bands("l", 7, 100, 130, 360, stripe=(2, 100)), out=back)           # a melonize frame, fused
+    _cuda.edit_rgb(rgb, edit=edit, out=back)      # the README edit, fused
     _cuda.edit_rgb(rgb, out=back)                 # identity edit: exact round trip
 torch.cuda.synchronize()
 assert torch.equal(back, rgb)

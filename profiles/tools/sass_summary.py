@@ -10,9 +10,9 @@ import sys
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "husl-numpy_b200", "nphusl", "libnphusl_cuda.so")
-WATCH = ["UBLKCP", "SYNCS", "LDGSTS", "STG.E.ENL2.256", "STG.E.128", "LDG.E.128", "LDG.E.CONSTANT", "LDS", "STS", "MUFU",
+WATCH = ["UBLKCP", "SYNCS", "LDGSTS", "LDG.E.ENL2.256", "STG.E.ENL2.256", "STG.E.128", "LDG.E.128", "LDG.E.CONSTANT", "LDS", "STS", "MUFU",
          "DFMA", "DMUL", "DADD", "FFMA", "FMNMX3", "PRMT", "BAR", "CALL"]
-KEEP = re.compile(r"k_(fwd_tma|inv_tma|inv_cp|fwd_u8|edit<|fwd_lut_tile|fwd_flt|inv_flt|gray_hue|husl_edit|nv12<|to_nv12|fwd_planar|inv_planes_cp|rows_fwd)")
+KEEP = re.compile(r"k_(fwd_tma|inv_tma|inv_direct|inv_cp|bands|fwd_u8|edit<|fwd_lut_tile|fwd_flt|inv_flt|gray_hue|husl_edit|nv12<|to_nv12|fwd_planar|inv_planes_cp|rows_fwd)")
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 arch = sorted(set(re.findall(r"arch = (sm_\w+)", sass)))
