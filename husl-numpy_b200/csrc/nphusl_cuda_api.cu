@@ -34,6 +34,9 @@ using namespace husl;
 
 thread_local std::string t_err;
 thread_local bool t_host_async = false;
+// set by run_streamed around a kernel whose OUTPUT pointer is the device alias of a page-locked host buffer: kernels that
+// would write it in 4-byte pieces (k_inv_direct) give way to the ones that write whole tiles (bulk stores)
+thread_local bool t_out_is_host_alias = false;
 // host -> host calls: the small side in place (NPHUSL_ZERO_COPY=0 turns it off, an A/B knob)
 bool zero_copy_enabled() {
     static const bool v = [] {
@@ -462,7 +465,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
             if ((rc = flt_attr(attr32, c, k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, ED>, sm))) return rc; \
             k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST, ED><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK, sm, s>>>( \
                 (const float *)in, (uint32_t *)out, tiles, ea); \
-        } else if (aligned(in, 32)) { \
+        } else if (aligned(in, 32) && !t_out_is_host_alias) { \
             k_inv_direct<INVD_BLOCK, 1, ED><<<grid_for(n / 4, INVD_BLOCK, c.sms), INVD_BLOCK, 0, s>>>((const double *)in, (uint32_t *)out, n / 4, ea); \
             tile_px = 4; \
         } else { \
@@ -502,7 +505,7 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
                 k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK,
                                                                (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP, s>>>(
                     (const float *)in, (uint32_t *)out, tiles);
-            else if (aligned(in, 32)) {
+            else if (aligned(in, 32) && !t_out_is_host_alias) {
                 k_inv_direct<INVD_BLOCK, 1><<<grid_for(n / 4, INVD_BLOCK, c.sms), INVD_BLOCK, 0, s>>>((const double *)in, (uint32_t *)out, n / 4);
                 tile_px = 4;
             } else
@@ -796,7 +799,9 @@ int run_streamed(DevCtx &c, const void *src, int src_loc, size_t in_px, void *ds
             in_dev = (const char *)src + off * in_px;
         }
         void *out_dev = dst_alias ? (void *)(dst_alias + off * out_px) : (dst_host ? g.dout[s] : (void *)((char *)dst + off * out_px));
+        t_out_is_host_alias = dst_alias != nullptr;
         int krc = kernel(in_dev, out_dev, npx, g.st[s]);
+        t_out_is_host_alias = false;
         if (krc) return krc;
         if (dst_host && !dst_alias) {
             char *hp = (char *)dst + off * out_px;
