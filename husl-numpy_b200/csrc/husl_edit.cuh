@@ -124,6 +124,7 @@ __device__ __forceinline__ void edit_on_load<8>(const EditArg<8> &e, float &h, f
 template <>
 __device__ __forceinline__ void edit_on_load<9>(const EditArg<9> &e, float &h, float &s, float &l) { apply_bands<true>(e.a, h, s, l); }
 
+#ifndef HUSL_HOST_EMUL      // the kernels below are device code only (tests/emul builds apply_edit / apply_bands for the host)
 // ---------------------------------------------------------------------------------
 // in-place (or out-of-place) edit of an interleaved HUSL array: what a caller's
 // `hsl[..., 2][mask] *= 0.5` (README.md:77-81) does, as one pass over the array
@@ -194,5 +195,7 @@ k_husl_edit_wide(const unsigned char *in, unsigned char *out, long long n_groups
         st_256(out + g * 96, q[0]); st_256(out + g * 96 + 32, q[1]); st_256(out + g * 96 + 64, q[2]);
     }
 }
+
+#endif  // HUSL_HOST_EMUL
 
 }  // namespace husl

@@ -34,6 +34,10 @@ __device__ __forceinline__ float mufu_sin(float x) { return emul_noise(sinf(x));
 __device__ __forceinline__ float mufu_cos(float x) { return emul_noise(cosf(x)); }
 __device__ __forceinline__ uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 __device__ __forceinline__ float __saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }   // NaN -> 0 like the .SAT modifier
+// round-to-nearest single operations the compiler may not contract (the host build runs with -ffp-contract=off)
+__device__ __forceinline__ float __fmul_rn(float a, float b) { return a * b; }
+__device__ __forceinline__ float __fadd_rn(float a, float b) { return a + b; }
+__device__ __forceinline__ float __fsub_rn(float a, float b) { return a - b; }
 #else
 __device__ __forceinline__ float mufu_rcp(float x) {
     float r;

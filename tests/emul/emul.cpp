@@ -20,6 +20,7 @@ static inline float emul_noise(float v) {
     return v;
 }
 #include "../../husl-numpy_b200/csrc/husl_math.cuh"
+#include "../../husl-numpy_b200/csrc/husl_edit.cuh"
 
 using namespace husl;
 
@@ -28,6 +29,19 @@ static double lin_d(double c) { return c > 0.04045 ? pow((c + 0.055) / 1.055, 2.
 
 extern "C" {
 void emul_set_noise(int ulps) { g_noise_ulps = ulps; }
+
+// the HUSL-space stages of the fused / edit-on-load kernels on float32 HUSL triplets (csrc/husl_edit.cuh)
+void emul_apply_bands(float *hsl, long long n, const nphusl_bands *b, int stripe) {
+    const BandsDev a = bands_dev(*b);
+    for (long long i = 0; i < n; ++i) {
+        if (stripe) apply_bands<true>(a, hsl[3 * i], hsl[3 * i + 1], hsl[3 * i + 2]);
+        else apply_bands<false>(a, hsl[3 * i], hsl[3 * i + 1], hsl[3 * i + 2]);
+    }
+}
+void emul_apply_edit(float *hsl, long long n, const nphusl_edit *e) {
+    for (long long i = 0; i < n; ++i) apply_edit<true, true, true>(*e, hsl[3 * i], hsl[3 * i + 1], hsl[3 * i + 2]);
+}
+int emul_bands_last(const nphusl_bands *b) { return (int)bands_dev(*b).last; }
 
 // device linearisation of float channels vs the float64 formula: returns max relative error
 double emul_lin_max_rel_err(const double *c, long long n) {

@@ -14,6 +14,7 @@ import pytest
 
 import oracle as orc
 from conftest import hue_diff
+from specs import bands_spec
 
 pytestmark = pytest.mark.gpu
 
@@ -1700,24 +1701,6 @@ def test_device_generated_tables_vs_the_reference_tables_on_the_cube(cu, cube):
 
 
 # ---- the banded map of the reference's callers (examples.py:56-103) ----
-
-def bands_spec(hsl32, src, width, total, h_even, h_odd, stripe=None):
-    """hue_watermelon / one frame of melonize (examples.py:56-103) on a float32 HUSL array, written the
-    way the callers write it: for low, high in chunk(total, width): select = (x > low) & (x < high) ...
-    Band edges and centres in float32 (exact for the integer parameters the callers use)."""
-    f = np.float32
-    x = hsl32[..., src].copy()
-    out = hsl32.copy()
-    k = 0
-    while f(k) * f(width) < f(total):
-        lo, hi = f(k) * f(width), min(f(k + 1) * f(width), f(total))
-        out[..., 0][(x > lo) & (x < hi)] = f(h_odd if k & 1 else h_even)
-        if stripe:
-            c = f(0.5) * (lo + hi)
-            out[..., 1][(x > c - f(stripe[0])) & (x < c + f(stripe[0]))] = f(stripe[1])
-        k += 1
-    return out
-
 
 def test_banded_map_hue_watermelon_and_melonize(cu):
     """nphusl._cuda.Bands: to_rgb(hsl, edit=Bands(...)) and the fused edit_rgb(rgb, edit=Bands(...)) equal

@@ -119,3 +119,69 @@ def test_float32_channels_without_float64(emul, noise):
     emul.emul_fwd_f32(_p(a), _p(got), ctypes.c_longlong(len(a)))
     assert np.isnan(got[0]).any() and np.isnan(got[1]).any()
     assert np.all(np.abs(got[2:, 0] - 19.916405993809086) < 1e-3) and np.all(got[2:, 1] < 1e-3)
+
+
+# ---- the HUSL-space stages (csrc/husl_edit.cuh) on the CPU --------------------------------------------
+
+class _Bands(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_int), ("width", ctypes.c_float), ("total", ctypes.c_float), ("h_even", ctypes.c_float),
+                ("h_odd", ctypes.c_float), ("s_half", ctypes.c_float), ("s_value", ctypes.c_float)]
+
+
+class _Edit(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ("h_lo", "h_hi", "s_lo", "s_hi", "l_lo", "l_hi")] + [("invert", ctypes.c_int)] + \
+               [(n, ctypes.c_float) for n in ("h_mul", "h_add", "s_mul", "s_add", "l_mul", "l_add")]
+
+
+def test_banded_map_closed_form_equals_the_callers_loop(emul):
+    """apply_bands evaluates the callers' `for low, high in chunk(total, width)` loops (examples.py:56-103) without a loop:
+    x * (1 / width) proposes a band, the float32 edges decide, the stripe test looks at three band centres.  Swept against
+    the loop itself (tests/specs.py) over every band edge +- a few ulps, values below 0 and beyond `total`, NaN and
+    infinities, for integer and fractional widths, widths that do and do not divide the range, stripes wider than a band."""
+    from specs import bands_spec
+    from nphusl import chunk
+    rng = np.random.default_rng(3)
+    cases = [(0, 45, 360, None), (0, 45, 360, (3, 90)), (2, 7, 100, (2, 100)), (2, 1, 100, (2, 100)), (2, 3, 100, (2, 100)),
+             (2, 100, 100, (2, 100)), (2, 250, 100, (2, 100)), (1, 12.5, 100, (1.5, 40)), (0, 0.1, 360, (0.01, 5)),
+             (2, 33, 100, (20, 50)), (0, 359.99, 360, (1, 1)), (1, 1e-3, 1, (1e-4, 2)), (0, 7.3, 355.5, (0.7, 9))]
+    for src, width, total, stripe in cases:
+        nb = len(list(chunk(int(total), int(width)))) if float(width).is_integer() and float(total).is_integer() else None
+        b = _Bands(src, width, total, 130, 360, stripe[0] if stripe else 0, stripe[1] if stripe else 0)
+        last = emul.emul_bands_last(ctypes.byref(b))
+        if nb is not None:
+            assert last == nb - 1, (width, total, last, nb)            # the band count of the callers' chunk()
+        edges = np.arange(0, last + 3, dtype=np.float32) * np.float32(width)
+        x = np.concatenate([_ulps(np.repeat(edges, 9), np.tile(np.arange(-4, 5), edges.size)),
+                            _ulps(np.full(9, total, np.float32), np.arange(-4, 5)),
+                            rng.uniform(-0.2 * total, 1.3 * total, 20000).astype(np.float32),
+                            np.array([0.0, -0.0, np.nan, np.inf, -np.inf, -1e30, 1e30], np.float32)])
+        hsl = np.stack([rng.uniform(0, 360, x.size), rng.uniform(0, 100, x.size), rng.uniform(0, 100, x.size)], 1).astype(np.float32)
+        hsl[:, src] = x
+        want = bands_spec(hsl, src, width, total, 130, 360, stripe)
+        got = hsl.copy()
+        emul.emul_apply_bands(_p(got), ctypes.c_longlong(len(got)), ctypes.byref(b), 1 if stripe else 0)
+        bad = np.flatnonzero(~np.all((got == want) | (np.isnan(got) & np.isnan(want)), axis=1))
+        assert bad.size == 0, (src, width, total, stripe, x[bad][:6], got[bad][:3], want[bad][:3])
+        if not stripe:                                                  # the <true> instantiation is valid for s_half <= 0 too
+            got2 = hsl.copy()
+            emul.emul_apply_bands(_p(got2), ctypes.c_longlong(len(got2)), ctypes.byref(b), 1)
+            assert np.array_equal(got2, got, equal_nan=True)
+
+
+def test_edit_stage_equals_the_numpy_statement(emul):
+    """apply_edit<true, true, true> against tests/specs.py: hue arcs through 0, bounded and unbounded ranges, inversion, every
+    combination of edited channels; untouched channels and unselected pixels bit for bit."""
+    from specs import edit_spec
+    rng = np.random.default_rng(4)
+    n = 50000
+    hsl = np.stack([rng.uniform(0, 360, n), rng.uniform(0, 100, n), rng.uniform(0, 100, n)], 1).astype(np.float32)
+    hsl[:64, 0] = np.repeat(np.array([0, 250, 290, 360], np.float32), 16)
+    inf = float("inf")
+    for kw in (dict(hue=(250, 290), invert=True, l=(0.5, 0)), dict(lightness=(0, 62), l=(0, 0)), dict(saturation=(-inf, 80), l=(0, 0)),
+               dict(hue=(300, 40), saturation=(10, 95), lightness=(5, 90), h=(1.0, 77.5), s=(1.5, -5), l=(0.8, 3)),
+               dict(hue=(10, 200), h=(-1.0, 0.0)), dict(h=(2.0, 100.0), s=(0.0, 100.0)), dict(invert=True, l=(2.0, 0))):
+        e = _Edit(*(kw.get("hue", (-inf, inf)) + kw.get("saturation", (-inf, inf)) + kw.get("lightness", (-inf, inf))),
+                  int(kw.get("invert", False)), *(kw.get("h", (1.0, 0.0)) + kw.get("s", (1.0, 0.0)) + kw.get("l", (1.0, 0.0))))
+        got = hsl.copy()
+        emul.emul_apply_edit(_p(got), ctypes.c_longlong(n), ctypes.byref(e))
+        assert np.array_equal(got, edit_spec(hsl, **kw)), kw
