@@ -67,6 +67,9 @@ def main():
     ap.add_argument("--video-frames", type=int, default=1000)
     ap.add_argument("--only-video", action="store_true", help="run config 5 only")
     ap.add_argument("--skip-video", action="store_true", help="skip config 5")
+    ap.add_argument("--with-video", action="store_true",
+                    help="also run this tool's own round-1 config-5 loop (superseded: bench.py --workload video measures configs[4] "
+                         "through nphusl._shard.stream_frames, without per-thread setup and equality checks in the timed region)")
     args = ap.parse_args()
     devices = [int(d) for d in args.devices.split(",")]
     nphusl.enable_cuda()
@@ -76,8 +79,10 @@ def main():
 
     if not args.only_video:
         run_configs_1_to_4(out, ref, rng)
-    if not args.skip_video:
+    if args.with_video or args.only_video:
         run_config_5(out, ref, rng, args, devices)
+    else:
+        out["config5_video_e2e"] = "see bench.py --workload video (`video` in profiles/r02_bench_n*.json)"
     print(json.dumps(out, indent=1))
 
 
@@ -159,9 +164,9 @@ def run_configs_1_to_4(out, ref, rng):
           "max_dH_vs_oracle": float(hue_diff(h_g, h_o)[o_sat].max()),
           "gray_lightness_max_err": float(np.abs(nphusl.to_husl(grey4)[..., 2]
                                                  - orc.rgb_to_husl(np.repeat(grey4[..., None], 3, -1))[..., 2]).max())}
-    if ref.cy is not None:
-        f4 = img4 / 255.0
-        c3["cpu_ref_cython_to_hue"] = mpix(px4, best(lambda: ref.cy._rgb_to_hue(f4), 3))
+    if ref.pkg is not None:                                  # the reference package's own to_hue (its Cython + OpenMP path)
+        c3["cpu_ref_to_hue"] = mpix(px4, best(lambda: ref.pkg.to_hue(img4), 3))
+        c3["cpu_ref_to_hue_gray"] = mpix(px4, best(lambda: ref.pkg.to_hue(grey4), 3))
     out["config3_hue_4Mpx"] = c3
 
     # ---- config 4: device-resident 4K batches, to_husl -> lightness edit -> to_rgb --------
