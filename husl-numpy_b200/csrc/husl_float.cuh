@@ -215,14 +215,15 @@ k_inv_flt(const TIn *__restrict__ in, TOut *__restrict__ out, long long n_tiles)
 // 256-bit accesses: a thread owns 4 pixels = 96 bytes on either side, three LDG.256 in, three STG.256 out, no shared
 // memory at all -- the access pattern that took the explicit edit pass from 0.76 to 0.93 of the copy peak
 // (husl_edit.cuh: k_husl_edit_wide).  32-byte aligned bases; n_groups = n / 4, the rest goes to k_inv_any.
+// `out` may be `in` (a thread reads its 96 bytes before it writes them): plain loads, no __restrict__.
 __global__ void __launch_bounds__(256)
-k_inv_flt_wide(const double *__restrict__ in, double *__restrict__ out, long long n_groups) {
+k_inv_flt_wide(const double *in, double *out, long long n_groups) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
         double v[12];
-        ldg_f64x4(in + 12 * g, v[0], v[1], v[2], v[3]);
-        ldg_f64x4(in + 12 * g + 4, v[4], v[5], v[6], v[7]);
-        ldg_f64x4(in + 12 * g + 8, v[8], v[9], v[10], v[11]);
+        ld_f64x4(in + 12 * g, v[0], v[1], v[2], v[3]);
+        ld_f64x4(in + 12 * g + 4, v[4], v[5], v[6], v[7]);
+        ld_f64x4(in + 12 * g + 8, v[8], v[9], v[10], v[11]);
         double r[12];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -50,6 +50,10 @@ __device__ __forceinline__ uint32_t ldg_u32(const uint32_t *p) { return __ldg(p)
 __device__ __forceinline__ void ldg_f64x4(const double *p, double &a, double &b, double &c, double &d) {
     asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
+// the same through the coherent path (buffers the kernel may also write)
+__device__ __forceinline__ void ld_f64x4(const double *p, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void stg_f64x4(double *p, double a, double b, double c, double d) {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }

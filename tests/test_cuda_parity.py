@@ -1830,3 +1830,21 @@ def test_edit_husl_pass_group_sizes_alignment_and_guard_bands(cu, dtype):
             for b, fill in ((buf, -7.0), (other, -9.0)):
                 g = b.cpu().numpy()
                 assert np.all(g[:pad + off] == fill) and np.all(g[pad + off + 3 * n:] == fill), (n, off)
+
+
+def test_float64_rgb_out_of_float64_husl_in_the_same_buffer(cu):
+    """to_rgb(hsl, dtype=float64, out=hsl): the float-RGB result written over the HUSL array it came from (k_inv_flt_wide
+    reads a thread's 96 bytes before it writes them; tails through the one-pixel-per-thread kernel) equals the
+    out-of-place call, and both are within 2e-5 of the reference-made fixture values."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(91)
+    for n in (3, 4, 127, 128, 4741, 270 * 480):
+        hsl = np.stack([rng.uniform(0, 360, n), rng.uniform(0, 100, n), rng.uniform(0, 100, n)], 1)
+        d = torch.from_numpy(hsl).cuda()
+        want = cu._husl_to_rgb(d, dtype=np.float64).copy_to_host()
+        r = cu._husl_to_rgb(d, dtype=np.float64, out=d)
+        assert r is d and np.array_equal(d.cpu().numpy(), want)
+        ref = orc.husl_to_rgb_float(hsl) if hasattr(orc, "husl_to_rgb_float") else None
+        if ref is not None:
+            assert np.abs(want - ref).max() < 2e-5
+        assert want.min() >= 0.0 and want.max() <= 1.0
