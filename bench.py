@@ -799,7 +799,7 @@ def run_cuda(args):
                 ("to_rgb_f64_u8_edit", "k_inv_direct<edit>", lambda: _cuda._husl_to_rgb(dev_hsl, out=dev_out, stream=stream, edit=edit), 27),
                 ("to_husl_u8_f64_lut", "k_fwd_lut", lambda: _cuda._rgb_to_husl(dev_in, out=dev_hsl, stream=stream, mode="lut"), 27),
                 ("to_husl_u8_f32", "k_fwd_u8<float>", lambda: _cuda._rgb_to_husl(dev_in, out=h32, stream=stream), 15),
-                ("to_rgb_f32_u8", "k_inv_cp<float>", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream), 15),
+                ("to_rgb_f32_u8", "k_inv_direct32", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream), 15),
                 ("to_rgb_f32_u8_edit", "k_inv_cp<float,edit>", lambda: _cuda._husl_to_rgb(h32, out=dev_out, stream=stream, edit=edit), 15),
                 ("to_hue_u8_f64", "k_fwd_u8<double,hue>", lambda: _cuda._rgb_to_hue(dev_in, out=hue64, stream=stream), 11),
                 ("to_hue_u8_f32", "k_fwd_u8<float,hue>", lambda: _cuda._rgb_to_hue(dev_in, out=hue32, stream=stream), 7),

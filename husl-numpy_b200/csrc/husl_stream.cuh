@@ -346,6 +346,33 @@ k_inv_direct(const double *__restrict__ in, uint32_t *__restrict__ out, long lon
     }
 }
 
+// The float32 inverse without a ring: 4 pixels (48 bytes = three 128-bit loads, lanes 48 bytes apart: neighbouring requests
+// share their sectors through L1) per thread.  Only the edit-free instantiation fits the 32 registers that 2 x 1024 threads per SM
+// need, and only that shape beats the cp.async ring (0.1646 against 0.1694 ms; 1024 x 1, 512 x 2 ... 256 x 8: 0.177 - 0.21 ms), so
+// to_rgb(edit=...) of float32 HUSL stays on k_inv_cp.
+template <int BLOCK, int MINB, int ED = -1>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_inv_direct32(const float4 *__restrict__ in, uint32_t *__restrict__ out, long long n_groups, const EditArg<ED> ea = EditArg<ED>()) {
+    const long long stride = (long long)gridDim.x * BLOCK;
+    for (long long g = (long long)blockIdx.x * BLOCK + threadIdx.x; g < n_groups; g += stride) {
+        const long long r = n_groups - 1 - g;
+        const float4 a = __ldg(in + 3 * r), b = __ldg(in + 3 * r + 1), c = __ldg(in + 3 * r + 2);
+        const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        uint32_t q[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float h = v[3 * j], s = v[3 * j + 1], l = v[3 * j + 2], R, G, B;
+            edit_on_load<ED>(ea, h, s, l);
+            rgb255_from_husl<false, false>(h, s, l, R, G, B);
+            q[3 * j] = round_u8_bits(R); q[3 * j + 1] = round_u8_bits(G); q[3 * j + 2] = round_u8_bits(B);
+        }
+        uint32_t *dst = out + 3 * r;
+        dst[0] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+        dst[1] = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+        dst[2] = __byte_perm(__byte_perm(q[8], q[9], 0x0040), __byte_perm(q[10], q[11], 0x0040), 0x5410);
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // (b') rgb_from_husl, float32 HUSL: per-lane 16-byte async copies (LDGSTS) ring
 // ---------------------------------------------------------------------------------

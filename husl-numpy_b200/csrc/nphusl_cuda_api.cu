@@ -501,6 +501,12 @@ int run_inv_dev(DevCtx &c, const void *in, int in_dt, void *out, int out_dt, lon
             // tuned on B200 (profiles/r01_ab_variants.txt).  float32 input is bound by the math
             // pipes: 3-stage LDGSTS ring; float64 input is HBM-bound: 3-stage bulk-copy (TMA)
             // ring with mbarriers, 2 CTAs/SM
+            if (in_dt == NPHUSL_F32 && !t_out_is_host_alias) {
+                // no ring either: 4 pixels (three 128-bit loads) per thread, 2 x 1024 threads per SM at 32 registers keep the same
+                // ~96 KB per SM in flight as k_inv_direct: 0.1694 -> 0.1646 ms (session 3 sweep; every smaller shape loses)
+                k_inv_direct32<1024, 2><<<grid_for(n / 4, 1024, c.sms * 2), 1024, 0, s>>>((const float4 *)in, (uint32_t *)out, n / 4);
+                tile_px = 4;
+            } else
             if (in_dt == NPHUSL_F32)   // 4 CTAs x 384 threads = 48 warps/SM at 40 registers
                 k_inv_cp<INV32_BLOCK, INV32_MINB, INV32_IST><<<grid_for(tiles, INV32_BLOCK / 32, c.sms * INV32_MINB), INV32_BLOCK,
                                                                (INV32_BLOCK / 32) * InvCpSmem<INV32_IST>::PER_WARP, s>>>(
