@@ -79,6 +79,111 @@ k_skel(const uint32_t *__restrict__ in, unsigned char *__restrict__ out, long lo
 }
 
 template <typename F> float best_ms(F launch, int reps = 15);
+// ONE-SHOT grid: the kernel without arithmetic and without its table, every CTA (16 warps) converts K tiles per warp and exits;
+// the hardware hands CTAs out as SMs become free (what a ticket schedule imitates)
+template <int K>
+__global__ void __launch_bounds__(512, 1)
+k_skel_oneshot(const uint32_t *__restrict__ in, unsigned char *__restrict__ out, long long n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int TB = 3072, OST = 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *obuf = smem + warp * (OST * TB);
+    long long tile = (long long)blockIdx.x * (16 * K) + warp;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    if (tile < n_tiles) { const uint32_t *p = in + tile * 96 + lane * 3; w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2); }
+    int st = 0;
+#pragma unroll 1
+    for (int k = 0; k < K && tile < n_tiles; ++k, tile += 16) {
+        uint32_t n0 = 0, n1 = 0, n2 = 0;
+        if (k + 1 < K && tile + 16 < n_tiles) { const uint32_t *p = in + (tile + 16) * 96 + lane * 3; n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OST - 1) : "memory");
+        __syncwarp();
+        unsigned char *wr = obuf + st * TB + lane * 96;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) *reinterpret_cast<double2 *>(wr + 16 * j) = make_double2((double)__uint_as_float(w0 + j), (double)__uint_as_float(w1 ^ w2));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + tile * TB), "r"(smem_addr(obuf + st * TB)), "r"(TB) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        st ^= 1;
+        w0 = n0; w1 = n1; w2 = n2;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// PERSISTENT CTAs with WARP-granular tickets: warp slot w of every CTA draws from counter[w]; ticket t -> tile t * 16 + w, so the
+// tiles are handed out in address order, no CTA barrier.  Tickets are drawn two tiles ahead (one for the input prefetch).
+template <bool TABLE, int RUN>
+__global__ void __launch_bounds__(512, 1)
+k_skel_tickets(const uint32_t *__restrict__ in, unsigned char *__restrict__ out, long long n_tiles, unsigned *ctr) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int TB = 3072, OST = 2, TAB = TABLE ? 65536 : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (TABLE) { for (int i = threadIdx.x; i < 8192; i += blockDim.x) reinterpret_cast<float2 *>(smem)[i] = make_float2(i, 1); __syncthreads(); }
+    unsigned char *obuf = smem + TAB + warp * (OST * TB);
+    auto draw = [&]() -> long long {       // next run of RUN tiles of this warp slot: first tile index
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(ctr + warp * 64, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        return ((long long)t * RUN) * 16 + warp;
+    };
+    long long cur = draw(), nxt = draw();
+    unsigned pend = 0;                     // lane 0: the ticket drawn during this run, collected (shuffled) when the run ends
+    if (lane == 0) pend = atomicAdd(ctr + warp * 64, 1u);
+    int r = 0;
+    long long tile = cur;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    if (tile < n_tiles) { const uint32_t *p = in + tile * 96 + lane * 3; w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2); }
+    int st = 0;
+    float acc = 0;
+    while (tile < n_tiles) {
+        // the tile after this one: the next of the run, or the first of the next run (whose ticket is already here)
+        long long ntile;
+        if (r + 1 < RUN) ntile = tile + 16; else ntile = nxt;
+        uint32_t n0 = 0, n1 = 0, n2 = 0;
+        if (ntile < n_tiles) { const uint32_t *p = in + ntile * 96 + lane * 3; n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); }
+        if (r + 1 == RUN) {                  // ntile took `nxt`; the ticket after it was requested a whole run ago
+            nxt = ((long long)__shfl_sync(0xffffffffu, pend, 0) * RUN) * 16 + warp;
+            if (lane == 0) pend = atomicAdd(ctr + warp * 64, 1u);
+        }
+        if (TABLE) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc += reinterpret_cast<const float2 *>(smem)[((w0 >> (8 * k)) & 255) * 32 + lane].x;
+                acc += reinterpret_cast<const float2 *>(smem)[((w1 >> (8 * k)) & 255) * 32 + lane].x;
+                acc += reinterpret_cast<const float2 *>(smem)[((w2 >> (8 * k)) & 255) * 32 + lane].x;
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(OST - 1) : "memory");
+        __syncwarp();
+        unsigned char *wr = obuf + st * TB + lane * 96;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) *reinterpret_cast<double2 *>(wr + 16 * j) = make_double2((double)__uint_as_float(w0 + j) + acc, (double)__uint_as_float(w1 ^ w2));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + tile * TB), "r"(smem_addr(obuf + st * TB)), "r"(TB) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        st ^= 1;
+        w0 = n0; w1 = n1; w2 = n2;
+        tile = ntile;
+        r = (r + 1 == RUN) ? 0 : r + 1;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+template <bool TABLE, int RUN>
+float run_tickets(const uint32_t *in, unsigned char *out, long long tiles, int sms, unsigned *ctr) {
+    const int sm = (TABLE ? 65536 : 0) + 16 * 2 * 3072;
+    cudaFuncSetAttribute(k_skel_tickets<TABLE, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    return best_ms([&] { cudaMemsetAsync(ctr, 0, 4096); k_skel_tickets<TABLE, RUN><<<sms, 512, sm>>>(in, out, tiles, ctr); });
+}
+template <int K>
+float run_oneshot(const uint32_t *in, unsigned char *out, long long tiles) {
+    cudaFuncSetAttribute(k_skel_oneshot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 3072);
+    return best_ms([&] { k_skel_oneshot<K><<<(unsigned)((tiles + 16 * K - 1) / (16 * K)), 512, 16 * 2 * 3072>>>(in, out, tiles); });
+}
 // The same with the input arriving through a ring of TMA bulk loads (cp.async.bulk + mbarrier, IST tiles ahead): loads of the
 // async proxy are not something the generic-proxy MEMBAR of fence.proxy.async waits for.
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -187,6 +292,16 @@ int main() {
     rep("staging rewritten, 1 buffer per warp", run<2, 1>(in, out, tiles, sms));
     rep("staging rewritten, 3 buffers per warp", run<2, 3>(in, out, tiles, sms));
     rep("staging rewritten, 4 buffers per warp", run<2, 4>(in, out, tiles, sms));
+    unsigned *ctr; CK(cudaMalloc(&ctr, 4096));
+    rep("PERSISTENT, warp-granular tickets (16 counters), runs of 1 tile, no table", run_tickets<false, 1>(in, out, tiles, sms, ctr));
+    rep("... runs of 1 tile, with the table and its lookups", run_tickets<true, 1>(in, out, tiles, sms, ctr));
+    rep("... runs of 2 tiles, with the table", run_tickets<true, 2>(in, out, tiles, sms, ctr));
+    rep("... runs of 4 tiles, with the table", run_tickets<true, 4>(in, out, tiles, sms, ctr));
+    rep("ONE-SHOT grid: reads + staging + bulk stores, 1 tile per warp per CTA", run_oneshot<1>(in, out, tiles));
+    rep("... 2 tiles per warp per CTA", run_oneshot<2>(in, out, tiles));
+    rep("ONE-SHOT grid: reads + staging + bulk stores, 4 tiles per warp per CTA", run_oneshot<4>(in, out, tiles));
+    rep("... 16 tiles per warp per CTA", run_oneshot<16>(in, out, tiles));
+    rep("... 64 tiles per warp per CTA", run_oneshot<64>(in, out, tiles));
     rep("kernel without arithmetic, input reads with L2 evict-first + L1 no-allocate", run<39, 2>(in, out, tiles, sms));
     rep("kernel without arithmetic + L2 prefetch of the input 4 tiles ahead", run<23, 2, 4>(in, out, tiles, sms));
     rep("... 16 tiles ahead", run<23, 2, 16>(in, out, tiles, sms));
