@@ -4,7 +4,12 @@
 //                         (dispatched for float64 output, the HBM-bound case)
 //   k_inv_tma<TIn>    (b) rgb_from_husl : HUSL arrives through a ring of TMA bulk loads + mbarriers
 //                         (dispatched for float64 input)
-//   k_inv_cp          (b) rgb_from_husl, float32 input: the same ring filled by per-lane cp.async
+//                         (float64 input with a 16- but not 32-byte aligned base, and host -> host calls that
+//                         write their uint8 result in place over the link)
+//   k_inv_direct      (b) float64 input, 32-byte aligned: NO ring -- a thread reads its own 4 pixels with three
+//                         256-bit loads; the kernel that ships for device arrays since session 3 of round 2
+//   k_inv_cp          (b) rgb_from_husl, float32 input with an edit on load: the ring filled by per-lane cp.async
+//   k_inv_direct32    (b) float32 input without an edit: no ring either (three 128-bit loads per thread)
 //
 // Same per-pixel math as husl_kernels.cuh (husl_math.cuh); what changes is how
 // the wide side of each kernel (the 12 / 24 B-per-pixel HUSL stream) moves:
